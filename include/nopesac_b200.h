@@ -1,0 +1,143 @@
+/*
+ * nopesac_b200 — C ABI of the B200-native (sm_100a) NopeSAC one-plane RANSAC pose path.
+ *
+ * The reference (IceTTTb/NopeSAC @ 53c69c8) is pure Python/PyTorch and has no FFI of its own; each
+ * entry point below replaces the eager-PyTorch block of the reference named in its comment
+ * (paths relative to NopeSAC_Net/modeling/).  INTEGRATION.md shows the ctypes binding a reference
+ * maintainer would add inside PlaneCameraHead / MatchingHead.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to caller-owned memory (fp32 / int32, row-major, contiguous
+ *     unless a leading dimension is given); the library never allocates, frees or retains it;
+ *   - `stream` is a cudaStream_t passed as void*; everything is enqueued on it, nothing synchronises;
+ *   - return value 0 = success, negative nsac_status otherwise; nsac_last_error() gives the message
+ *     (thread-local); no exceptions, no exit();
+ *   - quaternions are (w,x,y,z); poses are (t[3], q[4]).
+ */
+#ifndef NOPESAC_B200_H
+#define NOPESAC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSAC_VERSION 100
+
+typedef enum {
+  NSAC_OK = 0,
+  NSAC_ERR_ARG = -1,      /* bad shape / null pointer / misalignment */
+  NSAC_ERR_LAUNCH = -2,   /* CUDA launch / runtime error */
+  NSAC_ERR_UNSUPPORTED = -3
+} nsac_status;
+
+/* activation codes for nsac_linear / nsac_conv epilogues */
+#define NSAC_ACT_NONE 0
+#define NSAC_ACT_RELU 1
+#define NSAC_ACT_LEAKY 2  /* LeakyReLU(0.01), camera_modules.py:47 */
+
+/* INFERENCE_OUT_CAM_TYPE (camera_head.py:930) */
+#define NSAC_CAM_SOFT 0
+#define NSAC_CAM_AVG_ALL 1
+#define NSAC_CAM_MIN_COST 2
+#define NSAC_CAM_MAX_SCORE 3
+
+int nsac_version(void);
+const char* nsac_last_error(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense layer: out[M,N] = act(x[M,K] . w[N,K]^T + bias).  Replaces every nn.Linear / MLP layer on
+ * the path (camera_modules.py:226-244; gnn.py:56-67).  `bias` may be NULL.  If bias_group_rows > 0
+ * the bias is a matrix [ceil(M/bias_group_rows), N] and row r uses bias row r / bias_group_rows
+ * (folds the broadcast initial-pose half of cat[init_feat, geo_feat], camera_head.py:980-986).
+ * ldx / ldo are row strides in floats (>= K / >= N).
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_linear(const float* x, int ldx, const float* w, const float* bias, int bias_group_rows,
+                float* out, int ldo, int M, int N, int K, int act, void* stream);
+
+/* LayerNorm over the last dim C (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x).
+ * gnn.py:90,94-96. */
+int nsac_layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res,
+                   int ldres, float* out, int ldo, int rows, int C, void* stream);
+
+/* Multi-head full attention (gnn.py:19-44): q [B,L,H*D], k,v [B,S,H*D] with row strides ldq/ldkv,
+ * out [B,L,H*D]; softmax(QK^T / sqrt(D)) V, no masks (inference). D must be 32. */
+int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out,
+                   int ldo, int B, int L, int S, int H, int D, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Matching tail (matching_head.py:75-99, 113-128, 228-234, 259-306 + camera_modules.py:15-34):
+ * geometry penalties from the matcher pose cam[B,7]=(t,q), descriptor similarity desc1.desc2/16,
+ * minus offset/offset_mult and angle/normal_mult, dustbin padding with bin_score, `iters` log-domain
+ * Sinkhorn iterations, then the mutual-NN + threshold assignment.
+ *   desc1 [B,n1,C], desc2 [B,n2,C], planes1 [B,n1,3], planes2 [B,n2,3]
+ *   -> log_scores_padded [B,n1+1,n2+1], assign [B,n1,n2] (0/1 floats)
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_match_sinkhorn_assign(const float* desc1, const float* desc2, const float* planes1,
+                               const float* planes2, const float* cam, const float* bin_score,
+                               float offset_mult, float normal_mult, int iters, float threshold,
+                               int B, int n1, int n2, int C, float* log_scores_padded, float* assign,
+                               void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Geo sequences (camera_head.py:1352-1425 called three times at :513-517, :555-569) + the 8-vector of
+ * :937-957.  The hypothesis list of pair b is the row-major nonzeros of assign[b] (torch.nonzero
+ * order), or — when hyp_pairs != NULL — the explicit list hyp_pairs[H,2] (int32, shared by all pairs).
+ *   planes1 [B,n1,3], planes2 [B,n2,3], t0 [B,3], q0 [B,4]
+ *   -> geo_local [B,NQ,6], geo_global [B,NQ,6], sig [B,NQ] (+-1), geo8 [B,NQ,8],
+ *      matched_num [B] int32, pair_idx [B,NQ,2] int32 (-1 padded)
+ * No host synchronisation (the reference syncs on torch.nonzero).
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_geo_sequence(const float* planes1, const float* planes2, const float* assign,
+                      const int32_t* hyp_pairs, int H, const float* t0, const float* q0, int B, int n1,
+                      int n2, int NQ, float* geo_local, float* geo_global, float* sig, float* geo8,
+                      int32_t* matched_num, int32_t* pair_idx, void* stream);
+
+/* Pose heads on per-hypothesis features (camera_head.py:990, 1018): q = normalize(Wr f + br),
+ * t = Wt f + bt for rows [rows,256]; either branch may be NULL. */
+int nsac_pose_heads(const float* feat_rot, const float* feat_tran, const float* w_rots,
+                    const float* b_rots, const float* w_trans, const float* b_trans, int rows, int C,
+                    float* q_out, float* t_out, void* stream);
+
+/* Score-MLP weights (camera_head.py:134-138): MLP(NQ,128,64,3) + Linear(64,1), rot and trans twins. */
+typedef struct {
+  const float* w1; const float* b1;   /* [128,NQ], [128] */
+  const float* w2; const float* b2;   /* [128,128], [128] */
+  const float* w3; const float* b3;   /* [64,128], [64] */
+  const float* w4; const float* b4;   /* [1,64], [1] */
+} nsac_score_mlp;
+
+/* ------------------------------------------------------------------------------------------------
+ * Hypothesis scoring + pose selection (camera_head.py:964-1115): for pair b with m = matched_num[b]
+ * one-plane hypotheses (index 0 = initial pose q0/t0, 1..m = q_h/t_h), residuals of every hypothesis
+ * against the m matched plane pairs, the two score MLPs, softmax over the m+1 hypotheses, and the
+ * avg / soft / min-cost / max-score selection.  Per-sample semantics for m == 0 / m == 1 (:964, :1068).
+ *   geo_local [B,NQ,6]; q_h [B,NQ,4]; t_h [B,NQ,3]; q0 [B,4]; t0 [B,3];
+ *   feat_rot/feat_tran [B,NQ,256] (fused one-plane features); feat_rot0/feat_tran0 [B,256];
+ *   -> pose [B,16] = (t[3], q[4], t_avg[3], q_avg[4], matched_num, 0)
+ *      optional: score_rot/score_tran [B,NQ+1]; sel_idx [B,2] int32 (-1 unless min-cost/max-score);
+ *      diag [3,B,NQ+1,NQ] = (l2_dist, normal_dist deg, offset_dist)
+ *   workspace: nsac_score_workspace_bytes(B, NQ) bytes.
+ * ---------------------------------------------------------------------------------------------- */
+size_t nsac_score_workspace_bytes(int B, int NQ);
+int nsac_score_aggregate(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
+                         const float* t0, const float* feat_rot, const float* feat_tran,
+                         const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
+                         const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp,
+                         const float* w_rots, const float* b_rots, const float* w_trans,
+                         const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
+                         float* score_rot, float* score_tran, int32_t* sel_idx, float* diag,
+                         void* workspace, void* stream);
+
+/* Assignment pruning with the refined pose (camera_head.py:605-629): keep matches whose warped normal
+ * angle < 45 deg and offset distance < 1 m.  pose rows are (t[3], q[4], ...) with stride ldpose. */
+int nsac_prune_assignment(const float* assign, const float* planes1, const float* planes2,
+                          const float* pose, int ldpose, int B, int n1, int n2, float* assign_out,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOPESAC_B200_H */

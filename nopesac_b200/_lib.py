@@ -1,0 +1,69 @@
+"""ctypes binding of libnopesac_b200.so (include/nopesac_b200.h).  No fallback: if the library is
+missing or a call fails, an exception is raised."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from .build import LIB_PATH
+
+c_float_p = C.c_void_p   # device pointers travel as integers
+c_int_p = C.c_void_p
+
+
+class ScoreMLP(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
+
+
+_SIGNATURES = {
+    "nsac_version": (C.c_int, []),
+    "nsac_last_error": (C.c_char_p, []),
+    "nsac_linear": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
+                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_layernorm": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
+                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
+                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_match_sinkhorn_assign": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                             C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),
+    "nsac_geo_sequence": (C.c_int, [c_float_p, c_float_p, c_float_p, c_int_p, C.c_int, c_float_p, c_float_p,
+                                    C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p,
+                                    c_float_p, c_int_p, c_int_p, C.c_void_p]),
+    "nsac_pose_heads": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, C.c_int,
+                                  C.c_int, c_float_p, c_float_p, C.c_void_p]),
+    "nsac_score_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nsac_score_aggregate": (C.c_int, [c_float_p] * 9 + [c_int_p, C.POINTER(ScoreMLP), C.POINTER(ScoreMLP)] +
+                             [c_float_p] * 4 + [C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p,
+                                                c_int_p, c_float_p, C.c_void_p, C.c_void_p]),
+    "nsac_prune_assignment": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, c_float_p, C.c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nopesac_b200 has no CPU / eager fallback).")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(status: int, what: str):
+    if status != 0:
+        msg = lib().nsac_last_error().decode("utf-8", "replace")
+        raise RuntimeError(f"{what} failed (status {status}): {msg}")

@@ -1,0 +1,393 @@
+"""CAMERA_HEAD of the path — same registry surface, constructor, call signature, 6-tuple return value and
+state-dict names as the reference `PlaneCameraHead` (camera_net/camera_head.py:21-138, 140-149, 400-640),
+computed by the CUDA kernels of libnopesac_b200 and *batched*: every `[0]`-indexed shortcut of the
+reference (quaternion sign flips :436,:600; early exits on matched_nums[0] :964,:1052,:1068) is applied
+per pair inside the kernels, with no host synchronisation anywhere on the path.
+
+    CAMERA_HEAD_REGISTRY.get(cfg.MODEL.CAMERA_HEAD.NAME)(cfg, input_shape)
+    output_cameras, trans_list, rot_list, [log_scores_padded], output_planeAss, pose_ref_outputs = head(
+        features1, features2, planeParam1, planeParam2, planeApp1, planeApp2, matching_net=matching_head)
+
+Inference only.  Extra keyword arguments (not in the reference):
+    hyp_pairs     int32 [H,2]  explicit hypothesis list (the "P planes x H hypotheses" stress mapping,
+                               SURVEY.md §8(d)); the matcher still runs and its assignment is reported.
+    initial_pose  (t [B,3], q [B,4])  skips the pixel pose network (stage set S3).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import ops
+from .compat import Registry, ShapeSpec
+
+__all__ = ["build_camera_head", "CAMERA_HEAD_REGISTRY", "PlaneCameraHead"]
+
+CAMERA_HEAD_REGISTRY = Registry("CAMERA_HEAD")
+CAMERA_HEAD_REGISTRY.__doc__ = "Registry for camera head. The call is expected to return an nn.Module."
+
+
+def build_camera_head(cfg, input_shape):
+    """camera_head.py:27-32."""
+    return CAMERA_HEAD_REGISTRY.get(cfg.MODEL.CAMERA_HEAD.NAME)(cfg, input_shape)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers (names = reference state-dict keys; initialisers as in the reference)
+# ---------------------------------------------------------------------------------------------------
+def _c2_xavier_fill(m):
+    nn.init.kaiming_uniform_(m.weight, a=1)
+    if m.bias is not None:
+        nn.init.constant_(m.bias, 0)
+
+
+def _c2_msra_fill(m):
+    nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+    if m.bias is not None:
+        nn.init.constant_(m.bias, 0)
+
+
+class MLP(nn.Module):
+    """camera_modules.py:226-244 (parameters only; evaluated through ops.linear)."""
+
+    def __init__(self, input_dim, hidden_dim, output_dim, num_layers):
+        super().__init__()
+        self.num_layers = num_layers
+        h = [hidden_dim] * (num_layers - 1)
+        self.layers = nn.ModuleList(nn.Linear(n, k) for n, k in zip([input_dim] + h, h + [output_dim]))
+        for layer in self.layers:
+            _c2_xavier_fill(layer)
+
+    def run(self, x: torch.Tensor, final_act: int = ops.ACT_NONE, out: Optional[torch.Tensor] = None):
+        for i, layer in enumerate(self.layers):
+            last = i == self.num_layers - 1
+            x = ops.linear(x, layer.weight, layer.bias, ops.ACT_RELU if not last else final_act,
+                           out=out if last else None)
+        return x
+
+
+class _NormConv(nn.Conv2d):
+    """detectron2.layers.Conv2d parameter layout: conv weight (+bias) and an optional `.norm` child."""
+
+    def __init__(self, cin, cout, k, padding=0, norm: Optional[nn.Module] = None, bias=True):
+        super().__init__(cin, cout, kernel_size=k, stride=1, padding=padding, bias=bias)
+        if norm is not None:
+            self.norm = norm
+
+
+def conv2d(in_channels, out_channels, kernel_size=3, stride=1, padding=None):
+    """camera_modules.py:36-48."""
+    return nn.Sequential(
+        nn.Conv2d(in_channels, out_channels, kernel_size=kernel_size, stride=stride, padding=padding, bias=False),
+        nn.BatchNorm2d(out_channels, eps=0.001, momentum=0.01),
+        nn.LeakyReLU(inplace=True),
+    )
+
+
+class BasePixelDecoder(nn.Module):
+    """camera_modules.py:246-333 (res2 dropped; GroupNorm(32) when NORM == "GN")."""
+
+    def __init__(self, cfg, input_shape: Dict[str, ShapeSpec]):
+        super().__init__()
+        shapes = {k: v for k, v in input_shape.items() if k in cfg.MODEL.SEM_SEG_HEAD.IN_FEATURES}
+        items = sorted(shapes.items(), key=lambda x: x[1].stride)[1:]
+        self.in_features = [k for k, _ in items]
+        conv_dim, mask_dim = cfg.MODEL.SEM_SEG_HEAD.CONVS_DIM, cfg.MODEL.SEM_SEG_HEAD.MASK_DIM
+        norm = cfg.MODEL.SEM_SEG_HEAD.NORM
+        assert norm in ("GN", ""), f"SEM_SEG_HEAD.NORM={norm!r} not supported"
+        mk = (lambda: nn.GroupNorm(32, conv_dim)) if norm == "GN" else (lambda: None)
+        use_bias = norm == ""
+        for idx, (_, spec) in enumerate(items):
+            if idx == len(items) - 1:
+                oc = _NormConv(spec.channels, conv_dim, 3, 1, mk(), use_bias)
+                _c2_xavier_fill(oc)
+                self.add_module(f"layer_{idx + 1}", oc)
+            else:
+                lc = _NormConv(spec.channels, conv_dim, 1, 0, mk(), use_bias)
+                oc = _NormConv(conv_dim, conv_dim, 3, 1, mk(), use_bias)
+                _c2_xavier_fill(lc)
+                _c2_xavier_fill(oc)
+                self.add_module(f"adapter_{idx + 1}", lc)
+                self.add_module(f"layer_{idx + 1}", oc)
+        self.mask_dim = mask_dim
+        self.mask_features = _NormConv(conv_dim, mask_dim, 3, 1)
+        _c2_xavier_fill(self.mask_features)
+
+
+# ---------------------------------------------------------------------------------------------------
+@CAMERA_HEAD_REGISTRY.register()
+class PlaneCameraHead(nn.Module):
+    def __init__(self, cfg, input_shape):
+        super().__init__()
+        self.cfg = cfg
+        self.plane_matcher_on = cfg.MODEL.EMBEDDING_ON and cfg.MODEL.MASK_ON
+        self.rand_cam_on = cfg.MODEL.CAMERA_HEAD.RAND_ON
+        self.cam_rec_on = cfg.MODEL.CAMERA_HEAD.CAM_REC_ON
+        self.cam_ref_on = cfg.MODEL.CAMERA_HEAD.REFINE_ON
+        self.use_sparsePlane_Top1Cam_testSet = cfg.MODEL.CAMERA_HEAD.INFERENCE_SP_TOPCAM_ON
+        self.num_queries = cfg.MODEL.SEM_SEG_HEAD.NUM_OBJECT_QUERIES
+        self.inference_out_cam_type = cfg.MODEL.CAMERA_HEAD.INFERENCE_OUT_CAM_TYPE
+        self.matching_score_threshold = cfg.TEST.MATCHING_SCORE_THRESHOLD
+        self.warp_plane_in_cam_ref_on = cfg.MODEL.CAMERA_HEAD.WARP_PLANE_IN_CAM_REF_ON
+        if self.use_sparsePlane_Top1Cam_testSet:
+            raise NotImplementedError("INFERENCE_SP_TOPCAM_ON (cached SparsePlanes top-1 camera) is out of scope")
+        if not self.warp_plane_in_cam_ref_on:
+            raise NotImplementedError("WARP_PLANE_IN_CAM_REF_ON=False is not used by any reference config")
+        if cfg.TEST.POSE_REFINEMENT_WITH_GT_MATCHERS:
+            raise NotImplementedError("GT-matcher ablation (camera_head.py:520-547) is out of scope")
+
+        # pixel camera head (camera_head.py:76-114)
+        self.pixel_decoder = BasePixelDecoder(cfg, input_shape)
+        self.convs_backbone = nn.Sequential(
+            conv2d(256, 256, 3, padding=1), conv2d(256, 256, 3, padding=1), nn.MaxPool2d(2, 2),
+            conv2d(256, 256, 3, padding=1), conv2d(256, 256, 3, padding=1), nn.MaxPool2d(2, 2),
+            conv2d(256, 256, 3, padding=1), conv2d(256, 256, 3, padding=1))
+        for block in self.convs_backbone:
+            if isinstance(block, nn.Sequential):
+                _c2_msra_fill(block[0])
+        strides = (1, 2, 1, 2, 1, 2)
+        self.convs_trans = nn.Sequential(*[conv2d(300 if i == 0 else 128, 128, 3, stride=s, padding=1)
+                                           for i, s in enumerate(strides)])
+        self.convs_rots = nn.Sequential(*[conv2d(300 if i == 0 else 128, 128, 3, stride=s, padding=1)
+                                          for i, s in enumerate(strides)])
+        self.fc_trans = nn.Linear(768, 256)
+        self.fc_rots = nn.Linear(768, 256)
+        # shared pose regressors (:64-65)
+        self.trans = nn.Linear(256, 3)
+        self.rots = nn.Linear(256, 4)
+        if self.cam_rec_on:       # AIM (:116-120)
+            self.rot_emb_proj = MLP(4, 256, 256, 6)
+            self.trans_emb_proj = MLP(3, 256, 256, 6)
+        if self.cam_ref_on:       # NOPE-SAC refinement (:122-138)
+            self.geo_encoder = MLP(8, 1024, 1024, 6)
+            self.geo_proj_s1 = MLP(1024, 1024, 1024, 3)
+            self.decoder_rot = MLP(1024, 512, 256, 6)
+            self.geo_proj_s2 = MLP(1024 + 256, 1024, 1024, 3)
+            self.decoder_tran = MLP(1024, 512, 256, 6)
+            self.decoder_rot2 = MLP(512, 512, 256, 3)
+            self.decoder_tran2 = MLP(512, 512, 256, 3)
+            self.normal_score_proj = MLP(self.num_queries, 128, 64, 3)
+            self.rot_score_reg = nn.Linear(64, 1)
+            self.param_score_proj = MLP(self.num_queries, 128, 64, 3)
+            self.trans_score_reg = nn.Linear(64, 1)
+        self._packed = None
+
+    # ------------------------------------------------------------------ weight packing
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def prepare(self):
+        if self._packed is None:
+            with torch.no_grad():
+                pk = {}
+                if self.cam_ref_on:
+                    for name in ("decoder_rot2", "decoder_tran2"):
+                        w = getattr(self, name).layers[0].weight
+                        pk[name + ".w_init"] = w[:, :256].contiguous()   # half applied to the initial-pose feature
+                        pk[name + ".w_geo"] = w[:, 256:].contiguous()    # half applied to the one-plane feature
+                    for name, reg in (("normal_score_proj", "rot_score_reg"), ("param_score_proj", "trans_score_reg")):
+                        m = getattr(self, name)
+                        r = getattr(self, reg)
+                        pk[name] = tuple(t.detach().contiguous() for t in (
+                            m.layers[0].weight, m.layers[0].bias, m.layers[1].weight, m.layers[1].bias,
+                            m.layers[2].weight, m.layers[2].bias, r.weight, r.bias))
+                self._packed = pk
+        return self._packed
+
+    # ------------------------------------------------------------------ K1: pixel pose network
+    @staticmethod
+    def _conv_block(block, x):
+        conv, bn = block[0], block[1]
+        x = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
+        x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
+        return F.leaky_relu(x, 0.01)
+
+    @staticmethod
+    def _norm_conv(m, x, relu):
+        x = F.conv2d(x, m.weight, m.bias, 1, m.padding)
+        if hasattr(m, "norm"):
+            x = F.group_norm(x, m.norm.num_groups, m.norm.weight, m.norm.bias, m.norm.eps)
+        return F.relu(x) if relu else x
+
+    def _pixel_decoder_features(self, feats):
+        pd = self.pixel_decoder
+        names = pd.in_features[::-1]               # res5, res4, res3
+        y = None
+        for idx, f in enumerate(names):
+            lvl = len(names) - idx
+            x = feats[f]
+            if idx == 0:
+                y = self._norm_conv(getattr(pd, f"layer_{lvl}"), x, True)
+            else:
+                cur = self._norm_conv(getattr(pd, f"adapter_{lvl}"), x, False)
+                y = cur + F.interpolate(y, size=cur.shape[-2:], mode="nearest")
+                y = self._norm_conv(getattr(pd, f"layer_{lvl}"), y, True)
+        return self._norm_conv(pd.mask_features, y, False)
+
+    def _forward_pixel_camera_head(self, features1, features2):
+        """camera_head.py:642-670.  ROUND-1 STATUS: the convolutions of this stage still go through
+        cuDNN (library plumbing, TF32 off so results stay fp32); the split-bf16 tcgen05 implicit-GEMM
+        replacement is the next item in DESIGN.md.  Everything downstream is libnopesac_b200."""
+        prev = torch.backends.cudnn.allow_tf32
+        torch.backends.cudnn.allow_tf32 = False
+        try:
+            B = features1["res5"].shape[0]
+            both = {k: torch.cat([features1[k], features2[k]], 0) for k in self.pixel_decoder.in_features}
+            x = self._pixel_decoder_features(both)
+            for blk in self.convs_backbone:
+                x = F.max_pool2d(x, 2, 2) if isinstance(blk, nn.MaxPool2d) else self._conv_block(blk, x)
+            x1, x2 = x[:B], x[B:]
+            _, c, h, w = x1.shape
+            f2v = x2.transpose(2, 3).reshape(B, c, -1).transpose(1, 2)
+            corr = torch.matmul(f2v, x1.reshape(B, c, -1)).view(B, h * w, h, w)
+            aff = F.softmax(corr, dim=1)
+            feats = []
+            for convs, fc in ((self.convs_trans, self.fc_trans), (self.convs_rots, self.fc_rots)):
+                y = aff
+                for blk in convs:
+                    y = self._conv_block(blk, y)
+                feats.append(ops.linear(torch.flatten(y, 1), fc.weight, fc.bias, ops.ACT_RELU))
+        finally:
+            torch.backends.cudnn.allow_tf32 = prev
+        trans_feat, rots_feat = feats
+        rot, tran = ops.pose_heads(rots_feat, trans_feat, self.rots.weight, self.rots.bias,
+                                   self.trans.weight, self.trans.bias)
+        return tran, rot, trans_feat, rots_feat
+
+    # ------------------------------------------------------------------ K2: AIM (:685-735)
+    def _forward_rec_heads(self, initial_rot, initial_trans):
+        rot_feat = self.rot_emb_proj.run(initial_rot, ops.ACT_RELU)
+        trans_feat = self.trans_emb_proj.run(initial_trans + 1e-10, ops.ACT_RELU)
+        rec_rot, rec_trans = ops.pose_heads(rot_feat, trans_feat, self.rots.weight, self.rots.bias,
+                                            self.trans.weight, self.trans.bias)
+        return rec_rot, rot_feat, rec_trans, trans_feat
+
+    # ------------------------------------------------------------------ K7: hypothesis features (:957-986)
+    def _hypothesis_features(self, geo8, rot_feat0, trans_feat0, B, NQ):
+        pk = self.prepare()
+        rows = B * NQ
+        dev = geo8.device
+        fea = self.geo_encoder.run(geo8.view(rows, 8))
+        cat = torch.empty(rows, 1280, device=dev, dtype=torch.float32)       # cat[s1, rot] of :961
+        self.geo_proj_s1.run(fea, out=cat[:, :1024])
+        self.decoder_rot.run(cat[:, :1024], out=cat[:, 1024:])
+        s2 = self.geo_proj_s2.run(cat)
+        ftran = self.decoder_tran.run(s2)
+        fused = []
+        for name, feat0, geo_feat in (("decoder_rot2", rot_feat0, cat[:, 1024:]), ("decoder_tran2", trans_feat0, ftran)):
+            m = getattr(self, name)
+            # cat[init_feat (broadcast over the pair's rows), geo_feat] @ W^T  ==  geo_feat @ W_geo^T + per-pair bias
+            gb = ops.linear(feat0, pk[name + ".w_init"], m.layers[0].bias)
+            x = ops.linear(geo_feat, pk[name + ".w_geo"], gb, ops.ACT_RELU, bias_group_rows=NQ)
+            x = ops.linear(x, m.layers[1].weight, m.layers[1].bias, ops.ACT_RELU)
+            fused.append(ops.linear(x, m.layers[2].weight, m.layers[2].bias, ops.ACT_RELU))   # F.relu(decoder_*2(.))
+        return fused[0], fused[1]
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, features1, features2, planeParam1, planeParam2, planeApp1=None, planeApp2=None,
+                gt_pose=None, gt_corr_matrix=None, batched_inputs=None, ite=0, matching_net=None,
+                hyp_pairs=None, initial_pose=None, want_diag=False):
+        if self.training:
+            raise NotImplementedError("nopesac_b200.PlaneCameraHead is inference-only")
+        return self.inference_Joint(features1, features2, planeParam1, planeParam2, planeApp1, planeApp2,
+                                    matching_net=matching_net, hyp_pairs=hyp_pairs, initial_pose=initial_pose,
+                                    want_diag=want_diag)
+
+    @torch.no_grad()
+    def inference_Joint(self, cam_feats1, cam_feats2, planeParam1, planeParam2, planeApp1, planeApp2,
+                        gt_corr_matrix=None, batched_inputs=None, gt_pose=None, matching_net=None,
+                        hyp_pairs=None, initial_pose=None, want_diag=False):
+        device = planeParam1.device
+        B = planeParam1.shape[0]
+        NQ = self.num_queries
+        trans_list, rot_list = [], []
+        output_cameras = {"camera_zero": {"tran": torch.zeros(1, 3, device=device),
+                                          "rot": torch.tensor([[1., 0., 0., 0.]], device=device)}}
+        out_cam_type = self.inference_out_cam_type if self.cam_ref_on else "initial"
+
+        if initial_pose is None:
+            initial_trans, initial_rot, pix_tfeat, pix_rfeat = self._forward_pixel_camera_head(cam_feats1, cam_feats2)
+        else:
+            initial_trans, initial_rot = initial_pose
+            pix_tfeat = pix_rfeat = None
+        # w >= 0, per pair (the reference flips the whole batch by sample 0, :436-437)
+        initial_rot = torch.where(initial_rot[:, 0:1] < 0, -initial_rot, initial_rot)
+        trans_list.append(initial_trans)
+        rot_list.append(initial_rot)
+        output_cameras["camera_init"] = {"tran": initial_trans, "rot": initial_rot}
+        if not self.plane_matcher_on:
+            output_cameras["camera"] = {"tran": trans_list[-1], "rot": rot_list[-1]}
+            return output_cameras, trans_list, rot_list, [], {}, None
+
+        if self.cam_rec_on:
+            q0, rot_feat0, t0, trans_feat0 = self._forward_rec_heads(initial_rot, initial_trans)
+            trans_list.append(t0)
+            rot_list.append(q0)
+            output_cameras["camera_initRec"] = {"tran": t0, "rot": q0}
+        else:
+            if pix_rfeat is None:
+                raise ValueError("initial_pose override needs CAM_REC_ON (the pixel features are skipped)")
+            q0, rot_feat0, t0, trans_feat0 = initial_rot, pix_rfeat, initial_trans, pix_tfeat
+
+        # ------------------------------------------------------------ matching (:493-503)
+        if matching_net is None or not hasattr(matching_net, "match"):
+            raise RuntimeError("matching_net must be a nopesac_b200.MatchingHead")
+        cam = torch.cat([t0, q0], dim=-1)
+        log_scores_padded, assignment = matching_net.match(planeApp1, planeApp2, cam, planeParam1, planeParam2,
+                                                           match_threshold=self.matching_score_threshold)
+        output_planeAss = {"pred_assignment_beforeRef0": assignment.clone()}
+        if out_cam_type == "initial":
+            output_planeAss["pred_assignment"] = assignment.clone()
+            output_cameras["camera"] = {"tran": trans_list[0], "rot": rot_list[0]}
+            return output_cameras, trans_list, rot_list, [log_scores_padded], output_planeAss, None
+
+        # ------------------------------------------------------------ geo sequences (:513-569)
+        geo_local, geo_global, sig, geo8, matched_num, pair_idx = ops.geo_sequence(
+            planeParam1, planeParam2, assignment, t0, q0, NQ, hyp_pairs=hyp_pairs)
+
+        # ------------------------------------------------------------ refinement head (:925-1115)
+        fused_rot, fused_tran = self._hypothesis_features(geo8, rot_feat0, trans_feat0, B, NQ)
+        q_h, t_h = ops.pose_heads(fused_rot, fused_tran, self.rots.weight, self.rots.bias,
+                                  self.trans.weight, self.trans.bias)
+        pk = self.prepare()
+        res = ops.score_aggregate(geo_local, q_h.view(B, NQ, 4), t_h.view(B, NQ, 3), q0, t0,
+                                  fused_rot.view(B, NQ, 256), fused_tran.view(B, NQ, 256), rot_feat0, trans_feat0,
+                                  matched_num, pk["normal_score_proj"], pk["param_score_proj"],
+                                  self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
+                                  out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag)
+        pose = res["pose"]
+        ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
+        avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]
+        trans_list += [avg_trans, ref_trans]
+        rot_list += [avg_rot, ref_rot]
+        output_cameras["camera_avgRef0"] = {"tran": avg_trans, "rot": avg_rot}
+        output_cameras["camera_softRef0"] = {"tran": ref_trans, "rot": ref_rot}
+
+        # ------------------------------------------------------------ assignment pruning (:605-629)
+        # (the sign flip of :600-601 does not change R, which is quadratic in q)
+        pruned = ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
+        output_planeAss["pred_assignment_afterRef0"] = pruned.clone()
+        output_planeAss["pred_assignment"] = pruned.clone()
+        output_cameras["camera"] = {"tran": ref_trans, "rot": ref_rot}
+
+        all_rots = torch.cat([q0.unsqueeze(1), q_h.view(B, NQ, 4)], 1)
+        all_trans = torch.cat([t0.unsqueeze(1), t_h.view(B, NQ, 3)], 1)
+        output_cameras["camera_onePP"] = {"tran": all_trans, "rot": all_rots}   # padded to NQ+1; see matched_num
+        pose_ref_outputs = {
+            "pred_trans": ref_trans, "pred_rot": ref_rot, "pred_trans_avg": avg_trans, "pred_rot_avg": avg_rot,
+            "all_pred_trans": all_trans, "all_pred_rots": all_rots,
+            "score_soft_rot": res["score_rot"], "score_soft_offset": res["score_tran"],
+            "sig_seq": sig, "matched_num": matched_num, "sel_idx": res["sel_idx"], "pair_idx": pair_idx,
+            "geo_local": geo_local, "geo_global": geo_global, "pose": pose,
+        }
+        if want_diag:
+            pose_ref_outputs.update(l2_dist=res["diag"][0], normal_dist=res["diag"][1], offset_dist=res["diag"][2])
+        return output_cameras, trans_list, rot_list, [log_scores_padded], output_planeAss, pose_ref_outputs

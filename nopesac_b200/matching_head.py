@@ -1,0 +1,168 @@
+"""MATCHING_HEAD of the path — same registry surface, constructor, call signature, return value and
+state-dict names as the reference `MatchingHead` (matching_net/matching_head.py:15-133,
+transformer/gnn.py:46-138), computed by the CUDA kernels of libnopesac_b200.
+
+    MATCHING_HEAD_REGISTRY.get("MatchingHead")(cfg)
+    losses, log_scores_padded = head(planeApp1, planeApp2, matcher_inputCam, params1, params2)
+
+Inference only (the training losses of the reference are out of scope).  In addition to the
+reference return value the fused matcher kernel also yields the mutual-NN assignment matrix
+(camera_modules.py:15-34); the camera head picks it up through `match()`.
+"""
+from __future__ import annotations
+
+import torch
+from torch import nn
+
+from . import ops
+from .compat import Registry
+
+__all__ = ["build_matching_head", "MATCHING_HEAD_REGISTRY", "MatchingHead"]
+
+MATCHING_HEAD_REGISTRY = Registry("MATCHING_HEAD")
+MATCHING_HEAD_REGISTRY.__doc__ = "Registry for plane matching head"
+
+
+def build_matching_head(cfg):
+    # the reference ignores cfg.MODEL.MATCHING_HEAD.NAME (matching_head.py:20-21)
+    return MATCHING_HEAD_REGISTRY.get("MatchingHead")(cfg)
+
+
+class _EncoderLayerParams(nn.Module):
+    """Parameter container with the names of gnn.py:56-71."""
+
+    def __init__(self, d_model: int):
+        super().__init__()
+        self.q_proj = nn.Linear(d_model, d_model, bias=False)
+        self.k_proj = nn.Linear(d_model, d_model, bias=False)
+        self.v_proj = nn.Linear(d_model, d_model, bias=False)
+        self.merge = nn.Linear(d_model, d_model, bias=False)
+        self.mlp = nn.Sequential(
+            nn.Linear(d_model * 2, d_model * 2, bias=False), nn.ReLU(True), nn.Linear(d_model * 2, d_model, bias=False))
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+
+
+class _GNNParams(nn.Module):
+    def __init__(self, d_model: int, nhead: int, layer_names):
+        super().__init__()
+        self.d_model, self.nhead, self.layer_names = d_model, nhead, list(layer_names)
+        self.layers = nn.ModuleList([_EncoderLayerParams(d_model) for _ in self.layer_names])
+        for p in self.parameters():
+            if p.dim() > 1:
+                nn.init.xavier_uniform_(p)
+
+
+@MATCHING_HEAD_REGISTRY.register()
+class MatchingHead(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.offset_multiplier = cfg.MODEL.MATCHING_HEAD.OFFSET_MULTIPLIER
+        self.normal_multiplier = cfg.MODEL.MATCHING_HEAD.NORMAL_MULTIPLIER
+        self.gnn = _GNNParams(256, 8, ["self", "cross"] * 9)
+        self.planeDesc_proj = nn.Conv1d(256, 256, kernel_size=1, bias=True)
+        self.bin_score = torch.nn.Parameter(torch.tensor(1.0), requires_grad=True)
+        self.sinkhorn_iterations = 200
+        self.max_length = cfg.MODEL.SEM_SEG_HEAD.NUM_OBJECT_QUERIES
+        self.mask_on = True
+        self.planeApp_proj = nn.Conv1d(256, 256, kernel_size=1, bias=True)
+        self.match_threshold = cfg.TEST.MATCHING_SCORE_THRESHOLD
+        self._packed = None
+
+    # ------------------------------------------------------------------ weight packing
+    def _load_from_state_dict(self, *a, **k):
+        self._packed = None
+        return super()._load_from_state_dict(*a, **k)
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def prepare(self):
+        """Fused QKV / KV weight matrices (built once; invalidated by load_state_dict / .to())."""
+        if self._packed is None:
+            with torch.no_grad():
+                pk = []
+                for lyr in self.gnn.layers:
+                    wq, wk, wv = lyr.q_proj.weight, lyr.k_proj.weight, lyr.v_proj.weight
+                    pk.append({
+                        "qkv": torch.cat([wq, wk, wv], 0).contiguous(),
+                        "q": wq.detach().contiguous(),
+                        "kv": torch.cat([wk, wv], 0).contiguous(),
+                        "merge": lyr.merge.weight.detach().contiguous(),
+                        "mlp0": lyr.mlp[0].weight.detach().contiguous(),
+                        "mlp2": lyr.mlp[2].weight.detach().contiguous(),
+                        "n1w": lyr.norm1.weight.detach(), "n1b": lyr.norm1.bias.detach(),
+                        "n2w": lyr.norm2.weight.detach(), "n2b": lyr.norm2.bias.detach(),
+                    })
+                self._packed = {
+                    "layers": pk,
+                    "app_w": self.planeApp_proj.weight.detach().reshape(256, 256).contiguous(),
+                    "app_b": self.planeApp_proj.bias.detach().contiguous(),
+                    "desc_w": self.planeDesc_proj.weight.detach().reshape(256, 256).contiguous(),
+                    "desc_b": self.planeDesc_proj.bias.detach().contiguous(),
+                }
+        return self._packed
+
+    # ------------------------------------------------------------------ GNN (gnn.py:73-138)
+    @staticmethod
+    def _layer(w, X, xs, ss, B, L, S, self_attn: bool):
+        """X [rows,512]: columns 0:256 hold the token features, 256:512 the message slot.  xs / ss are
+        row slices (start, stop) of the query stream and of the source stream."""
+        x = X[xs[0]:xs[1]]
+        if self_attn:
+            qkv = ops.linear(x[:, :256], w["qkv"])
+            q, k, v = qkv[:, :256], qkv[:, 256:512], qkv[:, 512:]
+        else:
+            q = ops.linear(x[:, :256], w["q"])
+            kv = ops.linear(X[ss[0]:ss[1], :256], w["kv"])
+            k, v = kv[:, :256], kv[:, 256:]
+        msg = ops.attention(q, k, v, B, L, S)
+        msg = ops.linear(msg, w["merge"])
+        ops.layernorm(msg, w["n1w"], w["n1b"], out=x[:, 256:])          # message slot of cat[x, message]
+        h = ops.linear(x, w["mlp0"], act=ops.ACT_RELU)
+        msg = ops.linear(h, w["mlp2"])
+        ops.layernorm(msg, w["n2w"], w["n2b"], res=x[:, :256], out=x[:, :256])   # x + norm2(mlp(...))
+
+    def _descriptors(self, planeApp1, planeApp2):
+        pk = self.prepare()
+        B, n1, _ = planeApp1.shape
+        n2 = planeApp2.shape[1]
+        R0, R1 = B * n1, B * n2
+        X = torch.empty(R0 + R1, 512, device=planeApp1.device, dtype=torch.float32)
+        ops.linear(planeApp1.reshape(R0, 256), pk["app_w"], pk["app_b"], out=X[:R0, :256])
+        ops.linear(planeApp2.reshape(R1, 256), pk["app_w"], pk["app_b"], out=X[R0:, :256])
+        s0, s1 = (0, R0), (R0, R0 + R1)
+        for w, name in zip(pk["layers"], self.gnn.layer_names):
+            if name == "self":
+                self._layer(w, X, s0, s0, B, n1, n1, True)
+                self._layer(w, X, s1, s1, B, n2, n2, True)
+            else:
+                self._layer(w, X, s0, s1, B, n1, n2, False)
+                self._layer(w, X, s1, s0, B, n2, n1, False)     # sees the UPDATED feat0 (gnn.py:133-134)
+        desc = ops.linear(X[:, :256], pk["desc_w"], pk["desc_b"])
+        return desc[:R0].view(B, n1, 256), desc[R0:].view(B, n2, 256)
+
+    # ------------------------------------------------------------------ public
+    @torch.no_grad()
+    def match(self, planeApp1, planeApp2, matcher_inputCam, parameters1_local, parameters2_local,
+              match_threshold=None, normal_decay=1.0, offset_deacy=1.0):
+        """-> (log_scores_padded [B,n1+1,n2+1], assignment [B,n1,n2])."""
+        if matcher_inputCam is None:
+            raise NotImplementedError("matcher_inputCam=None is a training-only branch of the reference")
+        if normal_decay != 1.0 or offset_deacy != 1.0:
+            raise NotImplementedError("decay factors other than 1.0 are never used by the reference (camera_head.py:490-497)")
+        d1, d2 = self._descriptors(planeApp1.float(), planeApp2.float())
+        thr = self.match_threshold if match_threshold is None else match_threshold
+        return ops.match_sinkhorn_assign(d1, d2, parameters1_local, parameters2_local, matcher_inputCam,
+                                         self.bin_score.detach(), float(self.offset_multiplier),
+                                         float(self.normal_multiplier), self.sinkhorn_iterations, float(thr))
+
+    def forward(self, planeApp1, planeApp2, matcher_inputCam, parameters1_local, parameters2_local,
+                indices1=None, indices2=None, gt_corr_matrix=None, suffix="", normal_decay=1.0, offset_deacy=1.0):
+        if self.training:
+            raise NotImplementedError("nopesac_b200.MatchingHead is inference-only")
+        lsp, _ = self.match(planeApp1, planeApp2, matcher_inputCam, parameters1_local, parameters2_local,
+                            normal_decay=normal_decay, offset_deacy=offset_deacy)
+        return {}, lsp

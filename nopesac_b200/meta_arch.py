@@ -1,0 +1,115 @@
+"""META_ARCH boundary of the path: `PlaneTR_NopeSAC` under `META_ARCH_REGISTRY`, the thing that CALLS the
+hot path in the reference (meta_arch/siamese_planeTR.py:33-34, 338-450).
+
+Only the hot-path children are built natively — `matching_head` and `camera_head_list.0`, under the
+reference's attribute names so the `matching_head.*` / `camera_head_list.0.*` keys of a reference
+checkpoint load unchanged (`load_reference_state_dict`).  The single-view plane detector (backbone +
+PlaneTRHead + mask post-processing, siamese_planeTR.py:452-473, 625-803) is upstream of the path and out
+of scope this round: its per-view outputs enter through `batched_inputs`:
+
+    batched_inputs = [{"0": view, "1": view}, ...]      # any batch size (the reference asserts 1, :340)
+    view = {"pred_plane": [n,3], "pred_plane_feats": [n,256] or [1,n,256],
+            "cam_feats": {"res2".."res5": [C,h,w] or [1,C,h,w]}}
+
+and `forward` returns the reference's per-pair result dicts (:411-431): every `camera*` key with
+{"tran","rot"} and the `pred_assignment*` matrices (as device tensors; `.cpu().numpy()` packing of
+:384-399 is left to the caller so that no host sync happens inside).  Pairs of one call must have the
+same number of planes per view (pad upstream, or call per group).
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+from torch import nn
+
+from .camera_head import build_camera_head
+from .compat import Registry, ShapeSpec
+from .matching_head import build_matching_head
+
+__all__ = ["META_ARCH_REGISTRY", "PlaneTR_NopeSAC", "build_model"]
+
+META_ARCH_REGISTRY = Registry("META_ARCH")
+
+# detectron2 build_resnet_backbone(R50).output_shape() for OUT_FEATURES res2..res5
+RESNET50_OUTPUT_SHAPE = {
+    "res2": ShapeSpec(channels=256, stride=4), "res3": ShapeSpec(channels=512, stride=8),
+    "res4": ShapeSpec(channels=1024, stride=16), "res5": ShapeSpec(channels=2048, stride=32),
+}
+
+
+def build_model(cfg):
+    """detectron2.modeling.build_model: META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)."""
+    model = META_ARCH_REGISTRY.get(cfg.MODEL.META_ARCHITECTURE)(cfg)
+    return model.to(torch.device(cfg.MODEL.DEVICE)) if torch.cuda.is_available() or cfg.MODEL.DEVICE == "cpu" else model
+
+
+@META_ARCH_REGISTRY.register()
+class PlaneTR_NopeSAC(nn.Module):
+    def __init__(self, cfg):
+        super().__init__()
+        self.cfg = cfg
+        self.mask_on = cfg.MODEL.MASK_ON
+        self.embedding_on = cfg.MODEL.EMBEDDING_ON
+        self.camera_on = cfg.MODEL.CAMERA_ON
+        self.camera_refine_on = cfg.MODEL.CAMERA_HEAD.REFINE_ON
+        # camCls kmeans pickles (siamese_planeTR.py:119-128) are loaded by the reference but never used in
+        # forward, and cannot be unpickled without sklearn 0.21 / spherecluster: deliberately skipped.
+        self.matching_head = build_matching_head(cfg) if self.embedding_on else None
+        self.camera_head_list = nn.ModuleList()
+        if self.camera_on:
+            self.camera_head_list.append(build_camera_head(cfg, RESNET50_OUTPUT_SHAPE))
+        self.eval()
+
+    @property
+    def device(self):
+        return next(self.parameters()).device
+
+    def load_reference_state_dict(self, state_dict: Dict[str, torch.Tensor]):
+        """Loads the hot-path keys of a full reference checkpoint; returns the keys that were ignored
+        (backbone / sem_seg_head / criterion)."""
+        mine = {k: v for k, v in state_dict.items()
+                if k.startswith("matching_head.") or k.startswith("camera_head_list.0.")}
+        missing, unexpected = self.load_state_dict(mine, strict=False)
+        if missing:
+            raise KeyError(f"reference checkpoint lacks hot-path keys: {missing[:5]} ...")
+        return sorted(set(state_dict) - set(mine))
+
+    @staticmethod
+    def _stack_views(batched_inputs, view: str, device):
+        planes = torch.stack([bi[view]["pred_plane"].reshape(-1, 3) for bi in batched_inputs]).to(device).float()
+        feats = torch.stack([bi[view]["pred_plane_feats"].reshape(-1, 256) for bi in batched_inputs]).to(device).float()
+        cam = {}
+        for k in batched_inputs[0][view]["cam_feats"]:
+            cam[k] = torch.stack([bi[view]["cam_feats"][k].reshape(bi[view]["cam_feats"][k].shape[-3:])
+                                  for bi in batched_inputs]).to(device).float()
+        return planes, feats, cam
+
+    @torch.no_grad()
+    def forward(self, batched_inputs: List[dict]):
+        return self.inference(batched_inputs)
+
+    @torch.no_grad()
+    def inference(self, batched_inputs: List[dict]):
+        assert not self.training
+        B = len(batched_inputs)
+        if not self.camera_on:
+            zero = {"camera": {"tran": torch.zeros(3), "rot": torch.tensor([1., 0., 0., 0.])}}
+            return [dict(zero) for _ in range(B)]
+        dev = self.device
+        p1, a1, f1 = self._stack_views(batched_inputs, "0", dev)
+        p2, a2, f2 = self._stack_views(batched_inputs, "1", dev)
+        cams, _, _, _, planeAss, _ = self.camera_head_list[0](
+            f1, f2, p1, p2, planeApp1=a1, planeApp2=a2, batched_inputs=batched_inputs,
+            matching_net=self.matching_head)
+        results = []
+        for i in range(B):
+            r = {"0": batched_inputs[i]["0"], "1": batched_inputs[i]["1"], "pred_aff": None,
+                 "depth": {"0": None, "1": None}}
+            for key, value in cams.items():
+                j = i if value["tran"].shape[0] == B else 0      # camera_zero is [1,3] regardless of B
+                r[key] = {"tran": value["tran"][j], "rot": value["rot"][j]}
+            for key, value in planeAss.items():
+                r[key] = value[i]
+            results.append(r)
+        return results

@@ -1,0 +1,204 @@
+"""PyTorch-tensor wrappers over the C ABI (include/nopesac_b200.h): tensors in, tensors out, everything
+enqueued on the current CUDA stream, no host synchronisation.  `launch_count()` counts the kernels of
+this library that were enqueued (bench.py's `gpu_launches`)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+
+ACT_NONE, ACT_RELU, ACT_LEAKY = 0, 1, 2
+CAM_TYPES = {"soft": 0, "avg-all": 1, "min-cost": 2, "max-score": 3}
+
+_launches = 0
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def reset_launch_count():
+    global _launches
+    _launches = 0
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float32):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: expected a CUDA tensor (nopesac_b200 has no CPU path)")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+    return t
+
+
+def _c(t: torch.Tensor, name: str, dtype=torch.float32):
+    return _chk(t, name, dtype).contiguous()
+
+
+def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
+           out: Optional[torch.Tensor] = None, bias_group_rows: int = 0) -> torch.Tensor:
+    """out[M,N] = act(x[M,K] @ w[N,K]^T + bias).  `x` / `out` may be column slices of wider row-major
+    buffers (stride(0) is passed as the leading dimension)."""
+    _chk(x, "x"); _chk(w, "w")
+    assert x.dim() == 2 and w.dim() == 2 and x.stride(1) == 1 and w.is_contiguous(), "linear: layout"
+    M, K = x.shape
+    N = w.shape[0]
+    assert w.shape[1] == K, f"linear: K mismatch {w.shape} vs {x.shape}"
+    if out is None:
+        out = torch.empty(M, N, device=x.device, dtype=torch.float32)
+    assert out.shape == (M, N) and out.stride(1) == 1
+    if bias is not None:
+        _chk(bias, "bias")
+        assert bias.is_contiguous() and bias.shape[-1] == N
+    ldx = x.stride(0) if M > 1 else max(K, x.stride(0))
+    ldo = out.stride(0) if M > 1 else max(N, out.stride(0))
+    st = _lib.lib().nsac_linear(_p(x), ldx, _p(w), _p(bias), bias_group_rows, _p(out), ldo, M, N, K, act, _stream())
+    _lib.check(st, "nsac_linear")
+    _count()
+    return out
+
+
+def layernorm(x, gamma, beta, res=None, out=None):
+    _chk(x, "x")
+    rows, Cdim = x.shape
+    if out is None:
+        out = torch.empty(rows, Cdim, device=x.device, dtype=torch.float32)
+    st = _lib.lib().nsac_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), _p(res),
+                                   0 if res is None else res.stride(0), _p(out), out.stride(0), rows, Cdim, _stream())
+    _lib.check(st, "nsac_layernorm")
+    _count()
+    return out
+
+
+def attention(q, k, v, B, L, S, H=8, D=32, out=None):
+    """q [B*L, H*D] (row stride ldq), k/v [B*S, H*D] (same row stride) -> [B*L, H*D]."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
+    assert k.stride(0) == v.stride(0)
+    if out is None:
+        out = torch.empty(B * L, H * D, device=q.device, dtype=torch.float32)
+    st = _lib.lib().nsac_attention(_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), out.stride(0),
+                                   B, L, S, H, D, _stream())
+    _lib.check(st, "nsac_attention")
+    _count()
+    return out
+
+
+def match_sinkhorn_assign(desc1, desc2, planes1, planes2, cam, bin_score, offset_mult=4.0, normal_mult=8.0,
+                          iters=200, threshold=0.2):
+    desc1, desc2 = _c(desc1, "desc1"), _c(desc2, "desc2")
+    planes1, planes2, cam = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(cam, "cam")
+    bin_score = _c(bin_score.reshape(1), "bin_score")
+    B, n1, Cd = desc1.shape
+    n2 = desc2.shape[1]
+    lsp = torch.empty(B, n1 + 1, n2 + 1, device=desc1.device, dtype=torch.float32)
+    assign = torch.empty(B, n1, n2, device=desc1.device, dtype=torch.float32)
+    st = _lib.lib().nsac_match_sinkhorn_assign(_p(desc1), _p(desc2), _p(planes1), _p(planes2), _p(cam), _p(bin_score),
+                                               offset_mult, normal_mult, iters, threshold, B, n1, n2, Cd,
+                                               _p(lsp), _p(assign), _stream())
+    _lib.check(st, "nsac_match_sinkhorn_assign")
+    _count()
+    return lsp, assign
+
+
+def geo_sequence(planes1, planes2, assign, t0, q0, num_queries, hyp_pairs=None):
+    planes1, planes2, t0, q0 = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(t0, "t0"), _c(q0, "q0")
+    B, n1, _ = planes1.shape
+    n2 = planes2.shape[1]
+    dev = planes1.device
+    NQ = num_queries
+    H = 0
+    if hyp_pairs is not None:
+        hyp_pairs = _c(hyp_pairs, "hyp_pairs", torch.int32)
+        H = hyp_pairs.shape[0]
+    else:
+        assign = _c(assign, "assign")
+    geo_local = torch.empty(B, NQ, 6, device=dev)
+    geo_global = torch.empty(B, NQ, 6, device=dev)
+    sig = torch.empty(B, NQ, device=dev)
+    geo8 = torch.empty(B, NQ, 8, device=dev)
+    mnum = torch.empty(B, device=dev, dtype=torch.int32)
+    pidx = torch.empty(B, NQ, 2, device=dev, dtype=torch.int32)
+    st = _lib.lib().nsac_geo_sequence(_p(planes1), _p(planes2), _p(assign) if hyp_pairs is None else None,
+                                      _p(hyp_pairs), H, _p(t0), _p(q0), B, n1, n2, NQ, _p(geo_local), _p(geo_global),
+                                      _p(sig), _p(geo8), _p(mnum), _p(pidx), _stream())
+    _lib.check(st, "nsac_geo_sequence")
+    _count()
+    return geo_local, geo_global, sig, geo8, mnum, pidx
+
+
+def pose_heads(feat_rot, feat_tran, w_rots, b_rots, w_trans, b_trans):
+    rows = (feat_rot if feat_rot is not None else feat_tran).shape[0]
+    dev = (feat_rot if feat_rot is not None else feat_tran).device
+    q = torch.empty(rows, 4, device=dev) if feat_rot is not None else None
+    t = torch.empty(rows, 3, device=dev) if feat_tran is not None else None
+    fr = None if feat_rot is None else _c(feat_rot, "feat_rot")
+    ft = None if feat_tran is None else _c(feat_tran, "feat_tran")
+    st = _lib.lib().nsac_pose_heads(_p(fr), _p(ft), _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), rows, 256,
+                                    _p(q), _p(t), _stream())
+    _lib.check(st, "nsac_pose_heads")
+    _count()
+    return q, t
+
+
+def _score_mlp_struct(ws):
+    s = _lib.ScoreMLP()
+    for name, t in zip(("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4"), ws):
+        _chk(t, name)
+        assert t.is_contiguous()
+        setattr(s, name, t.data_ptr())
+    return s
+
+
+def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num,
+                    rot_mlp, tran_mlp, w_rots, b_rots, w_trans, b_trans, out_cam_type="soft",
+                    want_scores=True, want_diag=False):
+    """rot_mlp / tran_mlp: 8-tuples (w1,b1,w2,b2,w3,b3,w4,b4). Returns dict(pose, score_rot, score_tran,
+    sel_idx, diag)."""
+    B, NQ, _ = geo_local.shape
+    dev = geo_local.device
+    args = [_c(a, n) for a, n in ((geo_local, "geo_local"), (q_h, "q_h"), (t_h, "t_h"), (q0, "q0"), (t0, "t0"),
+                                  (feat_rot, "feat_rot"), (feat_tran, "feat_tran"), (feat_rot0, "feat_rot0"),
+                                  (feat_tran0, "feat_tran0"))]
+    matched_num = _c(matched_num, "matched_num", torch.int32)
+    pose = torch.empty(B, 16, device=dev)
+    sr = torch.empty(B, NQ + 1, device=dev) if want_scores else None
+    stt = torch.empty(B, NQ + 1, device=dev) if want_scores else None
+    sel = torch.empty(B, 2, device=dev, dtype=torch.int32)
+    diag = torch.zeros(3, B, NQ + 1, NQ, device=dev) if want_diag else None
+    L = _lib.lib()
+    ws = torch.empty(L.nsac_score_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
+    rs, ts = _score_mlp_struct(rot_mlp), _score_mlp_struct(tran_mlp)
+    st = L.nsac_score_aggregate(*[_p(a) for a in args], _p(matched_num), C.byref(rs), C.byref(ts),
+                                _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
+                                _p(pose), _p(sr), _p(stt), _p(sel), _p(diag), _p(ws), _stream())
+    _lib.check(st, "nsac_score_aggregate")
+    _count(3)
+    return {"pose": pose, "score_rot": sr, "score_tran": stt, "sel_idx": sel, "diag": diag}
+
+
+def prune_assignment(assign, planes1, planes2, pose):
+    assign, planes1, planes2 = _c(assign, "assign"), _c(planes1, "planes1"), _c(planes2, "planes2")
+    _chk(pose, "pose")
+    assert pose.stride(1) == 1
+    B, n1, n2 = assign.shape
+    out = torch.empty_like(assign)
+    st = _lib.lib().nsac_prune_assignment(_p(assign), _p(planes1), _p(planes2), _p(pose), pose.stride(0), B, n1, n2,
+                                          _p(out), _stream())
+    _lib.check(st, "nsac_prune_assignment")
+    _count()
+    return out
