@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Bench of the NopeSAC one-plane RANSAC pose path on B200 (see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" = one pass of the hot path (PlaneCameraHead.inference_Joint incl. the matching head: pixel pose
+network -> AIM -> GNN + Sinkhorn matcher -> geo sequences -> hypothesis generation -> scoring -> soft
+aggregation -> assignment pruning; stage set S4 of SURVEY.md §8d) over one batch of synthetic pairs.
+Workload at every N: BASELINE.json configs[1] per GPU — 64 pairs, 16 planes/view, NUM_OBJECT_QUERIES = 256 with
+all 16x16 candidate plane pairs as one-plane hypotheses (257 hypotheses x 256 residual columns per pair),
+backbone feature maps of a 480x640 input.  N > 1 (torchrun): pairs are sharded 64/GPU (weak scaling) and
+every step ends with ONE NCCL all-gather of the [64,16] per-pair results — the only collective of the path.
+
+value    pairs/s with all inputs resident in HBM (inputs 2.2 GB/GPU >> 126 MB L2: no flush needed).
+e2e      pairs/s through the same public call with HOST (pinned) inputs: H2D of the step's inputs and D2H of the
+         [B,16] result inside the timed region.
+roofline the hypothesis-scoring kernel (nsac_score_aggregate) timed alone with CUDA events on a launch that
+         moves > 256 MB (B=512, m=NQ=256), algorithmic bytes of SURVEY.md §8d over measured HBM copy bandwidth.
+cpu_baseline / --impl reference: the CPU oracle port (oracle/restate.py — the reference is Python and cannot
+         travel to the GPU box) on the host cores, per-pair loop at batch size 1 like the reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+PAIRS_PER_GPU = 64
+PLANES = 16
+NQ = 256
+WORKLOAD = ("camera head S4 (pixel pose net + AIM + GNN/Sinkhorn matcher + 256 one-plane hypotheses + scoring + soft "
+            "aggregation + pruning), 64 synthetic 480x640 pairs/GPU, 16 planes/view, NUM_OBJECT_QUERIES=256 (all 16x16 "
+            "plane pairs as hypotheses), fp32, random-init weights, from backbone feature maps")
+METRIC = "image-pairs/sec (480x640, 16 planes x 256 hyp)"
+
+
+def score_algorithmic_bytes(B, m, nq):
+    """per pair 24m + (28 + 8C)(m+1) + 68, C=256, + score-MLP weights once per launch."""
+    per_pair = 24 * m + 2076 * (m + 1) + 68
+    weights = 8 * (nq * 128 + 128 + 128 * 128 + 128 + 128 * 64 + 64 + 64 + 1)
+    return B * per_pair + weights
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            if len(r) < 9:
+                continue
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_pairs_per_s(num_pairs: int, threads: int, warm: int = 1):
+    """The oracle port on the host: per-pair loop at bs=1 (the only mode the reference supports), same
+    workload shape, same weights."""
+    from oracle import restate
+    from nopesac_b200 import synthetic
+    from tests import util
+    torch.set_num_threads(threads)
+    sd, msd = util.make_weights(NQ)
+    hp = synthetic.all_pairs_hypotheses(PLANES, NQ)
+    batches = [synthetic.make_batch(1000 + i, 1, PLANES, with_features=True) for i in range(num_pairs + warm)]
+
+    def one(b):
+        with torch.no_grad():
+            return restate.inference_joint(sd, msd, b.feats1, b.feats2, b.planes1, b.planes2, b.app1, b.app2,
+                                           num_queries=NQ, hyp_pairs=hp)
+    for b in batches[:warm]:
+        one(b)
+    t0 = time.perf_counter()
+    for b in batches[warm:]:
+        one(b)
+    dt = time.perf_counter() - t0
+    return num_pairs / dt, dt
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 4
+    vals = []
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_reference_pairs_per_s(1, threads, warm=1)
+    t_all = time.perf_counter()
+    for _ in range(args.steps):
+        v, _ = cpu_reference_pairs_per_s(sample, threads, warm=0)
+        vals.append(v)
+    wall = time.perf_counter() - t_all
+    value = statistics.mean(vals)
+    desc = f"{sample} pairs/step x {args.steps} steps of the same workload, per-pair loop at batch size 1"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_step": sample, "device": "cpu"},
+        "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": wall,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs timed by the cpu_baseline leg")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from nopesac_b200 import ops, synthetic
+    from tests import util   # seeded weights (shapes from tests/golden/state_shapes.json)
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.pairs
+
+    head, match, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    hp = synthetic.all_pairs_hypotheses(PLANES, NQ).to(dev, torch.int32)
+    host = synthetic.make_batch(rank * B, B, PLANES)                 # planes / appearance: seeded on the host
+    f1, f2 = synthetic.device_features(B, dev, seed=7 + rank)       # 2.2 GB of feature maps: drawn on the device
+    dbatch = host.to(dev)
+    gathered = torch.empty(world * B, 16, device=dev) if world > 1 else None
+
+    def step(p1, p2, a1, a2, fa, fb):
+        out = head(fa, fb, p1, p2, a1, a2, matching_net=match, hyp_pairs=hp)
+        pose = out[5]["pose"]
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pose)
+            return gathered
+        return pose
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------------ value: inputs resident in HBM
+    for _ in range(args.warmup):
+        step(dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, f1, f2)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.reset_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step(dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, f1, f2)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ops.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total / 1e3)
+
+    # ------------------------------------------------------------------ e2e: host (pinned) inputs
+    pin = lambda x: x.contiguous().pin_memory()
+    h_small = [pin(x) for x in (host.planes1, host.planes2, host.app1, host.app2)]
+    h_f1 = {k: pin(v.cpu()) for k, v in f1.items()}
+    h_f2 = {k: pin(v.cpu()) for k, v in f2.items()}
+    h_out = torch.empty(world * B if world > 1 else B, 16).pin_memory()
+    h2d = sum(x.numel() * x.element_size() for x in h_small) + \
+        sum(v.numel() * v.element_size() for d in (h_f1, h_f2) for v in d.values())
+    d2h = h_out.numel() * h_out.element_size()
+
+    def e2e_step():
+        s = [x.to(dev, non_blocking=True) for x in h_small]
+        fa = {k: v.to(dev, non_blocking=True) for k, v in h_f1.items()}
+        fb = {k: v.to(dev, non_blocking=True) for k, v in h_f2.items()}
+        h_out.copy_(step(s[0], s[1], s[2], s[3], fa, fb), non_blocking=True)
+
+    e2e_steps = max(3, min(args.steps, 5))
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * e2e_steps / (float(t.item()) / 1e3)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ------------------------------------------------------------------ roofline: scoring kernel alone
+    peak, peak_src = measured_peaks()
+    RB, m = 512, NQ
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo_local = rnd(RB, NQ, 6)
+    q_h = torch.nn.functional.normalize(rnd(RB, NQ, 4), dim=-1)
+    t_h = rnd(RB, NQ, 3) * 0.3
+    q0 = torch.nn.functional.normalize(rnd(RB, 4), dim=-1)
+    t0 = rnd(RB, 3) * 0.3
+    fr, ft = rnd(RB, NQ, 256), rnd(RB, NQ, 256)
+    fr0, ft0 = rnd(RB, 256), rnd(RB, 256)
+    mnum = torch.full((RB,), m, device=dev, dtype=torch.int32)
+    pk = head.prepare()
+
+    def score_once():
+        return ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
+                                   pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
+                                   head.trans.bias, out_cam_type="soft", want_scores=False)
+    for _ in range(3):
+        score_once()
+    torch.cuda.synchronize()
+    reps = 10
+    e0.record()
+    for _ in range(reps):
+        score_once()          # 276 MB of inputs per launch > L2: no flush needed
+    e1.record()
+    torch.cuda.synchronize()
+    score_ms = e0.elapsed_time(e1) / reps
+    alg = score_algorithmic_bytes(RB, m, NQ)
+    achieved = alg / (score_ms / 1e3) / 1e9
+    roofline = {"kernel": "nsac_score_aggregate (K8+K9), B=512, m=NQ=256", "bound": "hbm", "achieved": achieved,
+                "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": score_ms}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, dt = cpu_reference_pairs_per_s(args.cpu_pairs, threads)
+        cpu_baseline = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
+                        "sample": f"{args.cpu_pairs} pairs of the same workload after 1 warm-up pair, per-pair loop at "
+                                  f"batch size 1 (oracle/restate.py), {dt:.1f} s"}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "planes_per_view": PLANES, "num_object_queries": NQ,
+                   "stage_set": "S4", "l2": "inputs (2.2 GB/GPU) exceed the 126 MB L2; no flush",
+                   "parallelism": f"pairs sharded over {world} GPU(s), one NCCL all-gather of [B,16] results"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": launches,
+        "roofline": roofline,
+        "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -11,6 +11,9 @@ per pair inside the kernels, with no host synchronisation anywhere on the path.
 Inference only.  Extra keyword arguments (not in the reference):
     hyp_pairs     int32 [H,2]  explicit hypothesis list (the "P planes x H hypotheses" stress mapping,
                                SURVEY.md §8(d)); the matcher still runs and its assignment is reported.
+    assignment_override [B,n1,n2]  0/1 matrix whose row-major nonzeros replace the matcher's assignment as
+                               the hypothesis list of each pair (what POSE_REFINEMENT_WITH_GT_MATCHERS does in
+                               the reference, camera_head.py:520-547, minus the dataset lookup).
     initial_pose  (t [B,3], q [B,4])  skips the pixel pose network (stage set S3).
 """
 from __future__ import annotations
@@ -294,17 +297,17 @@ class PlaneCameraHead(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, features1, features2, planeParam1, planeParam2, planeApp1=None, planeApp2=None,
                 gt_pose=None, gt_corr_matrix=None, batched_inputs=None, ite=0, matching_net=None,
-                hyp_pairs=None, initial_pose=None, want_diag=False):
+                hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None):
         if self.training:
             raise NotImplementedError("nopesac_b200.PlaneCameraHead is inference-only")
         return self.inference_Joint(features1, features2, planeParam1, planeParam2, planeApp1, planeApp2,
                                     matching_net=matching_net, hyp_pairs=hyp_pairs, initial_pose=initial_pose,
-                                    want_diag=want_diag)
+                                    want_diag=want_diag, assignment_override=assignment_override)
 
     @torch.no_grad()
     def inference_Joint(self, cam_feats1, cam_feats2, planeParam1, planeParam2, planeApp1, planeApp2,
                         gt_corr_matrix=None, batched_inputs=None, gt_pose=None, matching_net=None,
-                        hyp_pairs=None, initial_pose=None, want_diag=False):
+                        hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None):
         device = planeParam1.device
         B = planeParam1.shape[0]
         NQ = self.num_queries
@@ -351,7 +354,8 @@ class PlaneCameraHead(nn.Module):
 
         # ------------------------------------------------------------ geo sequences (:513-569)
         geo_local, geo_global, sig, geo8, matched_num, pair_idx = ops.geo_sequence(
-            planeParam1, planeParam2, assignment, t0, q0, NQ, hyp_pairs=hyp_pairs)
+            planeParam1, planeParam2, assignment if assignment_override is None else assignment_override,
+            t0, q0, NQ, hyp_pairs=hyp_pairs)
 
         # ------------------------------------------------------------ refinement head (:925-1115)
         fused_rot, fused_tran = self._hypothesis_features(geo8, rot_feat0, trans_feat0, B, NQ)

@@ -1,0 +1,175 @@
+"""GPU parity tests proper (-m gpu): the CUDA path, called through the C ABI (nopesac_b200.ops -> ctypes ->
+libnopesac_b200.so), against (1) the committed golden fixtures produced by the live reference and (2) the CPU
+oracle on the same seeded inputs.  Bars (BASELINE.json north_star):
+  bit-exact : assignment matrices, matched_num, sig_seq, argmin/argmax selections
+  1e-4 abs  : every camera* tran/rot, per-hypothesis poses, score_soft_*, exp(log_scores_padded)
+  1e-4 rel  : raw log-scores
+"""
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+TOL = util.ABS_TOL
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _run_cuda_case(case, pair_indices, want_diag=False):
+    dev = _gpu()
+    head, match, sd, msd = util.build_cuda_heads(case["NQ"], case["cam"], case["thr"], dev)
+    bs = [util.case_batch(case, pi) for pi in pair_indices]
+    cat = lambda f: torch.cat([f(b) for b in bs], 0).to(dev)
+    p1, p2, a1, a2 = cat(lambda b: b.planes1), cat(lambda b: b.planes2), cat(lambda b: b.app1), cat(lambda b: b.app2)
+    f1 = f2 = ip = None
+    if case["feats"]:
+        f1 = {k: torch.cat([b.feats1[k] for b in bs], 0).to(dev) for k in bs[0].feats1}
+        f2 = {k: torch.cat([b.feats2[k] for b in bs], 0).to(dev) for k in bs[0].feats2}
+    else:
+        poses = [util.initial_pose_for(pi) for pi in pair_indices]
+        ip = (torch.cat([p[0] for p in poses]).to(dev), torch.cat([p[1] for p in poses]).to(dev))
+    hp = util.case_hyp_pairs(case)
+    hp = None if hp is None else hp.to(dev, torch.int32)
+    out = head(f1, f2, p1, p2, a1, a2, matching_net=match, hyp_pairs=hp, initial_pose=ip, want_diag=want_diag)
+    torch.cuda.synchronize()
+    return out
+
+
+def _check_against(want, cams, lsp, ass, pro, i, tag):
+    """want: flat golden/oracle dict of pair i of the batch."""
+    m = int(want["matched_num"])
+    assert int(pro["matched_num"][i]) == m, f"{tag}: matched_num"
+    d = util.maxdiff
+    assert d(cams["camera_init"]["tran"][i], want["camera_init_t"][0]) <= TOL, f"{tag}: camera_init tran"
+    assert d(cams["camera_init"]["rot"][i], want["camera_init_q"][0]) <= TOL, f"{tag}: camera_init rot"
+    assert d(cams["camera_initRec"]["tran"][i], want["camera_initRec_t"][0]) <= TOL, f"{tag}: initRec tran"
+    assert d(cams["camera_initRec"]["rot"][i], want["camera_initRec_q"][0]) <= TOL, f"{tag}: initRec rot"
+    # matcher: probabilities abs, raw log-scores relative, assignment exact
+    wl = want["log_scores_padded"][0]
+    gl = lsp[0][i].cpu()
+    assert d(gl.exp(), wl.exp()) <= TOL, f"{tag}: exp(log_scores) off by {d(gl.exp(), wl.exp())}"
+    rel = float(((gl - wl).abs() / wl.abs().clamp_min(1.0)).max())
+    assert rel <= 5 * util.LOG_REL_TOL, f"{tag}: log-scores rel {rel}"
+    assert torch.equal(ass["pred_assignment_beforeRef0"][i].cpu(), want["assignment_before"][0]), f"{tag}: assignment"
+    if "assignment_after" in want:
+        assert torch.equal(ass["pred_assignment"][i].cpu(), want["assignment_after"][0]), f"{tag}: pruned assignment"
+    # geo sequences + sig (discrete)
+    assert torch.equal(pro["sig_seq"][i].cpu(), want["sig_seq"]), f"{tag}: sig_seq"
+    assert d(pro["geo_local"][i], want["geo_local"]) == 0.0, f"{tag}: geo_local (pure gather) must be exact"
+    assert d(pro["geo_global"][i], want["geo_global"]) <= 1e-5, f"{tag}: geo_global"
+    # refined poses
+    assert d(cams["camera"]["tran"][i], want["pred_trans"][0]) <= TOL, f"{tag}: camera tran {d(cams['camera']['tran'][i], want['pred_trans'][0])}"
+    assert d(cams["camera"]["rot"][i], want["pred_rot"][0]) <= TOL, f"{tag}: camera rot {d(cams['camera']['rot'][i], want['pred_rot'][0])}"
+    assert d(cams["camera_avgRef0"]["tran"][i], want["pred_trans_avg"][0]) <= TOL, f"{tag}: avg tran"
+    assert d(cams["camera_avgRef0"]["rot"][i], want["pred_rot_avg"][0]) <= TOL, f"{tag}: avg rot"
+    if "all_pred_rots" in want:
+        assert d(pro["all_pred_rots"][i, :m + 1], want["all_pred_rots"][0]) <= TOL, f"{tag}: all_pred_rots"
+        assert d(pro["all_pred_trans"][i, :m + 1], want["all_pred_trans"][0]) <= TOL, f"{tag}: all_pred_trans"
+        sr, st = pro["score_soft_rot"][i].cpu(), pro["score_soft_offset"][i].cpu()
+        assert d(sr[:m + 1], want["score_soft_rot"][0, :, 0]) <= TOL, f"{tag}: score_soft_rot"
+        assert d(st[:m + 1], want["score_soft_offset"][0, :, 0]) <= TOL, f"{tag}: score_soft_offset"
+        if m + 1 < sr.numel():
+            assert float(sr[m + 1:].abs().max()) == 0.0 and float(st[m + 1:].abs().max()) == 0.0, f"{tag}: padded scores"
+    if "l2_dist" in want and "l2_dist" in pro:
+        # diagnostics only (sample-0 outputs of the reference); distances are unbounded -> abs + rel bar
+        close = lambda a, b, atol: torch.allclose(a.cpu(), b, rtol=1e-4, atol=atol)
+        assert close(pro["l2_dist"][i, :m + 1, :m], want["l2_dist"][0], TOL), f"{tag}: l2_dist"
+        assert close(pro["normal_dist"][i, :m + 1, :m], want["normal_dist"][0], 2e-2), f"{tag}: normal_dist (deg; acos is ill-conditioned near 0)"
+        assert close(pro["offset_dist"][i, :m + 1, :m], want["offset_dist"][0], TOL), f"{tag}: offset_dist"
+
+
+def _selection_from_reference(want, case):
+    """Index the reference picked in min-cost / max-score mode = the row of all_pred_* equal to its output."""
+    rows_r = (want["all_pred_rots"][0] == want["pred_rot"][0]).all(-1).nonzero()[:, 0]
+    rows_t = (want["all_pred_trans"][0] == want["pred_trans"][0]).all(-1).nonzero()[:, 0]
+    return int(rows_r[0]), int(rows_t[0])
+
+
+@pytest.mark.parametrize("name", util.golden_names())
+def test_cuda_matches_golden(name):
+    g = util.load_golden(name)
+    case = g["case"]
+    pairs = case["pairs"]
+    cams, _, _, lsp, ass, pro = _run_cuda_case(case, pairs, want_diag=case["NQ"] <= 64)
+    for i, (pi, want) in enumerate(zip(pairs, g["outputs"])):
+        _check_against(want, cams, lsp, ass, pro, i, f"{name}[pair {pi}]")
+        if case["cam"] in ("min-cost", "max-score") and int(want["matched_num"]) > 1:
+            sr, st = _selection_from_reference(want, case)
+            got = pro["sel_idx"][i].cpu().tolist()
+            assert got == [sr, st], f"{name}[pair {pi}]: selection {got} != reference {[sr, st]}"
+
+
+def test_batched_equals_per_pair_oracle():
+    """A batch with DIFFERENT hypothesis counts per pair (0, 1, 5, 16, 48) in one launch equals the per-pair
+    loop of the oracle — the [0]-indexed shortcuts of the reference (:964, :1052, :1068) are applied per
+    sample (SURVEY.md §7 'Batch semantics' / 'Variable m per pair')."""
+    dev = _gpu()
+    from oracle import restate
+    from nopesac_b200 import synthetic
+    NQ, P, B = 50, 16, 6
+    head, match, sd, msd = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    b = synthetic.make_batch(20, B, P)
+    over = torch.zeros(B, P, P)
+    over[1, 3, 7] = 1
+    over[2, [0, 2, 5, 9, 15], [4, 4, 1, 0, 15]] = 1
+    over[3] = torch.eye(P)
+    over[4, :3] = 1
+    over[5, torch.arange(P), b.perm[5]] = 1
+    poses = [util.initial_pose_for(100 + i) for i in range(B)]
+    ip = (torch.cat([p[0] for p in poses]), torch.cat([p[1] for p in poses]))
+    outs = []
+    with torch.no_grad():
+        for i in range(B):
+            outs.append(restate.inference_joint(sd, msd, None, None, b.planes1[i:i + 1], b.planes2[i:i + 1],
+                                                b.app1[i:i + 1], b.app2[i:i + 1], num_queries=NQ,
+                                                hyp_pairs=torch.nonzero(over[i]), initial_pose=(ip[0][i:i + 1], ip[1][i:i + 1])))
+    assert [o["matched_num"] for o in outs] == [0, 1, 5, 16, 48, 16]
+    bd = b.to(dev)
+    cams, _, _, lsp, ass, pro = head(None, None, bd.planes1, bd.planes2, bd.app1, bd.app2, matching_net=match,
+                                     initial_pose=(ip[0].to(dev), ip[1].to(dev)), assignment_override=over.to(dev))
+    torch.cuda.synchronize()
+    for i, o in enumerate(outs):
+        _check_against(util.oracle_to_flat(o), cams, lsp, ass, pro, i, f"ragged batch pair {i} (m={o['matched_num']})")
+
+
+def test_linear_kernel_against_torch():
+    """nsac_linear vs torch fp64 on odd shapes (K = 3, 8; N = 3; strided in/out; grouped bias)."""
+    dev = _gpu()
+    g = torch.Generator().manual_seed(0)
+    from nopesac_b200 import ops
+    for (M, N, K, act) in ((7, 3, 3, 0), (130, 256, 8, 1), (257, 129, 1024, 2), (64, 512, 1280, 1), (1, 4, 256, 0)):
+        x = torch.randn(M, K, generator=g)
+        w = torch.randn(N, K, generator=g) / K ** 0.5
+        bias = torch.randn(N, generator=g)
+        ref = x.double() @ w.double().T + bias.double()
+        ref = torch.relu(ref) if act == 1 else (torch.nn.functional.leaky_relu(ref, 0.01) if act == 2 else ref)
+        got = ops.linear(x.to(dev), w.to(dev), bias.to(dev), act)
+        assert util.maxdiff(got, ref) <= 2e-5, (M, N, K, util.maxdiff(got, ref))
+    # strided input / output + grouped bias
+    M, N, K, G = 96, 64, 32, 8
+    buf = torch.randn(M, 100, generator=g).to(dev)
+    w = torch.randn(N, K, generator=g).to(dev)
+    gb = torch.randn(M // G, N, generator=g).to(dev)
+    out = torch.zeros(M, 200, device=dev)
+    ops.linear(buf[:, 4:4 + K], w, gb, 0, out=out[:, 8:8 + N], bias_group_rows=G)
+    ref = buf[:, 4:4 + K].double() @ w.double().T + gb.double().repeat_interleave(G, 0)
+    assert util.maxdiff(out[:, 8:8 + N], ref) <= 2e-5
+    assert float(out[:, :8].abs().max()) == 0.0 and float(out[:, 8 + N:].abs().max()) == 0.0
+
+
+def test_cabi_error_reporting():
+    """Bad arguments return an error code + message instead of crashing (SURVEY.md §8b 'Errors')."""
+    _gpu()
+    from nopesac_b200 import _lib
+    L = _lib.lib()
+    st = L.nsac_linear(None, 4, None, None, 0, None, 4, 4, 4, 4, 0, None)
+    assert st == -1 and b"null pointer" in L.nsac_last_error()
+    with pytest.raises(RuntimeError):
+        from nopesac_b200 import ops
+        ops.linear(torch.zeros(2, 2), torch.zeros(2, 2))      # CPU tensors: no CPU path
