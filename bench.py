@@ -167,6 +167,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-value", action="store_true", help="profiling runs: skip the e2e / roofline / cpu legs")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs timed by the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -232,6 +233,14 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
+
+    if args.only_value:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
+                              "ms_per_step": ms_total / args.steps, "gpu_launches": launches, "partial": True}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ------------------------------------------------------------------ e2e: host (pinned) inputs
     pin = lambda x: x.contiguous().pin_memory()

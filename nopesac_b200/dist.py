@@ -1,0 +1,45 @@
+"""Multi-GPU plumbing of the path: image pairs are independent, so they are block-sharded over the ranks
+(rank r owns pairs [r*B/R, (r+1)*B/R), the reference's own data parallelism: test_NopeSAC.py:209-216 +
+detectron2 InferenceSampler) and the ONLY exchange is one all-gather of the [B_local,16] fp32 per-pair result
+rows (pose 7 + avg pose 7 + matched_num + pad = 64 B/pair), replacing the pickled-object `comm.gather` of
+evaluation/mp3d_evaluation.py:317-318.  One process per GPU, `torch.distributed` (NCCL on GPUs, gloo in the
+CPU tests)."""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+RESULT_WIDTH = 16
+
+
+def shard_range(num_pairs: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous block split; the first `num_pairs % world` ranks take one extra pair."""
+    base, rem = divmod(num_pairs, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def shard_sizes(num_pairs: int, world: int):
+    return [shard_range(num_pairs, r, world)[1] - shard_range(num_pairs, r, world)[0] for r in range(world)]
+
+
+def gather_results(local_rows: torch.Tensor, num_pairs: int, group=None) -> torch.Tensor:
+    """All-gather of the per-pair result rows -> [num_pairs, 16] on every rank, in global pair order."""
+    if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return local_rows
+    world = dist.get_world_size(group)
+    sizes = shard_sizes(num_pairs, world)
+    assert local_rows.shape == (sizes[dist.get_rank(group)], RESULT_WIDTH), (local_rows.shape, sizes)
+    if len(set(sizes)) == 1:
+        out = torch.empty(num_pairs, RESULT_WIDTH, dtype=local_rows.dtype, device=local_rows.device)
+        dist.all_gather_into_tensor(out, local_rows.contiguous(), group=group)
+        return out
+    # ragged tail: pad every shard to the largest one, gather once, strip the padding
+    mx = max(sizes)
+    padded = torch.zeros(mx, RESULT_WIDTH, dtype=local_rows.dtype, device=local_rows.device)
+    padded[: local_rows.shape[0]] = local_rows
+    out = torch.empty(world * mx, RESULT_WIDTH, dtype=local_rows.dtype, device=local_rows.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * mx: r * mx + sizes[r]] for r in range(world)], 0)

@@ -78,18 +78,19 @@ FEATURE_SHAPES = {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5"
 
 def make_pair(pair_idx: int, planes_per_view: int = 16, with_features: bool = False,
               height: int = 480, width: int = 640, negative_k: bool = False):
-    """One planted pair. `negative_k` moves the GT translation beyond the nearest plane so that some
-    warp factors k = 1 + t.b/|b|^2 are negative (sig_seq = -1 coverage, camera_head.py:568-569)."""
+    """One planted pair. `negative_k` pulls every other plane to within a few centimetres of the camera so
+    that the (re-embedded) initial translation lies beyond it and some warp factors k = 1 + t.b/|b|^2 are
+    negative (sig_seq = -1 coverage, camera_head.py:568-569)."""
     g = torch.Generator().manual_seed(SEED_BASE + pair_idx)
     P = planes_per_view
     n = torch.nn.functional.normalize(torch.randn(P, 3, generator=g), dim=-1)
     d = torch.rand(P, 1, generator=g) * 3.0 + 0.5
+    if negative_k:
+        d[::2] = d[::2] * 0.02
     p1 = n * d
     rv = (torch.rand(3, generator=g) * 2 - 1) * 0.6
     q = rotvec_to_quat(rv)
     t = (torch.rand(3, generator=g) * 2 - 1) * 0.4
-    if negative_k:
-        t = t * 12.0
     flip = torch.tensor(FLIP)
     perm = torch.randperm(P, generator=g)
     p2 = torch.empty(P, 3)
