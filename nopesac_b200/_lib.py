@@ -20,6 +20,10 @@ _SIGNATURES = {
     "nsac_last_error": (C.c_char_p, []),
     "nsac_linear": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_gemm_bf16x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p, C.c_int,
+                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_int, C.c_void_p,
+                                   C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_split_bf16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nsac_layernorm": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,

@@ -1,0 +1,425 @@
+// Split-bf16 tensor-core GEMM for sm_100a: the dense-contraction engine of the path
+//   (hypothesis-generation MLP chain K7, GNN projections K4, pixel-pose convolutions K1 via im2col).
+//
+//   out[M,N] = act( A[M,K] . W[N,K]^T + bias ),  A = a_hi + a_lo, W = w_hi + w_lo  (bf16 planes)
+//            ~ a_hi.w_hi + a_lo.w_hi + a_hi.w_lo   accumulated in fp32           ("bf16x3")
+//
+// The reference computes these layers in fp32 and the parity bar is 1e-4 abs after ~28 chained layers;
+// single-pass bf16 / tf32 misses it, the 3-term split keeps ~2^-17 relative error per product
+// at 1/3 of the bf16 tensor rate.  `passes` = 1 / 2 / 3 selects hi.hi / + lo.hi / + hi.lo.
+//
+// Design (one persistent CTA per SM, warp-specialised, no register accumulators):
+//   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) of the four operand planes into a
+//                              3-stage shared-memory ring, mbarrier complete_tx signalling
+//   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N,
+//                              K=16) on K-major SW128 descriptors; tcgen05.commit frees ring slots and
+//                              publishes the accumulator; also owns tcgen05.alloc / dealloc
+//   warps 2..5  epilogue       tcgen05.ld (32x32b.x32) of the fp32 accumulator from TMEM (double-buffered so
+//                              the epilogue of tile i overlaps the MMAs of tile i+1), bias (+ per-pair bias
+//                              rows), activation, then fp32 rows and/or re-split bf16 hi/lo planes for the
+//                              next layer straight from registers
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                 // 64 bf16 = one 128-byte swizzle row
+constexpr int UMMA_K = 16;
+constexpr int NUM_THREADS = 192;            // 6 warps
+constexpr uint32_t SPIN_LIMIT = 1u << 28;   // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int STAGES = BLOCK_N == 128 ? 3 : 2;
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
+  static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;             // double-buffered accumulator (power of two)
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ------------------------------------------------------------------------------------------------ PTX
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout):
+//   [0,14) start address >> 4 | [16,30) leading byte offset >> 4 (=1, unused for swizzled K-major)
+//   [32,46) stride byte offset >> 4 (= 8 rows x 128 B = 1024 -> 64) | [46,48) version = 1 | [61,64) layout = 2
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == NSAC_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == NSAC_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+struct GemmParams {
+  const float* bias;
+  int bias_group_rows;
+  int M, N, K, act, passes;
+  float* out_f32;
+  int ldo;
+  __nv_bfloat16* out_hi;
+  __nv_bfloat16* out_lo;
+  int ld_split;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+                   const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   const GemmParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint64_t* full = bars;                       // [STAGES]
+  uint64_t* empty = bars + C::STAGES;          // [STAGES]
+  uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]
+  uint64_t* tmem_empty = tmem_full + 2;        // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int num_tiles = tiles_m * tiles_n;
+  const int num_kb = p.K / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
+    for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_base_slot)), "r"((uint32_t)C::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_base_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx = (p.passes >= 2 ? 2 * C::A_BYTES : C::A_BYTES) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * C::STAGE_BYTES;
+          mbar_expect_tx(&full[stage], tx);
+          tma_load_2d(st, &map_a_hi, &full[stage], kb * BLOCK_K, m0);
+          if (p.passes >= 2) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
+          tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, &full[stage], kb * BLOCK_K, n0);
+          if (p.passes >= 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, &full[stage], kb * BLOCK_K, n0);
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+          const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + C::A_BYTES);
+          const uint64_t w_hi = make_sw128_desc(st + 2 * C::A_BYTES), w_lo = make_sw128_desc(st + 2 * C::A_BYTES + C::W_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance the start address inside the swizzle row
+            umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
+            if (p.passes >= 2) umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
+            if (p.passes >= 3) umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+          }
+          tcgen05_commit(&empty[stage]);                      // slot reusable once these MMAs retire
+          if (kb == num_kb - 1) tcgen05_commit(&tmem_full[acc]);   // accumulator complete
+          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps 2..5
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tcgen05_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      const bool row_ok = row < p.M;
+      const float* brow = nullptr;
+      if (p.bias) brow = p.bias_group_rows > 0 ? p.bias + (size_t)((row_ok ? row : 0) / p.bias_group_rows) * p.N : p.bias;
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
+        const int col0 = n0 + c;
+        if (row_ok && col0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float x = __uint_as_float(v[i]);
+            if (brow && col0 + i < p.N) x += __ldg(brow + col0 + i);
+            f[i] = apply_act(x, p.act);
+          }
+          const bool full_chunk = col0 + 32 <= p.N;
+          if (p.out_f32) {
+            float* dst = p.out_f32 + (size_t)row * p.ldo + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (col0 + i < p.N) dst[i] = f[i];
+            }
+          }
+          if (p.out_hi) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
+              hi[i >> 1] = pack_bf16(h0, h1);
+              lo[i >> 1] = pack_bf16(l0, l1);
+            }
+            __nv_bfloat16* dh = p.out_hi + (size_t)row * p.ld_split + col0;
+            __nv_bfloat16* dl = p.out_lo + (size_t)row * p.ld_split + col0;
+            if (full_chunk) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4) {
+                *reinterpret_cast<uint4*>(dh + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+                *reinterpret_cast<uint4*>(dl + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                if (col0 + i < p.N) {
+                  const __nv_bfloat16 h = __float2bfloat16_rn(f[i]);
+                  dh[i] = h;
+                  dl[i] = __float2bfloat16_rn(f[i] - __bfloat162float(h));
+                }
+              }
+            }
+          }
+        }
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
+  }
+}
+
+// fp32 [rows, K] -> bf16 hi / lo planes [rows, ld_split], zero-padded to ld_split columns
+__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, int rows, int K, __nv_bfloat16* __restrict__ hi,
+                                  __nv_bfloat16* __restrict__ lo, int ld_split) {
+  const size_t total = (size_t)rows * ld_split;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(idx / ld_split), c = (int)(idx - (size_t)r * ld_split);
+    const float v = c < K ? x[(size_t)r * ldx + c] : 0.f;
+    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    hi[idx] = h;
+    lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  }
+  return fn;
+}
+
+// row-major bf16 [rows, K] with row stride ld (elements): box = [box_rows x 64 elements], 128-byte swizzle
+bool make_map(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int BLOCK_N>
+int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
+                const GemmParams& p, cudaStream_t s) {
+  using C = Cfg<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_set = true;
+  }
+  const int tiles = nsac_cdiv(p.M, BLOCK_M) * nsac_cdiv(p.N, BLOCK_N);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_bf16x3_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
+  NSAC_CHECK_LAUNCH("nsac_gemm_bf16x3");
+  return NSAC_OK;
+}
+}  // namespace
+
+extern "C" int nsac_gemm_bf16x3(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                                int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
+                                int passes, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                                void* stream) {
+  NSAC_REQUIRE(a_hi && w_hi, "nsac_gemm_bf16x3: null operand");
+  NSAC_REQUIRE(passes >= 1 && passes <= 3, "nsac_gemm_bf16x3: passes must be 1..3");
+  NSAC_REQUIRE((passes < 2 || a_lo) && (passes < 3 || w_lo), "nsac_gemm_bf16x3: missing lo plane for %d passes", passes);
+  NSAC_REQUIRE(M >= 0 && N >= 8 && K >= BLOCK_K && K % BLOCK_K == 0, "nsac_gemm_bf16x3: need K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  NSAC_REQUIRE(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "nsac_gemm_bf16x3: lda/ldw must be >= K and multiples of 8");
+  NSAC_REQUIRE(out_f32 || out_hi, "nsac_gemm_bf16x3: no output requested");
+  NSAC_REQUIRE(!out_f32 || (ldo >= N && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0),
+               "nsac_gemm_bf16x3: fp32 output must be 16-byte aligned with ldo %% 4 == 0");
+  NSAC_REQUIRE(!out_hi || (out_lo && ld_split >= N && ld_split % 8 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0),
+               "nsac_gemm_bf16x3: split output needs both planes, 16-byte alignment and ld_split %% 8 == 0");
+  NSAC_REQUIRE(act >= 0 && act <= 2, "nsac_gemm_bf16x3: bad act %d", act);
+  for (const void* ptr : {a_hi, a_lo, w_hi, w_lo})
+    NSAC_REQUIRE(!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "nsac_gemm_bf16x3: operands must be 16-byte aligned");
+  if (M == 0) return NSAC_OK;
+  const int block_n = (N % 256 == 0 && (long long)nsac_cdiv(M, BLOCK_M) * (N / 256) >= sm_count()) ? 256 : 128;
+  CUtensorMap mah, mal, mwh, mwl;
+  bool ok = make_map(&mah, a_hi, M, K, lda, BLOCK_M) && make_map(&mal, a_lo ? a_lo : a_hi, M, K, lda, BLOCK_M) &&
+            make_map(&mwh, w_hi, N, K, ldw, block_n) && make_map(&mwl, w_lo ? w_lo : w_hi, N, K, ldw, block_n);
+  if (!ok) {
+    nsac_set_error("nsac_gemm_bf16x3: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
+    return NSAC_ERR_LAUNCH;
+  }
+  GemmParams p;
+  p.bias = bias; p.bias_group_rows = bias_group_rows; p.M = M; p.N = N; p.K = K; p.act = act; p.passes = passes;
+  p.out_f32 = out_f32; p.ldo = ldo;
+  p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo); p.ld_split = ld_split;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  return block_n == 256 ? launch_gemm<256>(mah, mal, mwh, mwl, p, s) : launch_gemm<128>(mah, mal, mwh, mwl, p, s);
+}
+
+extern "C" int nsac_split_bf16(const float* x, int ldx, int rows, int K, void* hi, void* lo, int ld_split, void* stream) {
+  NSAC_REQUIRE(x && hi && lo, "nsac_split_bf16: null pointer");
+  NSAC_REQUIRE(rows >= 0 && K >= 1 && ldx >= K && ld_split >= K, "nsac_split_bf16: bad shape");
+  if (rows == 0) return NSAC_OK;
+  const size_t total = (size_t)rows * ld_split;
+  int blocks = (int)((total + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  split_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, rows, K, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ld_split);
+  NSAC_CHECK_LAUNCH("nsac_split_bf16");
+  return NSAC_OK;
+}

@@ -73,6 +73,89 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
+class Split:
+    """bf16 hi / lo planes of an fp32 matrix [rows, K] (x ~ hi + lo), row stride `ld` (multiple of 64 for
+    freshly made ones, columns K..ld zero) — the operand format of the tcgen05 GEMM engine."""
+    __slots__ = ("hi", "lo", "K")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor, K: int):
+        self.hi, self.lo, self.K = hi, lo, K
+
+    @property
+    def rows(self):
+        return self.hi.shape[0]
+
+    def cols(self, a: int, b: int) -> "Split":
+        """Column slice view [rows, a:b] (keeps the parent's row stride)."""
+        return Split(self.hi[:, a:b], self.lo[:, a:b], b - a)
+
+    def rows_slice(self, a: int, b: int) -> "Split":
+        return Split(self.hi[a:b], self.lo[a:b], self.K)
+
+    @staticmethod
+    def empty(rows: int, K: int, device) -> "Split":
+        ld = (K + 63) // 64 * 64
+        hi = torch.zeros(rows, ld, device=device, dtype=torch.bfloat16) if ld != K else \
+            torch.empty(rows, ld, device=device, dtype=torch.bfloat16)
+        lo = torch.zeros_like(hi) if ld != K else torch.empty_like(hi)
+        return Split(hi, lo, K)
+
+    def float(self) -> torch.Tensor:
+        return self.hi[:, :self.K].float() + self.lo[:, :self.K].float()
+
+
+def split(x: torch.Tensor, out: Optional[Split] = None) -> Split:
+    """fp32 [rows, K] -> Split (zero-padded to a multiple of 64 columns)."""
+    _chk(x, "x")
+    assert x.dim() == 2 and x.stride(1) == 1
+    rows, K = x.shape
+    if out is None:
+        ld = (K + 63) // 64 * 64
+        out = Split(torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16),
+                    torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16), K)
+        width = ld
+    else:
+        width = out.hi.shape[1]
+    assert out.hi.stride(0) == out.lo.stride(0)
+    # the kernel writes `ld_split` contiguous columns per row: only whole-buffer outputs are supported here
+    assert out.hi.is_contiguous() and out.lo.is_contiguous()
+    st = _lib.lib().nsac_split_bf16(_p(x), x.stride(0) if rows > 1 else max(K, x.stride(0)), rows, K, _p(out.hi), _p(out.lo),
+                                    width, _stream())
+    _lib.check(st, "nsac_split_bf16")
+    _count()
+    return out
+
+
+def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, passes: int = 3,
+            want_f32: bool = True, want_split: bool = False, out_f32: Optional[torch.Tensor] = None,
+            out_split: Optional[Split] = None, bias_group_rows: int = 0):
+    """tcgen05 split-bf16 GEMM: act(a @ w^T + bias) -> (fp32 [M,N] or None, Split or None)."""
+    M, N = a.rows, w.rows
+    Kp = a.hi.shape[1] if a.hi.shape[1] % 64 == 0 else None
+    K = min(a.hi.shape[1], w.hi.shape[1]) if Kp is None else a.hi.shape[1]
+    assert a.K == w.K, f"gemm_tc: K mismatch {a.K} vs {w.K}"
+    K = (a.K + 63) // 64 * 64
+    assert a.hi.shape[1] >= K or a.hi.stride(0) >= K, "gemm_tc: A planes must be zero-padded to a multiple of 64 columns"
+    assert w.hi.shape[1] >= K, "gemm_tc: W planes must be zero-padded to a multiple of 64 columns"
+    dev = a.hi.device
+    if want_f32 and out_f32 is None:
+        out_f32 = torch.empty(M, N, device=dev, dtype=torch.float32)
+    if want_split and out_split is None:
+        out_split = Split.empty(M, N, dev)
+    if bias is not None:
+        _chk(bias, "bias")
+        assert bias.is_contiguous() and bias.shape[-1] == N
+    ldo = 0 if out_f32 is None else (out_f32.stride(0) if M > 1 else max(N, out_f32.stride(0)))
+    lds = 0 if out_split is None else out_split.hi.stride(0)
+    st = _lib.lib().nsac_gemm_bf16x3(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), _p(bias),
+                                     bias_group_rows, M, N, K, act, passes, _p(out_f32), ldo,
+                                     None if out_split is None else _p(out_split.hi),
+                                     None if out_split is None else _p(out_split.lo), lds, _stream())
+    _lib.check(st, "nsac_gemm_bf16x3")
+    _count()
+    return out_f32, out_split
+
+
 def layernorm(x, gamma, beta, res=None, out=None):
     _chk(x, "x")
     rows, Cdim = x.shape
