@@ -59,17 +59,25 @@ int nsac_linear(const float* x, int ldx, const float* w, const float* bias, int 
 
 /* ------------------------------------------------------------------------------------------------
  * Tensor-core dense layer (tcgen05 / TMEM / TMA, sm_100a): same contract as nsac_linear but the operands are
- * bf16 hi/lo planes of the fp32 matrices (x = x_hi + x_lo, w = w_hi + w_lo, row strides lda / ldw in elements,
- * multiples of 8, K % 64 == 0 with zero padding) and the product is accumulated in fp32 as
- * x_hi.w_hi (+ x_lo.w_hi (+ x_hi.w_lo)) for passes = 1 (2 (3)); passes = 3 is fp32-accurate to ~1e-5 relative.
- * Outputs: fp32 rows (out_f32, may be NULL) and / or re-split bf16 planes for the next layer (out_hi/out_lo,
- * may be NULL).  nsac_split_bf16 produces the planes from an fp32 matrix (zero-padded to ld_split columns).
+ * 16-bit hi/lo planes of the fp32 matrices (x ~ x_hi + x_lo; row strides lda / ldw in elements, multiples of
+ * 8; K % 64 == 0 with zero padding) and the product is accumulated in fp32 as
+ * x_hi.w_hi (+ x_lo.w_hi (+ x_hi.w_lo (+ x_lo.w_lo))) for passes = 1 (2 (3 (4))).
+ *   fmt NSAC_SPLIT_F16 : fp16 planes, ~2^-22 relative per operand (3 passes ~ fp32); requires |x| <= 65504
+ *                        (overflow -> inf -> NaN outputs, never silently wrong)
+ *   fmt NSAC_SPLIT_BF16: bf16 planes, fp32 exponent range, ~2^-17 relative per operand
+ * out = act(out_scale * acc + bias): out_scale undoes a power-of-two pre-scaling of the weight planes.
+ * Outputs: fp32 rows (out_f32, may be NULL) and / or re-split planes for the next layer (out_hi/out_lo, may
+ * be NULL).  nsac_split16 produces planes of x*scale from an fp32 matrix (zero-padded to ld_split columns).
  * Replaces the large nn.Linear layers of camera_head.py:957-962, 980-986 and gnn.py:85-93.
  * ---------------------------------------------------------------------------------------------- */
-int nsac_gemm_bf16x3(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
-                     const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes,
-                     float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream);
-int nsac_split_bf16(const float* x, int ldx, int rows, int K, void* hi, void* lo, int ld_split, void* stream);
+#define NSAC_SPLIT_F16 0
+#define NSAC_SPLIT_BF16 1
+int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                    const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
+                    float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                    void* stream);
+int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,
+                 int ld_split, void* stream);
 
 /* LayerNorm over the last dim C (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x).
  * gnn.py:90,94-96. */

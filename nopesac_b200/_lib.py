@@ -20,10 +20,11 @@ _SIGNATURES = {
     "nsac_last_error": (C.c_char_p, []),
     "nsac_linear": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
                               C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "nsac_gemm_bf16x3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p, C.c_int,
-                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_int, C.c_void_p,
-                                   C.c_void_p, C.c_int, C.c_void_p]),
-    "nsac_split_bf16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_gemm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p, C.c_int,
+                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_split16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_int, C.c_void_p]),
     "nsac_layernorm": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,

@@ -65,11 +65,35 @@ class MLP(nn.Module):
             _c2_xavier_fill(layer)
 
     def run(self, x: torch.Tensor, final_act: int = ops.ACT_NONE, out: Optional[torch.Tensor] = None):
+        """Exact-fp32 CUDA-core path (small batches / K not a multiple of 64)."""
         for i, layer in enumerate(self.layers):
             last = i == self.num_layers - 1
             x = ops.linear(x, layer.weight, layer.bias, ops.ACT_RELU if not last else final_act,
                            out=out if last else None)
         return x
+
+    def split_weights(self):
+        """hi/lo planes of every layer whose K is a multiple of 64 (None otherwise)."""
+        return [ops.split_weight(l.weight) if l.weight.shape[1] % 64 == 0 else None for l in self.layers]
+
+    def run_tc(self, x, wsplit, final_act: int = ops.ACT_NONE, out_split: Optional["ops.Split"] = None,
+               want_f32: bool = False, first_bias=None, first_group_rows: int = 0, first_weight=None, passes: int = 3):
+        """tcgen05 split-bf16 path.  `x` is an ops.Split, or an fp32 matrix when layer 0 has a small K (that
+        layer then runs on the CUDA cores and is re-split).  Returns (fp32 or None, Split)."""
+        f32 = None
+        for i, layer in enumerate(self.layers):
+            last = i == self.num_layers - 1
+            act = ops.ACT_RELU if not last else final_act
+            w = wsplit[i] if not (i == 0 and first_weight is not None) else first_weight
+            bias = layer.bias if not (i == 0 and first_bias is not None) else first_bias
+            grp = first_group_rows if i == 0 else 0
+            if w is None:
+                assert i == 0 and isinstance(x, torch.Tensor)
+                x = ops.split(ops.linear(x, layer.weight, bias, act))
+                continue
+            f32, x = ops.gemm_tc(x, w, bias, act, passes=passes, want_f32=want_f32 and last, want_split=True,
+                                 out_split=out_split if last else None, bias_group_rows=grp)
+        return f32, x
 
 
 class _NormConv(nn.Conv2d):
@@ -177,6 +201,7 @@ class PlaneCameraHead(nn.Module):
             self.param_score_proj = MLP(self.num_queries, 128, 64, 3)
             self.trans_score_reg = nn.Linear(64, 1)
         self._packed = None
+        self.tc_passes = 3     # MMA passes of the tensor-core layers (3 = hi.hi + lo.hi + hi.lo on fp16 planes, ~fp32)
 
     # ------------------------------------------------------------------ weight packing
     def _load_from_state_dict(self, *a, **k):
@@ -204,6 +229,18 @@ class PlaneCameraHead(nn.Module):
                             m.layers[2].weight, m.layers[2].bias, r.weight, r.bias))
                 self._packed = pk
         return self._packed
+
+    def prepare_tc(self):
+        """hi/lo weight planes for the tcgen05 engine (device-side; built once per weight version)."""
+        pk = self.prepare()
+        if "geo_encoder.split" not in pk:
+            with torch.no_grad():
+                for name in ("geo_encoder", "geo_proj_s1", "decoder_rot", "geo_proj_s2", "decoder_tran",
+                             "decoder_rot2", "decoder_tran2"):
+                    pk[name + ".split"] = getattr(self, name).split_weights()
+                for name in ("decoder_rot2", "decoder_tran2"):
+                    pk[name + ".w_geo_split"] = ops.split_weight(pk[name + ".w_geo"])
+        return pk
 
     # ------------------------------------------------------------------ K1: pixel pose network
     @staticmethod
@@ -275,23 +312,27 @@ class PlaneCameraHead(nn.Module):
 
     # ------------------------------------------------------------------ K7: hypothesis features (:957-986)
     def _hypothesis_features(self, geo8, rot_feat0, trans_feat0, B, NQ):
-        pk = self.prepare()
+        """The ~28-layer one-plane pose MLP chain on the tcgen05 split-precision engine (fp16 hi/lo planes, 3 passes: ~fp32).
+        Activations stay as 16-bit hi/lo planes between layers; cat[s1, rot] (:961) is a column slice of one
+        1280-wide plane pair, cat[init_feat, geo_feat] (:983-986) becomes a per-pair bias."""
+        pk = self.prepare_tc()
         rows = B * NQ
         dev = geo8.device
-        fea = self.geo_encoder.run(geo8.view(rows, 8))
-        cat = torch.empty(rows, 1280, device=dev, dtype=torch.float32)       # cat[s1, rot] of :961
-        self.geo_proj_s1.run(fea, out=cat[:, :1024])
-        self.decoder_rot.run(cat[:, :1024], out=cat[:, 1024:])
-        s2 = self.geo_proj_s2.run(cat)
-        ftran = self.decoder_tran.run(s2)
+        P = self.tc_passes
+        _, fea = self.geo_encoder.run_tc(geo8.view(rows, 8), pk["geo_encoder.split"], passes=P)
+        cat = ops.Split.empty(rows, 1280, dev)
+        self.geo_proj_s1.run_tc(fea, pk["geo_proj_s1.split"], out_split=cat.cols(0, 1024), passes=P)
+        self.decoder_rot.run_tc(cat.cols(0, 1024), pk["decoder_rot.split"], out_split=cat.cols(1024, 1280), passes=P)
+        _, s2 = self.geo_proj_s2.run_tc(cat, pk["geo_proj_s2.split"], passes=P)
+        _, ftran = self.decoder_tran.run_tc(s2, pk["decoder_tran.split"], passes=P)
         fused = []
-        for name, feat0, geo_feat in (("decoder_rot2", rot_feat0, cat[:, 1024:]), ("decoder_tran2", trans_feat0, ftran)):
+        for name, feat0, geo_feat in (("decoder_rot2", rot_feat0, cat.cols(1024, 1280)), ("decoder_tran2", trans_feat0, ftran)):
             m = getattr(self, name)
             # cat[init_feat (broadcast over the pair's rows), geo_feat] @ W^T  ==  geo_feat @ W_geo^T + per-pair bias
             gb = ops.linear(feat0, pk[name + ".w_init"], m.layers[0].bias)
-            x = ops.linear(geo_feat, pk[name + ".w_geo"], gb, ops.ACT_RELU, bias_group_rows=NQ)
-            x = ops.linear(x, m.layers[1].weight, m.layers[1].bias, ops.ACT_RELU)
-            fused.append(ops.linear(x, m.layers[2].weight, m.layers[2].bias, ops.ACT_RELU))   # F.relu(decoder_*2(.))
+            f32, _ = m.run_tc(geo_feat, pk[name + ".split"], final_act=ops.ACT_RELU, want_f32=True, first_bias=gb,
+                              first_group_rows=NQ, first_weight=pk[name + ".w_geo_split"], passes=P)
+            fused.append(f32)                                                     # F.relu(decoder_*2(.))
         return fused[0], fused[1]
 
     # ------------------------------------------------------------------ forward

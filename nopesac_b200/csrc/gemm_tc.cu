@@ -1,14 +1,31 @@
 // Split-bf16 tensor-core GEMM for sm_100a: the dense-contraction engine of the path
 //   (hypothesis-generation MLP chain K7, GNN projections K4, pixel-pose convolutions K1 via im2col).
 //
-//   out[M,N] = act( A[M,K] . W[N,K]^T + bias ),  A = a_hi + a_lo, W = w_hi + w_lo  (bf16 planes)
-//            ~ a_hi.w_hi + a_lo.w_hi + a_hi.w_lo   accumulated in fp32           ("bf16x3")
+//   out[M,N] = act( A[M,K] . W[N,K]^T + bias ),  A = a_hi + a_lo, W = w_hi + w_lo   (16-bit planes)
+//            = a_hi.w_hi + a_lo.w_hi + a_hi.w_lo (+ a_lo.w_lo)   accumulated in fp32 (TMEM)
 //
 // The reference computes these layers in fp32 and the parity bar is 1e-4 abs after ~28 chained layers;
-// single-pass bf16 / tf32 misses it, the 3-term split keeps ~2^-17 relative error per product
-// at 1/3 of the bf16 tensor rate.  `passes` = 1 / 2 / 3 selects hi.hi / + lo.hi / + hi.lo.
+// single-pass bf16 / tf32 misses it.  Two plane formats (`fmt`), same kernel:
+//   NSAC_SPLIT_F16  (default) hi = fp16(x), lo = fp16(x - hi): 22 significant bits, ~2^-22 relative per
+//                   operand with 3 passes.  Needs |x| <= 65504 (an overflow becomes inf and then NaN poses —
+//                   loud, like the reference's own NaN guards); elements below 6e-5 carry <= 3e-8 absolute
+//                   error (fp16 subnormals); weight matrices are pre-scaled by a power of two (undone exactly
+//                   in the epilogue via `out_scale`) so small weights keep their relative precision.
+//   NSAC_SPLIT_BF16 hi = bf16(x), lo = bf16(x - hi): fp32's exponent range but only 16 significant bits —
+//                   measured here on the pose chain: 1.0-1.4e-4 on per-hypothesis poses, i.e. over the bar.
+// (kind::f16 does not accept mixed fp16/bf16 operands in one MMA — tried: illegal instruction.)
+// `passes` = 1 / 2 / 3 / 4 selects hi.hi / + lo.hi / + hi.lo / + lo.lo.
 //
-// Design (one persistent CTA per SM, warp-specialised, no register accumulators):
+// Accumulation accuracy.  The tensor core adds into its fp32 accumulator with truncation, so the error of one
+// long tcgen05 accumulation chain grows LINEARLY with the number of MMAs (measured: 3e-9 * K relative, 4e-6 at
+// K = 1280 — as large as the bf16-plane representation error).  Two counter-measures, both free of extra
+// tensor work: (1) the hi.hi products and the (2^-11 smaller) lo terms go to SEPARATE TMEM accumulators, so
+// the lo terms neither lengthen the main chain nor lose bits against it; (2) the K loop is cut into chunks of
+// CHUNK_KB x 64 elements that ping-pong between two TMEM buffers while the otherwise idle epilogue warps add
+// the finished chunk into fp32 REGISTER accumulators (exact IEEE adds) — the same ping-pong overlaps the
+// epilogue of one tile with the MMAs of the next.
+//
+// Design (one persistent CTA per SM, warp-specialised):
 //   warp 0      TMA producer   cp.async.bulk.tensor (SWIZZLE_128B) of the four operand planes into a
 //                              3-stage shared-memory ring, mbarrier complete_tx signalling
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N,
@@ -20,6 +37,7 @@
 //                              next layer straight from registers
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace {
@@ -30,14 +48,18 @@ constexpr int UMMA_K = 16;
 constexpr int NUM_THREADS = 192;            // 6 warps
 constexpr uint32_t SPIN_LIMIT = 1u << 28;   // bounded mbarrier spins: a protocol bug traps instead of hanging the GPU
 
+constexpr int CHUNK_KB = 4;                 // K-blocks (x64 elements) accumulated inside the tensor core per chunk
+
 template <int BLOCK_N>
 struct Cfg {
-  static constexpr int STAGES = BLOCK_N == 128 ? 3 : 2;
+  static constexpr int STAGES = 3;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
-  static constexpr int TMEM_COLS = 2 * BLOCK_N;             // double-buffered accumulator (power of two)
+  static constexpr int ACC_COLS = 2 * BLOCK_N;              // one buffer = hi.hi accumulator + lo-terms accumulator
+  static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
 
 // ------------------------------------------------------------------------------------------------ PTX
@@ -112,9 +134,11 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
-// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format BF16 (1) @7/@10, K-major both, N>>3 @17, M>>4 @24
-__host__ __device__ constexpr uint32_t make_idesc(int m, int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+// cute::UMMA::InstrDescriptor: c_format F32 (1) @4, a/b format (F16 = 0, BF16 = 1) @7/@10, K-major both,
+// N>>3 @17, M>>4 @24
+__host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool bf16) {
+  return (1u << 4) | ((bf16 ? 1u : 0u) << 7) | ((bf16 ? 1u : 0u) << 10) | ((uint32_t)(n >> 3) << 17) |
+         ((uint32_t)(m >> 4) << 24);
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {
@@ -123,20 +147,33 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
-}
 
 struct GemmParams {
   const float* bias;
   int bias_group_rows;
-  int M, N, K, act, passes;
+  int M, N, K, act, passes, fmt;
+  float out_scale;          // multiplies the accumulator before bias (undoes the power-of-two weight pre-scale)
   float* out_f32;
   int ldo;
-  __nv_bfloat16* out_hi;
-  __nv_bfloat16* out_lo;
+  uint16_t* out_hi;
+  uint16_t* out_lo;
   int ld_split;
 };
+
+// x -> (hi, lo) 16-bit planes in the requested format
+__device__ __forceinline__ void split16(float x, int fmt, uint16_t& hi, uint16_t& lo) {
+  if (fmt == NSAC_SPLIT_F16) {
+    const __half h = __float2half_rn(x);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+  }
+}
+
+
 
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -196,55 +233,84 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.fmt == NSAC_SPLIT_BF16);
       int stage = 0; uint32_t phase = 0;
-      int acc = 0; uint32_t acc_phase = 0;
+      uint32_t chunk_ctr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full[stage], phase);
+        for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB, ++chunk_ctr) {
+          const uint32_t buf = chunk_ctr & 1, buf_phase = (chunk_ctr >> 1) & 1;
+          mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
           tcgen05_fence_after();
-          const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
-          const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + C::A_BYTES);
-          const uint64_t w_hi = make_sw128_desc(st + 2 * C::A_BYTES), w_lo = make_sw128_desc(st + 2 * C::A_BYTES + C::W_BYTES);
+          const uint32_t d_main = tmem_base + buf * C::ACC_COLS, d_lo = d_main + BLOCK_N;
+          const int kb1 = kb0 + CHUNK_KB < num_kb ? kb0 + CHUNK_KB : num_kb;
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
+            const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + C::A_BYTES);
+            const uint64_t w_hi = make_sw128_desc(st + 2 * C::A_BYTES), w_lo = make_sw128_desc(st + 2 * C::A_BYTES + C::W_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance the start address inside the swizzle row
-            umma_bf16(d_tmem, a_hi + koff, w_hi + koff, idesc, (kb | k) != 0);
-            if (p.passes >= 2) umma_bf16(d_tmem, a_lo + koff, w_hi + koff, idesc, 1);
-            if (p.passes >= 3) umma_bf16(d_tmem, a_hi + koff, w_lo + koff, idesc, 1);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance the start address inside the swizzle row
+              const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
+              umma_bf16(d_main, a_hi + koff, w_hi + koff, idesc, first);
+              if (p.passes >= 2) umma_bf16(d_lo, a_lo + koff, w_hi + koff, idesc, first);
+              if (p.passes >= 3) umma_bf16(d_lo, a_hi + koff, w_lo + koff, idesc, 1);
+              if (p.passes >= 4) umma_bf16(d_lo, a_lo + koff, w_lo + koff, idesc, 1);
+            }
+            tcgen05_commit(&empty[stage]);                 // slot reusable once these MMAs retire
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
-          tcgen05_commit(&empty[stage]);                      // slot reusable once these MMAs retire
-          if (kb == num_kb - 1) tcgen05_commit(&tmem_full[acc]);   // accumulator complete
-          if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+          tcgen05_commit(&tmem_full[buf]);                 // chunk complete -> epilogue warps
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
     // ===================================================================== epilogue warps 2..5
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
-    int acc = 0; uint32_t acc_phase = 0;
+    const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+    uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
+      float sum[BLOCK_N];
+#pragma unroll
+      for (int i = 0; i < BLOCK_N; ++i) sum[i] = 0.f;
+      for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB, ++chunk_ctr) {
+        const uint32_t buf = chunk_ctr & 1, buf_phase = (chunk_ctr >> 1) & 1;
+        mbar_wait(&tmem_full[buf], buf_phase);
+        tcgen05_fence_after();
+        const uint32_t t_main = tmem_base + lane_base + buf * C::ACC_COLS;
+#pragma unroll
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(t_main + c, v);
+          if (p.passes >= 2) {
+            uint32_t u[32];
+            tmem_ld32(t_main + BLOCK_N + c, u);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[c + i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) sum[c + i] += __uint_as_float(v[i]);
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[buf]);
+      }
+      // ---- bias, activation, stores
       const int row = m0 + quad * 32 + lane;
       const bool row_ok = row < p.M;
       const float* brow = nullptr;
       if (p.bias) brow = p.bias_group_rows > 0 ? p.bias + (size_t)((row_ok ? row : 0) / p.bias_group_rows) * p.N : p.bias;
-#pragma unroll 1
+#pragma unroll
       for (int c = 0; c < BLOCK_N; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BLOCK_N + c), v);
         const int col0 = n0 + c;
         if (row_ok && col0 < p.N) {
           float f[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
-            float x = __uint_as_float(v[i]);
+            float x = sum[c + i] * p.out_scale;
             if (brow && col0 + i < p.N) x += __ldg(brow + col0 + i);
             f[i] = apply_act(x, p.act);
           }
@@ -264,14 +330,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int i = 0; i < 32; i += 2) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(f[i]), h1 = __float2bfloat16_rn(f[i + 1]);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(f[i] - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(f[i + 1] - __bfloat162float(h1));
-              hi[i >> 1] = pack_bf16(h0, h1);
-              lo[i >> 1] = pack_bf16(l0, l1);
+              uint16_t h0, l0, h1, l1;
+              split16(f[i], p.fmt, h0, l0);
+              split16(f[i + 1], p.fmt, h1, l1);
+              hi[i >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+              lo[i >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
             }
-            __nv_bfloat16* dh = p.out_hi + (size_t)row * p.ld_split + col0;
-            __nv_bfloat16* dl = p.out_lo + (size_t)row * p.ld_split + col0;
+            uint16_t* dh = p.out_hi + (size_t)row * p.ld_split + col0;
+            uint16_t* dl = p.out_lo + (size_t)row * p.ld_split + col0;
             if (full_chunk) {
 #pragma unroll
               for (int i = 0; i < 16; i += 4) {
@@ -282,19 +348,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
 #pragma unroll
               for (int i = 0; i < 32; ++i) {
                 if (col0 + i < p.N) {
-                  const __nv_bfloat16 h = __float2bfloat16_rn(f[i]);
-                  dh[i] = h;
-                  dl[i] = __float2bfloat16_rn(f[i] - __bfloat162float(h));
+                  dh[i] = (i & 1) ? (uint16_t)(hi[i >> 1] >> 16) : (uint16_t)(hi[i >> 1] & 0xffff);
+                  dl[i] = (i & 1) ? (uint16_t)(lo[i >> 1] >> 16) : (uint16_t)(lo[i >> 1] & 0xffff);
                 }
               }
             }
           }
         }
       }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
   tcgen05_fence_before();
@@ -305,16 +366,17 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   }
 }
 
-// fp32 [rows, K] -> bf16 hi / lo planes [rows, ld_split], zero-padded to ld_split columns
-__global__ void split_bf16_kernel(const float* __restrict__ x, int ldx, int rows, int K, __nv_bfloat16* __restrict__ hi,
-                                  __nv_bfloat16* __restrict__ lo, int ld_split) {
+// fp32 [rows, K] * scale -> hi / lo 16-bit planes [rows, ld_split], zero-padded to ld_split columns
+__global__ void split16_kernel(const float* __restrict__ x, int ldx, int rows, int K, float scale, int fmt,
+                               uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, int ld_split) {
   const size_t total = (size_t)rows * ld_split;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx / ld_split), c = (int)(idx - (size_t)r * ld_split);
-    const float v = c < K ? x[(size_t)r * ldx + c] : 0.f;
-    const __nv_bfloat16 h = __float2bfloat16_rn(v);
+    const float v = c < K ? x[(size_t)r * ldx + c] * scale : 0.f;
+    uint16_t h, l;
+    split16(v, fmt, h, l);
     hi[idx] = h;
-    lo[idx] = __float2bfloat16_rn(v - __bfloat162float(h));
+    lo[idx] = l;
   }
 }
 
@@ -336,14 +398,14 @@ EncodeTiledFn get_encode_fn() {
 }
 
 // row-major bf16 [rows, K] with row stride ld (elements): box = [box_rows x 64 elements], 128-byte swizzle
-bool make_map(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows) {
+bool make_map(CUtensorMap* map, const void* base, int rows, int K, int ld, int box_rows, bool is_bf16) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
   cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+  return enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -371,55 +433,60 @@ int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   const int tiles = nsac_cdiv(p.M, BLOCK_M) * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_bf16x3_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
-  NSAC_CHECK_LAUNCH("nsac_gemm_bf16x3");
+  NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }
 }  // namespace
 
-extern "C" int nsac_gemm_bf16x3(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
-                                int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
-                                int passes, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
-                                void* stream) {
-  NSAC_REQUIRE(a_hi && w_hi, "nsac_gemm_bf16x3: null operand");
-  NSAC_REQUIRE(passes >= 1 && passes <= 3, "nsac_gemm_bf16x3: passes must be 1..3");
-  NSAC_REQUIRE((passes < 2 || a_lo) && (passes < 3 || w_lo), "nsac_gemm_bf16x3: missing lo plane for %d passes", passes);
-  NSAC_REQUIRE(M >= 0 && N >= 8 && K >= BLOCK_K && K % BLOCK_K == 0, "nsac_gemm_bf16x3: need K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
-  NSAC_REQUIRE(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "nsac_gemm_bf16x3: lda/ldw must be >= K and multiples of 8");
-  NSAC_REQUIRE(out_f32 || out_hi, "nsac_gemm_bf16x3: no output requested");
+extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                               int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
+                               int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
+                               void* out_lo, int ld_split, void* stream) {
+  NSAC_REQUIRE(a_hi && w_hi, "nsac_gemm_split: null operand");
+  NSAC_REQUIRE(passes >= 1 && passes <= 4, "nsac_gemm_split: passes must be 1..4");
+  NSAC_REQUIRE((passes < 2 || a_lo) && (passes < 3 || w_lo), "nsac_gemm_split: missing lo plane for %d passes", passes);
+  NSAC_REQUIRE(M >= 0 && N >= 8 && K >= BLOCK_K && K % BLOCK_K == 0, "nsac_gemm_split: need K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
+  NSAC_REQUIRE(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "nsac_gemm_split: lda/ldw must be >= K and multiples of 8");
+  NSAC_REQUIRE(out_f32 || out_hi, "nsac_gemm_split: no output requested");
   NSAC_REQUIRE(!out_f32 || (ldo >= N && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0),
-               "nsac_gemm_bf16x3: fp32 output must be 16-byte aligned with ldo %% 4 == 0");
+               "nsac_gemm_split: fp32 output must be 16-byte aligned with ldo %% 4 == 0");
   NSAC_REQUIRE(!out_hi || (out_lo && ld_split >= N && ld_split % 8 == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0 &&
                            (reinterpret_cast<uintptr_t>(out_lo) & 15) == 0),
-               "nsac_gemm_bf16x3: split output needs both planes, 16-byte alignment and ld_split %% 8 == 0");
-  NSAC_REQUIRE(act >= 0 && act <= 2, "nsac_gemm_bf16x3: bad act %d", act);
+               "nsac_gemm_split: split output needs both planes, 16-byte alignment and ld_split %% 8 == 0");
+  NSAC_REQUIRE(act >= 0 && act <= 2, "nsac_gemm_split: bad act %d", act);
+  NSAC_REQUIRE(fmt == NSAC_SPLIT_F16 || fmt == NSAC_SPLIT_BF16, "nsac_gemm_split: bad plane format %d", fmt);
   for (const void* ptr : {a_hi, a_lo, w_hi, w_lo})
-    NSAC_REQUIRE(!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "nsac_gemm_bf16x3: operands must be 16-byte aligned");
+    NSAC_REQUIRE(!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "nsac_gemm_split: operands must be 16-byte aligned");
   if (M == 0) return NSAC_OK;
-  const int block_n = (N % 256 == 0 && (long long)nsac_cdiv(M, BLOCK_M) * (N / 256) >= sm_count()) ? 256 : 128;
+  const int block_n = 128;
   CUtensorMap mah, mal, mwh, mwl;
-  bool ok = make_map(&mah, a_hi, M, K, lda, BLOCK_M) && make_map(&mal, a_lo ? a_lo : a_hi, M, K, lda, BLOCK_M) &&
-            make_map(&mwh, w_hi, N, K, ldw, block_n) && make_map(&mwl, w_lo ? w_lo : w_hi, N, K, ldw, block_n);
+  const bool bf = fmt == NSAC_SPLIT_BF16;
+  bool ok = make_map(&mah, a_hi, M, K, lda, BLOCK_M, bf) && make_map(&mal, a_lo ? a_lo : a_hi, M, K, lda, BLOCK_M, bf) &&
+            make_map(&mwh, w_hi, N, K, ldw, block_n, bf) && make_map(&mwl, w_lo ? w_lo : w_hi, N, K, ldw, block_n, bf);
   if (!ok) {
-    nsac_set_error("nsac_gemm_bf16x3: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
+    nsac_set_error("nsac_gemm_split: cuTensorMapEncodeTiled failed (M=%d N=%d K=%d lda=%d ldw=%d)", M, N, K, lda, ldw);
     return NSAC_ERR_LAUNCH;
   }
   GemmParams p;
   p.bias = bias; p.bias_group_rows = bias_group_rows; p.M = M; p.N = N; p.K = K; p.act = act; p.passes = passes;
+  p.fmt = fmt; p.out_scale = out_scale;
   p.out_f32 = out_f32; p.ldo = ldo;
-  p.out_hi = static_cast<__nv_bfloat16*>(out_hi); p.out_lo = static_cast<__nv_bfloat16*>(out_lo); p.ld_split = ld_split;
+  p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return block_n == 256 ? launch_gemm<256>(mah, mal, mwh, mwl, p, s) : launch_gemm<128>(mah, mal, mwh, mwl, p, s);
+  return launch_gemm<128>(mah, mal, mwh, mwl, p, s);
 }
 
-extern "C" int nsac_split_bf16(const float* x, int ldx, int rows, int K, void* hi, void* lo, int ld_split, void* stream) {
-  NSAC_REQUIRE(x && hi && lo, "nsac_split_bf16: null pointer");
-  NSAC_REQUIRE(rows >= 0 && K >= 1 && ldx >= K && ld_split >= K, "nsac_split_bf16: bad shape");
+extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,
+                            int ld_split, void* stream) {
+  NSAC_REQUIRE(x && hi && lo, "nsac_split16: null pointer");
+  NSAC_REQUIRE(rows >= 0 && K >= 1 && ldx >= K && ld_split >= K, "nsac_split16: bad shape");
+  NSAC_REQUIRE(fmt == NSAC_SPLIT_F16 || fmt == NSAC_SPLIT_BF16, "nsac_split16: bad plane format %d", fmt);
   if (rows == 0) return NSAC_OK;
   const size_t total = (size_t)rows * ld_split;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 16) blocks = 148 * 16;
-  split_bf16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, rows, K, static_cast<__nv_bfloat16*>(hi), static_cast<__nv_bfloat16*>(lo), ld_split);
-  NSAC_CHECK_LAUNCH("nsac_split_bf16");
+  split16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, ldx, rows, K, scale, fmt, static_cast<uint16_t*>(hi), static_cast<uint16_t*>(lo), ld_split);
+  NSAC_CHECK_LAUNCH("nsac_split16");
   return NSAC_OK;
 }

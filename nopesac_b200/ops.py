@@ -73,13 +73,19 @@ def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None
     return out
 
 
-class Split:
-    """bf16 hi / lo planes of an fp32 matrix [rows, K] (x ~ hi + lo), row stride `ld` (multiple of 64 for
-    freshly made ones, columns K..ld zero) — the operand format of the tcgen05 GEMM engine."""
-    __slots__ = ("hi", "lo", "K")
+SPLIT_F16, SPLIT_BF16 = 0, 1
+_SPLIT_DTYPE = {SPLIT_F16: torch.float16, SPLIT_BF16: torch.bfloat16}
 
-    def __init__(self, hi: torch.Tensor, lo: torch.Tensor, K: int):
-        self.hi, self.lo, self.K = hi, lo, K
+
+class Split:
+    """16-bit hi / lo planes of an fp32 matrix [rows, K]: x * scale ~ hi + lo — the operand format of the tcgen05
+    GEMM engine.  fp16 planes (default) carry 22 significant bits and need |x * scale| <= 65504; bf16 planes carry
+    16 bits with fp32's range.  Row stride `ld` is a multiple of 64 for freshly made ones (columns K..ld zero).
+    `scale` is a power of two (weights are pre-scaled so that small entries stay out of fp16's subnormals)."""
+    __slots__ = ("hi", "lo", "K", "fmt", "scale")
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor, K: int, fmt: int = SPLIT_F16, scale: float = 1.0):
+        self.hi, self.lo, self.K, self.fmt, self.scale = hi, lo, K, fmt, scale
 
     @property
     def rows(self):
@@ -87,53 +93,53 @@ class Split:
 
     def cols(self, a: int, b: int) -> "Split":
         """Column slice view [rows, a:b] (keeps the parent's row stride)."""
-        return Split(self.hi[:, a:b], self.lo[:, a:b], b - a)
-
-    def rows_slice(self, a: int, b: int) -> "Split":
-        return Split(self.hi[a:b], self.lo[a:b], self.K)
+        return Split(self.hi[:, a:b], self.lo[:, a:b], b - a, self.fmt, self.scale)
 
     @staticmethod
-    def empty(rows: int, K: int, device) -> "Split":
+    def empty(rows: int, K: int, device, fmt: int = SPLIT_F16) -> "Split":
         ld = (K + 63) // 64 * 64
-        hi = torch.zeros(rows, ld, device=device, dtype=torch.bfloat16) if ld != K else \
-            torch.empty(rows, ld, device=device, dtype=torch.bfloat16)
-        lo = torch.zeros_like(hi) if ld != K else torch.empty_like(hi)
-        return Split(hi, lo, K)
+        mk = torch.zeros if ld != K else torch.empty
+        return Split(mk(rows, ld, device=device, dtype=_SPLIT_DTYPE[fmt]), mk(rows, ld, device=device, dtype=_SPLIT_DTYPE[fmt]),
+                     K, fmt)
 
     def float(self) -> torch.Tensor:
-        return self.hi[:, :self.K].float() + self.lo[:, :self.K].float()
+        return (self.hi[:, :self.K].float() + self.lo[:, :self.K].float()) / self.scale
 
 
-def split(x: torch.Tensor, out: Optional[Split] = None) -> Split:
-    """fp32 [rows, K] -> Split (zero-padded to a multiple of 64 columns)."""
+def split(x: torch.Tensor, fmt: int = SPLIT_F16, scale: float = 1.0) -> Split:
+    """fp32 [rows, K] -> Split of x * scale (zero-padded to a multiple of 64 columns)."""
     _chk(x, "x")
     assert x.dim() == 2 and x.stride(1) == 1
     rows, K = x.shape
-    if out is None:
-        ld = (K + 63) // 64 * 64
-        out = Split(torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16),
-                    torch.empty(rows, ld, device=x.device, dtype=torch.bfloat16), K)
-        width = ld
-    else:
-        width = out.hi.shape[1]
-    assert out.hi.stride(0) == out.lo.stride(0)
-    # the kernel writes `ld_split` contiguous columns per row: only whole-buffer outputs are supported here
-    assert out.hi.is_contiguous() and out.lo.is_contiguous()
-    st = _lib.lib().nsac_split_bf16(_p(x), x.stride(0) if rows > 1 else max(K, x.stride(0)), rows, K, _p(out.hi), _p(out.lo),
-                                    width, _stream())
-    _lib.check(st, "nsac_split_bf16")
+    ld = (K + 63) // 64 * 64
+    out = Split(torch.empty(rows, ld, device=x.device, dtype=_SPLIT_DTYPE[fmt]),
+                torch.empty(rows, ld, device=x.device, dtype=_SPLIT_DTYPE[fmt]), K, fmt, scale)
+    st = _lib.lib().nsac_split16(_p(x), x.stride(0) if rows > 1 else max(K, x.stride(0)), rows, K, scale, fmt,
+                                 _p(out.hi), _p(out.lo), ld, _stream())
+    _lib.check(st, "nsac_split16")
     _count()
     return out
+
+
+def split_weight(w: torch.Tensor, fmt: int = SPLIT_F16) -> Split:
+    """Weight planes, pre-scaled by a power of two so that max|w| lands in [4096, 8192) for fp16 planes (one-off,
+    at prepare() time: reads max|w| back to the host)."""
+    scale = 1.0
+    if fmt == SPLIT_F16:
+        mx = float(w.detach().abs().max())
+        if mx > 0:
+            import math
+            scale = 2.0 ** math.floor(math.log2(8192.0 / mx))
+    return split(w.detach().contiguous(), fmt, scale)
 
 
 def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, passes: int = 3,
             want_f32: bool = True, want_split: bool = False, out_f32: Optional[torch.Tensor] = None,
             out_split: Optional[Split] = None, bias_group_rows: int = 0):
-    """tcgen05 split-bf16 GEMM: act(a @ w^T + bias) -> (fp32 [M,N] or None, Split or None)."""
+    """tcgen05 split-precision GEMM: act(a @ w^T + bias) -> (fp32 [M,N] or None, Split or None)."""
     M, N = a.rows, w.rows
-    Kp = a.hi.shape[1] if a.hi.shape[1] % 64 == 0 else None
-    K = min(a.hi.shape[1], w.hi.shape[1]) if Kp is None else a.hi.shape[1]
     assert a.K == w.K, f"gemm_tc: K mismatch {a.K} vs {w.K}"
+    assert a.fmt == w.fmt, "gemm_tc: operand plane formats differ"
     K = (a.K + 63) // 64 * 64
     assert a.hi.shape[1] >= K or a.hi.stride(0) >= K, "gemm_tc: A planes must be zero-padded to a multiple of 64 columns"
     assert w.hi.shape[1] >= K, "gemm_tc: W planes must be zero-padded to a multiple of 64 columns"
@@ -141,17 +147,19 @@ def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = 
     if want_f32 and out_f32 is None:
         out_f32 = torch.empty(M, N, device=dev, dtype=torch.float32)
     if want_split and out_split is None:
-        out_split = Split.empty(M, N, dev)
+        out_split = Split.empty(M, N, dev, a.fmt)
+    if out_split is not None:
+        assert out_split.fmt == a.fmt and out_split.scale == 1.0
     if bias is not None:
         _chk(bias, "bias")
         assert bias.is_contiguous() and bias.shape[-1] == N
     ldo = 0 if out_f32 is None else (out_f32.stride(0) if M > 1 else max(N, out_f32.stride(0)))
     lds = 0 if out_split is None else out_split.hi.stride(0)
-    st = _lib.lib().nsac_gemm_bf16x3(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), _p(bias),
-                                     bias_group_rows, M, N, K, act, passes, _p(out_f32), ldo,
-                                     None if out_split is None else _p(out_split.hi),
-                                     None if out_split is None else _p(out_split.lo), lds, _stream())
-    _lib.check(st, "nsac_gemm_bf16x3")
+    st = _lib.lib().nsac_gemm_split(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), _p(bias),
+                                    bias_group_rows, M, N, K, act, passes, a.fmt, 1.0 / (a.scale * w.scale),
+                                    _p(out_f32), ldo, None if out_split is None else _p(out_split.hi),
+                                    None if out_split is None else _p(out_split.lo), lds, _stream())
+    _lib.check(st, "nsac_gemm_split")
     _count()
     return out_f32, out_split
 
