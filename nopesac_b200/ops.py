@@ -257,9 +257,10 @@ def _score_mlp_struct(ws):
 
 def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num,
                     rot_mlp, tran_mlp, w_rots, b_rots, w_trans, b_trans, out_cam_type="soft",
-                    want_scores=True, want_diag=False):
+                    want_scores=True, want_diag=False, precision="fp16"):
     """rot_mlp / tran_mlp: 8-tuples (w1,b1,w2,b2,w3,b3,w4,b4). Returns dict(pose, score_rot, score_tran,
-    sel_idx, diag)."""
+    sel_idx, diag).  precision "fp16" = tcgen05 path (score MLPs single-pass fp16, fp32 accumulate);
+    "fp32" = exact CUDA-core path (always used when the diagnostic outputs are requested)."""
     B, NQ, _ = geo_local.shape
     dev = geo_local.device
     args = [_c(a, n) for a, n in ((geo_local, "geo_local"), (q_h, "q_h"), (t_h, "t_h"), (q0, "q0"), (t0, "t0"),
@@ -272,8 +273,16 @@ def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0,
     sel = torch.empty(B, 2, device=dev, dtype=torch.int32)
     diag = torch.zeros(3, B, NQ + 1, NQ, device=dev) if want_diag else None
     L = _lib.lib()
-    ws = torch.empty(L.nsac_score_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
     rs, ts = _score_mlp_struct(rot_mlp), _score_mlp_struct(tran_mlp)
+    if precision == "fp16" and not want_diag:
+        ws = torch.empty(L.nsac_score_tc_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
+        st = L.nsac_score_aggregate_tc(*[_p(a) for a in args], _p(matched_num), C.byref(rs), C.byref(ts),
+                                       _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
+                                       _p(pose), _p(sr), _p(stt), _p(sel), _p(ws), _stream())
+        _lib.check(st, "nsac_score_aggregate_tc")
+        _count(3)
+        return {"pose": pose, "score_rot": sr, "score_tran": stt, "sel_idx": sel, "diag": None}
+    ws = torch.empty(L.nsac_score_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
     st = L.nsac_score_aggregate(*[_p(a) for a in args], _p(matched_num), C.byref(rs), C.byref(ts),
                                 _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
                                 _p(pose), _p(sr), _p(stt), _p(sel), _p(diag), _p(ws), _stream())

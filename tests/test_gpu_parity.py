@@ -205,21 +205,63 @@ def test_score_kernel_on_oracle_inputs():
     for cam in ("soft", "avg-all", "min-cost", "max-score"):
         with torch.no_grad():
             want = restate.score_and_select(sd, fr, ft, rf0, tf0, o["geo_local"][None], o["matched_num"], q0, t0, cam)
-        res = ops.score_aggregate(c(o["geo_local"][None]), c(qh[None]), c(th[None]), c(q0), c(t0), c(fr[None]), c(ft[None]),
-                                  c(rf0), c(tf0), torch.tensor([o["matched_num"]], dtype=torch.int32, device=dev),
-                                  mlp("normal_score_proj", "rot_score_reg"), mlp("param_score_proj", "trans_score_reg"),
-                                  c(sd["rots.weight"]), c(sd["rots.bias"]), c(sd["trans.weight"]), c(sd["trans.bias"]),
-                                  out_cam_type=cam, want_diag=True)
-        m = o["matched_num"]
-        pose = res["pose"][0].cpu()
-        assert util.maxdiff(pose[0:3], want["pred_trans"][0]) <= 1e-5 and util.maxdiff(pose[3:7], want["pred_rot"][0]) <= 1e-5, cam
-        assert util.maxdiff(pose[7:10], want["pred_trans_avg"][0]) <= 1e-5 and util.maxdiff(pose[10:14], want["pred_rot_avg"][0]) <= 1e-5
-        assert int(pose[14]) == m
-        assert util.maxdiff(res["score_rot"][0, :m + 1], want["score_soft_rot"][0, :, 0]) <= 1e-5
-        assert util.maxdiff(res["score_tran"][0, :m + 1], want["score_soft_offset"][0, :, 0]) <= 1e-5
-        if cam in ("min-cost", "max-score"):
-            assert res["sel_idx"][0].cpu().tolist() == [want["sel_rot"], want["sel_tran"]], cam
-        assert torch.allclose(res["diag"][0, 0, :m + 1, :m].cpu(), want["l2_dist"][0], rtol=1e-5, atol=1e-5)
+        # exact CUDA-core path (1e-5) and tensor-core path (score MLPs single-pass fp16: 1e-4 bar)
+        for precision, tol in (("fp32", 1e-5), ("fp16", 1e-4)):
+            res = ops.score_aggregate(c(o["geo_local"][None]), c(qh[None]), c(th[None]), c(q0), c(t0), c(fr[None]), c(ft[None]),
+                                      c(rf0), c(tf0), torch.tensor([o["matched_num"]], dtype=torch.int32, device=dev),
+                                      mlp("normal_score_proj", "rot_score_reg"), mlp("param_score_proj", "trans_score_reg"),
+                                      c(sd["rots.weight"]), c(sd["rots.bias"]), c(sd["trans.weight"]), c(sd["trans.bias"]),
+                                      out_cam_type=cam, want_diag=precision == "fp32", precision=precision)
+            torch.cuda.synchronize()
+            m = o["matched_num"]
+            pose = res["pose"][0].cpu()
+            tag = f"{cam}/{precision}"
+            assert util.maxdiff(pose[0:3], want["pred_trans"][0]) <= tol and util.maxdiff(pose[3:7], want["pred_rot"][0]) <= tol, tag
+            assert util.maxdiff(pose[7:10], want["pred_trans_avg"][0]) <= tol and util.maxdiff(pose[10:14], want["pred_rot_avg"][0]) <= tol, tag
+            assert int(pose[14]) == m
+            assert util.maxdiff(res["score_rot"][0, :m + 1], want["score_soft_rot"][0, :, 0]) <= tol, tag
+            assert util.maxdiff(res["score_tran"][0, :m + 1], want["score_soft_offset"][0, :, 0]) <= tol, tag
+            assert float(res["score_rot"][0, m + 1:].abs().max()) == 0.0
+            if cam in ("min-cost", "max-score"):
+                assert res["sel_idx"][0].cpu().tolist() == [want["sel_rot"], want["sel_tran"]], tag
+            if precision == "fp32":
+                assert torch.allclose(res["diag"][0, 0, :m + 1, :m].cpu(), want["l2_dist"][0], rtol=1e-5, atol=1e-5)
+
+
+def test_score_tc_kernel_ragged_batch_vs_exact_kernel():
+    """The tensor-core scoring path against the exact CUDA-core path on a batch with every m regime
+    (0, 1, 2, 63, 64, 65, 128, 129, 255, 256 of NQ = 256) — tiles, k-block tails and the empty cases."""
+    dev = _gpu()
+    from nopesac_b200 import ops
+    NQ = 256
+    ms = [0, 1, 2, 63, 64, 65, 128, 129, 255, 256]
+    B = len(ms)
+    head, _, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    pk = head.prepare()
+    g = torch.Generator(device=dev).manual_seed(11)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo = rnd(B, NQ, 6)
+    qh = torch.nn.functional.normalize(rnd(B, NQ, 4), dim=-1)
+    th = rnd(B, NQ, 3) * 0.3
+    q0 = torch.nn.functional.normalize(rnd(B, 4), dim=-1)
+    t0 = rnd(B, 3) * 0.3
+    # feature scale 0.3 keeps the regressed poses O(1), the regime the 1e-4 absolute bar is defined for
+    fr, ft, fr0, ft0 = rnd(B, NQ, 256) * 0.3, rnd(B, NQ, 256) * 0.3, rnd(B, 256) * 0.3, rnd(B, 256) * 0.3
+    mnum = torch.tensor(ms, device=dev, dtype=torch.int32)
+    for i, m in enumerate(ms):       # padded rows are zero in the real pipeline
+        geo[i, m:] = 0
+    for cam in ("soft", "min-cost", "max-score"):
+        out = {}
+        for precision in ("fp32", "fp16"):
+            out[precision] = ops.score_aggregate(geo, qh, th, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
+                                                 pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
+                                                 head.trans.bias, out_cam_type=cam, precision=precision)
+        torch.cuda.synchronize()
+        a, b = out["fp32"], out["fp16"]
+        assert util.maxdiff(a["pose"], b["pose"]) <= 1e-4, (cam, util.maxdiff(a["pose"], b["pose"]))
+        assert util.maxdiff(a["score_rot"], b["score_rot"]) <= 1e-4 and util.maxdiff(a["score_tran"], b["score_tran"]) <= 1e-4, cam
+        if cam == "min-cost":      # distances are fp32 on both paths: same argmin
+            assert torch.equal(a["sel_idx"], b["sel_idx"]), cam
 
 
 def test_linear_kernel_against_torch():
