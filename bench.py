@@ -290,12 +290,12 @@ def main():
     fr, ft = rnd(RB, NQ, 256), rnd(RB, NQ, 256)
     fr0, ft0 = rnd(RB, 256), rnd(RB, 256)
     mnum = torch.full((RB,), m, device=dev, dtype=torch.int32)
-    pk = head.prepare()
+    pk = head.prepare_tc()
 
     def score_once():
         return ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
                                    pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
-                                   head.trans.bias, out_cam_type="soft", want_scores=False)
+                                   head.trans.bias, out_cam_type="soft", want_scores=False, pack=pk["score_pack"])
     for _ in range(3):
         score_once()
     torch.cuda.synchronize()

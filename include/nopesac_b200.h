@@ -156,13 +156,17 @@ int nsac_score_aggregate(const float* geo_local, const float* q_h, const float* 
 /* Same contract on the tensor pipe (tcgen05 / TMEM / TMA): residuals on the CUDA cores feed the score MLPs as
  * fp16 tcgen05.mma operands (single pass, fp32 accumulation; hypothesis 0 and all selections stay exact fp32),
  * softmax + feature aggregation are streamed flash-style.  No diagnostic outputs on this path.
- * workspace: nsac_score_tc_workspace_bytes(B, NQ) bytes, 256-byte aligned. */
+ *   nsac_score_pack builds the device-side weight pack once per weight version (fp16 padded copies of the two
+ *   score MLPs, folded last layers, transposed fp32 copies) into `pack` (nsac_score_pack_bytes(NQ) bytes);
+ *   workspace: nsac_score_tc_workspace_bytes(B, NQ) bytes.  Both buffers 256-byte aligned. */
+size_t nsac_score_pack_bytes(int NQ);
+int nsac_score_pack(const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp, int NQ, void* pack,
+                    void* stream);
 size_t nsac_score_tc_workspace_bytes(int B, int NQ);
 int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
                             const float* t0, const float* feat_rot, const float* feat_tran,
                             const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
-                            const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp,
-                            const float* w_rots, const float* b_rots, const float* w_trans,
+                            const void* pack, const float* w_rots, const float* b_rots, const float* w_trans,
                             const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
                             float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
                             void* stream);

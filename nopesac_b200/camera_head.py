@@ -240,6 +240,7 @@ class PlaneCameraHead(nn.Module):
                     pk[name + ".split"] = getattr(self, name).split_weights()
                 for name in ("decoder_rot2", "decoder_tran2"):
                     pk[name + ".w_geo_split"] = ops.split_weight(pk[name + ".w_geo"])
+                pk["score_pack"] = ops.score_pack(pk["normal_score_proj"], pk["param_score_proj"], self.num_queries)
         return pk
 
     # ------------------------------------------------------------------ K1: pixel pose network
@@ -402,12 +403,13 @@ class PlaneCameraHead(nn.Module):
         fused_rot, fused_tran = self._hypothesis_features(geo8, rot_feat0, trans_feat0, B, NQ)
         q_h, t_h = ops.pose_heads(fused_rot, fused_tran, self.rots.weight, self.rots.bias,
                                   self.trans.weight, self.trans.bias)
-        pk = self.prepare()
+        pk = self.prepare_tc()
         res = ops.score_aggregate(geo_local, q_h.view(B, NQ, 4), t_h.view(B, NQ, 3), q0, t0,
                                   fused_rot.view(B, NQ, 256), fused_tran.view(B, NQ, 256), rot_feat0, trans_feat0,
                                   matched_num, pk["normal_score_proj"], pk["param_score_proj"],
                                   self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
-                                  out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag)
+                                  out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
+                                  pack=pk["score_pack"])
         pose = res["pose"]
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]

@@ -42,10 +42,10 @@ constexpr int KB = 64;             // residual columns per k-block (one 128-byte
 constexpr int C_FEAT = 256;
 constexpr int W_STAGES = 2, A_STAGES = 2;
 constexpr int BLK_BYTES = TILE_H * KB * 2;           // 16 KB: one [128 x 64] fp16 operand block
-constexpr int NUM_WARPS = 18, NUM_THREADS = NUM_WARPS * 32;
+constexpr int NUM_WARPS = 22, NUM_THREADS = NUM_WARPS * 32;
 constexpr int R_WARP0 = 6, R_WARPS = 8, R_THREADS = R_WARPS * 32;
-constexpr int G_WARP0 = 14, G_THREADS = 128;
-constexpr uint32_t SPIN_LIMIT = 1u << 28;
+constexpr int G_WARP0 = 14, G_THREADS = 256;
+constexpr uint32_t SPIN_LIMIT = 1u << 24;   // x ~200 ns: seconds, then trap instead of hanging the GPU
 constexpr int PART_HDR = 4;                          // max, sumexp, pad, pad (keeps the vectors 16-byte aligned)
 constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch): header, wsum[256], fsum[256]
 
@@ -53,12 +53,15 @@ constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch)
 constexpr int OFF_W2 = 0;                                        // [branch][kblock 0..1][16 KB]
 constexpr int OFF_W1 = OFF_W2 + 4 * BLK_BYTES;                   // [stage][branch][16 KB]
 constexpr int OFF_A = OFF_W1 + W_STAGES * 2 * BLK_BYTES;         // [stage][branch][16 KB]
-constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [A_STAGES][64][12] floats
+constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [A_STAGES][64][3] float4 column constants
 constexpr int OFF_VEC = OFF_CJ + A_STAGES * KB * 12 * 4;         // b1[2][128], b2[2][128], w34[2][128] floats
 constexpr int OFF_LOGIT = OFF_VEC + 6 * HID * 4;                 // [2 bufs][2 branches][128] floats
-constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [2 branches][128] floats (min-cost distance sums)
-constexpr int OFF_BAR = OFF_ROWSUM + 2 * TILE_H * 4;
+constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [4 quarters][2 branches][128] floats (min-cost sums)
+constexpr int OFF_EXP = OFF_ROWSUM + 4 * 2 * TILE_H * 4;         // [2 branches][128] softmax numerators of the tile
+constexpr int OFF_GPART = OFF_EXP + 2 * TILE_H * 4;              // [2 branches][64 threads][9] odd-row partials (+1 pad)
+constexpr int OFF_BAR = OFF_GPART + 2 * 64 * 12 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 // tensor-memory columns
 constexpr uint32_t TM_D = 0;          // D_rot [0,128), D_tran [128,256)
@@ -79,6 +82,8 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Waiting warps must not steal issue slots from the residual warps: back off with nanosleep between probes
+// (the first ncu capture had 40 % of all issued instructions in these spin loops).
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
@@ -89,6 +94,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done) : "r"(addr), "r"(parity) : "memory");
     if (done) break;
+    __nanosleep(spins < 8 ? 40 : 200);
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
@@ -159,21 +165,48 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
 // With u = R n^ (unit) and d = |p0|: b = d u, e.b = d^2 + d (t.u), so pi0 = A (d + t.u) u; for t = 0 its direction is u.
 //   rot  : exp(-| u - n1 |)                 (F.normalize of both sides)
 //   trans: exp(-| A (d + t.u) u - pi1 |)
-__device__ __forceinline__ void residual_pair(const float (&R)[9], float tx, float ty, float tz, const float* __restrict__ c,
-                                              float& xr, float& xt, float& dr, float& dt) {
-  const float ux = fmaf(R[0], c[0], fmaf(R[1], c[1], R[2] * c[2]));
-  const float uy = fmaf(R[3], c[0], fmaf(R[4], c[1], R[5] * c[2]));
-  const float uz = fmaf(R[6], c[0], fmaf(R[7], c[1], R[8] * c[2]));
-  const float ax = ux - c[3], ay = uy - c[4], az = uz - c[5];
-  dr = sqrtf(fmaf(ax, ax, fmaf(ay, ay, az * az)));
+__device__ __forceinline__ float fast_sqrt(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// c0 = (n^x, n^y, n^z, n1x), c1 = (n1y, n1z, pi1x, pi1y), c2 = (pi1z, A, Bc, valid)
+template <bool SUMS>
+__device__ __forceinline__ void residual_pair(const float (&R)[9], float tx, float ty, float tz, const float4 c0, const float4 c1,
+                                              const float4 c2, float& xr, float& xt, float& sum_r, float& sum_t) {
+  const float ux = fmaf(R[0], c0.x, fmaf(R[1], c0.y, R[2] * c0.z));
+  const float uy = fmaf(R[3], c0.x, fmaf(R[4], c0.y, R[5] * c0.z));
+  const float uz = fmaf(R[6], c0.x, fmaf(R[7], c0.y, R[8] * c0.z));
+  const float ax = ux - c0.w, ay = uy - c1.x, az = uz - c1.y;
+  const float dr = fast_sqrt(fmaf(ax, ax, fmaf(ay, ay, az * az)));
   const float tu = fmaf(tx, ux, fmaf(ty, uy, tz * uz));
-  const float g = fmaf(c[9], tu, c[10]);
-  const float wx = fmaf(g, ux, -c[6]), wy = fmaf(g, uy, -c[7]), wz = fmaf(g, uz, -c[8]);
-  dt = sqrtf(fmaf(wx, wx, fmaf(wy, wy, wz * wz)));
-  xr = c[11] * exp2f(-1.4426950408889634f * dr);
-  xt = c[11] * exp2f(-1.4426950408889634f * dt);
-  dr *= c[11];
-  dt *= c[11];
+  const float g = fmaf(c2.y, tu, c2.z);
+  const float wx = fmaf(g, ux, -c1.z), wy = fmaf(g, uy, -c1.w), wz = fmaf(g, uz, -c2.x);
+  const float dt = fast_sqrt(fmaf(wx, wx, fmaf(wy, wy, wz * wz)));
+  xr = c2.w * fast_exp2(-1.4426950408889634f * dr);     // c2.w = 1 for matched columns, 0 for the padded tail
+  xt = c2.w * fast_exp2(-1.4426950408889634f * dt);
+  if (SUMS) { sum_r = fmaf(c2.w, dr, sum_r); sum_t = fmaf(c2.w, dt, sum_t); }
+}
+
+// column constants of matched plane pair j from geo_local row (p0, p1)
+__device__ __forceinline__ void column_constants(const float* __restrict__ g6, bool valid, float4& c0, float4& c1, float4& c2) {
+  c0 = c1 = c2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (valid) {
+    float ax = g6[0], ay = -g6[1], az = -g6[2];
+    const float d = normalize3(ax, ay, az);
+    const float px = g6[3], py = -g6[4], pz = -g6[5];
+    float nx = px, ny = py, nz = pz;
+    normalize3(nx, ny, nz);
+    const float dd = d + 1e-5f, A = d * d / (dd * dd);
+    c0 = make_float4(ax, ay, az, nx);
+    c1 = make_float4(ny, nz, px, py);
+    c2 = make_float4(pz, A, A * d, 1.f);
+  }
 }
 
 struct TcParams {
@@ -190,6 +223,7 @@ struct TcParams {
   float* partials;          // [B][tiles][2][PART_STRIDE]
 };
 
+template <bool SUMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_constant__ CUtensorMap map_w1t,
                 const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w2t, const TcParams p) {
@@ -197,10 +231,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
-  float* cj = reinterpret_cast<float*>(smem + OFF_CJ);
+  float4* cj = reinterpret_cast<float4*>(smem + OFF_CJ);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
   float* s_logit = reinterpret_cast<float*>(smem + OFF_LOGIT);
   float* s_rowsum = reinterpret_cast<float*>(smem + OFF_ROWSUM);
+  float* s_exp = reinterpret_cast<float*>(smem + OFF_EXP);
+  float* s_gpart = reinterpret_cast<float*>(smem + OFF_GPART);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int H1n = p.NQ + 1;
@@ -362,94 +398,96 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     }
   } else if (warp < G_WARP0) {
     // ================================================================================= residual warps 6..13
+    // thread = 2 hypothesis rows (rp, rp + 64) x 16 columns of the k-block: the column constants are loaded once
+    // (3 LDS.128) and used for both rows
     const int rt = threadIdx.x - R_WARP0 * 32;       // 0..255
-    const int row = rt & 127, half = rt >> 7;        // this thread: hypothesis row, and chunks [4*half, 4*half+4)
+    const int rp = rt & 63, quarter = rt >> 6;       // rows rp / rp+64, chunks 2*quarter, 2*quarter+1
     int as = 0; uint32_t aph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.tiles_per_pair, tile = item % p.tiles_per_pair;
       const int m = p.matched_num[b];
       if (tile * TILE_H >= m) continue;
       const int nkb = (m + KB - 1) / KB;
-      const int hidx = tile * TILE_H + row;           // index into q_h / t_h (hypothesis h = hidx + 1)
-      const bool hv = hidx < m;
-      float R[9], tx = 0.f, ty = 0.f, tz = 0.f;
-      {
+      float R[2][9], tr[2][3];
+      bool hv[2];
+#pragma unroll
+      for (int s2 = 0; s2 < 2; ++s2) {
+        const int hidx = tile * TILE_H + rp + 64 * s2;   // index into q_h / t_h (hypothesis h = hidx + 1)
+        hv[s2] = hidx < m;
         float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f;
-        if (hv) {
+        tr[s2][0] = tr[s2][1] = tr[s2][2] = 0.f;
+        if (hv[s2]) {
           const float4 q = *reinterpret_cast<const float4*>(p.q_h + ((size_t)b * p.NQ + hidx) * 4);
           const float* t = p.t_h + ((size_t)b * p.NQ + hidx) * 3;
           qw = q.x; qx = q.y; qy = q.z; qz = q.w;
-          tx = t[0]; ty = t[1]; tz = t[2];
+          tr[s2][0] = t[0]; tr[s2][1] = t[1]; tr[s2][2] = t[2];
         }
         const Mat3 M = quat_to_rot(qw, qx, qy, qz);
 #pragma unroll
-        for (int i = 0; i < 9; ++i) R[i] = M.m[i];
+        for (int i = 0; i < 9; ++i) R[s2][i] = M.m[i];
       }
-      float sum_r = 0.f, sum_t = 0.f;
+      float sum_r[2] = {0.f, 0.f}, sum_t[2] = {0.f, 0.f};
       const float* gl = p.geo_local + (size_t)b * p.NQ * 6;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
-        float* cjs = cj + as * KB * 12;
+        float4* cjs = cj + as * KB * 3;
         if (rt < KB) {
           const int j = kb * KB + rt;
-          float c[12];
-#pragma unroll
-          for (int i = 0; i < 12; ++i) c[i] = 0.f;
-          if (j < m) {
-            float ax = gl[j * 6 + 0], ay = -gl[j * 6 + 1], az = -gl[j * 6 + 2];
-            const float d = normalize3(ax, ay, az);
-            c[0] = ax; c[1] = ay; c[2] = az;
-            c[6] = gl[j * 6 + 3]; c[7] = -gl[j * 6 + 4]; c[8] = -gl[j * 6 + 5];
-            float nx = c[6], ny = c[7], nz = c[8];
-            normalize3(nx, ny, nz);
-            c[3] = nx; c[4] = ny; c[5] = nz;
-            const float dd = d + 1e-5f;
-            c[9] = d * d / (dd * dd);
-            c[10] = c[9] * d;
-            c[11] = 1.f;
-          }
-#pragma unroll
-          for (int i = 0; i < 12; ++i) cjs[rt * 12 + i] = c[i];
+          float4 c0, c1, c2;
+          column_constants(gl + (size_t)(j < m ? j : 0) * 6, j < m, c0, c1, c2);
+          cjs[rt * 3 + 0] = c0; cjs[rt * 3 + 1] = c1; cjs[rt * 3 + 2] = c2;
         }
         named_bar_sync(1, R_THREADS);
         uint8_t* a_rot = smem + OFF_A + as * 2 * BLK_BYTES;
         uint8_t* a_tran = a_rot + BLK_BYTES;
 #pragma unroll 1
-        for (int ci = 0; ci < 4; ++ci) {
-          const int chunk = half * 4 + ci;
-          float xr[8], xt[8];
+        for (int c4i = 0; c4i < 4; ++c4i) {                 // 4 groups of 4 columns = this thread's 16 columns
+          const int chunk = quarter * 2 + (c4i >> 1), sub = c4i & 1;
+          float xr[2][4], xt[2][4];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            float dr, dt;
-            residual_pair(R, tx, ty, tz, cjs + (chunk * 8 + e) * 12, xr[e], xt[e], dr, dt);
-            sum_r += dr; sum_t += dt;
-          }
-          if (!hv) {
+          for (int e = 0; e < 4; ++e) {
+            const int col = chunk * 8 + sub * 4 + e;
+            const float4 c0 = cjs[col * 3 + 0], c1 = cjs[col * 3 + 1], c2 = cjs[col * 3 + 2];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) xr[e] = xt[e] = 0.f;
+            for (int s2 = 0; s2 < 2; ++s2)
+              residual_pair<SUMS>(R[s2], tr[s2][0], tr[s2][1], tr[s2][2], c0, c1, c2, xr[s2][e], xt[s2][e], sum_r[s2], sum_t[s2]);
           }
-          const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4);   // 128-byte swizzle
-          *reinterpret_cast<uint4*>(a_rot + off) = make_uint4(pack_h2(xr[0], xr[1]), pack_h2(xr[2], xr[3]), pack_h2(xr[4], xr[5]), pack_h2(xr[6], xr[7]));
-          *reinterpret_cast<uint4*>(a_tran + off) = make_uint4(pack_h2(xt[0], xt[1]), pack_h2(xt[2], xt[3]), pack_h2(xt[4], xt[5]), pack_h2(xt[6], xt[7]));
+#pragma unroll
+          for (int s2 = 0; s2 < 2; ++s2) {
+            const float keep = hv[s2] ? 1.f : 0.f;
+            const int row = rp + 64 * s2;
+            const uint32_t off = (uint32_t)row * 128u + (uint32_t)((chunk ^ (row & 7)) << 4) + (uint32_t)(sub * 8);   // 128-byte swizzle
+            *reinterpret_cast<uint2*>(a_rot + off) = make_uint2(pack_h2(keep * xr[s2][0], keep * xr[s2][1]), pack_h2(keep * xr[s2][2], keep * xr[s2][3]));
+            *reinterpret_cast<uint2*>(a_tran + off) = make_uint2(pack_h2(keep * xt[s2][0], keep * xt[s2][1]), pack_h2(keep * xt[s2][2], keep * xt[s2][3]));
+          }
         }
         fence_proxy_async();
         mbar_arrive(&bars[BAR_A_FULL + as]);
         if (++as == A_STAGES) { as = 0; aph ^= 1; }
       }
-      if (p.need_sums) {      // sum_j of the masked distances (argmin in 'min-cost', :1090-1093); two threads per row
-        if (half == 0) { s_rowsum[row] = sum_r; s_rowsum[TILE_H + row] = sum_t; }
+      if (SUMS) {   // sum_j of the masked distances (argmin in 'min-cost', :1090-1093): 4 column quarters per row, fixed order
+#pragma unroll
+        for (int s2 = 0; s2 < 2; ++s2) {
+          s_rowsum[(quarter * 2 + 0) * TILE_H + rp + 64 * s2] = sum_r[s2];
+          s_rowsum[(quarter * 2 + 1) * TILE_H + rp + 64 * s2] = sum_t[s2];
+        }
         named_bar_sync(1, R_THREADS);
-        if (half == 1 && hv) {
-          p.sums[(size_t)b * H1n + hidx + 1] = s_rowsum[row] + sum_r;
-          p.sums[(size_t)p.B * H1n + (size_t)b * H1n + hidx + 1] = s_rowsum[TILE_H + row] + sum_t;
+        if (rt < TILE_H && tile * TILE_H + rt < m) {
+          float a = 0.f, c = 0.f;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) { a += s_rowsum[(q4 * 2 + 0) * TILE_H + rt]; c += s_rowsum[(q4 * 2 + 1) * TILE_H + rt]; }
+          const int h = tile * TILE_H + rt + 1;
+          p.sums[(size_t)b * H1n + h] = a;
+          p.sums[(size_t)p.B * H1n + (size_t)b * H1n + h] = c;
         }
         named_bar_sync(1, R_THREADS);
       }
     }
   } else {
-    // ================================================================================= gather warps 14..17
-    const int gt = threadIdx.x - G_WARP0 * 32;       // 0..127
-    const int br = gt >> 6, c4 = (gt & 63) * 4;      // branch, first of this thread's 4 feature channels
+    // ================================================================================= gather warps 14..21
+    // thread = (branch, row parity, 4 feature channels): 12 float4 loads in flight per thread, 48 KB per SM
+    const int gt = threadIdx.x - G_WARP0 * 32;       // 0..255
+    const int br = gt >> 7, par = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
     int lbuf = 0; uint32_t lph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.tiles_per_pair, tile = item % p.tiles_per_pair;
@@ -460,34 +498,53 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       const float* lg = s_logit + (lbuf * 2 + br) * TILE_H;
       float mx = -INFINITY;
       for (int r = 0; r < rows; ++r) mx = fmaxf(mx, lg[r]);
+      float* ex = s_exp + br * TILE_H;
+      {
+        const int r = par * 64 + t64;
+        ex[r] = r < rows ? __expf(lg[r] - mx) : 0.f;
+      }
+      named_bar_sync(4 + br, 128);
       const float* f = (br == 0 ? p.feat_rot : p.feat_tran) + ((size_t)b * p.NQ + (size_t)tile * TILE_H) * C_FEAT + c4;
       float4 ws = make_float4(0.f, 0.f, 0.f, 0.f), fs = make_float4(0.f, 0.f, 0.f, 0.f);
       float se = 0.f;
-      int r = 0;
-      for (; r + 16 <= rows; r += 16) {
-        float4 v[16];
+      int r = par;
+      for (; r + 22 < rows; r += 24) {       // 12 rows of this parity in flight
+        float4 v[12];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(f + (size_t)(r + u) * C_FEAT));
+        for (int u = 0; u < 12; ++u) v[u] = __ldg(reinterpret_cast<const float4*>(f + (size_t)(r + 2 * u) * C_FEAT));
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const float e = __expf(lg[r + u] - mx);
+        for (int u = 0; u < 12; ++u) {
+          const float e = ex[r + 2 * u];
           se += e;
           ws.x = fmaf(e, v[u].x, ws.x); ws.y = fmaf(e, v[u].y, ws.y); ws.z = fmaf(e, v[u].z, ws.z); ws.w = fmaf(e, v[u].w, ws.w);
           fs.x += v[u].x; fs.y += v[u].y; fs.z += v[u].z; fs.w += v[u].w;
         }
       }
-      for (; r < rows; ++r) {
+      for (; r < rows; r += 2) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(f + (size_t)r * C_FEAT));
-        const float e = __expf(lg[r] - mx);
+        const float e = ex[r];
         se += e;
         ws.x = fmaf(e, v.x, ws.x); ws.y = fmaf(e, v.y, ws.y); ws.z = fmaf(e, v.z, ws.z); ws.w = fmaf(e, v.w, ws.w);
         fs.x += v.x; fs.y += v.y; fs.z += v.z; fs.w += v.w;
       }
-      float* part = p.partials + (((size_t)b * p.tiles_per_pair + tile) * 2 + br) * PART_STRIDE;
-      if ((gt & 63) == 0) { part[0] = mx; part[1] = se; }
-      *reinterpret_cast<float4*>(part + PART_HDR + c4) = ws;
-      *reinterpret_cast<float4*>(part + PART_HDR + C_FEAT + c4) = fs;
-      __syncwarp();
+      float* gp = s_gpart + (br * 64 + t64) * 12;
+      if (par == 1) {
+        *reinterpret_cast<float4*>(gp) = ws;
+        *reinterpret_cast<float4*>(gp + 4) = fs;
+        gp[8] = se;
+      }
+      named_bar_sync(4 + br, 128);
+      if (par == 0) {
+        const float4 w1 = *reinterpret_cast<const float4*>(gp), f1 = *reinterpret_cast<const float4*>(gp + 4);
+        ws.x += w1.x; ws.y += w1.y; ws.z += w1.z; ws.w += w1.w;
+        fs.x += f1.x; fs.y += f1.y; fs.z += f1.z; fs.w += f1.w;
+        se += gp[8];
+        float* part = p.partials + (((size_t)b * p.tiles_per_pair + tile) * 2 + br) * PART_STRIDE;
+        if (t64 == 0) { part[0] = mx; part[1] = se; }
+        *reinterpret_cast<float4*>(part + PART_HDR + c4) = ws;
+        *reinterpret_cast<float4*>(part + PART_HDR + C_FEAT + c4) = fs;
+      }
+      named_bar_sync(4 + br, 128);      // s_exp / s_gpart free for the next tile
       if (lane == 0) mbar_arrive(&bars[BAR_LOGIT_FREE + lbuf]);
       if (++lbuf == 2) { lbuf = 0; lph ^= 1; }
     }
@@ -501,16 +558,23 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------ weight packing
-// pack layout (bytes): [w1h_rot fp16 128 x NQp][w1h_tran][w2h_rot fp16 128x128][w2h_tran][vecs fp32: b1[2][128] b2[2][128]
-// w34[2][128]][c34[2] fp32]
+// pack layout: [w1h_rot fp16 128 x NQp][w1h_tran][w2h_rot fp16 128x128][w2h_tran]
+//              [vecs fp32: b1[2][128] b2[2][128] w34[2][128]][c34[2] + pad to 8]
+//              [w1t fp32 [2][NQ][128]][w2t fp32 [2][128][128]]      (transposed copies for the row-0 kernel)
 __host__ __device__ inline size_t pack_w1_bytes(int NQp) { return (size_t)HID * NQp * 2; }
+__host__ __device__ inline size_t pack_off_vecs(int NQp) { return 2 * pack_w1_bytes(NQp) + 2 * (size_t)HID * HID * 2; }
+__host__ __device__ inline size_t pack_off_w1t(int NQp) { return pack_off_vecs(NQp) + (6 * HID + 8) * sizeof(float); }
+__host__ __device__ inline size_t pack_off_w2t(int NQ, int NQp) { return pack_off_w1t(NQp) + 2 * (size_t)NQ * HID * sizeof(float); }
+__host__ __device__ inline size_t pack_total_bytes(int NQ, int NQp) { return pack_off_w2t(NQ, NQp) + 2 * (size_t)HID * HID * sizeof(float); }
 
 __global__ void score_pack_kernel(nsac_score_mlp r, nsac_score_mlp t, int NQ, int NQp, uint8_t* pack) {
   __half* w1[2] = {reinterpret_cast<__half*>(pack), reinterpret_cast<__half*>(pack + pack_w1_bytes(NQp))};
   __half* w2[2] = {reinterpret_cast<__half*>(pack + 2 * pack_w1_bytes(NQp)),
                    reinterpret_cast<__half*>(pack + 2 * pack_w1_bytes(NQp) + HID * HID * 2)};
-  float* vecs = reinterpret_cast<float*>(pack + 2 * pack_w1_bytes(NQp) + 2 * HID * HID * 2);
+  float* vecs = reinterpret_cast<float*>(pack + pack_off_vecs(NQp));
   float* c34 = vecs + 6 * HID;
+  float* w1t = reinterpret_cast<float*>(pack + pack_off_w1t(NQp));
+  float* w2t = reinterpret_cast<float*>(pack + pack_off_w2t(NQ, NQp));
   const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
   for (int br = 0; br < 2; ++br) {
     const nsac_score_mlp& p = br == 0 ? r : t;
@@ -519,6 +583,14 @@ __global__ void score_pack_kernel(nsac_score_mlp r, nsac_score_mlp t, int NQ, in
       w1[br][i] = __float2half_rn(k < NQ ? p.w1[(size_t)o * NQ + k] : 0.f);
     }
     for (int i = tid; i < HID * HID; i += nth) w2[br][i] = __float2half_rn(p.w2[i]);
+    for (int i = tid; i < NQ * HID; i += nth) {
+      const int j = i / HID, o = i - j * HID;
+      w1t[(size_t)br * NQ * HID + i] = p.w1[(size_t)o * NQ + j];
+    }
+    for (int i = tid; i < HID * HID; i += nth) {
+      const int k = i / HID, o = i - k * HID;
+      w2t[(size_t)br * HID * HID + i] = p.w2[(size_t)o * HID + k];
+    }
     for (int k = tid; k < HID; k += nth) {
       vecs[br * HID + k] = p.b1[k];
       vecs[2 * HID + br * HID + k] = p.b2[k];
@@ -534,18 +606,110 @@ __global__ void score_pack_kernel(nsac_score_mlp r, nsac_score_mlp t, int NQ, in
   }
 }
 
-// ------------------------------------------------------------------------------------------------ selection kernel
-__device__ __forceinline__ float block_reduce(float v, float* red, bool is_max) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  v = is_max ? warp_max(v) : warp_sum(v);
+// ------------------------------------------------------------------------------------------------ hypothesis 0
+// Hypothesis 0 (the initial pose, camera_head.py:991, 1019) is one row per pair: 8 pairs per CTA so every weight that
+// is loaded (coalesced, transposed fp32 copies) feeds 8 FMAs; exact fp32.  Also the masked distance sums of row 0.
+constexpr int ROW0_PAIRS = 8;
+
+struct Row0Params {
+  const float* geo_local; const float* q0; const float* t0; const int32_t* matched_num;
+  const float* w1t; const float* w2t; const float* vecs;   // vecs: b1[2][128], b2[2][128], w34[2][128]
+  int B, NQ;
+  float* logits; float* sums;
+};
+
+__global__ void __launch_bounds__(256)
+score_row0_kernel(const Row0Params p) {
+  extern __shared__ float sm[];
+  float* x0 = sm;                                  // [2][NQ][8]
+  float* h1 = x0 + 2 * p.NQ * ROW0_PAIRS;          // [2][128][8]
+  float* red = h1 + 2 * HID * ROW0_PAIRS;          // [2][4 warps][8]
+  __shared__ int s_maxm;
+  const int b0 = blockIdx.x * ROW0_PAIRS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, H1n = p.NQ + 1;
+  if (tid == 0) {
+    int mm = 0;
+    for (int i = 0; i < ROW0_PAIRS; ++i) if (b0 + i < p.B) mm = max(mm, p.matched_num[b0 + i]);
+    s_maxm = mm;
+  }
+  for (int i = tid; i < 2 * p.NQ * ROW0_PAIRS; i += blockDim.x) x0[i] = 0.f;
   __syncthreads();
-  if (lane == 0) red[warp] = v;
+  const int maxm = s_maxm;
+  {   // residual row of hypothesis 0: warp w <-> pair b0 + w
+    const int b = b0 + warp;
+    if (b < p.B) {
+      const int m = p.matched_num[b];
+      const float* q = p.q0 + (size_t)b * 4;
+      const float* t = p.t0 + (size_t)b * 3;
+      const Mat3 Mr = quat_to_rot(q[0], q[1], q[2], q[3]);
+      float R[9];
+#pragma unroll
+      for (int i = 0; i < 9; ++i) R[i] = Mr.m[i];
+      const float* gl = p.geo_local + (size_t)b * p.NQ * 6;
+      float sr = 0.f, st = 0.f;
+      for (int j = lane; j < m; j += 32) {
+        float4 c0, c1, c2;
+        column_constants(gl + (size_t)j * 6, true, c0, c1, c2);
+        float xr, xt;
+        residual_pair<true>(R, t[0], t[1], t[2], c0, c1, c2, xr, xt, sr, st);
+        x0[(0 * p.NQ + j) * ROW0_PAIRS + warp] = xr;
+        x0[(1 * p.NQ + j) * ROW0_PAIRS + warp] = xt;
+      }
+      sr = warp_sum(sr); st = warp_sum(st);
+      if (lane == 0) {
+        p.sums[(size_t)b * H1n] = sr;
+        p.sums[(size_t)p.B * H1n + (size_t)b * H1n] = st;
+      }
+    }
+  }
   __syncthreads();
-  float r = red[0];
-  for (int w = 1; w < nw; ++w) r = is_max ? fmaxf(r, red[w]) : r + red[w];
-  return r;
+  const int br = tid >> 7, t = tid & 127;
+  float acc[ROW0_PAIRS];
+  {   // layer 1
+    const float* w = p.w1t + (size_t)br * p.NQ * HID + t;
+    const float* x = x0 + (size_t)br * p.NQ * ROW0_PAIRS;
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
+    for (int j = 0; j < maxm; ++j) {
+      const float wv = __ldg(w + (size_t)j * HID);
+      const float4 xa = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS), xb = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS + 4);
+      acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
+      acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
+    }
+    const float bias = p.vecs[br * HID + t];
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) h1[((size_t)br * HID + t) * ROW0_PAIRS + i] = fmaxf(acc[i] + bias, 0.f);
+  }
+  __syncthreads();
+  {   // layer 2 + folded layer 3 / regressor
+    const float* w = p.w2t + (size_t)br * HID * HID + t;
+    const float* x = h1 + (size_t)br * HID * ROW0_PAIRS;
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
+    for (int k = 0; k < HID; ++k) {
+      const float wv = __ldg(w + (size_t)k * HID);
+      const float4 xa = *reinterpret_cast<const float4*>(x + k * ROW0_PAIRS), xb = *reinterpret_cast<const float4*>(x + k * ROW0_PAIRS + 4);
+      acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
+      acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
+    }
+    const float bias = p.vecs[2 * HID + br * HID + t], w34 = p.vecs[4 * HID + br * HID + t];
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) {
+      const float v = warp_sum(fmaxf(acc[i] + bias, 0.f) * w34);
+      if (lane == 0) red[(br * 4 + (warp & 3)) * ROW0_PAIRS + i] = v;
+    }
+  }
+  __syncthreads();
+  if (tid < 2 * ROW0_PAIRS) {
+    const int br2 = tid / ROW0_PAIRS, i = tid % ROW0_PAIRS, b = b0 + i;
+    if (b < p.B) {
+      float v = 0.f;
+      for (int w4 = 0; w4 < 4; ++w4) v += red[(br2 * 4 + w4) * ROW0_PAIRS + i];
+      p.logits[(size_t)br2 * p.B * H1n + (size_t)b * H1n] = v;     // like the tile logits: without the constant c34
+    }
+  }
 }
 
+// ------------------------------------------------------------------------------------------------ selection kernel
 __device__ int block_arg_extreme(const float* vals, int n, bool want_max, float* redv, int* redi) {
   float best = want_max ? -INFINITY : INFINITY;
   int bi = 0x7fffffff;
@@ -575,51 +739,20 @@ __device__ int block_arg_extreme(const float* vals, int n, bool want_max, float*
 constexpr int SEL_THREADS = 256;
 
 struct SelParams {
-  const float* geo_local; const float* q_h; const float* t_h; const float* q0; const float* t0;
+  const float* q_h; const float* t_h; const float* q0; const float* t0;
   const float* feat_rot0; const float* feat_tran0; const int32_t* matched_num;
-  nsac_score_mlp rot, tran;
   const float* w_rots; const float* b_rots; const float* w_trans; const float* b_trans;
-  const float* c34;        // [2]
   float* logits; float* sums; const float* partials;
   int B, NQ, tiles_per_pair, out_cam_type;
   float* pose; float* score_rot; float* score_tran; int32_t* sel_idx;
 };
-
-// exact-fp32 MLP(NQ,128,64,3)+Linear(64,1) on ONE input row x[0..m) held in shared memory; 128 threads of a branch
-__device__ float score_row_mlp(const nsac_score_mlp& w, const float* x, int m, int NQ, float* h1, float* h2, int t /*0..127*/,
-                               int bar_id) {
-  float a = w.b1[t];
-  const float* wr = w.w1 + (size_t)t * NQ;
-  for (int j = 0; j < m; ++j) a = fmaf(x[j], wr[j], a);
-  h1[t] = fmaxf(a, 0.f);
-  named_bar_sync(bar_id, 128);
-  a = w.b2[t];
-  wr = w.w2 + (size_t)t * HID;
-  for (int k = 0; k < HID; ++k) a = fmaf(h1[k], wr[k], a);
-  h2[t] = fmaxf(a, 0.f);
-  named_bar_sync(bar_id, 128);
-  float out = 0.f;
-  if (t < 64) {
-    a = w.b3[t];
-    wr = w.w3 + (size_t)t * HID;
-    for (int k = 0; k < HID; ++k) a = fmaf(h2[k], wr[k], a);
-    out = a * w.w4[t];
-  }
-  out = warp_sum(out);
-  named_bar_sync(bar_id, 128);
-  if ((t & 31) == 0) h1[t >> 5] = out;
-  named_bar_sync(bar_id, 128);
-  return h1[0] + h1[1] + w.b4[0];
-}
 
 __global__ void __launch_bounds__(SEL_THREADS)
 score_select_tc_kernel(const SelParams p) {
   extern __shared__ float sm[];
   const int C = C_FEAT;
   const int b = blockIdx.x, tid = threadIdx.x, H1n = p.NQ + 1;
-  float* x0 = sm;                      // [2][NQ] residual scores of hypothesis 0
-  float* hbuf = x0 + 2 * p.NQ;         // [2][2][128]
-  float* fe = hbuf + 4 * HID;          // [4][256]: avg_rot, avg_tran, soft_rot, soft_tran
+  float* fe = sm;                      // [4][256]: avg_rot, avg_tran, soft_rot, soft_tran
   float* red = fe + 4 * C;             // [SEL_THREADS]
   int* redi = reinterpret_cast<int*>(red + SEL_THREADS);
   float* outv = reinterpret_cast<float*>(redi + SEL_THREADS);   // [16]
@@ -636,52 +769,15 @@ score_select_tc_kernel(const SelParams p) {
     if (tid == 0) { P[14] = 0.f; P[15] = 0.f; }
     return;
   }
-  // ---- hypothesis 0 = the initial pose (camera_head.py:991, 1019): residual row + exact score MLPs
-  {
-    const float* q = p.q0 + (size_t)b * 4;
-    const float* t = p.t0 + (size_t)b * 3;
-    const Mat3 Mr = quat_to_rot(q[0], q[1], q[2], q[3]);
-    float R[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) R[i] = Mr.m[i];
-    const float* gl = p.geo_local + (size_t)b * p.NQ * 6;
-    float sr = 0.f, st = 0.f;
-    for (int j = tid; j < m; j += blockDim.x) {
-      float c[12];
-      float ax = gl[j * 6 + 0], ay = -gl[j * 6 + 1], az = -gl[j * 6 + 2];
-      const float d = normalize3(ax, ay, az);
-      c[0] = ax; c[1] = ay; c[2] = az;
-      c[6] = gl[j * 6 + 3]; c[7] = -gl[j * 6 + 4]; c[8] = -gl[j * 6 + 5];
-      float nx = c[6], ny = c[7], nz = c[8];
-      normalize3(nx, ny, nz);
-      c[3] = nx; c[4] = ny; c[5] = nz;
-      const float dd = d + 1e-5f;
-      c[9] = d * d / (dd * dd); c[10] = c[9] * d; c[11] = 1.f;
-      float xr, xt, dr, dt;
-      residual_pair(R, t[0], t[1], t[2], c, xr, xt, dr, dt);
-      x0[j] = xr; x0[p.NQ + j] = xt;
-      sr += dr; st += dt;
-    }
-    sr = block_reduce(sr, red, false);
-    st = block_reduce(st, red, false);
-    __syncthreads();
-    const int br = tid >> 7, t128 = tid & 127;
-    const float l0 = score_row_mlp(br == 0 ? p.rot : p.tran, x0 + br * p.NQ, m, p.NQ, hbuf + br * 2 * HID, hbuf + br * 2 * HID + HID,
-                                   t128, 2 + br);
-    if (t128 == 0) {
-      misc[br] = l0;
-      p.logits[(size_t)br * p.B * H1n + (size_t)b * H1n] = l0;
-      p.sums[(size_t)br * p.B * H1n + (size_t)b * H1n] = br == 0 ? sr : st;
-    }
-  }
+  if (tid < 2) misc[tid] = p.logits[(size_t)tid * p.B * H1n + (size_t)b * H1n];     // hypothesis 0 (score_row0_kernel)
   __syncthreads();
   // ---- merge the tile partials with hypothesis 0 (log-sum-exp rescale)
   const int ntile = (m + TILE_H - 1) / TILE_H;
   if (tid < 2) {
     const int br = tid;
-    float M = misc[br] - p.c34[br];          // tile logits come without the constant c34; compare like with like
+    float M = misc[br];                      // every logit here lacks the constant c34 (softmax-invariant)
     for (int t = 0; t < ntile; ++t) M = fmaxf(M, p.partials[(((size_t)b * p.tiles_per_pair + t) * 2 + br) * PART_STRIDE]);
-    float S = expf(misc[br] - p.c34[br] - M);
+    float S = expf(misc[br] - M);
     for (int t = 0; t < ntile; ++t) {
       const float* part = p.partials + (((size_t)b * p.tiles_per_pair + t) * 2 + br) * PART_STRIDE;
       S += expf(part[0] - M) * part[1];
@@ -695,8 +791,8 @@ score_select_tc_kernel(const SelParams p) {
   float* lr = p.logits + (size_t)b * H1n;
   float* lt = p.logits + (size_t)p.B * H1n + (size_t)b * H1n;
   for (int h = tid; h <= m; h += blockDim.x) {
-    const float a = expf((h == 0 ? lr[0] - p.c34[0] : lr[h]) - Mr_) / Sr_;
-    const float c = expf((h == 0 ? lt[0] - p.c34[1] : lt[h]) - Mt_) / St_;
+    const float a = expf(lr[h] - Mr_) / Sr_;
+    const float c = expf(lt[h] - Mt_) / St_;
     lr[h] = a; lt[h] = c;                     // logits buffer now holds the scores
     if (p.score_rot) p.score_rot[(size_t)b * H1n + h] = a;
     if (p.score_tran) p.score_tran[(size_t)b * H1n + h] = c;
@@ -724,8 +820,8 @@ score_select_tc_kernel(const SelParams p) {
       ar += pr[PART_HDR + C + c];
       at += pt[PART_HDR + C + c];
     }
-    wr = (wr + expf(misc[0] - p.c34[0] - Mr_) * f0r) / Sr_;
-    wt = (wt + expf(misc[1] - p.c34[1] - Mt_) * f0t) / St_;
+    wr = (wr + expf(misc[0] - Mr_) * f0r) / Sr_;
+    wt = (wt + expf(misc[1] - Mt_) * f0t) / St_;
     if (m > 1) {  // the initial pose joins the average only when m > 1 (:1052-1063)
       const float w = 1.f / (float)(m + 1);
       ar = (ar + f0r) * w;
@@ -811,30 +907,45 @@ int sm_count() {
   return n;
 }
 inline int nq_padded(int NQ) { return (NQ + KB - 1) / KB * KB; }
-inline size_t pack_bytes(int NQ) { return 2 * pack_w1_bytes(nq_padded(NQ)) + 2 * (size_t)HID * HID * 2 + (6 * HID + 8) * sizeof(float); }
 inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 }  // namespace
+
+extern "C" size_t nsac_score_pack_bytes(int NQ) {
+  return NQ < 1 ? 0 : align256(pack_total_bytes(NQ, nq_padded(NQ)));
+}
+
+extern "C" int nsac_score_pack(const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp, int NQ, void* pack, void* stream) {
+  NSAC_REQUIRE(rot_mlp && tran_mlp && pack && NQ >= 1, "nsac_score_pack: bad arguments");
+  NSAC_REQUIRE((reinterpret_cast<uintptr_t>(pack) & 255) == 0, "nsac_score_pack: pack buffer must be 256-byte aligned");
+  const nsac_score_mlp* mm[2] = {rot_mlp, tran_mlp};
+  for (int i = 0; i < 2; ++i)
+    NSAC_REQUIRE(mm[i]->w1 && mm[i]->b1 && mm[i]->w2 && mm[i]->b2 && mm[i]->w3 && mm[i]->b3 && mm[i]->w4 && mm[i]->b4,
+                 "nsac_score_pack: incomplete score MLP weights");
+  score_pack_kernel<<<64, 256, 0, static_cast<cudaStream_t>(stream)>>>(*rot_mlp, *tran_mlp, NQ, nq_padded(NQ), static_cast<uint8_t*>(pack));
+  NSAC_CHECK_LAUNCH("score_pack_kernel");
+  return NSAC_OK;
+}
 
 extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) {
   if (B < 0 || NQ < 1) return 0;
   const size_t per = (size_t)B * (NQ + 1);
   const int tiles = (NQ + TILE_H - 1) / TILE_H;
-  return align256(pack_bytes(NQ)) + align256(4 * per * sizeof(float)) + (size_t)B * tiles * 2 * PART_STRIDE * sizeof(float) + 256;
+  return align256(4 * per * sizeof(float)) + (size_t)B * tiles * 2 * PART_STRIDE * sizeof(float) + 256;
 }
 
 extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
                                        const float* t0, const float* feat_rot, const float* feat_tran,
                                        const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
-                                       const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp, const float* w_rots,
-                                       const float* b_rots, const float* w_trans, const float* b_trans, int B, int NQ,
-                                       int out_cam_type, float* pose, float* score_rot, float* score_tran, int32_t* sel_idx,
-                                       void* workspace, void* stream) {
+                                       const void* pack, const float* w_rots, const float* b_rots, const float* w_trans,
+                                       const float* b_trans, int B, int NQ, int out_cam_type, float* pose, float* score_rot,
+                                       float* score_tran, int32_t* sel_idx, void* workspace, void* stream) {
   NSAC_REQUIRE(geo_local && q_h && t_h && q0 && t0 && feat_rot && feat_tran && feat_rot0 && feat_tran0 && matched_num &&
-                   rot_mlp && tran_mlp && w_rots && b_rots && w_trans && b_trans && pose && workspace,
+                   pack && w_rots && b_rots && w_trans && b_trans && pose && workspace,
                "nsac_score_aggregate_tc: null pointer");
   NSAC_REQUIRE(B >= 0 && NQ >= 1, "nsac_score_aggregate_tc: bad shape B=%d NQ=%d", B, NQ);
   NSAC_REQUIRE(out_cam_type >= 0 && out_cam_type <= 3, "nsac_score_aggregate_tc: bad out_cam_type %d", out_cam_type);
-  NSAC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "nsac_score_aggregate_tc: workspace must be 256-byte aligned");
+  NSAC_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0 && (reinterpret_cast<uintptr_t>(pack) & 255) == 0,
+               "nsac_score_aggregate_tc: workspace / pack must be 256-byte aligned");
   NSAC_REQUIRE((reinterpret_cast<uintptr_t>(feat_rot) & 15) == 0 && (reinterpret_cast<uintptr_t>(feat_tran) & 15) == 0 &&
                    (reinterpret_cast<uintptr_t>(q_h) & 15) == 0,
                "nsac_score_aggregate_tc: feature / quaternion tensors must be 16-byte aligned");
@@ -843,19 +954,29 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   const int NQp = nq_padded(NQ), tiles = (NQ + TILE_H - 1) / TILE_H;
   const size_t per = (size_t)B * (NQ + 1);
   uint8_t* ws = static_cast<uint8_t*>(workspace);
-  uint8_t* pack = ws;
-  float* logits = reinterpret_cast<float*>(ws + align256(pack_bytes(NQ)));
+  const uint8_t* pk = static_cast<const uint8_t*>(pack);
+  float* logits = reinterpret_cast<float*>(ws);
   float* sums = logits + 2 * per;
-  float* partials = reinterpret_cast<float*>(ws + align256(pack_bytes(NQ)) + align256(4 * per * sizeof(float)));
-  float* vecs = reinterpret_cast<float*>(pack + 2 * pack_w1_bytes(NQp) + 2 * HID * HID * 2);
+  float* partials = reinterpret_cast<float*>(ws + align256(4 * per * sizeof(float)));
+  const float* vecs = reinterpret_cast<const float*>(pk + pack_off_vecs(NQp));
 
-  score_pack_kernel<<<64, 256, 0, s>>>(*rot_mlp, *tran_mlp, NQ, NQp, pack);
-  NSAC_CHECK_LAUNCH("score_pack_kernel");
+  // hypothesis 0 of every pair (independent of the tile kernel)
+  Row0Params rp;
+  rp.geo_local = geo_local; rp.q0 = q0; rp.t0 = t0; rp.matched_num = matched_num;
+  rp.w1t = reinterpret_cast<const float*>(pk + pack_off_w1t(NQp));
+  rp.w2t = reinterpret_cast<const float*>(pk + pack_off_w2t(NQ, NQp));
+  rp.vecs = vecs; rp.B = B; rp.NQ = NQ; rp.logits = logits; rp.sums = sums;
+  const size_t row0_smem = sizeof(float) * ((size_t)2 * NQ * ROW0_PAIRS + 2 * HID * ROW0_PAIRS + 2 * 4 * ROW0_PAIRS);
+  NSAC_REQUIRE(row0_smem <= 200 * 1024, "nsac_score_aggregate_tc: NQ=%d too large", NQ);
+  if (row0_smem > 48 * 1024)
+    NSAC_CUDA(cudaFuncSetAttribute(score_row0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row0_smem));
+  score_row0_kernel<<<nsac_cdiv(B, ROW0_PAIRS), 256, row0_smem, s>>>(rp);
+  NSAC_CHECK_LAUNCH("score_row0_kernel");
 
   CUtensorMap m1r, m1t, m2r, m2t;
-  const bool ok = make_map_f16(&m1r, pack, HID, NQp) && make_map_f16(&m1t, pack + pack_w1_bytes(NQp), HID, NQp) &&
-                  make_map_f16(&m2r, pack + 2 * pack_w1_bytes(NQp), HID, HID) &&
-                  make_map_f16(&m2t, pack + 2 * pack_w1_bytes(NQp) + HID * HID * 2, HID, HID);
+  const bool ok = make_map_f16(&m1r, pk, HID, NQp) && make_map_f16(&m1t, pk + pack_w1_bytes(NQp), HID, NQp) &&
+                  make_map_f16(&m2r, pk + 2 * pack_w1_bytes(NQp), HID, HID) &&
+                  make_map_f16(&m2t, pk + 2 * pack_w1_bytes(NQp) + HID * HID * 2, HID, HID);
   if (!ok) {
     nsac_set_error("nsac_score_aggregate_tc: cuTensorMapEncodeTiled failed");
     return NSAC_ERR_LAUNCH;
@@ -866,24 +987,25 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   tp.need_sums = out_cam_type == NSAC_CAM_MIN_COST; tp.logits = logits; tp.sums = sums; tp.partials = partials;
   static bool attr = false;
   if (!attr) {
-    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
   const int items = B * tiles;
   const int grid = items < sm_count() ? items : sm_count();
-  score_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, tp);
+  if (tp.need_sums)
+    score_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, tp);
+  else
+    score_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, tp);
   NSAC_CHECK_LAUNCH("score_tc_kernel");
 
   SelParams sp;
-  sp.geo_local = geo_local; sp.q_h = q_h; sp.t_h = t_h; sp.q0 = q0; sp.t0 = t0; sp.feat_rot0 = feat_rot0; sp.feat_tran0 = feat_tran0;
-  sp.matched_num = matched_num; sp.rot = *rot_mlp; sp.tran = *tran_mlp; sp.w_rots = w_rots; sp.b_rots = b_rots;
-  sp.w_trans = w_trans; sp.b_trans = b_trans; sp.c34 = vecs + 6 * HID; sp.logits = logits; sp.sums = sums; sp.partials = partials;
+  sp.q_h = q_h; sp.t_h = t_h; sp.q0 = q0; sp.t0 = t0; sp.feat_rot0 = feat_rot0; sp.feat_tran0 = feat_tran0;
+  sp.matched_num = matched_num; sp.w_rots = w_rots; sp.b_rots = b_rots; sp.w_trans = w_trans; sp.b_trans = b_trans;
+  sp.logits = logits; sp.sums = sums; sp.partials = partials;
   sp.B = B; sp.NQ = NQ; sp.tiles_per_pair = tiles; sp.out_cam_type = out_cam_type; sp.pose = pose; sp.score_rot = score_rot;
   sp.score_tran = score_tran; sp.sel_idx = sel_idx;
-  const size_t sel_smem = sizeof(float) * (2 * (size_t)NQ + 4 * HID + 4 * C_FEAT + SEL_THREADS + 16 + 8) + sizeof(int) * SEL_THREADS;
-  NSAC_REQUIRE(sel_smem <= 200 * 1024, "nsac_score_aggregate_tc: NQ=%d too large", NQ);
-  if (sel_smem > 48 * 1024)
-    NSAC_CUDA(cudaFuncSetAttribute(score_select_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
+  const size_t sel_smem = sizeof(float) * (4 * C_FEAT + SEL_THREADS + 16 + 8) + sizeof(int) * SEL_THREADS;
   score_select_tc_kernel<<<B, SEL_THREADS, sel_smem, s>>>(sp);
   NSAC_CHECK_LAUNCH("score_select_tc_kernel");
   return NSAC_OK;

@@ -255,9 +255,21 @@ def _score_mlp_struct(ws):
     return s
 
 
+def score_pack(rot_mlp, tran_mlp, num_queries: int) -> torch.Tensor:
+    """Device-side weight pack of the tensor-core scoring path (build once per weight version)."""
+    L = _lib.lib()
+    dev = rot_mlp[0].device
+    pack = torch.empty(L.nsac_score_pack_bytes(num_queries), device=dev, dtype=torch.uint8)
+    rs, ts = _score_mlp_struct(rot_mlp), _score_mlp_struct(tran_mlp)
+    st = L.nsac_score_pack(C.byref(rs), C.byref(ts), num_queries, _p(pack), _stream())
+    _lib.check(st, "nsac_score_pack")
+    _count()
+    return pack
+
+
 def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num,
                     rot_mlp, tran_mlp, w_rots, b_rots, w_trans, b_trans, out_cam_type="soft",
-                    want_scores=True, want_diag=False, precision="fp16"):
+                    want_scores=True, want_diag=False, precision="fp16", pack=None):
     """rot_mlp / tran_mlp: 8-tuples (w1,b1,w2,b2,w3,b3,w4,b4). Returns dict(pose, score_rot, score_tran,
     sel_idx, diag).  precision "fp16" = tcgen05 path (score MLPs single-pass fp16, fp32 accumulate);
     "fp32" = exact CUDA-core path (always used when the diagnostic outputs are requested)."""
@@ -275,8 +287,10 @@ def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0,
     L = _lib.lib()
     rs, ts = _score_mlp_struct(rot_mlp), _score_mlp_struct(tran_mlp)
     if precision == "fp16" and not want_diag:
+        if pack is None:
+            pack = score_pack(rot_mlp, tran_mlp, NQ)
         ws = torch.empty(L.nsac_score_tc_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
-        st = L.nsac_score_aggregate_tc(*[_p(a) for a in args], _p(matched_num), C.byref(rs), C.byref(ts),
+        st = L.nsac_score_aggregate_tc(*[_p(a) for a in args], _p(matched_num), _p(pack),
                                        _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
                                        _p(pose), _p(sr), _p(stt), _p(sel), _p(ws), _stream())
         _lib.check(st, "nsac_score_aggregate_tc")

@@ -20,9 +20,9 @@ q0 = torch.nn.functional.normalize(rnd(B, 4), dim=-1)
 t0 = rnd(B, 3) * 0.3
 fr, ft, fr0, ft0 = rnd(B, NQ, 256), rnd(B, NQ, 256), rnd(B, 256), rnd(B, 256)
 mnum = torch.full((B,), NQ, device=dev, dtype=torch.int32)
-pk = head.prepare()
+pk = head.prepare_tc()
 for _ in range(reps):
     ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"], pk["param_score_proj"],
-                        head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias, want_scores=False)
+                        head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias, want_scores=False, pack=pk["score_pack"])
 torch.cuda.synchronize()
 print("done")
