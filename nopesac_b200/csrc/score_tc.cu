@@ -1,23 +1,24 @@
 // K8 + K9 on the Blackwell tensor pipe — hypothesis scoring and pose selection (camera_head.py:964-1115).
 //
 // Work item = (pair b, tile of 128 one-plane hypotheses h = 1 + 128*tile + r); hypothesis 0 (the initial pose)
-// is a single row and is scored by the per-pair selection kernel.  One persistent CTA per SM, 18 warps:
+// is a single row and is scored by a small batched kernel.  One persistent CTA per SM, 24 warps in 6 warpgroups
+// (setmaxnreg moves registers from the TMA / MMA / epilogue warps to the residual warps):
 //
 //   warp 0        TMA        W2 (both branches, resident) once; then per (tile, k-block) the two [128 x 64] fp16
 //                            slices of the first score-MLP layer W1 (rot / trans) into a 2-stage ring
 //   warp 1        MMA        layer 1: D_b[128x128] += X_b[128x64] . W1_b^T  (tcgen05.mma kind::f16, A and B from
 //                            shared memory);  layer 2: D_b = H1_b . W2_b^T with H1 read from TENSOR MEMORY (A operand
 //                            written there by the epilogue warps) — the hidden activations never touch shared memory
-//   warps 2-5     epilogue   TMEM -> registers: +b1, ReLU, pack fp16x2 -> tcgen05.st (H1);  then +b2, ReLU and the
+//   warps 4-7     epilogue   TMEM -> registers: +b1, ReLU, pack fp16x2 -> tcgen05.st (H1);  then +b2, ReLU and the
 //                            folded Linear(128,64)+Linear(64,1) dot product: one thread owns one hypothesis row, so
 //                            the logit needs no cross-thread reduction
-//   warps 6-13    residuals  the CUDA-core part: thread = (hypothesis row, 8-column chunk).  u = R_h n_j is shared by
+//   warps 8-15    residuals  the CUDA-core part: thread = (hypothesis row, 8-column chunk).  u = R_h n_j is shared by
 //                            both branches;  rot: exp(-|u - n1_j|);  trans: exp(-|A_j (d_j + t_h.u) u - pi1_j|)
 //                            (closed forms of the reference's warp + normalise, see residual_pair()); results are
 //                            written as fp16 straight into the 128-byte-swizzled K-major A-operand tiles (2-stage
 //                            ring), fence.proxy.async, mbarrier arrive.  The [B,NQ+1,NQ,3] temporaries of the
 //                            reference never exist.
-//   warps 14-17   gather     flash-style softmax partials: local max / sum of exp over the tile's logits and the
+//   warps 16-23   gather     flash-style softmax partials: local max / sum of exp over the tile's logits and the
 //                            exp-weighted + plain sums of the tile's [128,256] one-plane features — the only HBM
 //                            stream of the kernel (float4 loads, 16 rows in flight), overlapped with the residual
 //                            and tensor work of the NEXT tile
@@ -42,10 +43,16 @@ constexpr int KB = 64;             // residual columns per k-block (one 128-byte
 constexpr int C_FEAT = 256;
 constexpr int W_STAGES = 2, A_STAGES = 2;
 constexpr int BLK_BYTES = TILE_H * KB * 2;           // 16 KB: one [128 x 64] fp16 operand block
-constexpr int NUM_WARPS = 22, NUM_THREADS = NUM_WARPS * 32;
-constexpr int R_WARP0 = 6, R_WARPS = 8, R_THREADS = R_WARPS * 32;
-constexpr int G_WARP0 = 14, G_THREADS = 256;
-constexpr uint32_t SPIN_LIMIT = 1u << 24;   // x ~200 ns: seconds, then trap instead of hanging the GPU
+// warp roles, aligned to warpgroups of 4 warps so that setmaxnreg can move registers to the residual warps:
+//   WG0 = warps 0-3 (TMA, MMA, 2 idle)  40 regs | WG1 = warps 4-7 epilogue  72 regs
+//   WG2-3 = warps 8-15 residuals       112 regs | WG4-5 = warps 16-23 gather 72 regs
+// (launch: 768 x 80; setmaxnreg.inc can only draw on what the CTA's own warps released with setmaxnreg.dec:
+//  128*40 + 128*8 + 256*8 = 8192 = 256*32 — an inc that is not covered deadlocks)
+constexpr int NUM_WARPS = 24, NUM_THREADS = NUM_WARPS * 32;
+constexpr int E_WARP0 = 4;
+constexpr int R_WARP0 = 8, R_WARPS = 8, R_THREADS = R_WARPS * 32;
+constexpr int G_WARP0 = 16, G_THREADS = 256;
+constexpr uint32_t SPIN_LIMIT = 2000;      // suspended waits of up to ~10 ms each: ~20 s, then trap instead of hanging
 constexpr int PART_HDR = 4;                          // max, sumexp, pad, pad (keeps the vectors 16-byte aligned)
 constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch): header, wsum[256], fsum[256]
 
@@ -53,8 +60,8 @@ constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch)
 constexpr int OFF_W2 = 0;                                        // [branch][kblock 0..1][16 KB]
 constexpr int OFF_W1 = OFF_W2 + 4 * BLK_BYTES;                   // [stage][branch][16 KB]
 constexpr int OFF_A = OFF_W1 + W_STAGES * 2 * BLK_BYTES;         // [stage][branch][16 KB]
-constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [A_STAGES][64][3] float4 column constants
-constexpr int OFF_VEC = OFF_CJ + A_STAGES * KB * 12 * 4;         // b1[2][128], b2[2][128], w34[2][128] floats
+constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [W_STAGES][64][3] float4 column constants (TMA)
+constexpr int OFF_VEC = OFF_CJ + W_STAGES * KB * 12 * 4;         // b1[2][128], b2[2][128], w34[2][128] floats
 constexpr int OFF_LOGIT = OFF_VEC + 6 * HID * 4;                 // [2 bufs][2 branches][128] floats
 constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [4 quarters][2 branches][128] floats (min-cost sums)
 constexpr int OFF_EXP = OFF_ROWSUM + 4 * 2 * TILE_H * 4;         // [2 branches][128] softmax numerators of the tile
@@ -82,19 +89,19 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Waiting warps must not steal issue slots from the residual warps: back off with nanosleep between probes
-// (the first ncu capture had 40 % of all issued instructions in these spin loops).
+// Waiting warps must not steal issue slots from the working warps: try_wait with a suspend-time hint parks the
+// warp in hardware until the phase completes (the first ncu capture of the scoring kernel had 40 % of all issued
+// instructions in plain try_wait spin loops).  Bounded: a protocol bug traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0, spins = 0;
   while (true) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
     if (done) break;
-    __nanosleep(spins < 8 ? 40 : 200);
     if (++spins > SPIN_LIMIT) __trap();
   }
 }
@@ -102,6 +109,10 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -217,7 +228,8 @@ struct TcParams {
   const float* feat_tran;
   const int32_t* matched_num;
   const float* vecs;        // packed: b1[2][128], b2[2][128], w34[2][128]
-  int B, NQ, tiles_per_pair, need_sums;
+  const float4* cjg;        // [B][NQp][3] column constants (score_row0_kernel)
+  int B, NQ, NQp, tiles_per_pair, need_sums;
   float* logits;            // [2][B][NQ+1]
   float* sums;              // [2][B][NQ+1]
   float* partials;          // [B][tiles][2][PART_STRIDE]
@@ -228,7 +240,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_constant__ CUtensorMap map_w1t,
                 const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w2t, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // align inside the shared window with offset arithmetic (a generic-pointer round trip would turn every
+  // shared-memory access below into a generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   float4* cj = reinterpret_cast<float4*>(smem + OFF_CJ);
@@ -263,6 +277,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // setmaxnreg: ONE instruction per warpgroup (all 4 warps must execute the same one), inside the warpgroup's own
+  // branch so that the register limit is unambiguous on every control path
+  if (warp < E_WARP0) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
   if (warp == 0) {
     // ================================================================================= TMA producer
     if (lane == 0) {
@@ -279,10 +297,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         const int nkb = (m + KB - 1) / KB;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars[BAR_W_EMPTY + stage], phase ^ 1);
-          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES);
+          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES + KB * 48);
           uint8_t* dst = smem + OFF_W1 + stage * 2 * BLK_BYTES;
           tma_load_2d(dst, &map_w1r, &bars[BAR_W_FULL + stage], kb * KB, 0);
           tma_load_2d(dst + BLK_BYTES, &map_w1t, &bars[BAR_W_FULL + stage], kb * KB, 0);
+          // the k-block's 64 x 48 B of per-column geometry constants travel with the weights
+          bulk_load_1d(smem + OFF_CJ + stage * KB * 48, p.cjg + ((size_t)b * p.NQp + (size_t)kb * KB) * 3, KB * 48,
+                       &bars[BAR_W_FULL + stage]);
           if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -304,10 +325,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
           mbar_wait(&bars[BAR_A_FULL + as], aph);
           fence_after();
           const uint32_t a0 = smem_u32(smem + OFF_A + as * 2 * BLK_BYTES), w0 = smem_u32(smem + OFF_W1 + ws * 2 * BLK_BYTES);
-#pragma unroll
+#pragma unroll 1
           for (int br = 0; br < 2; ++br) {
             const uint64_t da = sw128_desc(a0 + br * BLK_BYTES), dw = sw128_desc(w0 + br * BLK_BYTES);
-#pragma unroll
+#pragma unroll 1
             for (int k = 0; k < KB / 16; ++k)
               umma_ss(tmem_base + TM_D + br * HID, da + 2 * k, dw + 2 * k, IDESC, (kb | k) != 0);
           }
@@ -320,9 +341,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         // layer 2: A = H1 (fp16 pairs in tensor memory), B = W2 (resident in shared memory)
         mbar_wait(&bars[BAR_H1_READY], tph);
         fence_after();
-#pragma unroll
+#pragma unroll 1
         for (int br = 0; br < 2; ++br) {
-#pragma unroll
+#pragma unroll 1
           for (int k = 0; k < HID / 16; ++k) {
             const uint64_t dw = sw128_desc(smem_u32(smem + OFF_W2 + (br * 2 + (k >> 2)) * BLK_BYTES)) + 2 * (k & 3);
             umma_ts(tmem_base + TM_D + br * HID, tmem_base + TM_H1 + br * (HID / 2) + k * 8, dw, IDESC, k != 0);
@@ -332,8 +353,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         tph ^= 1;
       }
     }
+  }   // warps 2, 3: idle (they only donate their registers)
   } else if (warp < R_WARP0) {
-    // ================================================================================= epilogue warps 2..5
+    // ================================================================================= epilogue warps 4..7
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     const int quad = warp & 3, row = quad * 32 + lane;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint32_t tph = 0; int lbuf = 0; uint32_t lph = 0;
@@ -397,12 +420,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       tph ^= 1;
     }
   } else if (warp < G_WARP0) {
-    // ================================================================================= residual warps 6..13
+    // ================================================================================= residual warps 8..15
     // thread = 2 hypothesis rows (rp, rp + 64) x 16 columns of the k-block: the column constants are loaded once
     // (3 LDS.128) and used for both rows
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
     const int rt = threadIdx.x - R_WARP0 * 32;       // 0..255
     const int rp = rt & 63, quarter = rt >> 6;       // rows rp / rp+64, chunks 2*quarter, 2*quarter+1
-    int as = 0; uint32_t aph = 0;
+    int as = 0; uint32_t aph = 0; int ws = 0; uint32_t wph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       const int b = item / p.tiles_per_pair, tile = item % p.tiles_per_pair;
       const int m = p.matched_num[b];
@@ -427,20 +451,13 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         for (int i = 0; i < 9; ++i) R[s2][i] = M.m[i];
       }
       float sum_r[2] = {0.f, 0.f}, sum_t[2] = {0.f, 0.f};
-      const float* gl = p.geo_local + (size_t)b * p.NQ * 6;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
-        float4* cjs = cj + as * KB * 3;
-        if (rt < KB) {
-          const int j = kb * KB + rt;
-          float4 c0, c1, c2;
-          column_constants(gl + (size_t)(j < m ? j : 0) * 6, j < m, c0, c1, c2);
-          cjs[rt * 3 + 0] = c0; cjs[rt * 3 + 1] = c1; cjs[rt * 3 + 2] = c2;
-        }
-        named_bar_sync(1, R_THREADS);
+        mbar_wait(&bars[BAR_W_FULL + ws], wph);           // column constants of this k-block have landed (TMA)
+        const float4* cjs = cj + ws * KB * 3;
         uint8_t* a_rot = smem + OFF_A + as * 2 * BLK_BYTES;
         uint8_t* a_tran = a_rot + BLK_BYTES;
-#pragma unroll 1
+#pragma unroll 2
         for (int c4i = 0; c4i < 4; ++c4i) {                 // 4 groups of 4 columns = this thread's 16 columns
           const int chunk = quarter * 2 + (c4i >> 1), sub = c4i & 1;
           float xr[2][4], xt[2][4];
@@ -464,6 +481,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         fence_proxy_async();
         mbar_arrive(&bars[BAR_A_FULL + as]);
         if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
       }
       if (SUMS) {   // sum_j of the masked distances (argmin in 'min-cost', :1090-1093): 4 column quarters per row, fixed order
 #pragma unroll
@@ -484,7 +502,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       }
     }
   } else {
-    // ================================================================================= gather warps 14..21
+    // ================================================================================= gather warps 16..23
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
     // thread = (branch, row parity, 4 feature channels): 12 float4 loads in flight per thread, 48 KB per SM
     const int gt = threadIdx.x - G_WARP0 * 32;       // 0..255
     const int br = gt >> 7, par = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
@@ -607,15 +626,16 @@ __global__ void score_pack_kernel(nsac_score_mlp r, nsac_score_mlp t, int NQ, in
 }
 
 // ------------------------------------------------------------------------------------------------ hypothesis 0
-// Hypothesis 0 (the initial pose, camera_head.py:991, 1019) is one row per pair: 8 pairs per CTA so every weight that
-// is loaded (coalesced, transposed fp32 copies) feeds 8 FMAs; exact fp32.  Also the masked distance sums of row 0.
-constexpr int ROW0_PAIRS = 8;
+// Hypothesis 0 (the initial pose, camera_head.py:991, 1019) is one row per pair: 4 pairs per CTA so every weight that
+// is loaded (coalesced, transposed fp32 copies, 8 loads in flight) feeds 4 FMAs; exact fp32.  Also the masked distance sums of row 0.
+constexpr int ROW0_PAIRS = 4;
 
 struct Row0Params {
   const float* geo_local; const float* q0; const float* t0; const int32_t* matched_num;
   const float* w1t; const float* w2t; const float* vecs;   // vecs: b1[2][128], b2[2][128], w34[2][128]
-  int B, NQ;
+  int B, NQ, NQp;
   float* logits; float* sums;
+  float4* cjg;             // out: [B][NQp][3] column constants for the tile kernel
 };
 
 __global__ void __launch_bounds__(256)
@@ -632,9 +652,19 @@ score_row0_kernel(const Row0Params p) {
     s_maxm = mm;
   }
   for (int i = tid; i < 2 * p.NQ * ROW0_PAIRS; i += blockDim.x) x0[i] = 0.f;
+  for (int i = tid; i < ROW0_PAIRS * p.NQp; i += blockDim.x) {      // geometry constants of every matched plane pair
+    const int b = b0 + i / p.NQp, j = i % p.NQp;
+    if (b < p.B) {
+      float4 c0, c1, c2;
+      const bool valid = j < p.matched_num[b];
+      column_constants(p.geo_local + ((size_t)b * p.NQ + (valid ? j : 0)) * 6, valid, c0, c1, c2);
+      float4* o = p.cjg + ((size_t)b * p.NQp + j) * 3;
+      o[0] = c0; o[1] = c1; o[2] = c2;
+    }
+  }
   __syncthreads();
   const int maxm = s_maxm;
-  {   // residual row of hypothesis 0: warp w <-> pair b0 + w
+  if (warp < ROW0_PAIRS) {   // residual row of hypothesis 0: warp w <-> pair b0 + w
     const int b = b0 + warp;
     if (b < p.B) {
       const int m = p.matched_num[b];
@@ -669,11 +699,21 @@ score_row0_kernel(const Row0Params p) {
     const float* x = x0 + (size_t)br * p.NQ * ROW0_PAIRS;
 #pragma unroll
     for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
-    for (int j = 0; j < maxm; ++j) {
+    int j = 0;
+    for (; j + 8 <= maxm; j += 8) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(j + u) * HID);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 xa = *reinterpret_cast<const float4*>(x + (j + u) * ROW0_PAIRS);
+        acc[0] = fmaf(wv[u], xa.x, acc[0]); acc[1] = fmaf(wv[u], xa.y, acc[1]); acc[2] = fmaf(wv[u], xa.z, acc[2]); acc[3] = fmaf(wv[u], xa.w, acc[3]);
+      }
+    }
+    for (; j < maxm; ++j) {
       const float wv = __ldg(w + (size_t)j * HID);
-      const float4 xa = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS), xb = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS + 4);
+      const float4 xa = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS);
       acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
-      acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
     }
     const float bias = p.vecs[br * HID + t];
 #pragma unroll
@@ -685,11 +725,15 @@ score_row0_kernel(const Row0Params p) {
     const float* x = h1 + (size_t)br * HID * ROW0_PAIRS;
 #pragma unroll
     for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
-    for (int k = 0; k < HID; ++k) {
-      const float wv = __ldg(w + (size_t)k * HID);
-      const float4 xa = *reinterpret_cast<const float4*>(x + k * ROW0_PAIRS), xb = *reinterpret_cast<const float4*>(x + k * ROW0_PAIRS + 4);
-      acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
-      acc[4] = fmaf(wv, xb.x, acc[4]); acc[5] = fmaf(wv, xb.y, acc[5]); acc[6] = fmaf(wv, xb.z, acc[6]); acc[7] = fmaf(wv, xb.w, acc[7]);
+    for (int k = 0; k < HID; k += 8) {
+      float wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * HID);
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const float4 xa = *reinterpret_cast<const float4*>(x + (k + u) * ROW0_PAIRS);
+        acc[0] = fmaf(wv[u], xa.x, acc[0]); acc[1] = fmaf(wv[u], xa.y, acc[1]); acc[2] = fmaf(wv[u], xa.z, acc[2]); acc[3] = fmaf(wv[u], xa.w, acc[3]);
+      }
     }
     const float bias = p.vecs[2 * HID + br * HID + t], w34 = p.vecs[4 * HID + br * HID + t];
 #pragma unroll
@@ -930,7 +974,8 @@ extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) {
   if (B < 0 || NQ < 1) return 0;
   const size_t per = (size_t)B * (NQ + 1);
   const int tiles = (NQ + TILE_H - 1) / TILE_H;
-  return align256(4 * per * sizeof(float)) + (size_t)B * tiles * 2 * PART_STRIDE * sizeof(float) + 256;
+  return align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float)) +
+         (size_t)B * nq_padded(NQ) * 48 + 256;
 }
 
 extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
@@ -958,6 +1003,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   float* logits = reinterpret_cast<float*>(ws);
   float* sums = logits + 2 * per;
   float* partials = reinterpret_cast<float*>(ws + align256(4 * per * sizeof(float)));
+  float4* cjg = reinterpret_cast<float4*>(ws + align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float)));
   const float* vecs = reinterpret_cast<const float*>(pk + pack_off_vecs(NQp));
 
   // hypothesis 0 of every pair (independent of the tile kernel)
@@ -965,7 +1011,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   rp.geo_local = geo_local; rp.q0 = q0; rp.t0 = t0; rp.matched_num = matched_num;
   rp.w1t = reinterpret_cast<const float*>(pk + pack_off_w1t(NQp));
   rp.w2t = reinterpret_cast<const float*>(pk + pack_off_w2t(NQ, NQp));
-  rp.vecs = vecs; rp.B = B; rp.NQ = NQ; rp.logits = logits; rp.sums = sums;
+  rp.vecs = vecs; rp.B = B; rp.NQ = NQ; rp.NQp = NQp; rp.logits = logits; rp.sums = sums; rp.cjg = cjg;
   const size_t row0_smem = sizeof(float) * ((size_t)2 * NQ * ROW0_PAIRS + 2 * HID * ROW0_PAIRS + 2 * 4 * ROW0_PAIRS);
   NSAC_REQUIRE(row0_smem <= 200 * 1024, "nsac_score_aggregate_tc: NQ=%d too large", NQ);
   if (row0_smem > 48 * 1024)
@@ -983,7 +1029,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   }
   TcParams tp;
   tp.geo_local = geo_local; tp.q_h = q_h; tp.t_h = t_h; tp.feat_rot = feat_rot; tp.feat_tran = feat_tran;
-  tp.matched_num = matched_num; tp.vecs = vecs; tp.B = B; tp.NQ = NQ; tp.tiles_per_pair = tiles;
+  tp.matched_num = matched_num; tp.vecs = vecs; tp.cjg = cjg; tp.B = B; tp.NQ = NQ; tp.NQp = NQp; tp.tiles_per_pair = tiles;
   tp.need_sums = out_cam_type == NSAC_CAM_MIN_COST; tp.logits = logits; tp.sums = sums; tp.partials = partials;
   static bool attr = false;
   if (!attr) {
