@@ -79,6 +79,33 @@ int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_h
 int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,
                  int ld_split, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pixel pose-regression network K1 (camera_head.py:642-683; camera_modules.py:36-48, 246-348) on the tensor-core
+ * engine.  Activations are NHWC ([N*H*W, C] rows), carried as fp32 and / or 16-bit hi/lo planes.
+ *   nsac_conv3x3_split   3x3 / stride 1 / pad 1 convolution as an IMPLICIT GEMM: the A tiles are gathered from the
+ *                        NHWC planes by 4-D TMA (the zero padding is TMA's out-of-bounds fill), weights are planes
+ *                        [Cout, 9*Cin] in (ky, kx, cin) order; BatchNorm(eval) is folded into weights + bias by
+ *                        the caller; epilogue as in nsac_gemm_split.  Replaces F.conv2d / cuDNN.
+ *   nsac_nchw_to_planes  backbone feature maps [N,C,HW] fp32 -> NHWC planes
+ *   nsac_groupnorm_nhwc  GroupNorm(G) (+ReLU) (+ nearest-2x-upsampled skip [N,H/2,W/2,C], camera_modules.py:344-347)
+ *   nsac_maxpool2_planes MaxPool2d(2,2) of an fp32 NHWC map -> planes
+ *   nsac_corr_softmax    compute_corr_softmax (camera_head.py:1117-1133): f1,f2 [B,HW,C] -> planes [B*HW, Cp]
+ *                        (channel c2 = w2*H + h2, zero padded to Cp)
+ *   nsac_im2col3x3_planes explicit im2col for the small strided convolutions (K order (ky,kx,c), padded to Kp)
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                       int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
+                       float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream);
+int nsac_nchw_to_planes(const float* x, int N, int C, int HW, int fmt, void* hi, void* lo, void* stream);
+int nsac_groupnorm_nhwc(const float* x, int N, int H, int W, int C, int G, const float* gamma, const float* beta,
+                        float eps, int relu, const float* skip_half_res, int fmt, float* out_f32, void* out_hi,
+                        void* out_lo, void* stream);
+int nsac_maxpool2_planes(const float* x, int N, int H, int W, int C, int fmt, void* hi, void* lo, void* stream);
+int nsac_corr_softmax(const float* f1, const float* f2, int B, int H, int W, int C, int Cp, int fmt, void* hi,
+                      void* lo, void* stream);
+int nsac_im2col3x3_planes(const float* x, int N, int H, int W, int C, int stride, int Kp, int fmt, void* hi,
+                          void* lo, void* stream);
+
 /* LayerNorm over the last dim C (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x).
  * gnn.py:90,94-96. */
 int nsac_layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res,

@@ -25,6 +25,18 @@ _SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nsac_split16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p]),
+    "nsac_conv3x3_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int, C.c_void_p,
+                                     C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_nchw_to_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsac_groupnorm_nhwc": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_float,
+                                      C.c_int, c_float_p, C.c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsac_maxpool2_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_void_p]),
+    "nsac_corr_softmax": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                    C.c_void_p, C.c_void_p]),
+    "nsac_im2col3x3_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                        C.c_void_p, C.c_void_p]),
     "nsac_layernorm": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
                                  C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,

@@ -22,7 +22,6 @@ from typing import Dict, Optional
 
 import torch
 from torch import nn
-from torch.nn import functional as F
 
 from . import ops
 from .compat import Registry, ShapeSpec
@@ -241,63 +240,118 @@ class PlaneCameraHead(nn.Module):
                 for name in ("decoder_rot2", "decoder_tran2"):
                     pk[name + ".w_geo_split"] = ops.split_weight(pk[name + ".w_geo"])
                 pk["score_pack"] = ops.score_pack(pk["normal_score_proj"], pk["param_score_proj"], self.num_queries)
+                self._prepare_pixel_tc(pk)
         return pk
 
-    # ------------------------------------------------------------------ K1: pixel pose network
+    # ------------------------------------------------------------------ K1 weights for the tensor-core engine
     @staticmethod
-    def _conv_block(block, x):
-        conv, bn = block[0], block[1]
-        x = F.conv2d(x, conv.weight, None, conv.stride, conv.padding)
-        x = F.batch_norm(x, bn.running_mean, bn.running_var, bn.weight, bn.bias, False, 0.0, bn.eps)
-        return F.leaky_relu(x, 0.01)
+    def _conv_planes(w, row_scale=None, cin_pad=None):
+        """conv weight [Cout,Cin,3,3] -> planes [Cout, 9*Cin'] in (ky, kx, cin) order (Cin zero-padded to cin_pad)."""
+        w = w.detach().permute(0, 2, 3, 1)
+        if cin_pad is not None and cin_pad > w.shape[-1]:
+            w = torch.nn.functional.pad(w, (0, cin_pad - w.shape[-1]))
+        if row_scale is not None:
+            w = w * row_scale[:, None, None, None]
+        return ops.split_weight(w.reshape(w.shape[0], -1).contiguous())
 
     @staticmethod
-    def _norm_conv(m, x, relu):
-        x = F.conv2d(x, m.weight, m.bias, 1, m.padding)
-        if hasattr(m, "norm"):
-            x = F.group_norm(x, m.norm.num_groups, m.norm.weight, m.norm.bias, m.norm.eps)
-        return F.relu(x) if relu else x
+    def _bn_fold(block):
+        """Conv-BN(eval)-LeakyReLU block (camera_modules.py:36-48): y = conv(x) * s + (beta - mean * s)."""
+        bn = block[1]
+        s = bn.weight.detach() / torch.sqrt(bn.running_var + bn.eps)
+        return s, (bn.bias.detach() - bn.running_mean * s).contiguous()
 
-    def _pixel_decoder_features(self, feats):
+    def _prepare_pixel_tc(self, pk):
         pd = self.pixel_decoder
-        names = pd.in_features[::-1]               # res5, res4, res3
-        y = None
-        for idx, f in enumerate(names):
-            lvl = len(names) - idx
-            x = feats[f]
-            if idx == 0:
-                y = self._norm_conv(getattr(pd, f"layer_{lvl}"), x, True)
-            else:
-                cur = self._norm_conv(getattr(pd, f"adapter_{lvl}"), x, False)
-                y = cur + F.interpolate(y, size=cur.shape[-2:], mode="nearest")
-                y = self._norm_conv(getattr(pd, f"layer_{lvl}"), y, True)
-        return self._norm_conv(pd.mask_features, y, False)
+        for name in ("layer_1", "layer_2", "layer_3", "mask_features"):
+            pk[f"pd.{name}.w"] = self._conv_planes(getattr(pd, name).weight)
+        for name in ("adapter_1", "adapter_2"):
+            w = getattr(pd, name).weight.detach()
+            pk[f"pd.{name}.w"] = ops.split_weight(w.reshape(w.shape[0], w.shape[1]).contiguous())
+        for i in (0, 1, 3, 4, 6, 7):
+            s, b = self._bn_fold(self.convs_backbone[i])
+            pk[f"cb.{i}.w"], pk[f"cb.{i}.b"] = self._conv_planes(self.convs_backbone[i][0].weight, s), b
+        # first conv of both correlation branches shares its input: one GEMM with N = 256, Cin 300 -> 320
+        ws, bs = [], []
+        for convs in (self.convs_trans, self.convs_rots):
+            s, b = self._bn_fold(convs[0])
+            w = convs[0][0].weight.detach().permute(0, 2, 3, 1)
+            w = torch.nn.functional.pad(w, (0, 320 - w.shape[-1])) * s[:, None, None, None]
+            ws.append(w.reshape(w.shape[0], -1))
+            bs.append(b)
+        pk["ct0.w"], pk["ct0.b"] = ops.split_weight(torch.cat(ws, 0).contiguous()), torch.cat(bs).contiguous()
+        for name, convs, fc in (("trans", self.convs_trans, self.fc_trans), ("rots", self.convs_rots, self.fc_rots)):
+            for i in range(1, 6):
+                s, b = self._bn_fold(convs[i])
+                pk[f"convs_{name}.{i}.w"], pk[f"convs_{name}.{i}.b"] = self._conv_planes(convs[i][0].weight, s), b
+            # reference flattens [B,128,2,3] channel-major (c*6 + h*3 + w); NHWC rows flatten as (h*3 + w)*128 + c
+            w = fc.weight.detach()
+            pk[f"fc_{name}.w_nhwc"] = w.view(w.shape[0], 128, -1).permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()
 
+    # ------------------------------------------------------------------ K1: pixel pose network
     def _forward_pixel_camera_head(self, features1, features2):
-        """camera_head.py:642-670.  ROUND-1 STATUS: the convolutions of this stage still go through
-        cuDNN (library plumbing, TF32 off so results stay fp32); the split-bf16 tcgen05 implicit-GEMM
-        replacement is the next item in DESIGN.md.  Everything downstream is libnopesac_b200."""
-        prev = torch.backends.cudnn.allow_tf32
-        torch.backends.cudnn.allow_tf32 = False
-        try:
-            B = features1["res5"].shape[0]
-            both = {k: torch.cat([features1[k], features2[k]], 0) for k in self.pixel_decoder.in_features}
-            x = self._pixel_decoder_features(both)
-            for blk in self.convs_backbone:
-                x = F.max_pool2d(x, 2, 2) if isinstance(blk, nn.MaxPool2d) else self._conv_block(blk, x)
-            x1, x2 = x[:B], x[B:]
-            _, c, h, w = x1.shape
-            f2v = x2.transpose(2, 3).reshape(B, c, -1).transpose(1, 2)
-            corr = torch.matmul(f2v, x1.reshape(B, c, -1)).view(B, h * w, h, w)
-            aff = F.softmax(corr, dim=1)
-            feats = []
-            for convs, fc in ((self.convs_trans, self.fc_trans), (self.convs_rots, self.fc_rots)):
-                y = aff
-                for blk in convs:
-                    y = self._conv_block(blk, y)
-                feats.append(ops.linear(torch.flatten(y, 1), fc.weight, fc.bias, ops.ACT_RELU))
-        finally:
-            torch.backends.cudnn.allow_tf32 = prev
+        """camera_head.py:642-670 on the tensor-core engine: NHWC activations, every convolution an (implicit) GEMM
+        (nsac_conv3x3_split / nsac_gemm_split, fp16 hi/lo planes, 3 passes), BatchNorm folded into the weights,
+        GroupNorm / nearest-upsample-add / max-pool / correlation-softmax as small fused kernels.  Both views are
+        stacked along the batch dimension (N = 2B images)."""
+        pk = self.prepare_tc()
+        pd = self.pixel_decoder
+        if not hasattr(pd.layer_3, "norm"):
+            raise NotImplementedError("SEM_SEG_HEAD.NORM must be 'GN' (as in every reference config)")
+        P = self.tc_passes
+        B = features1["res5"].shape[0]
+        N = 2 * B
+        LEAKY = ops.ACT_LEAKY
+
+        def planes(name):
+            f1, f2 = features1[name], features2[name]
+            _, C, H, W = f1.shape
+            out = ops.Split(torch.empty(N * H * W, C, device=f1.device, dtype=torch.float16),
+                            torch.empty(N * H * W, C, device=f1.device, dtype=torch.float16), C)
+            ops.nchw_to_planes(f1.float(), out=out, row_offset=0)
+            ops.nchw_to_planes(f2.float(), out=out, row_offset=B * H * W)
+            return out, H, W
+
+        def gn(x, H, W, m, relu, skip=None, f32=True, split=False):
+            return ops.groupnorm_nhwc(x, N, H, W, m.norm.weight, m.norm.bias, m.norm.num_groups, m.norm.eps, relu, skip,
+                                      want_f32=f32, want_split=split)
+
+        # --- BasePixelDecoder.forward_features (camera_modules.py:335-348): res5 -> res4 -> res3, top-down
+        p5, H5, W5 = planes("res5")
+        t, _ = ops.conv3x3_tc(p5, N, H5, W5, pk["pd.layer_3.w"], passes=P)
+        y5, _ = gn(t, H5, W5, pd.layer_3, True)
+        p4, H4, W4 = planes("res4")
+        t, _ = ops.gemm_tc(p4, pk["pd.adapter_2.w"], passes=P)
+        _, u4 = gn(t, H4, W4, pd.adapter_2, False, skip=y5, f32=False, split=True)
+        t, _ = ops.conv3x3_tc(u4, N, H4, W4, pk["pd.layer_2.w"], passes=P)
+        y4, _ = gn(t, H4, W4, pd.layer_2, True)
+        p3, H3, W3 = planes("res3")
+        t, _ = ops.gemm_tc(p3, pk["pd.adapter_1.w"], passes=P)
+        _, u3 = gn(t, H3, W3, pd.adapter_1, False, skip=y4, f32=False, split=True)
+        t, _ = ops.conv3x3_tc(u3, N, H3, W3, pk["pd.layer_1.w"], passes=P)
+        _, y3 = gn(t, H3, W3, pd.layer_1, True, f32=False, split=True)
+        _, x = ops.conv3x3_tc(y3, N, H3, W3, pk["pd.mask_features.w"], pd.mask_features.bias, passes=P,
+                              want_f32=False, want_split=True)
+        # --- convs_backbone (camera_head.py:78-91): conv-BN-LeakyReLU x2, pool, x2, pool, x2
+        H, W = H3, W3
+        for i in (0, 3, 6):
+            _, x = ops.conv3x3_tc(x, N, H, W, pk[f"cb.{i}.w"], pk[f"cb.{i}.b"], LEAKY, P, want_f32=False, want_split=True)
+            f, _ = ops.conv3x3_tc(x, N, H, W, pk[f"cb.{i + 1}.w"], pk[f"cb.{i + 1}.b"], LEAKY, P)
+            if i < 6:
+                x = ops.maxpool2_planes(f, N, H, W)
+                H, W = H // 2, W // 2
+        # --- correlation volume + softmax (:652, :1117-1133), then the two regression branches (:655-662)
+        HW = H * W
+        aff = ops.corr_softmax(f[:B * HW], f[B * HW:], B, H, W)
+        t, _ = ops.conv3x3_tc(aff, B, H, W, pk["ct0.w"], pk["ct0.b"], LEAKY, P)          # [B*HW, 256] = trans | rots
+        feats = []
+        for name, off, fc in (("trans", 0, self.fc_trans), ("rots", 128, self.fc_rots)):
+            y, h, w = t[:, off:off + 128].contiguous(), H, W
+            for i in range(1, 6):
+                stride = 2 if i % 2 == 1 else 1
+                cols, h, w = ops.im2col3x3_planes(y, B, h, w, stride)
+                y, _ = ops.gemm_tc(cols, pk[f"convs_{name}.{i}.w"], pk[f"convs_{name}.{i}.b"], LEAKY, passes=P)
+            feats.append(ops.linear(y.view(B, -1), pk[f"fc_{name}.w_nhwc"], fc.bias, ops.ACT_RELU))
         trans_feat, rots_feat = feats
         rot, tran = ops.pose_heads(rots_feat, trans_feat, self.rots.weight, self.rots.bias,
                                    self.trans.weight, self.trans.bias)

@@ -96,6 +96,12 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -153,6 +159,8 @@ struct GemmParams {
   const float* bias;
   int bias_group_rows;
   int M, N, K, act, passes, fmt;
+  // implicit-GEMM 3x3 / stride 1 / pad 1 convolution over NHWC planes (conv_taps == 9), else plain GEMM
+  int conv_taps, H, W, BW, BH, cblocks, tiles_x, tiles_y;
   float out_scale;          // multiplies the accumulator before bias (undoes the power-of-two weight pre-scale)
   float* out_f32;
   int ldo;
@@ -192,7 +200,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (p.M + BLOCK_M - 1) / BLOCK_M, tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const bool conv = p.conv_taps == 9;
+  const int tiles_per_img = p.tiles_x * p.tiles_y;     // conv: an M tile is a BW x BH pixel patch of one image
+  const int tiles_m = conv ? (p.M / (p.H * p.W)) * tiles_per_img : (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BLOCK_K;
 
@@ -216,15 +227,33 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     // ===================================================================== TMA producer
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx = (p.passes >= 2 ? 2 * C::A_BYTES : C::A_BYTES) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
+      const uint32_t a_bytes = conv ? (uint32_t)(p.BW * p.BH * BLOCK_K * 2) : (uint32_t)C::A_BYTES;   // box bytes
+      const uint32_t tx = (p.passes >= 2 ? 2 * a_bytes : a_bytes) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        const int tm = tile % tiles_m;
+        const int m0 = tm * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        int img = 0, y0 = 0, x0 = 0;
+        if (conv) {
+          img = tm / tiles_per_img;
+          const int t2 = tm % tiles_per_img;
+          y0 = (t2 / p.tiles_x) * p.BH;
+          x0 = (t2 % p.tiles_x) * p.BW;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
           mbar_expect_tx(&full[stage], tx);
-          tma_load_2d(st, &map_a_hi, &full[stage], kb * BLOCK_K, m0);
-          if (p.passes >= 2) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
+          if (conv) {
+            // k-block = (filter tap, 64-channel block): the A tile is the input patch shifted by the tap; TMA
+            // zero-fills the out-of-image halo (padding = 1), so no im2col matrix ever exists
+            const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            tma_load_4d(st, &map_a_hi, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+            if (p.passes >= 2) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+          } else {
+            tma_load_2d(st, &map_a_hi, &full[stage], kb * BLOCK_K, m0);
+            if (p.passes >= 2) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
+          }
           tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, &full[stage], kb * BLOCK_K, n0);
           if (p.passes >= 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, &full[stage], kb * BLOCK_K, n0);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -300,8 +329,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
       // ---- bias, activation, stores
-      const int row = m0 + quad * 32 + lane;
-      const bool row_ok = row < p.M;
+      int row = m0 + quad * 32 + lane;
+      bool row_ok = row < p.M;
+      if (conv) {      // tile row r = pixel (y0 + r / BW, x0 + r % BW) of image tm / tiles_per_img
+        const int tm = tile % tiles_m, img = tm / tiles_per_img, t2 = tm % tiles_per_img;
+        const int r = quad * 32 + lane;
+        const int y = (t2 / p.tiles_x) * p.BH + r / p.BW, x = (t2 % p.tiles_x) * p.BW + r % p.BW;
+        row_ok = r < p.BW * p.BH && y < p.H && x < p.W;
+        row = (img * p.H + y) * p.W + x;
+      }
       const float* brow = nullptr;
       if (p.bias) brow = p.bias_group_rows > 0 ? p.bias + (size_t)((row_ok ? row : 0) / p.bias_group_rows) * p.N : p.bias;
 #pragma unroll
@@ -424,20 +460,70 @@ int sm_count() {
 
 template <int BLOCK_N>
 int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                const GemmParams& p, cudaStream_t s) {
+                const GemmParams& p, int tiles_m, cudaStream_t s) {
   using C = Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
     NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
-  const int tiles = nsac_cdiv(p.M, BLOCK_M) * nsac_cdiv(p.N, BLOCK_N);
+  const int tiles = tiles_m * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   gemm_bf16x3_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
   NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }
+
+// NHWC 16-bit planes [N,H,W,C] as a 4-D tensor (C, W, H, N); box = [64 ch, BW, BH, 1], 128-byte swizzle
+bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, bool is_bf16) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BW, (cuuint32_t)BH, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
+             strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace
+
+// 3x3 / stride 1 / pad 1 convolution as an implicit GEMM: x planes [N,H,W,Cin] (Cin % 64 == 0), weight planes
+// [Cout, 9*Cin] in (ky, kx, cin) order; output rows are NHWC pixels [N*H*W, Cout].
+extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                  int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
+                                  float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+  NSAC_REQUIRE(x_hi && w_hi, "nsac_conv3x3_split: null operand");
+  NSAC_REQUIRE(passes >= 1 && passes <= 4 && (passes < 2 || x_lo) && (passes < 3 || w_lo), "nsac_conv3x3_split: bad passes / planes");
+  NSAC_REQUIRE(N >= 0 && H >= 1 && W >= 1 && Cin >= 64 && Cin % 64 == 0 && Cout >= 8, "nsac_conv3x3_split: bad shape (Cin %% 64 == 0)");
+  NSAC_REQUIRE(out_f32 || out_hi, "nsac_conv3x3_split: no output requested");
+  NSAC_REQUIRE(!out_f32 || (ldo >= Cout && ldo % 4 == 0 && (reinterpret_cast<uintptr_t>(out_f32) & 15) == 0), "nsac_conv3x3_split: fp32 output alignment");
+  NSAC_REQUIRE(!out_hi || (out_lo && ld_split >= Cout && ld_split % 8 == 0), "nsac_conv3x3_split: split output layout");
+  NSAC_REQUIRE(fmt == NSAC_SPLIT_F16 || fmt == NSAC_SPLIT_BF16, "nsac_conv3x3_split: bad plane format");
+  if (N == 0) return NSAC_OK;
+  // pixel patch of one M tile: BW x BH <= 128 rows
+  int BW, BH;
+  if (W <= 128) { BW = W; BH = 128 / W; if (BH > H) BH = H; }
+  else { BW = 128; BH = 1; }
+  if (W % 16 == 0 && W > 64) { BW = 16; BH = 8; }          // e.g. 80-wide maps: 16 x 8 patches fill all 128 rows
+  NSAC_REQUIRE(BW <= 256 && BH <= 256 && BW * BH <= 128, "nsac_conv3x3_split: cannot tile a %d x %d map", H, W);
+  const bool bf = fmt == NSAC_SPLIT_BF16;
+  const int K = 9 * Cin;
+  CUtensorMap mah, mal, mwh, mwl;
+  const bool ok = make_map_nhwc(&mah, x_hi, N, H, W, Cin, BW, BH, bf) && make_map_nhwc(&mal, x_lo ? x_lo : x_hi, N, H, W, Cin, BW, BH, bf) &&
+                  make_map(&mwh, w_hi, Cout, K, K, 128, bf) && make_map(&mwl, w_lo ? w_lo : w_hi, Cout, K, K, 128, bf);
+  if (!ok) {
+    nsac_set_error("nsac_conv3x3_split: cuTensorMapEncodeTiled failed (N=%d H=%d W=%d Cin=%d Cout=%d)", N, H, W, Cin, Cout);
+    return NSAC_ERR_LAUNCH;
+  }
+  GemmParams p;
+  p.bias = bias; p.bias_group_rows = 0; p.M = N * H * W; p.N = Cout; p.K = K; p.act = act; p.passes = passes;
+  p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
+  p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
+  p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64;
+  p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
+  return launch_gemm<128>(mah, mal, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+}
 
 extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
                                int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
@@ -473,8 +559,9 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
   p.fmt = fmt; p.out_scale = out_scale;
   p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
+  p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return launch_gemm<128>(mah, mal, mwh, mwl, p, s);
+  return launch_gemm<128>(mah, mal, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
 }
 
 extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,

@@ -164,6 +164,102 @@ def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = 
     return out_f32, out_split
 
 
+# ---------------------------------------------------------------------------------------------------
+# pixel pose network pieces (NHWC activations: [N*H*W, C] rows)
+# ---------------------------------------------------------------------------------------------------
+def _empty_split(rows, cols, device, fmt=SPLIT_F16):
+    return Split(torch.empty(rows, cols, device=device, dtype=_SPLIT_DTYPE[fmt]),
+                 torch.empty(rows, cols, device=device, dtype=_SPLIT_DTYPE[fmt]), cols, fmt)
+
+
+def nchw_to_planes(x: torch.Tensor, fmt: int = SPLIT_F16, out: Optional[Split] = None, row_offset: int = 0) -> Split:
+    """[N,C,H,W] fp32 -> NHWC planes [N*H*W, C] (optionally into rows [row_offset, row_offset + N*H*W) of `out`)."""
+    x = _c(x, "x")
+    N, Cc, H, W = x.shape
+    if out is None:
+        out = _empty_split(N * H * W, Cc, x.device, fmt)
+    assert out.hi.is_contiguous() and out.hi.shape[1] == Cc and out.rows >= row_offset + N * H * W
+    dst = Split(out.hi[row_offset:], out.lo[row_offset:], Cc, fmt)
+    st = _lib.lib().nsac_nchw_to_planes(_p(x), N, Cc, H * W, fmt, _p(dst.hi), _p(dst.lo), _stream())
+    _lib.check(st, "nsac_nchw_to_planes")
+    _count()
+    return out
+
+
+def conv3x3_tc(x: Split, N: int, H: int, W: int, w: Split, bias=None, act: int = ACT_NONE, passes: int = 3,
+               want_f32: bool = True, want_split: bool = False):
+    """3x3 / stride 1 / pad 1 convolution (implicit GEMM, 4-D TMA gather).  x: NHWC planes [N*H*W, Cin] (contiguous),
+    w: planes [Cout, 9*Cin] in (ky, kx, cin) order.  -> (fp32 [N*H*W, Cout] or None, Split or None)."""
+    Cin, Cout = x.hi.shape[1], w.rows
+    assert x.hi.is_contiguous() and x.lo.is_contiguous() and x.rows == N * H * W and Cin % 64 == 0
+    assert w.hi.is_contiguous() and w.hi.shape[1] == 9 * Cin and x.fmt == w.fmt
+    dev = x.hi.device
+    out_f32 = torch.empty(N * H * W, Cout, device=dev, dtype=torch.float32) if want_f32 else None
+    out_split = Split.empty(N * H * W, Cout, dev, x.fmt) if want_split else None
+    if bias is not None:
+        _chk(bias, "bias")
+    st = _lib.lib().nsac_conv3x3_split(_p(x.hi), _p(x.lo), _p(w.hi), _p(w.lo), _p(bias), N, H, W, Cin, Cout, act, passes,
+                                       x.fmt, 1.0 / (x.scale * w.scale), _p(out_f32), Cout if want_f32 else 0,
+                                       None if out_split is None else _p(out_split.hi),
+                                       None if out_split is None else _p(out_split.lo),
+                                       0 if out_split is None else out_split.hi.stride(0), _stream())
+    _lib.check(st, "nsac_conv3x3_split")
+    _count()
+    return out_f32, out_split
+
+
+def groupnorm_nhwc(x: torch.Tensor, N: int, H: int, W: int, gamma, beta, groups: int = 32, eps: float = 1e-5,
+                   relu: bool = False, skip: Optional[torch.Tensor] = None, want_f32: bool = True, want_split: bool = False,
+                   fmt: int = SPLIT_F16):
+    """GroupNorm over NHWC rows [N*H*W, C] (+ReLU) (+ nearest-2x-upsampled `skip` [N*(H/2)*(W/2), C])."""
+    x = _c(x, "x")
+    Cc = x.shape[1]
+    out_f32 = torch.empty_like(x) if want_f32 else None
+    out_split = _empty_split(x.shape[0], Cc, x.device, fmt) if want_split else None
+    st = _lib.lib().nsac_groupnorm_nhwc(_p(x), N, H, W, Cc, groups, _p(gamma), _p(beta), eps, int(relu), _p(skip), fmt,
+                                        _p(out_f32), None if out_split is None else _p(out_split.hi),
+                                        None if out_split is None else _p(out_split.lo), _stream())
+    _lib.check(st, "nsac_groupnorm_nhwc")
+    _count()
+    return out_f32, out_split
+
+
+def maxpool2_planes(x: torch.Tensor, N: int, H: int, W: int, fmt: int = SPLIT_F16) -> Split:
+    x = _c(x, "x")
+    Cc = x.shape[1]
+    out = _empty_split(N * (H // 2) * (W // 2), Cc, x.device, fmt)
+    st = _lib.lib().nsac_maxpool2_planes(_p(x), N, H, W, Cc, fmt, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_maxpool2_planes")
+    _count()
+    return out
+
+
+def corr_softmax(f1: torch.Tensor, f2: torch.Tensor, B: int, H: int, W: int, fmt: int = SPLIT_F16) -> Split:
+    """compute_corr_softmax on NHWC features [B*H*W, C] -> planes [B*H*W, Cp] (Cp = H*W rounded up to 64)."""
+    f1, f2 = _c(f1, "f1"), _c(f2, "f2")
+    Cp = (H * W + 63) // 64 * 64
+    out = _empty_split(B * H * W, Cp, f1.device, fmt)
+    out.K = Cp
+    st = _lib.lib().nsac_corr_softmax(_p(f1), _p(f2), B, H, W, f1.shape[1], Cp, fmt, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_corr_softmax")
+    _count()
+    return out
+
+
+def im2col3x3_planes(x: torch.Tensor, N: int, H: int, W: int, stride: int, fmt: int = SPLIT_F16):
+    """Explicit 3x3 / pad 1 im2col of an fp32 NHWC map -> (planes [N*Ho*Wo, Kp], Ho, Wo)."""
+    x = _c(x, "x")
+    Cc = x.shape[1]
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    Kp = (9 * Cc + 63) // 64 * 64
+    out = _empty_split(N * Ho * Wo, Kp, x.device, fmt)
+    out.K = 9 * Cc
+    st = _lib.lib().nsac_im2col3x3_planes(_p(x), N, H, W, Cc, stride, Kp, fmt, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_im2col3x3_planes")
+    _count()
+    return out, Ho, Wo
+
+
 def layernorm(x, gamma, beta, res=None, out=None):
     _chk(x, "x")
     rows, Cdim = x.shape
