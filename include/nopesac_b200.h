@@ -106,15 +106,17 @@ int nsac_corr_softmax(const float* f1, const float* f2, int B, int H, int W, int
 int nsac_im2col3x3_planes(const float* x, int N, int H, int W, int C, int stride, int Kp, int fmt, void* hi,
                           void* lo, void* stream);
 
-/* LayerNorm over the last dim C (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x).
- * gnn.py:90,94-96. */
+/* LayerNorm over the last dim C (eps 1e-5) with optional residual: out = (res ? res : 0) + LN(x); optionally also
+ * as fp16 hi/lo operand planes (out_hi/out_lo, row stride ld_split) for the tensor-core engine.  gnn.py:90,94-96. */
 int nsac_layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res,
-                   int ldres, float* out, int ldo, int rows, int C, void* stream);
+                   int ldres, float* out, int ldo, void* out_hi, void* out_lo, int ld_split, int rows, int C,
+                   void* stream);
 
 /* Multi-head full attention (gnn.py:19-44): q [B,L,H*D], k,v [B,S,H*D] with row strides ldq/ldkv,
- * out [B,L,H*D]; softmax(QK^T / sqrt(D)) V, no masks (inference). D must be 32. */
+ * out [B,L,H*D] fp32 and / or fp16 hi/lo planes; softmax(QK^T / sqrt(D)) V, no masks (inference). D must be 32. */
 int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out,
-                   int ldo, int B, int L, int S, int H, int D, void* stream);
+                   int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S, int H, int D,
+                   void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Matching tail (matching_head.py:75-99, 113-128, 228-234, 259-306 + camera_modules.py:15-34):

@@ -38,9 +38,10 @@ _SIGNATURES = {
     "nsac_im2col3x3_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                         C.c_void_p, C.c_void_p]),
     "nsac_layernorm": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_int, c_float_p,
-                                 C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                 C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
-                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+                                 C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                 C.c_void_p]),
     "nsac_match_sinkhorn_assign": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                              C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),

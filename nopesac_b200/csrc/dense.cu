@@ -6,6 +6,7 @@
 // The split-bf16 tcgen05 engine (gemm_tc.cu) takes over the large contractions; this file stays the
 // exact-fp32 path for small / odd shapes (K = 3, 4, 8, N = 3, 4) and the bring-up reference.
 #include <stdarg.h>
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -175,9 +176,16 @@ extern "C" int nsac_linear(const float* x, int ldx, const float* w, const float*
 // LayerNorm (+ residual), one warp per row
 // ------------------------------------------------------------------------------------------------
 namespace {
+__device__ __forceinline__ void split_f16(float x, uint16_t& hi, uint16_t& lo) {
+  const __half h = __float2half_rn(x);
+  hi = __half_as_ushort(h);
+  lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+}
+
 __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ gamma,
                                  const float* __restrict__ beta, const float* res, int ldres,
-                                 float* out, int ldo, int rows, int C) {  // res may alias out (in-place residual)
+                                 float* out, int ldo, uint16_t* out_hi, uint16_t* out_lo, int ld_split, int rows,
+                                 int C) {  // res may alias out (in-place residual)
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -195,19 +203,25 @@ __global__ void layernorm_kernel(const float* __restrict__ x, int ldx, const flo
     float y = (xr[c] - mean) * rstd * gamma[c] + beta[c];
     if (res) y += res[(size_t)row * ldres + c];
     out[(size_t)row * ldo + c] = y;
+    if (out_hi) {       // fp16 hi/lo operand planes for the tensor-core engine
+      uint16_t h, l;
+      split_f16(y, h, l);
+      out_hi[(size_t)row * ld_split + c] = h;
+      out_lo[(size_t)row * ld_split + c] = l;
+    }
   }
 }
 }  // namespace
 
 extern "C" int nsac_layernorm(const float* x, int ldx, const float* gamma, const float* beta,
-                              const float* res, int ldres, float* out, int ldo, int rows, int C,
-                              void* stream) {
+                              const float* res, int ldres, float* out, int ldo, void* out_hi, void* out_lo,
+                              int ld_split, int rows, int C, void* stream) {
   NSAC_REQUIRE(x && gamma && beta && out, "nsac_layernorm: null pointer");
   NSAC_REQUIRE(rows >= 0 && C > 0 && ldx >= C && ldo >= C, "nsac_layernorm: bad shape");
   if (rows == 0) return NSAC_OK;
   const int wpb = 8;
   layernorm_kernel<<<nsac_cdiv(rows, wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-      x, ldx, gamma, beta, res, ldres, out, ldo, rows, C);
+      x, ldx, gamma, beta, res, ldres, out, ldo, static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo), ld_split, rows, C);
   NSAC_CHECK_LAUNCH("nsac_layernorm");
   return NSAC_OK;
 }
@@ -219,6 +233,7 @@ extern "C" int nsac_layernorm(const float* x, int ldx, const float* gamma, const
 namespace {
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                  const float* __restrict__ v, int ldkv, float* __restrict__ out, int ldo,
+                                 uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int ld_split,
                                  int L, int S, int H) {
   extern __shared__ float sm[];  // per warp: K [S][33], V [S][33], p [S]
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -260,15 +275,23 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
     __syncwarp();
     float acc = 0.f;
     for (int s = 0; s < S; ++s) acc = fmaf(ps[s], Vs[s * 33 + lane], acc);
-    out[((size_t)b * L + l) * ldo + h * 32 + lane] = acc / sum;
+    const float o = acc / sum;
+    if (out) out[((size_t)b * L + l) * ldo + h * 32 + lane] = o;
+    if (out_hi) {
+      uint16_t hh, ll;
+      split_f16(o, hh, ll);
+      out_hi[((size_t)b * L + l) * ld_split + h * 32 + lane] = hh;
+      out_lo[((size_t)b * L + l) * ld_split + h * 32 + lane] = ll;
+    }
     __syncwarp();
   }
 }
 }  // namespace
 
 extern "C" int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv,
-                              float* out, int ldo, int B, int L, int S, int H, int D, void* stream) {
-  NSAC_REQUIRE(q && k && v && out, "nsac_attention: null pointer");
+                              float* out, int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S,
+                              int H, int D, void* stream) {
+  NSAC_REQUIRE(q && k && v && (out || (out_hi && out_lo)), "nsac_attention: null pointer");
   NSAC_REQUIRE(D == 32, "nsac_attention: head dim must be 32 (got %d)", D);
   NSAC_REQUIRE(H >= 1 && H <= 32 && L >= 0 && S >= 1, "nsac_attention: bad shape");
   if (B == 0 || L == 0) return NSAC_OK;
@@ -276,7 +299,8 @@ extern "C" int nsac_attention(const float* q, int ldq, const float* k, const flo
   NSAC_REQUIRE(smem <= 200 * 1024, "nsac_attention: S=%d too large for the shared-memory staging", S);
   if (smem > 48 * 1024)
     NSAC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_kernel<<<B, H * 32, smem, static_cast<cudaStream_t>(stream)>>>(q, ldq, k, v, ldkv, out, ldo, L, S, H);
+  attention_kernel<<<B, H * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+      q, ldq, k, v, ldkv, out, ldo, static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo), ld_split, L, S, H);
   NSAC_CHECK_LAUNCH("nsac_attention");
   return NSAC_OK;
 }

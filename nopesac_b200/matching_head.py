@@ -69,6 +69,7 @@ class MatchingHead(nn.Module):
         self.planeApp_proj = nn.Conv1d(256, 256, kernel_size=1, bias=True)
         self.match_threshold = cfg.TEST.MATCHING_SCORE_THRESHOLD
         self._packed = None
+        self.tc_passes = 3     # MMA passes of the tensor-core layers (fp16 hi/lo planes, ~fp32)
 
     # ------------------------------------------------------------------ weight packing
     def _load_from_state_dict(self, *a, **k):
@@ -106,42 +107,56 @@ class MatchingHead(nn.Module):
         return self._packed
 
     # ------------------------------------------------------------------ GNN (gnn.py:73-138)
+    def prepare_tc(self):
+        """fp16 hi/lo planes of every GNN / projection weight for the tensor-core engine."""
+        pk = self.prepare()
+        if "tc" not in pk:
+            with torch.no_grad():
+                pk["tc"] = [{k: ops.split_weight(w[k]) for k in ("qkv", "q", "kv", "merge", "mlp0", "mlp2")} for w in pk["layers"]]
+                pk["app_ws"], pk["desc_ws"] = ops.split_weight(pk["app_w"]), ops.split_weight(pk["desc_w"])
+        return pk
+
     @staticmethod
-    def _layer(w, X, xs, ss, B, L, S, self_attn: bool):
-        """X [rows,512]: columns 0:256 hold the token features, 256:512 the message slot.  xs / ss are
-        row slices (start, stop) of the query stream and of the source stream."""
-        x = X[xs[0]:xs[1]]
+    def _layer(w, ws, X, Xp, xs, ss, B, L, S, self_attn: bool, P: int):
+        """X [rows,512] fp32 and Xp (its fp16 hi/lo planes): columns 0:256 hold the token features, 256:512 the
+        message slot, so cat[x, message] (gnn.py:93) is free.  xs / ss = row ranges of the query / source stream.
+        All six linears run on the tcgen05 engine; attention and LayerNorm emit the operand planes directly."""
+        x, xp = X[xs[0]:xs[1]], Xp.rows_view(xs[0], xs[1])
         if self_attn:
-            qkv = ops.linear(x[:, :256], w["qkv"])
+            qkv, _ = ops.gemm_tc(xp.cols(0, 256), ws["qkv"], passes=P)
             q, k, v = qkv[:, :256], qkv[:, 256:512], qkv[:, 512:]
         else:
-            q = ops.linear(x[:, :256], w["q"])
-            kv = ops.linear(X[ss[0]:ss[1], :256], w["kv"])
+            q, _ = ops.gemm_tc(xp.cols(0, 256), ws["q"], passes=P)
+            kv, _ = ops.gemm_tc(Xp.rows_view(ss[0], ss[1]).cols(0, 256), ws["kv"], passes=P)
             k, v = kv[:, :256], kv[:, 256:]
-        msg = ops.attention(q, k, v, B, L, S)
-        msg = ops.linear(msg, w["merge"])
-        ops.layernorm(msg, w["n1w"], w["n1b"], out=x[:, 256:])          # message slot of cat[x, message]
-        h = ops.linear(x, w["mlp0"], act=ops.ACT_RELU)
-        msg = ops.linear(h, w["mlp2"])
-        ops.layernorm(msg, w["n2w"], w["n2b"], res=x[:, :256], out=x[:, :256])   # x + norm2(mlp(...))
+        msgp = ops.Split.empty(x.shape[0], 256, x.device)
+        ops.attention(q, k, v, B, L, S, out_split=msgp, want_f32=False)
+        msg, _ = ops.gemm_tc(msgp, ws["merge"], passes=P)
+        ops.layernorm(msg, w["n1w"], w["n1b"], out=x[:, 256:], out_split=xp.cols(256, 512))     # message slot
+        _, hp = ops.gemm_tc(xp, ws["mlp0"], act=ops.ACT_RELU, passes=P, want_f32=False, want_split=True)
+        msg, _ = ops.gemm_tc(hp, ws["mlp2"], passes=P)
+        ops.layernorm(msg, w["n2w"], w["n2b"], res=x[:, :256], out=x[:, :256], out_split=xp.cols(0, 256))  # x + norm2(.)
 
     def _descriptors(self, planeApp1, planeApp2):
-        pk = self.prepare()
+        pk = self.prepare_tc()
+        P = self.tc_passes
         B, n1, _ = planeApp1.shape
         n2 = planeApp2.shape[1]
         R0, R1 = B * n1, B * n2
-        X = torch.empty(R0 + R1, 512, device=planeApp1.device, dtype=torch.float32)
-        ops.linear(planeApp1.reshape(R0, 256), pk["app_w"], pk["app_b"], out=X[:R0, :256])
-        ops.linear(planeApp2.reshape(R1, 256), pk["app_w"], pk["app_b"], out=X[R0:, :256])
+        dev = planeApp1.device
+        X = torch.empty(R0 + R1, 512, device=dev, dtype=torch.float32)
+        Xp = ops.Split.empty(R0 + R1, 512, dev)
+        app = ops.split(torch.cat([planeApp1.reshape(R0, 256), planeApp2.reshape(R1, 256)], 0))
+        ops.gemm_tc(app, pk["app_ws"], pk["app_b"], passes=P, out_f32=X[:, :256], want_split=True, out_split=Xp.cols(0, 256))
         s0, s1 = (0, R0), (R0, R0 + R1)
-        for w, name in zip(pk["layers"], self.gnn.layer_names):
+        for w, ws, name in zip(pk["layers"], pk["tc"], self.gnn.layer_names):
             if name == "self":
-                self._layer(w, X, s0, s0, B, n1, n1, True)
-                self._layer(w, X, s1, s1, B, n2, n2, True)
+                self._layer(w, ws, X, Xp, s0, s0, B, n1, n1, True, P)
+                self._layer(w, ws, X, Xp, s1, s1, B, n2, n2, True, P)
             else:
-                self._layer(w, X, s0, s1, B, n1, n2, False)
-                self._layer(w, X, s1, s0, B, n2, n1, False)     # sees the UPDATED feat0 (gnn.py:133-134)
-        desc = ops.linear(X[:, :256], pk["desc_w"], pk["desc_b"])
+                self._layer(w, ws, X, Xp, s0, s1, B, n1, n2, False, P)
+                self._layer(w, ws, X, Xp, s1, s0, B, n2, n1, False, P)     # sees the UPDATED feat0 (gnn.py:133-134)
+        desc, _ = ops.gemm_tc(Xp.cols(0, 256), pk["desc_ws"], pk["desc_b"], passes=P)
         return desc[:R0].view(B, n1, 256), desc[R0:].view(B, n2, 256)
 
     # ------------------------------------------------------------------ public

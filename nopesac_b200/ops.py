@@ -91,6 +91,9 @@ class Split:
     def rows(self):
         return self.hi.shape[0]
 
+    def rows_view(self, a: int, b: int) -> "Split":
+        return Split(self.hi[a:b], self.lo[a:b], self.K, self.fmt, self.scale)
+
     def cols(self, a: int, b: int) -> "Split":
         """Column slice view [rows, a:b] (keeps the parent's row stride)."""
         return Split(self.hi[:, a:b], self.lo[:, a:b], b - a, self.fmt, self.scale)
@@ -260,29 +263,35 @@ def im2col3x3_planes(x: torch.Tensor, N: int, H: int, W: int, stride: int, fmt: 
     return out, Ho, Wo
 
 
-def layernorm(x, gamma, beta, res=None, out=None):
+def layernorm(x, gamma, beta, res=None, out=None, out_split: Optional[Split] = None):
+    """out = (res or 0) + LayerNorm(x); optionally also written as fp16 hi/lo planes (`out_split` view)."""
     _chk(x, "x")
     rows, Cdim = x.shape
     if out is None:
         out = torch.empty(rows, Cdim, device=x.device, dtype=torch.float32)
     st = _lib.lib().nsac_layernorm(_p(x), x.stride(0), _p(gamma), _p(beta), _p(res),
-                                   0 if res is None else res.stride(0), _p(out), out.stride(0), rows, Cdim, _stream())
+                                   0 if res is None else res.stride(0), _p(out), out.stride(0),
+                                   None if out_split is None else _p(out_split.hi),
+                                   None if out_split is None else _p(out_split.lo),
+                                   0 if out_split is None else out_split.hi.stride(0), rows, Cdim, _stream())
     _lib.check(st, "nsac_layernorm")
     _count()
     return out
 
 
-def attention(q, k, v, B, L, S, H=8, D=32, out=None):
-    """q [B*L, H*D] (row stride ldq), k/v [B*S, H*D] (same row stride) -> [B*L, H*D]."""
+def attention(q, k, v, B, L, S, H=8, D=32, out=None, out_split: Optional[Split] = None, want_f32: bool = True):
+    """q [B*L, H*D] (row stride ldq), k/v [B*S, H*D] (same row stride) -> [B*L, H*D] fp32 and / or planes."""
     _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
     assert k.stride(0) == v.stride(0)
-    if out is None:
+    if out is None and want_f32:
         out = torch.empty(B * L, H * D, device=q.device, dtype=torch.float32)
-    st = _lib.lib().nsac_attention(_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), out.stride(0),
-                                   B, L, S, H, D, _stream())
+    st = _lib.lib().nsac_attention(_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), 0 if out is None else out.stride(0),
+                                   None if out_split is None else _p(out_split.hi),
+                                   None if out_split is None else _p(out_split.lo),
+                                   0 if out_split is None else out_split.hi.stride(0), B, L, S, H, D, _stream())
     _lib.check(st, "nsac_attention")
     _count()
-    return out
+    return out if out is not None else out_split
 
 
 def match_sinkhorn_assign(desc1, desc2, planes1, planes2, cam, bin_score, offset_mult=4.0, normal_mult=8.0,
