@@ -638,12 +638,15 @@ struct Row0Params {
   float4* cjg;             // out: [B][NQp][3] column constants for the tile kernel
 };
 
-__global__ void __launch_bounds__(256)
+constexpr int ROW0_THREADS = 512;     // 2 K-halves x 2 branches x 128 output units
+
+__global__ void __launch_bounds__(ROW0_THREADS)
 score_row0_kernel(const Row0Params p) {
   extern __shared__ float sm[];
-  float* x0 = sm;                                  // [2][NQ][8]
-  float* h1 = x0 + 2 * p.NQ * ROW0_PAIRS;          // [2][128][8]
-  float* red = h1 + 2 * HID * ROW0_PAIRS;          // [2][4 warps][8]
+  float* x0 = sm;                                  // [2][NQ][4]
+  float* h1 = x0 + 2 * p.NQ * ROW0_PAIRS;          // [2][128][4]
+  float* part = h1 + 2 * HID * ROW0_PAIRS;         // [2 halves][2][128][4] partial pre-activations
+  float* red = part + 2 * 2 * HID * ROW0_PAIRS;    // [2][4 warps][4]
   __shared__ int s_maxm;
   const int b0 = blockIdx.x * ROW0_PAIRS, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, H1n = p.NQ + 1;
   if (tid == 0) {
@@ -664,10 +667,10 @@ score_row0_kernel(const Row0Params p) {
   }
   __syncthreads();
   const int maxm = s_maxm;
-  if (warp < ROW0_PAIRS) {   // residual row of hypothesis 0: warp w <-> pair b0 + w
-    const int b = b0 + warp;
+  {   // residual row of hypothesis 0: 4 warps per pair
+    const int b = b0 + (warp >> 2), sub = warp & 3;
     if (b < p.B) {
-      const int m = p.matched_num[b];
+      const int m = p.matched_num[b], pi = warp >> 2;
       const float* q = p.q0 + (size_t)b * 4;
       const float* t = p.t0 + (size_t)b * 3;
       const Mat3 Mr = quat_to_rot(q[0], q[1], q[2], q[3]);
@@ -676,56 +679,33 @@ score_row0_kernel(const Row0Params p) {
       for (int i = 0; i < 9; ++i) R[i] = Mr.m[i];
       const float* gl = p.geo_local + (size_t)b * p.NQ * 6;
       float sr = 0.f, st = 0.f;
-      for (int j = lane; j < m; j += 32) {
+      for (int j = sub * 32 + lane; j < m; j += 128) {
         float4 c0, c1, c2;
         column_constants(gl + (size_t)j * 6, true, c0, c1, c2);
         float xr, xt;
         residual_pair<true>(R, t[0], t[1], t[2], c0, c1, c2, xr, xt, sr, st);
-        x0[(0 * p.NQ + j) * ROW0_PAIRS + warp] = xr;
-        x0[(1 * p.NQ + j) * ROW0_PAIRS + warp] = xt;
+        x0[(0 * p.NQ + j) * ROW0_PAIRS + pi] = xr;
+        x0[(1 * p.NQ + j) * ROW0_PAIRS + pi] = xt;
       }
       sr = warp_sum(sr); st = warp_sum(st);
-      if (lane == 0) {
-        p.sums[(size_t)b * H1n] = sr;
-        p.sums[(size_t)p.B * H1n + (size_t)b * H1n] = st;
-      }
+      if (lane == 0) { part[warp * 2] = sr; part[warp * 2 + 1] = st; }
     }
   }
   __syncthreads();
-  const int br = tid >> 7, t = tid & 127;
+  if (tid < ROW0_PAIRS && b0 + tid < p.B) {      // masked distance sums of row 0 (fixed order over the 4 sub-warps)
+    float a = 0.f, c = 0.f;
+    for (int s4 = 0; s4 < 4; ++s4) { a += part[(tid * 4 + s4) * 2]; c += part[(tid * 4 + s4) * 2 + 1]; }
+    p.sums[(size_t)(b0 + tid) * H1n] = a;
+    p.sums[(size_t)p.B * H1n + (size_t)(b0 + tid) * H1n] = c;
+  }
+  __syncthreads();
+  const int half = tid >> 8, br = (tid >> 7) & 1, t = tid & 127;
   float acc[ROW0_PAIRS];
-  {   // layer 1
-    const float* w = p.w1t + (size_t)br * p.NQ * HID + t;
-    const float* x = x0 + (size_t)br * p.NQ * ROW0_PAIRS;
+  auto gemv = [&](const float* w, const float* x, int k0, int k1) {     // acc[i] += sum_k w[k][t] * x[k][i]
 #pragma unroll
     for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
-    int j = 0;
-    for (; j + 8 <= maxm; j += 8) {
-      float wv[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(j + u) * HID);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float4 xa = *reinterpret_cast<const float4*>(x + (j + u) * ROW0_PAIRS);
-        acc[0] = fmaf(wv[u], xa.x, acc[0]); acc[1] = fmaf(wv[u], xa.y, acc[1]); acc[2] = fmaf(wv[u], xa.z, acc[2]); acc[3] = fmaf(wv[u], xa.w, acc[3]);
-      }
-    }
-    for (; j < maxm; ++j) {
-      const float wv = __ldg(w + (size_t)j * HID);
-      const float4 xa = *reinterpret_cast<const float4*>(x + j * ROW0_PAIRS);
-      acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
-    }
-    const float bias = p.vecs[br * HID + t];
-#pragma unroll
-    for (int i = 0; i < ROW0_PAIRS; ++i) h1[((size_t)br * HID + t) * ROW0_PAIRS + i] = fmaxf(acc[i] + bias, 0.f);
-  }
-  __syncthreads();
-  {   // layer 2 + folded layer 3 / regressor
-    const float* w = p.w2t + (size_t)br * HID * HID + t;
-    const float* x = h1 + (size_t)br * HID * ROW0_PAIRS;
-#pragma unroll
-    for (int i = 0; i < ROW0_PAIRS; ++i) acc[i] = 0.f;
-    for (int k = 0; k < HID; k += 8) {
+    int k = k0;
+    for (; k + 8 <= k1; k += 8) {
       float wv[8];
 #pragma unroll
       for (int u = 0; u < 8; ++u) wv[u] = __ldg(w + (size_t)(k + u) * HID);
@@ -735,10 +715,40 @@ score_row0_kernel(const Row0Params p) {
         acc[0] = fmaf(wv[u], xa.x, acc[0]); acc[1] = fmaf(wv[u], xa.y, acc[1]); acc[2] = fmaf(wv[u], xa.z, acc[2]); acc[3] = fmaf(wv[u], xa.w, acc[3]);
       }
     }
+    for (; k < k1; ++k) {
+      const float wv = __ldg(w + (size_t)k * HID);
+      const float4 xa = *reinterpret_cast<const float4*>(x + k * ROW0_PAIRS);
+      acc[0] = fmaf(wv, xa.x, acc[0]); acc[1] = fmaf(wv, xa.y, acc[1]); acc[2] = fmaf(wv, xa.z, acc[2]); acc[3] = fmaf(wv, xa.w, acc[3]);
+    }
+  };
+  {   // layer 1: the two halves of the K range run on different thread groups
+    const int kmid = ((maxm + 1) / 2 + 7) / 8 * 8;
+    const int k0 = half == 0 ? 0 : min(kmid, maxm), k1 = half == 0 ? min(kmid, maxm) : maxm;
+    gemv(p.w1t + (size_t)br * p.NQ * HID + t, x0 + (size_t)br * p.NQ * ROW0_PAIRS, k0, k1);
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) part[((half * 2 + br) * HID + t) * ROW0_PAIRS + i] = acc[i];
+  }
+  __syncthreads();
+  if (half == 0) {
+    const float bias = p.vecs[br * HID + t];
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i)
+      h1[((size_t)br * HID + t) * ROW0_PAIRS + i] =
+          fmaxf(part[((0 * 2 + br) * HID + t) * ROW0_PAIRS + i] + part[((1 * 2 + br) * HID + t) * ROW0_PAIRS + i] + bias, 0.f);
+  }
+  __syncthreads();
+  {   // layer 2 (K = 128 split in halves) + folded layer 3 / regressor
+    gemv(p.w2t + (size_t)br * HID * HID + t, h1 + (size_t)br * HID * ROW0_PAIRS, half * (HID / 2), (half + 1) * (HID / 2));
+#pragma unroll
+    for (int i = 0; i < ROW0_PAIRS; ++i) part[((half * 2 + br) * HID + t) * ROW0_PAIRS + i] = acc[i];
+  }
+  __syncthreads();
+  if (half == 0) {
     const float bias = p.vecs[2 * HID + br * HID + t], w34 = p.vecs[4 * HID + br * HID + t];
 #pragma unroll
     for (int i = 0; i < ROW0_PAIRS; ++i) {
-      const float v = warp_sum(fmaxf(acc[i] + bias, 0.f) * w34);
+      const float pre = part[((0 * 2 + br) * HID + t) * ROW0_PAIRS + i] + part[((1 * 2 + br) * HID + t) * ROW0_PAIRS + i] + bias;
+      const float v = warp_sum(fmaxf(pre, 0.f) * w34);
       if (lane == 0) red[(br * 4 + (warp & 3)) * ROW0_PAIRS + i] = v;
     }
   }
@@ -1012,11 +1022,11 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   rp.w1t = reinterpret_cast<const float*>(pk + pack_off_w1t(NQp));
   rp.w2t = reinterpret_cast<const float*>(pk + pack_off_w2t(NQ, NQp));
   rp.vecs = vecs; rp.B = B; rp.NQ = NQ; rp.NQp = NQp; rp.logits = logits; rp.sums = sums; rp.cjg = cjg;
-  const size_t row0_smem = sizeof(float) * ((size_t)2 * NQ * ROW0_PAIRS + 2 * HID * ROW0_PAIRS + 2 * 4 * ROW0_PAIRS);
+  const size_t row0_smem = sizeof(float) * ((size_t)2 * NQ * ROW0_PAIRS + 2 * HID * ROW0_PAIRS + 4 * HID * ROW0_PAIRS + 2 * 4 * ROW0_PAIRS);
   NSAC_REQUIRE(row0_smem <= 200 * 1024, "nsac_score_aggregate_tc: NQ=%d too large", NQ);
   if (row0_smem > 48 * 1024)
     NSAC_CUDA(cudaFuncSetAttribute(score_row0_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row0_smem));
-  score_row0_kernel<<<nsac_cdiv(B, ROW0_PAIRS), 256, row0_smem, s>>>(rp);
+  score_row0_kernel<<<nsac_cdiv(B, ROW0_PAIRS), ROW0_THREADS, row0_smem, s>>>(rp);
   NSAC_CHECK_LAUNCH("score_row0_kernel");
 
   CUtensorMap m1r, m1t, m2r, m2t;
