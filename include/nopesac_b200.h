@@ -187,7 +187,11 @@ int nsac_score_aggregate(const float* geo_local, const float* q_h, const float* 
  * softmax + feature aggregation are streamed flash-style.  No diagnostic outputs on this path.
  *   nsac_score_pack builds the device-side weight pack once per weight version (fp16 padded copies of the two
  *   score MLPs, folded last layers, transposed fp32 copies) into `pack` (nsac_score_pack_bytes(NQ) bytes);
- *   workspace: nsac_score_tc_workspace_bytes(B, NQ) bytes.  Both buffers 256-byte aligned. */
+ *   workspace: nsac_score_tc_workspace_bytes(B, NQ) bytes.  Both buffers 256-byte aligned.
+ *   Fused result exchange (multi-GPU): if peer_rows != NULL it is a DEVICE array of num_peers pointers to the
+ *   [world*B, 16] result buffers of every rank (NVLink peer mappings, e.g. torch symmetric memory); the kernel
+ *   that finishes pair b also stores its row into row (row_offset + b) of each of them, replacing the all-gather
+ *   of mp3d_evaluation.py:317-318.  The caller issues one cross-rank barrier before reading. */
 size_t nsac_score_pack_bytes(int NQ);
 int nsac_score_pack(const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp, int NQ, void* pack,
                     void* stream);
@@ -198,7 +202,7 @@ int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const floa
                             const void* pack, const float* w_rots, const float* b_rots, const float* w_trans,
                             const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
                             float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
-                            void* stream);
+                            float* const* peer_rows, int num_peers, int row_offset, void* stream);
 
 /* Assignment pruning with the refined pose (camera_head.py:605-629): keep matches whose warped normal
  * angle < 45 deg and offset distance < 1 m.  pose rows are (t[3], q[4], ...) with stride ldpose. */

@@ -15,6 +15,8 @@ Inference only.  Extra keyword arguments (not in the reference):
                                the hypothesis list of each pair (what POSE_REFINEMENT_WITH_GT_MATCHERS does in
                                the reference, camera_head.py:520-547, minus the dataset lookup).
     initial_pose  (t [B,3], q [B,4])  skips the pixel pose network (stage set S3).
+    result_exchange  nopesac_b200.dist.FusedResultExchange: the selection kernel also stores every [16]-float result
+                               row into all ranks' result buffers over NVLink (multi-GPU; replaces the all-gather).
 """
 from __future__ import annotations
 
@@ -393,17 +395,17 @@ class PlaneCameraHead(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, features1, features2, planeParam1, planeParam2, planeApp1=None, planeApp2=None,
                 gt_pose=None, gt_corr_matrix=None, batched_inputs=None, ite=0, matching_net=None,
-                hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None):
+                hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None):
         if self.training:
             raise NotImplementedError("nopesac_b200.PlaneCameraHead is inference-only")
         return self.inference_Joint(features1, features2, planeParam1, planeParam2, planeApp1, planeApp2,
                                     matching_net=matching_net, hyp_pairs=hyp_pairs, initial_pose=initial_pose,
-                                    want_diag=want_diag, assignment_override=assignment_override)
+                                    want_diag=want_diag, assignment_override=assignment_override, result_exchange=result_exchange)
 
     @torch.no_grad()
     def inference_Joint(self, cam_feats1, cam_feats2, planeParam1, planeParam2, planeApp1, planeApp2,
                         gt_corr_matrix=None, batched_inputs=None, gt_pose=None, matching_net=None,
-                        hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None):
+                        hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None):
         device = planeParam1.device
         B = planeParam1.shape[0]
         NQ = self.num_queries
@@ -463,7 +465,7 @@ class PlaneCameraHead(nn.Module):
                                   matched_num, pk["normal_score_proj"], pk["param_score_proj"],
                                   self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
                                   out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
-                                  pack=pk["score_pack"])
+                                  pack=pk["score_pack"], exchange=result_exchange)
         pose = res["pose"]
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]

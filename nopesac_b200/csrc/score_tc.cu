@@ -799,7 +799,19 @@ struct SelParams {
   float* logits; float* sums; const float* partials;
   int B, NQ, tiles_per_pair, out_cam_type;
   float* pose; float* score_rot; float* score_tran; int32_t* sel_idx;
+  // fused result exchange: the 64-byte result row of pair b is also stored into row (row_offset + b) of every
+  // rank's [world*B, 16] buffer through NVLink peer mappings (replaces the all-gather collective)
+  float* const* peer_rows; int num_peers; int row_offset;
 };
+
+__device__ __forceinline__ void publish_row(const SelParams& p, int b, const float* P) {
+  __syncthreads();
+  if (p.peer_rows && threadIdx.x < 16) {
+    const float v = P[threadIdx.x];
+    for (int r = 0; r < p.num_peers; ++r) p.peer_rows[r][(size_t)(p.row_offset + b) * 16 + threadIdx.x] = v;
+    __threadfence_system();
+  }
+}
 
 __global__ void __launch_bounds__(SEL_THREADS)
 score_select_tc_kernel(const SelParams p) {
@@ -821,6 +833,7 @@ score_select_tc_kernel(const SelParams p) {
     if (tid < 3) { P[tid] = p.t0[b * 3 + tid]; P[7 + tid] = p.t0[b * 3 + tid]; }
     if (tid < 4) { P[3 + tid] = p.q0[b * 4 + tid]; P[10 + tid] = p.q0[b * 4 + tid]; }
     if (tid == 0) { P[14] = 0.f; P[15] = 0.f; }
+    publish_row(p, b, P);
     return;
   }
   if (tid < 2) misc[tid] = p.logits[(size_t)tid * p.B * H1n + (size_t)b * H1n];     // hypothesis 0 (score_row0_kernel)
@@ -924,6 +937,7 @@ score_select_tc_kernel(const SelParams p) {
     P[14] = (float)m;
     P[15] = 0.f;
   }
+  publish_row(p, b, P);
 }
 
 // ------------------------------------------------------------------------------------------------ host
@@ -993,7 +1007,9 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
                                        const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
                                        const void* pack, const float* w_rots, const float* b_rots, const float* w_trans,
                                        const float* b_trans, int B, int NQ, int out_cam_type, float* pose, float* score_rot,
-                                       float* score_tran, int32_t* sel_idx, void* workspace, void* stream) {
+                                       float* score_tran, int32_t* sel_idx, void* workspace,
+                                       float* const* peer_rows, int num_peers, int row_offset, void* stream) {
+  NSAC_REQUIRE(!peer_rows || (num_peers >= 1 && row_offset >= 0), "nsac_score_aggregate_tc: bad peer arguments");
   NSAC_REQUIRE(geo_local && q_h && t_h && q0 && t0 && feat_rot && feat_tran && feat_rot0 && feat_tran0 && matched_num &&
                    pack && w_rots && b_rots && w_trans && b_trans && pose && workspace,
                "nsac_score_aggregate_tc: null pointer");
@@ -1061,6 +1077,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   sp.logits = logits; sp.sums = sums; sp.partials = partials;
   sp.B = B; sp.NQ = NQ; sp.tiles_per_pair = tiles; sp.out_cam_type = out_cam_type; sp.pose = pose; sp.score_rot = score_rot;
   sp.score_tran = score_tran; sp.sel_idx = sel_idx;
+  sp.peer_rows = peer_rows; sp.num_peers = num_peers; sp.row_offset = row_offset;
   const size_t sel_smem = sizeof(float) * (4 * C_FEAT + SEL_THREADS + 16 + 8) + sizeof(int) * SEL_THREADS;
   score_select_tc_kernel<<<B, SEL_THREADS, sel_smem, s>>>(sp);
   NSAC_CHECK_LAUNCH("score_select_tc_kernel");

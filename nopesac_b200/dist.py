@@ -43,3 +43,30 @@ def gather_results(local_rows: torch.Tensor, num_pairs: int, group=None) -> torc
     out = torch.empty(world * mx, RESULT_WIDTH, dtype=local_rows.dtype, device=local_rows.device)
     dist.all_gather_into_tensor(out, padded, group=group)
     return torch.cat([out[r * mx: r * mx + sizes[r]] for r in range(world)], 0)
+
+
+class FusedResultExchange:
+    """Result exchange fused into the last kernel of the path: every rank owns a [world*B_local, 16] buffer in
+    symmetric (NVLink peer-mapped) memory; the selection kernel that finishes a pair stores its 64-byte row into the
+    corresponding row of EVERY rank's buffer (plain st.global on peer mappings), so no all-gather collective runs —
+    only one cross-rank barrier (`finish()`) before the rows are read.  `rows` is this rank's complete copy.
+
+    Needs one process per GPU with an initialised NCCL process group and NVLink / P2P access between the GPUs."""
+
+    def __init__(self, pairs_per_rank: int, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.row_offset = self.rank * pairs_per_rank
+        self.rows = symm_mem.empty((self.world * pairs_per_rank, RESULT_WIDTH), dtype=torch.float32, device=device)
+        self.rows.zero_()
+        self.handle = symm_mem.rendezvous(self.rows, group)
+        self.peer_ptrs_dev = int(self.handle.buffer_ptrs_dev)     # device array of `world` float* (one per rank)
+        torch.cuda.synchronize(device)
+        dist.barrier(group)
+
+    def finish(self) -> torch.Tensor:
+        """Cross-rank barrier on the current stream: afterwards `rows` holds the rows of all ranks."""
+        self.handle.barrier(channel=0)
+        return self.rows

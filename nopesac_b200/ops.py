@@ -374,9 +374,10 @@ def score_pack(rot_mlp, tran_mlp, num_queries: int) -> torch.Tensor:
 
 def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num,
                     rot_mlp, tran_mlp, w_rots, b_rots, w_trans, b_trans, out_cam_type="soft",
-                    want_scores=True, want_diag=False, precision="fp16", pack=None):
+                    want_scores=True, want_diag=False, precision="fp16", pack=None, exchange=None):
     """rot_mlp / tran_mlp: 8-tuples (w1,b1,w2,b2,w3,b3,w4,b4). Returns dict(pose, score_rot, score_tran,
-    sel_idx, diag).  precision "fp16" = tcgen05 path (score MLPs single-pass fp16, fp32 accumulate);
+    sel_idx, diag).  `exchange` (nopesac_b200.dist.FusedResultExchange) makes the selection kernel also store
+    every result row into all ranks' result buffers over NVLink.  precision "fp16" = tcgen05 path (score MLPs single-pass fp16, fp32 accumulate);
     "fp32" = exact CUDA-core path (always used when the diagnostic outputs are requested)."""
     B, NQ, _ = geo_local.shape
     dev = geo_local.device
@@ -397,10 +398,15 @@ def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0,
         ws = torch.empty(L.nsac_score_tc_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
         st = L.nsac_score_aggregate_tc(*[_p(a) for a in args], _p(matched_num), _p(pack),
                                        _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
-                                       _p(pose), _p(sr), _p(stt), _p(sel), _p(ws), _stream())
+                                       _p(pose), _p(sr), _p(stt), _p(sel), _p(ws),
+                                       None if exchange is None else C.c_void_p(exchange.peer_ptrs_dev),
+                                       0 if exchange is None else exchange.world, 0 if exchange is None else exchange.row_offset,
+                                       _stream())
         _lib.check(st, "nsac_score_aggregate_tc")
         _count(3)
         return {"pose": pose, "score_rot": sr, "score_tran": stt, "sel_idx": sel, "diag": None}
+    if exchange is not None:
+        raise RuntimeError("the fused result exchange needs the tensor-core scoring path (precision='fp16', no diagnostics)")
     ws = torch.empty(L.nsac_score_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
     st = L.nsac_score_aggregate(*[_p(a) for a in args], _p(matched_num), C.byref(rs), C.byref(ts),
                                 _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],

@@ -31,8 +31,9 @@ def batch_bytes(batch: Dict) -> int:
 
 
 class PairPipeline:
-    def __init__(self, head, matching_head, device, hyp_pairs: Optional[torch.Tensor] = None, post=None):
+    def __init__(self, head, matching_head, device, hyp_pairs: Optional[torch.Tensor] = None, post=None, result_exchange=None):
         self.head, self.match, self.device, self.hyp_pairs, self.post = head, matching_head, device, hyp_pairs, post
+        self.result_exchange = result_exchange
         self.copy_stream = torch.cuda.Stream(device)
         self.slots = [None, None]
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -63,7 +64,7 @@ class PairPipeline:
         cur.wait_event(self.copied[slot])
         d = self.slots[slot]
         out = self.head(d["feats1"], d["feats2"], d["planes1"], d["planes2"], d["app1"], d["app2"],
-                        matching_net=self.match, hyp_pairs=self.hyp_pairs)
+                        matching_net=self.match, hyp_pairs=self.hyp_pairs, result_exchange=self.result_exchange)
         rows = out[5]["pose"]
         if self.post is not None:
             rows = self.post(rows)                                     # e.g. the multi-GPU result all-gather
