@@ -183,10 +183,11 @@ int nsac_score_aggregate(const float* geo_local, const float* q_h, const float* 
                          void* workspace, void* stream);
 
 /* Same contract on the tensor pipe (tcgen05 / TMEM / TMA): residuals on the CUDA cores feed the score MLPs as
- * fp16 tcgen05.mma operands (single pass, fp32 accumulation; hypothesis 0 and all selections stay exact fp32),
- * softmax + feature aggregation are streamed flash-style.  No diagnostic outputs on this path.
+ * fp16 tcgen05.mma operands (single pass, fp32 accumulation; hypothesis 0 runs through the same tiles, all
+ * selections stay exact fp32), softmax + feature aggregation are streamed flash-style.  No diagnostic outputs
+ * on this path.
  *   nsac_score_pack builds the device-side weight pack once per weight version (fp16 padded copies of the two
- *   score MLPs, folded last layers, transposed fp32 copies) into `pack` (nsac_score_pack_bytes(NQ) bytes);
+ *   score MLPs, folded last layers) into `pack` (nsac_score_pack_bytes(NQ) bytes);
  *   workspace: nsac_score_tc_workspace_bytes(B, NQ) bytes.  Both buffers 256-byte aligned.
  *   Fused result exchange (multi-GPU): if peer_rows != NULL it is a DEVICE array of num_peers pointers to the
  *   [world*B, 16] result buffers of every rank (NVLink peer mappings, e.g. torch symmetric memory); the kernel
@@ -203,6 +204,9 @@ int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const floa
                             const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
                             float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
                             float* const* peer_rows, int num_peers, int row_offset, void* stream);
+/* Profiling aid: while `buf` (4 x 256 uint64 device words, zeroed by the caller) is set, CTA `cta` of the scoring
+ * kernel records %globaltimer at every role hand-off (rows: residual, mma, epilogue, gather).  NULL = off. */
+int nsac_debug_score_trace(void* buf, int cta);
 
 /* Assignment pruning with the refined pose (camera_head.py:605-629): keep matches whose warped normal
  * angle < 45 deg and offset distance < 1 m.  pose rows are (t[3], q[4], ...) with stride ldpose. */

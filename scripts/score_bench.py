@@ -1,0 +1,58 @@
+"""Times the hypothesis-scoring call (K8+K9, `nsac_score_aggregate_tc`) alone with CUDA events on the launch stream:
+the roofline configuration (B=512, m=NQ=256) and BASELINE.json configs[4] (hypothesis-count sweep 32/128/512/2048
+at B=64).  One JSON line per configuration; achieved GB/s = algorithmic bytes / time."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from nopesac_b200 import ops
+from tests import util
+import bench
+
+
+def run(B, NQ, reps, dev, peak):
+    head, _, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo_local = rnd(B, NQ, 6)
+    q_h = torch.nn.functional.normalize(rnd(B, NQ, 4), dim=-1)
+    t_h = rnd(B, NQ, 3) * 0.3
+    q0 = torch.nn.functional.normalize(rnd(B, 4), dim=-1)
+    t0 = rnd(B, 3) * 0.3
+    fr, ft, fr0, ft0 = rnd(B, NQ, 256), rnd(B, NQ, 256), rnd(B, 256), rnd(B, 256)
+    mnum = torch.full((B,), NQ, device=dev, dtype=torch.int32)
+    pk = head.prepare_tc()
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)
+
+    def once():
+        ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
+                            pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias,
+                            want_scores=False, pack=pk["score_pack"])
+    for _ in range(3):
+        once()
+    torch.cuda.synchronize()
+    alg = bench.score_algorithmic_bytes(B, NQ, NQ)
+    small = alg < (200 << 20)           # inputs fit in the 126 MB L2: flush between timed launches
+    times = []
+    for _ in range(reps):
+        if small:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    times.sort()
+    ms = sum(times) / len(times)
+    return {"B": B, "NQ": NQ, "m": NQ, "ms_mean": ms, "ms_min": times[0], "algorithmic_bytes": alg,
+            "achieved_gbs": alg / (ms / 1e3) / 1e9, "frac_of_measured_hbm": alg / (ms / 1e3) / 1e9 / peak,
+            "l2_flush_between_launches": small}
+
+
+if __name__ == "__main__":
+    dev = torch.device("cuda:0")
+    peak, _ = bench.measured_peaks()
+    cfgs = [(512, 256)] if len(sys.argv) > 1 and sys.argv[1] == "roofline" else \
+        [(512, 256), (64, 256), (64, 32), (64, 128), (64, 512), (64, 2048)]
+    for B, NQ in cfgs:
+        print(json.dumps(run(B, NQ, 20, dev, peak)), flush=True)
