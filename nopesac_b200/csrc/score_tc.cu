@@ -42,13 +42,14 @@ constexpr int HID = 128;           // hidden width of the score MLPs (UMMA N)
 constexpr int KB = 64;             // residual columns per k-block (one 128-byte swizzle row of fp16)
 constexpr int C_FEAT = 256;
 constexpr int W_STAGES = 2, A_STAGES = 2;
+static_assert(W_STAGES == A_STAGES, "the TMA producer advances both rings with one stage counter");
 constexpr int BLK_BYTES = TILE_H * KB * 2;           // 16 KB: one [128 x 64] fp16 operand block
 // warp roles, aligned to warpgroups of 4 warps so that setmaxnreg can move registers between the roles
 // (launch: 1024 threads x 64 registers = the whole register file):
-//   WG0-3 = warps 0-15  residuals (16)      64 regs   | WG4-5 = warps 16-23  gather              72 regs
-//   WG6   = warps 24-27 epilogue            72 regs   | WG7   = warps 28-31  TMA, MMA, 2 idle    40 regs
+//   WG0-3 = warps 0-15  residuals (16)      64 regs   | WG4-5 = warps 16-23  gather              64 regs
+//   WG6   = warps 24-27 epilogue            72 regs   | WG7   = warps 28-31  TMA, MMA, 2 idle    56 regs
 // setmaxnreg.inc can only draw on what the CTA's own warps released with setmaxnreg.dec (an inc that is not covered
-// deadlocks): released 128*24 = 3072 = claimed 128*8 + 256*8.
+// deadlocks): released 128*8 = 1024 = claimed 128*8.
 // Four residual warps per scheduler: the FMA-pipe phase (25 FFMA2-class instructions per row x column pair, 2 issue
 // cycles each) of one warp overlaps the MUFU phase (8 SQRT/EX2, 8 cycles each) of another - with two warps per
 // scheduler (r1e/s1 captures) the two pipes alternated instead of overlapping and neither was more than 38 % busy.
@@ -69,11 +70,12 @@ constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch)
 constexpr int OFF_W2 = 0;                                        // [branch][kblock 0..1][16 KB]
 constexpr int OFF_W1 = OFF_W2 + 4 * BLK_BYTES;                   // [stage][branch][16 KB]
 constexpr int OFF_A = OFF_W1 + W_STAGES * 2 * BLK_BYTES;         // [stage][branch][16 KB]
-constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [W_STAGES][64][3] float4 column constants (TMA)
-constexpr int OFF_VEC = OFF_CJ + W_STAGES * KB * 12 * 4;         // b1[2][128], b2[2][128], w34[2][128] floats
+constexpr int CJK_BYTES = 4096;                                   // per k-block: 2 KB column constants + 2 KB B fragments
+constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [W_STAGES][CJK_BYTES] column block of the k-block (TMA)
+constexpr int OFF_VEC = OFF_CJ + W_STAGES * CJK_BYTES;           // b1[2][128], b2[2][128], w34[2][128] floats
 constexpr int OFF_LOGIT = OFF_VEC + 6 * HID * 4;                 // [2 bufs][2 branches][128] floats
-constexpr int OFF_ROWC = OFF_LOGIT + 2 * 2 * TILE_H * 4;         // [16 warps][8 rows][12] floats: k R, t / k of the tile's rows
-constexpr int OFF_EXP = OFF_ROWC + 16 * 8 * 12 * 4;         // [2 branches][128] softmax numerators of the tile
+constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [2 column halves][2 branches][128] floats (min-cost sums)
+constexpr int OFF_EXP = OFF_ROWSUM + 2 * 2 * TILE_H * 4;         // [2 branches][128] softmax numerators of the tile
 constexpr int OFF_GPART = OFF_EXP + 2 * TILE_H * 4;              // [2 branches][64 threads][9] odd-row partials (+1 pad)
 constexpr int OFF_BAR = OFF_GPART + 2 * 64 * 12 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
@@ -174,11 +176,6 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
 // fp16 x fp16 -> fp32, K-major A and B, M = 128, N = 128
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TILE_H >> 4) << 24);
 
-__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
-  const __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&h);
-}
-
 // ------------------------------------------------------------------------------------------------ residual math
 // Column constants of matched plane pair j (cj[12]): n^ = unit(p0*flip) (0-2), n1 = unit(p1*flip) (3-5),
 // pi1 = p1*flip (6-8), A = d^2/(d+1e-5)^2 (9), Bc = A*d (10), valid (11).
@@ -244,42 +241,12 @@ __device__ __forceinline__ void column_fields(const float* __restrict__ g6, bool
     f[3] = CJ_BIG; f[6] = CJ_BIG;
   }
 }
-__device__ __forceinline__ void store_column_fields(float* __restrict__ cjg_pair_base, int j, const float (&f)[CJ_FIELDS]) {
-  float* o = cjg_pair_base + (size_t)(j >> 1) * (2 * CJ_FIELDS) + (j & 1);
-#pragma unroll
-  for (int i = 0; i < CJ_FIELDS; ++i) o[2 * i] = f[i];
-}
-
 // One hypothesis row against one column pair.  R = k * rotation, t = translation / k (see above).
 // Reference (camera_head.py:997-1035 with the warp of :1446-1453): e = R (p0*flip) + t, b = e - t, pi0 = (e.b/(|b|+1e-5)^2) b.
 // With u = R n^ (unit) and d = |p0|: b = d u, e.b = d^2 + d (t.u), so pi0 = A (d + t.u) u; for t = 0 its direction is u.
 //   rot  : exp(-| u - n1 |)                 (F.normalize of both sides)
 //   trans: exp(-| A (d + t.u) u - pi1 |)
-template <bool SUMS>
-__device__ __forceinline__ void residual_cp(const float (&R)[9], const float (&t)[3], const u64 (&c)[CJ_FIELDS], uint32_t& hr,
-                                            uint32_t& ht, u64& sum_r, u64& sum_t) {
-  const u64 ux = ffma2(bc2(R[0]), c[0], ffma2(bc2(R[1]), c[1], fmul2(bc2(R[2]), c[2])));
-  const u64 uy = ffma2(bc2(R[3]), c[0], ffma2(bc2(R[4]), c[1], fmul2(bc2(R[5]), c[2])));
-  const u64 uz = ffma2(bc2(R[6]), c[0], ffma2(bc2(R[7]), c[1], fmul2(bc2(R[8]), c[2])));
-  const u64 ax = fadd2(ux, c[3]), ay = fadd2(uy, c[4]), az = fadd2(uz, c[5]);
-  const u64 dr2 = ffma2(ax, ax, ffma2(ay, ay, fmul2(az, az)));
-  const u64 tu = ffma2(bc2(t[0]), ux, ffma2(bc2(t[1]), uy, fmul2(bc2(t[2]), uz)));
-  const u64 g = ffma2(tu, c[9], c[10]);
-  const u64 wx = ffma2(g, ux, c[6]), wy = ffma2(g, uy, c[7]), wz = ffma2(g, uz, c[8]);
-  const u64 dt2 = ffma2(wx, wx, ffma2(wy, wy, fmul2(wz, wz)));
-  float r0, r1, t0, t1;
-  upk2(dr2, r0, r1);
-  upk2(dt2, t0, t1);
-  r0 = fast_sqrt(r0); r1 = fast_sqrt(r1); t0 = fast_sqrt(t0); t1 = fast_sqrt(t1);
-  if (SUMS) {   // masked distance sums (in log2 units; rescaled by the caller)
-    sum_r = ffma2(c[11], pk2(r0, r1), sum_r);
-    sum_t = ffma2(c[11], pk2(t0, t1), sum_t);
-  }
-  hr = cvt_h2<false>(fast_exp2(-r0), fast_exp2(-r1));
-  ht = cvt_h2<false>(fast_exp2(-t0), fast_exp2(-t1));
-}
-
-// scalar twin (hypothesis-0 kernel): same constants, one column
+// scalar form (score_prep_kernel: hypothesis 0 of every pair), one column
 template <bool SUMS>
 __device__ __forceinline__ void residual_scalar(const float (&R)[9], const float (&t)[3], const float (&c)[CJ_FIELDS], float& xr,
                                                 float& xt, float& sum_r, float& sum_t) {
@@ -306,57 +273,101 @@ __device__ __forceinline__ void row_constants(float qw, float qx, float qy, floa
   t[0] = tx * (1.f / LOG2E); t[1] = ty * (1.f / LOG2E); t[2] = tz * (1.f / LOG2E);
 }
 
-// One warp's share of a k-block: 8 hypothesis rows (rw, rw+16, ...) x all 64 columns; lane = column pair.  The row
-// constants (k R, t / k: 12 floats) are warp-uniform broadcast LDS.128 from the warp's own shared-memory slots, the
-// column-pair constants stay in registers for all 8 rows (normal tiles) or are re-read per row, coalesced, from global
-// memory (row-0 tiles, where every row is another pair).  Each row x column pair leaves as one fp16x2 word per branch:
-// a warp writes one full 128-byte row of the swizzled A tile per store instruction (conflict-free).
-template <bool SUMS, bool ROW0>
-__device__ __forceinline__ void residual_kblock(const float* __restrict__ rowc, const ulonglong2* __restrict__ csrc,
-                                                int pb0, int last_pair, size_t pair_stride_u2, uint8_t* a_rot, int rw, int lane,
-                                                float (&sr)[8], float (&st)[8]) {
+// ---- u = (k R) n^ and t.u on the (legacy, warp-level) tensor path ------------------------------------------------------
+// The 3x3 rotation of every (row, column) pair is 9 of the 25 packed FMA-pipe instructions of residual_cp, and the FMA
+// pipe, the MUFU pipe and the issue slots are all ~equally loaded (s6 capture + scripts/ubench): the kernel is bound by
+// their sum.  mma.sync.m16n8k16 (HMMA.16816.F32: 8 cycles per warp instruction per scheduler, overlaps MUFU completely,
+// scripts/ubench/hmma.cu) computes u_c[16 rows x 8 columns] = A_c . B in one instruction with fp32-grade accuracy from
+// fp16 hi/lo splits laid out along K:   k-slots  q=0: (hi0 hi1 | hi2 0)  q=1: (lo0 lo1 | lo2 0)  q=2: (hi0 hi1 | hi2 0)
+//                                     B k-slots  q=0: (hi0 hi1 | hi2 0)  q=1: (hi0 hi1 | hi2 0)  q=2: (lo0 lo1 | lo2 0)
+// i.e. hi.hi + lo.hi + hi.lo (the dropped lo.lo term is < 4e-7 absolute).  Thread (g = lane / 4, q = lane % 4) owns the
+// k-slots (2q, 2q+1 | 2q+8, 2q+9) of rows g, g+8 (A) / column g (B) and receives rows g, g+8 x columns 2q, 2q+1 (D):
+// exactly one packed column pair per row.
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
+               : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+}
+__device__ __forceinline__ uint32_t h_bits(float x) { return (uint32_t)__half_as_ushort(__float2half_rn(x)); }
+// this thread's two A words (k-slots 2q,2q+1 and 2q+8,2q+9) of one row for the 3-vector v
+__device__ __forceinline__ void a_words(float v0, float v1, float v2, int q, uint32_t& w01, uint32_t& w2) {
+  if (q == 1) {      // lo parts
+    v0 -= __half2float(__float2half_rn(v0)); v1 -= __half2float(__float2half_rn(v1)); v2 -= __half2float(__float2half_rn(v2));
+  }
+  w01 = h_bits(v0) | (h_bits(v1) << 16);
+  w2 = h_bits(v2);
+  if (q == 3) { w01 = 0u; w2 = 0u; }
+}
+constexpr int CJ8_FIELDS = 8;         // per column: -k n1 (0-2), -k pi1 (3-5), A (6), Bc (7).  Shared-memory layout: [group of 4 column
+                                      // pairs][16-byte unit i = fields 2i, 2i+1][pair q][field parity][column parity] - the four pairs a
+                                      // warp reads with one LDS.128 are 64 contiguous bytes (one wavefront; the [pair][field] layout
+                                      // cost 8 wavefronts per load and the shared-memory pipe became the bottleneck, s7 timeline)
+
+// everything after u: one row x one column pair
+template <bool SUMS>
+__device__ __forceinline__ void residual_tail(u64 ux, u64 uy, u64 uz, u64 tu, const u64 (&c)[CJ8_FIELDS], u64 valid, uint32_t& hr,
+                                              uint32_t& ht, u64& sum_r, u64& sum_t) {
+  const u64 ax = fadd2(ux, c[0]), ay = fadd2(uy, c[1]), az = fadd2(uz, c[2]);
+  const u64 dr2 = ffma2(ax, ax, ffma2(ay, ay, fmul2(az, az)));
+  const u64 g = ffma2(tu, c[6], c[7]);
+  const u64 wx = ffma2(g, ux, c[3]), wy = ffma2(g, uy, c[4]), wz = ffma2(g, uz, c[5]);
+  const u64 dt2 = ffma2(wx, wx, ffma2(wy, wy, fmul2(wz, wz)));
+  float r0, r1, t0, t1;
+  upk2(dr2, r0, r1);
+  upk2(dt2, t0, t1);
+  r0 = fast_sqrt(r0); r1 = fast_sqrt(r1); t0 = fast_sqrt(t0); t1 = fast_sqrt(t1);
+  if (SUMS) {   // masked distance sums (in log2 units; rescaled by the caller)
+    sum_r = ffma2(valid, pk2(r0, r1), sum_r);
+    sum_t = ffma2(valid, pk2(t0, t1), sum_t);
+  }
+  hr = cvt_h2<false>(fast_exp2(-r0), fast_exp2(-r1));
+  ht = cvt_h2<false>(fast_exp2(-t0), fast_exp2(-t1));
+}
+
+// One warp's share of a k-block of a hypothesis tile: 16 rows (row block rb) x 32 columns (column half chalf) = 4 groups
+// of 8 columns; per group 4 HMMAs (u_x, u_y, u_z, t.u) and two row x column-pair tails per thread.
+template <bool SUMS>
+__device__ __forceinline__ void residual_kblock_mma(const uint32_t (&afrag)[4][4], const uint8_t* __restrict__ cjk, uint8_t* a_rot,
+                                                    int rb, int chalf, int lane, int col0, int m, u64 (&sum_r)[2], u64 (&sum_t)[2]) {
   uint8_t* a_tran = a_rot + BLK_BYTES;
-  u64 c[CJ_FIELDS];
-  if (!ROW0) {
+  const int g = lane >> 2, q = lane & 3;
+  const uint2* bfr = reinterpret_cast<const uint2*>(cjk + 2048) + (chalf * 4) * 32 + lane;
+  const ulonglong2* c8 = reinterpret_cast<const ulonglong2*>(cjk) + (chalf * 4) * 16 + q;
 #pragma unroll
-    for (int i = 0; i < CJ_FIELDS / 2; ++i) {
-      const ulonglong2 v = csrc[lane * (CJ_FIELDS / 2) + i];
+  for (int grp = 0; grp < 4; ++grp) {
+    const uint2 b = bfr[grp * 32];
+    float dx[4], dy[4], dz[4], dt[4];
+    hmma16816(dx, afrag[0], b.x, b.y);
+    hmma16816(dy, afrag[1], b.x, b.y);
+    hmma16816(dz, afrag[2], b.x, b.y);
+    hmma16816(dt, afrag[3], b.x, b.y);
+    u64 c[CJ8_FIELDS];
+#pragma unroll
+    for (int i = 0; i < CJ8_FIELDS / 2; ++i) {
+      const ulonglong2 v = c8[(grp * 4 + i) * 4];
       c[2 * i] = v.x; c[2 * i + 1] = v.y;
     }
-  }
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    if (ROW0) {     // row i = pair pb0 + 16 i (rows beyond the batch re-read the last pair; their results are ignored)
-      const ulonglong2* src = csrc + (size_t)min(pb0 + 16 * i, last_pair) * pair_stride_u2 + lane * (CJ_FIELDS / 2);
-#pragma unroll
-      for (int k = 0; k < CJ_FIELDS / 2; ++k) {
-        const ulonglong2 v = __ldg(src + k);
-        c[2 * k] = v.x; c[2 * k + 1] = v.y;
-      }
-    }
-    const float4 r0 = *reinterpret_cast<const float4*>(rowc + i * 12), r1 = *reinterpret_cast<const float4*>(rowc + i * 12 + 4),
-                 r2 = *reinterpret_cast<const float4*>(rowc + i * 12 + 8);
-    const float R[9] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w, r2.x};
-    const float tr[3] = {r2.y, r2.z, r2.w};
-    uint32_t hr, ht;
-    u64 s_r = 0ull, s_t = 0ull;
-    residual_cp<SUMS>(R, tr, c, hr, ht, s_r, s_t);
-    const int row = rw + 16 * i;
-    const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((lane >> 2) ^ (row & 7)) << 4) + (uint32_t)((lane & 3) << 2);   // 128-byte swizzle
-    *reinterpret_cast<uint32_t*>(a_rot + off) = hr;
-    *reinterpret_cast<uint32_t*>(a_tran + off) = ht;
+    u64 valid = 0ull;
     if (SUMS) {
-      float a0, a1, c0, c1;
-      upk2(s_r, a0, a1);
-      upk2(s_t, c0, c1);
-      sr[i] += a0 + a1;
-      st[i] += c0 + c1;
+      const int j = col0 + chalf * 32 + grp * 8 + 2 * q;
+      valid = pk2(j < m ? 1.f : 0.f, j + 1 < m ? 1.f : 0.f);
+    }
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2) {
+      uint32_t hr, ht;
+      residual_tail<SUMS>(pk2(dx[2 * h2], dx[2 * h2 + 1]), pk2(dy[2 * h2], dy[2 * h2 + 1]), pk2(dz[2 * h2], dz[2 * h2 + 1]),
+                          pk2(dt[2 * h2], dt[2 * h2 + 1]), c, valid, hr, ht, sum_r[h2], sum_t[h2]);
+      const int row = rb * 16 + g + 8 * h2;
+      const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((chalf * 4 + grp) ^ (row & 7)) << 4) + (uint32_t)(q << 2);   // 128-byte swizzle
+      *reinterpret_cast<uint32_t*>(a_rot + off) = hr;
+      *reinterpret_cast<uint32_t*>(a_tran + off) = ht;
     }
   }
 }
 
 // Optional in-kernel timeline (debug / profiling aid): one CTA records %globaltimer at role hand-offs into a host-provided
-// buffer (nsac_debug_score_trace).  [role][event] = ns; roles: 0 residual, 1 mma, 2 epilogue, 3 gather.
+// buffer (nsac_debug_score_trace).  [role][event] = ns; roles: 0 residual, 1 mma, 2 epilogue, 3 gather; rows 4 / 5 = start /
+// end time of every CTA.
 constexpr int TRACE_EVENTS = 256;
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
@@ -381,8 +392,7 @@ struct TcParams {
   const float* feat_tran;
   const int32_t* matched_num;
   const float* vecs;        // packed: b1[2][128], b2[2][128], w34[2][128]
-  const float* cjg;         // [B][NQp/2][12][2] column-pair constants (score_prep_kernel)
-  const int32_t* row0_nkb;  // [row0_tiles] k-blocks a row-0 tile has to cover (max m of its 128 pairs)
+  const uint8_t* cjk;       // [B][NQp/64][4096 B] per k-block: column constants + HMMA B fragments of the hypothesis tiles
   int B, NQ, NQp, tiles_per_pair, need_sums;
   int num_items, row0_tiles, row0_at;     // item list = B*tiles_per_pair hypothesis tiles + row0_tiles inserted at index row0_at
   float* logits;            // [2][B][NQ+1]
@@ -392,8 +402,9 @@ struct TcParams {
 
 // Work items.  A hypothesis tile = (pair b, hypotheses 1 + 128*tile ... ) scored against the pair's m matched columns.
 // A row-0 tile = hypothesis 0 (the initial pose, camera_head.py:991, 1019) of 128 consecutive pairs b .. b+127: row r
-// belongs to pair b + r and uses THAT pair's column constants, so the tensor-core path, the epilogue and the barrier
-// protocol are shared and only the residual warps read their constants per row (from global memory).
+// belongs to pair b + r.  Its residual rows exp(-d) are one row per pair, so score_prep_kernel computes them next to the
+// column constants ([2][B][NQp] fp16) and the TMA producer drops them straight into the A ring: the tile only costs its
+// MMAs and epilogue and shares the whole barrier protocol (the residual warps just pass their A-stage turns).
 struct Item { int b, tile, m, nkb; bool row0; };
 __device__ __forceinline__ bool decode_item(const TcParams& p, int item, Item& it) {
   int idx = item;
@@ -401,8 +412,8 @@ __device__ __forceinline__ bool decode_item(const TcParams& p, int item, Item& i
   if (item >= p.row0_at) {
     if (item < p.row0_at + p.row0_tiles) {
       const int t = item - p.row0_at;
-      it.row0 = true; it.b = t * TILE_H; it.tile = 0; it.m = 0; it.nkb = p.row0_nkb[t];
-      return it.nkb > 0;
+      it.row0 = true; it.b = t * TILE_H; it.tile = 0; it.m = 0; it.nkb = p.NQp / KB;
+      return true;
     }
     idx = item - p.row0_tiles;
   }
@@ -415,7 +426,8 @@ __device__ __forceinline__ bool decode_item(const TcParams& p, int item, Item& i
 template <bool SUMS>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_constant__ CUtensorMap map_w1t,
-                const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w2t, const TcParams p) {
+                const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w2t,
+                const __grid_constant__ CUtensorMap map_x0r, const __grid_constant__ CUtensorMap map_x0t, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window with offset arithmetic (a generic-pointer round trip would turn every
   // shared-memory access below into a generic LD/ST)
@@ -424,6 +436,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + BAR_COUNT);
   float* vec = reinterpret_cast<float*>(smem + OFF_VEC);
   float* s_logit = reinterpret_cast<float*>(smem + OFF_LOGIT);
+  float* s_rowsum = reinterpret_cast<float*>(smem + OFF_ROWSUM);
   float* s_exp = reinterpret_cast<float*>(smem + OFF_EXP);
   float* s_gpart = reinterpret_cast<float*>(smem + OFF_GPART);
 
@@ -431,11 +444,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   const int H1n = p.NQ + 1;
   const int num_items = p.num_items;
   int trace_n = 0;
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < TRACE_EVENTS) p.trace[4 * TRACE_EVENTS + blockIdx.x] = gtime();     // CTA start
 
   if (threadIdx.x == 0) {
     mbar_init(&bars[BAR_W2], 1);
     for (int s = 0; s < W_STAGES; ++s) { mbar_init(&bars[BAR_W_FULL + s], 1); mbar_init(&bars[BAR_W_EMPTY + s], 1); }
-    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&bars[BAR_A_FULL + s], R_WARPS); mbar_init(&bars[BAR_A_EMPTY + s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&bars[BAR_A_FULL + s], R_WARPS + 1); mbar_init(&bars[BAR_A_EMPTY + s], 1); }
     mbar_init(&bars[BAR_ACC_FULL], 1);
     mbar_init(&bars[BAR_H1_READY], 4);
     mbar_init(&bars[BAR_ACC2_FULL], 1);
@@ -455,7 +469,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   // setmaxnreg: ONE instruction per warpgroup (all 4 warps must execute the same one), inside the warpgroup's own
   // branch so that the register limit is unambiguous on every control path
   if (warp >= T_WARP) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == T_WARP) {
     // ================================================================================= TMA producer
     if (lane == 0) {
@@ -464,21 +478,31 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         tma_load_2d(smem + OFF_W2 + (0 * 2 + kb) * BLK_BYTES, &map_w2r, &bars[BAR_W2], kb * KB, 0);
         tma_load_2d(smem + OFF_W2 + (1 * 2 + kb) * BLK_BYTES, &map_w2t, &bars[BAR_W2], kb * KB, 0);
       }
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0;      // the W ring and the A ring advance together (one stage of each per k-block)
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         Item it;
         if (!decode_item(p, item, it)) continue;
         for (int kb = 0; kb < it.nkb; ++kb) {
           mbar_wait(&bars[BAR_W_EMPTY + stage], phase ^ 1);
-          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES + (it.row0 ? 0 : KB * 48));
+          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES + (it.row0 ? 0 : CJK_BYTES));
           uint8_t* dst = smem + OFF_W1 + stage * 2 * BLK_BYTES;
           tma_load_2d(dst, &map_w1r, &bars[BAR_W_FULL + stage], kb * KB, 0);
           tma_load_2d(dst + BLK_BYTES, &map_w1t, &bars[BAR_W_FULL + stage], kb * KB, 0);
-          // the k-block's 64 x 48 B of per-column geometry constants travel with the weights (a row-0 tile reads
-          // its per-row constants straight from global memory instead)
+          // the k-block's column block (2 KB of constants + 2 KB of HMMA B fragments) travels with the weights
           if (!it.row0)
-            bulk_load_1d(smem + OFF_CJ + stage * KB * 48, p.cjg + ((size_t)it.b * p.NQp + (size_t)kb * KB) * CJ_FIELDS, KB * 48,
+            bulk_load_1d(smem + OFF_CJ + stage * CJK_BYTES, p.cjk + ((size_t)it.b * (p.NQp / KB) + kb) * CJK_BYTES, CJK_BYTES,
                          &bars[BAR_W_FULL + stage]);
+          // A ring: the producer is the 17th arriver of every stage; for a row-0 tile its arrival carries the bytes of
+          // the two [128 pairs x 64 columns] fp16 residual blocks that TMA writes into the stage (rows >= B: zero fill)
+          mbar_wait(&bars[BAR_A_EMPTY + stage], phase ^ 1);
+          if (it.row0) {
+            uint8_t* a = smem + OFF_A + stage * 2 * BLK_BYTES;
+            mbar_expect_tx(&bars[BAR_A_FULL + stage], 2 * BLK_BYTES);
+            tma_load_2d(a, &map_x0r, &bars[BAR_A_FULL + stage], kb * KB, it.b);
+            tma_load_2d(a + BLK_BYTES, &map_x0t, &bars[BAR_A_FULL + stage], kb * KB, it.b);
+          } else {
+            mbar_arrive(&bars[BAR_A_FULL + stage]);
+          }
           if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -619,105 +643,131 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     }
   } else if (warp < G_WARP0) {
     // ================================================================================= residual warps 0..15
-    // warp rw = 8 hypothesis rows (rw + 16 i) x the 64 columns of the k-block, lane = column pair (residual_kblock).
-    // One row x one column pair = 25 packed FMA-pipe instructions + 4 MUFU.SQRT + 4 MUFU.EX2 + 2 cvt.
+    // Hypothesis tiles: warp rw = row block rw % 8 (16 rows) x column half rw / 8 (32 columns) per k-block; u and t.u come
+    // from 4 HMMAs per 8 columns (residual_kblock_mma), the rest (13 packed FMA-pipe instructions + 4 MUFU.SQRT + 4
+    // MUFU.EX2 + 2 cvt per row x column pair) runs on the CUDA cores.  Row-0 tiles: the A stages are filled by TMA, these
+    // warps only pass their turns.
     const int rw = warp - R_WARP0;                   // 0..15 (these warps keep the 64 registers of the launch)
-    float* rowc = reinterpret_cast<float*>(smem + OFF_ROWC) + rw * 8 * 12;
+    const int rb = rw & 7, chalf = rw >> 3, g = lane >> 2, q = lane & 3;
     int as = 0; uint32_t aph = 0; int ws = 0; uint32_t wph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       Item it;
       if (!decode_item(p, item, it)) continue;
-      __syncwarp();                                  // every lane is done with the previous tile's row constants
-      if (lane < 8) {
-        // rows beyond m (or beyond B) keep the identity pose: their A rows only reach their own (ignored) rows of D
-        const int row = rw + 16 * lane;
-        float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-        const float* qp = nullptr; const float* tp = nullptr;
-        if (it.row0) {
-          if (it.b + row < p.B) { qp = p.q0 + (size_t)(it.b + row) * 4; tp = p.t0 + (size_t)(it.b + row) * 3; }
-        } else {
-          const int hidx = it.tile * TILE_H + row;       // index into q_h / t_h (hypothesis h = hidx + 1)
-          if (hidx < it.m) { qp = p.q_h + ((size_t)it.b * p.NQ + hidx) * 4; tp = p.t_h + ((size_t)it.b * p.NQ + hidx) * 3; }
+      if (it.row0) {
+        for (int kb = 0; kb < it.nkb; ++kb) {
+          mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
         }
-        if (qp) {
-          const float4 q = *reinterpret_cast<const float4*>(qp);
-          qw = q.x; qx = q.y; qy = q.z; qz = q.w;
+        continue;
+      }
+      // ---- hypothesis tile: A fragments of this thread's two rows (g, g + 8 of row block rb), once per tile
+      uint32_t afrag[4][4];
+#pragma unroll
+      for (int h2 = 0; h2 < 2; ++h2) {
+        // rows beyond m keep the identity pose: their A rows only reach their own (ignored) rows of D
+        const int hidx = it.tile * TILE_H + rb * 16 + g + 8 * h2;       // index into q_h / t_h (hypothesis h = hidx + 1)
+        float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+        if (hidx < it.m) {
+          const float4 qq = *reinterpret_cast<const float4*>(p.q_h + ((size_t)it.b * p.NQ + hidx) * 4);
+          const float* tp = p.t_h + ((size_t)it.b * p.NQ + hidx) * 3;
+          qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
           tx = tp[0]; ty = tp[1]; tz = tp[2];
         }
         float R[9], tr[3];
         row_constants(qw, qx, qy, qz, tx, ty, tz, R, tr);
-        float4* o = reinterpret_cast<float4*>(rowc + lane * 12);
-        o[0] = make_float4(R[0], R[1], R[2], R[3]);
-        o[1] = make_float4(R[4], R[5], R[6], R[7]);
-        o[2] = make_float4(R[8], tr[0], tr[1], tr[2]);
+        a_words(R[0], R[1], R[2], q, afrag[0][h2], afrag[0][2 + h2]);
+        a_words(R[3], R[4], R[5], q, afrag[1][h2], afrag[1][2 + h2]);
+        a_words(R[6], R[7], R[8], q, afrag[2][h2], afrag[2][2 + h2]);
+        // t.u = (t / k) . ((k R) n^) = s . n^ with s = (k R)^T (t / k)
+        a_words(fmaf(tr[0], R[0], fmaf(tr[1], R[3], tr[2] * R[6])), fmaf(tr[0], R[1], fmaf(tr[1], R[4], tr[2] * R[7])),
+                fmaf(tr[0], R[2], fmaf(tr[1], R[5], tr[2] * R[8])), q, afrag[3][h2], afrag[3][2 + h2]);
       }
-      __syncwarp();
-      float sr[8], st[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) { sr[i] = 0.f; st[i] = 0.f; }
-      // two separate loops: if the row-0 variant (global loads) and the normal variant (shared loads) share one loop
-      // body, ptxas predicates both load kinds into the same registers and every FFMA2 of a normal tile waits on the
-      // long scoreboard of predicated-off LDGs
-      if (it.row0) {
-        const size_t pair_stride_u2 = (size_t)p.NQp * CJ_FIELDS / 4;       // one pair's constants, in 16-byte units
-        for (int kb = 0; kb < it.nkb; ++kb) {
-          mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
-          residual_kblock<SUMS, true>(rowc, reinterpret_cast<const ulonglong2*>(p.cjg + (size_t)kb * KB * CJ_FIELDS), it.b + rw,
-                                      p.B - 1, pair_stride_u2, smem + OFF_A + as * 2 * BLK_BYTES, rw, lane, sr, st);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
-          if (++as == A_STAGES) { as = 0; aph ^= 1; }
-          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-        }
-      } else {
-        for (int kb = 0; kb < it.nkb; ++kb) {
-          NSAC_TRACE(0, threadIdx.x == 0);
-          mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
-          NSAC_TRACE(0, threadIdx.x == 0);
-          mbar_wait(&bars[BAR_W_FULL + ws], wph);           // column constants of this k-block have landed (TMA)
-          NSAC_TRACE(0, threadIdx.x == 0);
-          residual_kblock<SUMS, false>(rowc, reinterpret_cast<const ulonglong2*>(smem + OFF_CJ + ws * KB * 48), 0, 0, 0,
-                                       smem + OFF_A + as * 2 * BLK_BYTES, rw, lane, sr, st);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
-          if (++as == A_STAGES) { as = 0; aph ^= 1; }
-          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
-        }
-      }
-      if (SUMS) {   // sum_j of the masked distances (argmin in 'min-cost', :1090-1093): lanes hold column-pair partials
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float a = warp_sum(sr[i]) * (1.f / LOG2E), c = warp_sum(st[i]) * (1.f / LOG2E);
-          const int row = rw + 16 * i;
-          if (lane == 0) {
-            if (it.row0) {
-              if (it.b + row < p.B) {
-                p.sums[(size_t)(it.b + row) * H1n] = a;
-                p.sums[(size_t)p.B * H1n + (size_t)(it.b + row) * H1n] = c;
-              }
-            } else if (it.tile * TILE_H + row < it.m) {
-              const int h = it.tile * TILE_H + row + 1;
-              p.sums[(size_t)it.b * H1n + h] = a;
-              p.sums[(size_t)p.B * H1n + (size_t)it.b * H1n + h] = c;
-            }
+      u64 sum_r[2] = {0ull, 0ull}, sum_t[2] = {0ull, 0ull};
+      // the next tile's poses are two dependent global round trips away (matched_num -> q_h / t_h rows): decode the next
+      // item now and prefetch its rows after the first k-block, so the per-tile preamble does not wait on DRAM
+      Item nx;
+      nx.row0 = true;
+      if (item + (int)gridDim.x < num_items && !decode_item(p, item + gridDim.x, nx)) nx.row0 = true;
+      for (int kb = 0; kb < it.nkb; ++kb) {
+        if (kb == 1 && !nx.row0 && q == 0) {
+          const int hidx = nx.tile * TILE_H + rb * 16 + g;
+          if (hidx + 8 < nx.m) {
+            const float* qp = p.q_h + ((size_t)nx.b * p.NQ + hidx) * 4;
+            const float* tp = p.t_h + ((size_t)nx.b * p.NQ + hidx) * 3;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(qp + 32));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + 24));
           }
         }
+        NSAC_TRACE(0, threadIdx.x == 0);
+        mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
+        NSAC_TRACE(0, threadIdx.x == 0);
+        mbar_wait(&bars[BAR_W_FULL + ws], wph);           // column block of this k-block has landed (TMA)
+        NSAC_TRACE(0, threadIdx.x == 0);
+        residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + ws * CJK_BYTES, smem + OFF_A + as * 2 * BLK_BYTES, rb, chalf, lane, kb * KB,
+                                  it.m, sum_r, sum_t);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
+        if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+      }
+      if (SUMS) {   // sum_j of the masked distances (argmin in 'min-cost', :1090-1093): 4 q-lanes x 2 column halves per row
+#pragma unroll
+        for (int h2 = 0; h2 < 2; ++h2) {
+          float a0, a1, c0, c1;
+          upk2(sum_r[h2], a0, a1);
+          upk2(sum_t[h2], c0, c1);
+          float a = a0 + a1, c = c0 + c1;
+          a += __shfl_xor_sync(NSAC_FULL_MASK, a, 1); a += __shfl_xor_sync(NSAC_FULL_MASK, a, 2);
+          c += __shfl_xor_sync(NSAC_FULL_MASK, c, 1); c += __shfl_xor_sync(NSAC_FULL_MASK, c, 2);
+          if (q == 0) {
+            s_rowsum[(chalf * 2 + 0) * TILE_H + rb * 16 + g + 8 * h2] = a * (1.f / LOG2E);
+            s_rowsum[(chalf * 2 + 1) * TILE_H + rb * 16 + g + 8 * h2] = c * (1.f / LOG2E);
+          }
+        }
+        named_bar_sync(1, R_THREADS);
+        const int rt = threadIdx.x - R_WARP0 * 32;
+        if (rt < TILE_H && it.tile * TILE_H + rt < it.m) {
+          const int h = it.tile * TILE_H + rt + 1;
+          p.sums[(size_t)it.b * H1n + h] = s_rowsum[0 * TILE_H + rt] + s_rowsum[2 * TILE_H + rt];
+          p.sums[(size_t)p.B * H1n + (size_t)it.b * H1n + h] = s_rowsum[1 * TILE_H + rt] + s_rowsum[3 * TILE_H + rt];
+        }
+        named_bar_sync(1, R_THREADS);
       }
     }
   } else {
     // ================================================================================= gather warps 16..23
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
-    // thread = (branch, row parity, 4 feature channels): 12 float4 loads in flight per thread = 48 KB per SM (Little's
-    // law: 41 GB/s per SM at ~1 us loaded latency; with 8 in flight and a 56-register cap ptxas kept only ~4.5 loads in
-    // flight and the whole kernel became gather-bound, s2/s3 captures: 235 us)
+    // thread = (branch, row parity, 4 feature channels): 10 float4 loads in flight per thread = 40 KB per SM (Little's
+    // law: 41 GB/s per SM at ~1 us loaded latency; with a 56-register cap ptxas kept only ~4.5 loads in flight and the
+    // whole kernel became gather-bound, s2/s3 captures).  These warps keep the 64 registers of the launch.
     const int gt = threadIdx.x - G_WARP0 * 32;       // 0..255
     const int br = gt >> 7, par = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
     int lbuf = 0; uint32_t lph = 0;
+    // The stream is latency-bound with what fits in registers (s9 timeline: 12 us per 262 KB tile = 22 GB/s per SM at
+    // ~1.5 us loaded DRAM latency), so every tile's rows are pulled into L2 one tile ahead with fire-and-forget
+    // prefetches (no registers held); the demand loads below then pay L2 latency only.
+    auto prefetch_tile = [&](const Item& x) {
+      if (x.row0) return;
+      const int nlines = min(TILE_H, x.m - x.tile * TILE_H) * (C_FEAT * 4 / 128);
+      const char* base = reinterpret_cast<const char*>((br == 0 ? p.feat_rot : p.feat_tran) + ((size_t)x.b * p.NQ + (size_t)x.tile * TILE_H) * C_FEAT);
+      for (int l = gt & 127; l < nlines; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
+    };
+    {
+      Item first;
+      if ((int)blockIdx.x < num_items && decode_item(p, blockIdx.x, first)) prefetch_tile(first);
+    }
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       Item it;
       if (!decode_item(p, item, it)) continue;
+      {
+        Item nx;
+        if (item + (int)gridDim.x < num_items && decode_item(p, item + gridDim.x, nx)) prefetch_tile(nx);
+      }
       NSAC_TRACE(3, threadIdx.x == G_WARP0 * 32);
       mbar_wait(&bars[BAR_LOGIT_READY + lbuf], lph);
       NSAC_TRACE(3, threadIdx.x == G_WARP0 * 32);
@@ -753,12 +803,12 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         se = warp_sum((e4.x + e4.y) + (e4.z + e4.w));
       }
       int r = par;
-      for (; r + 22 < rows; r += 24) {       // 12 rows of this parity in flight
-        ulonglong2 v[12];
+      for (; r + 18 < rows; r += 20) {       // 10 rows of this parity in flight
+        ulonglong2 v[10];
 #pragma unroll
-        for (int u = 0; u < 12; ++u) v[u] = __ldg(reinterpret_cast<const ulonglong2*>(f + (size_t)(r + 2 * u) * C_FEAT));
+        for (int u = 0; u < 10; ++u) v[u] = __ldg(reinterpret_cast<const ulonglong2*>(f + (size_t)(r + 2 * u) * C_FEAT));
 #pragma unroll
-        for (int u = 0; u < 12; ++u) {
+        for (int u = 0; u < 10; ++u) {
           const u64 e2 = bc2(ex[r + 2 * u]);
           wxy = ffma2(e2, v[u].x, wxy); wzw = ffma2(e2, v[u].y, wzw);
           fxy = fadd2(fxy, v[u].x); fzw = fadd2(fzw, v[u].y);
@@ -796,33 +846,61 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   }
   fence_before();
   __syncthreads();
+  if (p.trace && threadIdx.x == 0 && blockIdx.x < TRACE_EVENTS) p.trace[5 * TRACE_EVENTS + blockIdx.x] = gtime();     // CTA end
   if (warp == M_WARP) {
     fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TM_COLS));
   }
 }
 
-// Column constants of every (pair, column) + the k-block count of every row-0 tile.
-__global__ void score_prep_kernel(const float* __restrict__ geo_local, const int32_t* __restrict__ matched_num, int B, int NQ,
-                                  int NQp, float* __restrict__ cjg, int32_t* __restrict__ row0_nkb, int row0_tiles) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < B * NQp) {
-    const int b = i / NQp, j = i - b * NQp;
+// One block per pair: the column blocks of the hypothesis tiles and hypothesis 0 (the initial pose) of the pair.
+//   cjk [B][NQp/64][4096 B]    per k-block: column constants -k n1, -k pi1, A, Bc (CJ8 layout) + HMMA B fragments
+//                              [8 groups][32 lanes][2 words] of n^ (fp16 hi / hi / lo k-slots, see hmma16816)
+//   x0  [2][B][NQp] fp16       exp(-d) of hypothesis 0 against every column (0 beyond m): the A operand of the row-0 tiles
+//   sums[.][b][0]              masked distance sums of hypothesis 0 ('min-cost'), fixed summation order
+constexpr int PREP_THREADS = 256;
+__global__ void __launch_bounds__(PREP_THREADS)
+score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__ q0, const float* __restrict__ t0,
+                  const int32_t* __restrict__ matched_num, int B, int NQ, int NQp, uint8_t* __restrict__ cjk,
+                  __half* __restrict__ x0, float* __restrict__ sums) {
+  __shared__ float red[2][PREP_THREADS / 32];
+  const int b = blockIdx.x, tid = threadIdx.x, m = matched_num[b];
+  float R[9], ts[3];
+  row_constants(q0[b * 4 + 0], q0[b * 4 + 1], q0[b * 4 + 2], q0[b * 4 + 3], t0[b * 3 + 0], t0[b * 3 + 1], t0[b * 3 + 2], R, ts);
+  float sr = 0.f, st = 0.f;
+  for (int j = tid; j < NQp; j += PREP_THREADS) {
     float f[CJ_FIELDS];
-    const bool valid = j < matched_num[b];
+    const bool valid = j < m;
     column_fields(geo_local + ((size_t)b * NQ + (valid ? j : 0)) * 6, valid, f);
-    store_column_fields(cjg + (size_t)b * NQp * CJ_FIELDS, j, f);
-  }
-  if (blockIdx.x < row0_tiles && threadIdx.x < 32) {       // warp 0 of the first row0_tiles blocks: max m of 128 pairs
-    int mm = 0;
-    for (int r = threadIdx.x; r < TILE_H; r += 32) {
-      const int b = blockIdx.x * TILE_H + r;
-      if (b < B) mm = max(mm, matched_num[b]);
-    }
+    uint8_t* blk = cjk + ((size_t)b * (NQp / KB) + j / KB) * CJK_BYTES;
+    const int jj = j % KB;
+    // pair jj/2 = group (jj/8) of 4 pairs, q = (jj/2) % 4; field k -> unit k/2, field parity k%2
+    float* c8 = reinterpret_cast<float*>(blk) + (jj >> 3) * 64 + ((jj >> 1) & 3) * 4 + (jj & 1);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mm = max(mm, __shfl_xor_sync(NSAC_FULL_MASK, mm, o));
-    // every pair needs its hypothesis-0 logit only when m > 0 (m == 0 pairs copy the initial pose, :964-969)
-    if (threadIdx.x == 0) row0_nkb[blockIdx.x] = (mm + KB - 1) / KB;
+    for (int k = 0; k < CJ8_FIELDS; ++k) c8[(k >> 1) * 16 + (k & 1) * 2] = f[3 + k];
+    // B fragments: column jj -> group jj / 8, g = jj % 8; lanes 4g + q hold (k = 2q, 2q+1 | 2q+8, 2q+9)
+    uint32_t hi01, hi2, lo01, lo2;
+    a_words(f[0], f[1], f[2], 0, hi01, hi2);
+    a_words(f[0], f[1], f[2], 1, lo01, lo2);
+    uint2* bf = reinterpret_cast<uint2*>(blk + 2048) + (jj >> 3) * 32 + (jj & 7) * 4;
+    bf[0] = make_uint2(hi01, hi2);
+    bf[1] = make_uint2(hi01, hi2);
+    bf[2] = make_uint2(lo01, lo2);
+    bf[3] = make_uint2(0u, 0u);
+    // hypothesis 0 against column j
+    float xr, xt;
+    residual_scalar<true>(R, ts, f, xr, xt, sr, st);
+    x0[(size_t)b * NQp + j] = __float2half_rn(valid ? xr : 0.f);
+    x0[(size_t)B * NQp + (size_t)b * NQp + j] = __float2half_rn(valid ? xt : 0.f);
+  }
+  sr = warp_sum(sr); st = warp_sum(st);
+  if ((tid & 31) == 0) { red[0][tid >> 5] = sr; red[1][tid >> 5] = st; }
+  __syncthreads();
+  if (tid == 0) {
+    float a = 0.f, c = 0.f;
+    for (int w = 0; w < PREP_THREADS / 32; ++w) { a += red[0][w]; c += red[1][w]; }
+    sums[(size_t)b * (NQ + 1)] = a * (1.f / LOG2E);
+    sums[(size_t)B * (NQ + 1) + (size_t)b * (NQ + 1)] = c * (1.f / LOG2E);
   }
 }
 
@@ -1080,7 +1158,7 @@ inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static unsigned long long* g_score_trace = nullptr;
 static int g_score_trace_cta = 0;
 // Debug aid: the next nsac_score_aggregate_tc launches record the role timeline of CTA `cta` into `buf`
-// (4 * 256 uint64 device words, zero-filled by the caller); nullptr switches it off.
+// (6 * 256 uint64 device words, zero-filled by the caller); nullptr switches it off.
 extern "C" int nsac_debug_score_trace(void* buf, int cta) {
   g_score_trace = static_cast<unsigned long long*>(buf);
   g_score_trace_cta = cta;
@@ -1108,7 +1186,7 @@ extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) {
   const size_t per = (size_t)B * (NQ + 1);
   const int tiles = (NQ + TILE_H - 1) / TILE_H;
   return align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float)) +
-         align256((size_t)B * nq_padded(NQ) * 48) + align256((size_t)nsac_cdiv(B, TILE_H) * sizeof(int32_t)) + 256;
+         align256((size_t)B * nq_padded(NQ) * 64) + align256((size_t)2 * B * nq_padded(NQ) * sizeof(__half)) + 256;
 }
 
 extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
@@ -1138,20 +1216,20 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   float* logits = reinterpret_cast<float*>(ws);
   float* sums = logits + 2 * per;
   float* partials = reinterpret_cast<float*>(ws + align256(4 * per * sizeof(float)));
-  float* cjg = reinterpret_cast<float*>(ws + align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float)));
+  uint8_t* cjk = ws + align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float));
+  __half* x0 = reinterpret_cast<__half*>(cjk + align256((size_t)B * NQp * 64));
   const float* vecs = reinterpret_cast<const float*>(pk + pack_off_vecs(NQp));
-
-  int32_t* row0_nkb = reinterpret_cast<int32_t*>(reinterpret_cast<uint8_t*>(cjg) + align256((size_t)B * NQp * 48));
   const int row0_tiles = nsac_cdiv(B, TILE_H);
 
-  // column constants of every (pair, column) + k-block counts of the row-0 tiles
-  score_prep_kernel<<<nsac_cdiv(B * NQp, 256), 256, 0, s>>>(geo_local, matched_num, B, NQ, NQp, cjg, row0_nkb, row0_tiles);
+  // column blocks of every (pair, k-block) + hypothesis 0 of every pair
+  score_prep_kernel<<<B, PREP_THREADS, 0, s>>>(geo_local, q0, t0, matched_num, B, NQ, NQp, cjk, x0, sums);
   NSAC_CHECK_LAUNCH("score_prep_kernel");
 
-  CUtensorMap m1r, m1t, m2r, m2t;
+  CUtensorMap m1r, m1t, m2r, m2t, mx0r, mx0t;
   const bool ok = make_map_f16(&m1r, pk, HID, NQp) && make_map_f16(&m1t, pk + pack_w1_bytes(NQp), HID, NQp) &&
                   make_map_f16(&m2r, pk + 2 * pack_w1_bytes(NQp), HID, HID) &&
-                  make_map_f16(&m2t, pk + 2 * pack_w1_bytes(NQp) + HID * HID * 2, HID, HID);
+                  make_map_f16(&m2t, pk + 2 * pack_w1_bytes(NQp) + HID * HID * 2, HID, HID) &&
+                  make_map_f16(&mx0r, x0, B, NQp) && make_map_f16(&mx0t, x0 + (size_t)B * NQp, B, NQp);
   if (!ok) {
     nsac_set_error("nsac_score_aggregate_tc: cuTensorMapEncodeTiled failed");
     return NSAC_ERR_LAUNCH;
@@ -1159,7 +1237,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   TcParams tp;
   tp.trace = g_score_trace; tp.trace_cta = g_score_trace_cta;
   tp.geo_local = geo_local; tp.q_h = q_h; tp.t_h = t_h; tp.q0 = q0; tp.t0 = t0; tp.feat_rot = feat_rot; tp.feat_tran = feat_tran;
-  tp.matched_num = matched_num; tp.vecs = vecs; tp.cjg = cjg; tp.row0_nkb = row0_nkb;
+  tp.matched_num = matched_num; tp.vecs = vecs; tp.cjk = cjk;
   tp.B = B; tp.NQ = NQ; tp.NQp = NQp; tp.tiles_per_pair = tiles;
   tp.need_sums = out_cam_type == NSAC_CAM_MIN_COST; tp.logits = logits; tp.sums = sums; tp.partials = partials;
   static bool attr = false;
@@ -1176,9 +1254,9 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   tp.num_items = items; tp.row0_tiles = row0_tiles;
   tp.row0_at = (rem != 0 && rem + row0_tiles <= grid) ? rem : 0;
   if (tp.need_sums)
-    score_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, tp);
+    score_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, mx0r, mx0t, tp);
   else
-    score_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, tp);
+    score_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, mx0r, mx0t, tp);
   NSAC_CHECK_LAUNCH("score_tc_kernel");
 
   SelParams sp;
