@@ -204,8 +204,9 @@ int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const floa
                             const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
                             float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
                             float* const* peer_rows, int num_peers, int row_offset, void* stream);
-/* Profiling aid: while `buf` (6 x 256 uint64 device words, zeroed by the caller) is set, CTA `cta` of the scoring
- * kernel records %globaltimer at every role hand-off (rows: residual, mma, epilogue, gather; rows 4 / 5: start / end of every CTA).  NULL = off. */
+/* Profiling aid: while `buf` (8 x 256 uint64 device words, zeroed by the caller) is set, CTA `cta` of the scoring
+ * kernel records %globaltimer at every role hand-off (rows: residual, mma, epilogue, gather; rows 4 / 5: start / end of every CTA,
+ * rows 6 / 7: feature producer / consumer per chunk).  NULL = off. */
 int nsac_debug_score_trace(void* buf, int cta);
 
 /* Assignment pruning with the refined pose (camera_head.py:605-629): keep matches whose warped normal

@@ -61,24 +61,27 @@ constexpr int NUM_WARPS = 32, NUM_THREADS = NUM_WARPS * 32;
 constexpr int R_WARP0 = 0, R_WARPS = 16, R_THREADS = R_WARPS * 32;
 constexpr int G_WARP0 = 16, G_THREADS = 256;
 constexpr int E_WARP0 = 24;
-constexpr int T_WARP = 28, M_WARP = 29;
+constexpr int T_WARP = 28, M_WARP = 29, C_WARP = 30, F_WARP = 31;
 constexpr uint32_t SPIN_LIMIT = 2000;      // suspended waits of up to ~10 ms each: ~20 s, then trap instead of hanging
 constexpr int PART_HDR = 4;                          // max, sumexp, pad, pad (keeps the vectors 16-byte aligned)
 constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch): header, wsum[256], fsum[256]
 
 // shared memory map (offsets from a 1024-aligned base)
-constexpr int OFF_W2 = 0;                                        // [branch][kblock 0..1][16 KB]
-constexpr int OFF_W1 = OFF_W2 + 4 * BLK_BYTES;                   // [stage][branch][16 KB]
+constexpr int F_STAGES = 4, F_BYTES = 16384;                       // feature ring: 16 hypothesis rows x 256 fp32 per stage (the single
+                                                                   // producer thread needs ~0.26 us per bulk copy: 8 KB chunks capped the stream at 31 GB/s per SM)
+constexpr int F_ROWS = F_BYTES / (C_FEAT * 4);
+constexpr int OFF_F = 0;                                         // [F_STAGES][F_BYTES] feature ring (TMA bulk copies)
+constexpr int OFF_W1 = OFF_F + F_STAGES * F_BYTES;               // [stage][branch][16 KB]: W1 k-blocks, then the tile's two W2 k-blocks
 constexpr int OFF_A = OFF_W1 + W_STAGES * 2 * BLK_BYTES;         // [stage][branch][16 KB]
 constexpr int CJK_BYTES = 4096;                                   // per k-block: 2 KB column constants + 2 KB B fragments
-constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [W_STAGES][CJK_BYTES] column block of the k-block (TMA)
+constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [A_STAGES][CJK_BYTES] column block of the k-block (TMA)
 constexpr int OFF_VEC = OFF_CJ + W_STAGES * CJK_BYTES;           // b1[2][128], b2[2][128], w34[2][128] floats
 constexpr int OFF_LOGIT = OFF_VEC + 6 * HID * 4;                 // [2 bufs][2 branches][128] floats
 constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [2 column halves][2 branches][128] floats (min-cost sums)
 constexpr int OFF_EXP = OFF_ROWSUM + 2 * 2 * TILE_H * 4;         // [2 branches][128] softmax numerators of the tile
 constexpr int OFF_GPART = OFF_EXP + 2 * TILE_H * 4;              // [2 branches][64 threads][9] odd-row partials (+1 pad)
 constexpr int OFF_BAR = OFF_GPART + 2 * 64 * 12 * 4;
-constexpr int SMEM_BYTES = OFF_BAR + 256 + 1024;
+constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
 
 // tensor-memory columns
@@ -88,8 +91,10 @@ constexpr uint32_t TM_D2 = 256;       // layer 2: D2_rot [256,384), D2_tran [384
                                       // while the epilogue warps still read D2 (MMAs execute in issue order: no barrier)
 constexpr uint32_t TM_COLS = 512;
 
-enum { BAR_W2 = 0, BAR_W_FULL = 1, BAR_W_EMPTY = 3, BAR_A_FULL = 5, BAR_A_EMPTY = 7, BAR_ACC_FULL = 9, BAR_H1_READY = 10,
-       BAR_ACC2_FULL = 11, BAR_LOGIT_READY = 13, BAR_LOGIT_FREE = 15, BAR_COUNT = 17 };
+enum { BAR_CJ_FULL = 0, BAR_W_FULL = 2, BAR_W_EMPTY = 4, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_ACC_FULL = 10, BAR_H1_READY = 11,
+       BAR_ACC2_FULL = 12, BAR_LOGIT_READY = 13, BAR_LOGIT_FREE = 15, BAR_CJ_EMPTY = 17, BAR_F_FULL = 19,
+       BAR_F_EMPTY = BAR_F_FULL + F_STAGES, BAR_COUNT = BAR_F_EMPTY + F_STAGES };
+static_assert(BAR_COUNT * 8 + 8 <= 512, "barrier area");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -116,6 +121,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
     if (done) break;
     if (++spins > SPIN_LIMIT) __trap();
+  }
+}
+// Fine-grained rings (8 KB feature chunks, ~0.2 us apart): plain try_wait polling, no suspend hint - a parked warp
+// resumes too late for this cadence.  Only the 8 gather warps and the feature producer use it.
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) break;
+    if (++spins > (1u << 26)) __trap();
   }
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
@@ -393,6 +413,7 @@ struct TcParams {
   const int32_t* matched_num;
   const float* vecs;        // packed: b1[2][128], b2[2][128], w34[2][128]
   const uint8_t* cjk;       // [B][NQp/64][4096 B] per k-block: column constants + HMMA B fragments of the hypothesis tiles
+  const uint4* afr;         // [B][tiles*128][4] HMMA A fragments of every hypothesis row: hi (w01[4 comps], w2[4]), lo (w01[4], w2[4])
   int B, NQ, NQp, tiles_per_pair, need_sums;
   int num_items, row0_tiles, row0_at;     // item list = B*tiles_per_pair hypothesis tiles + row0_tiles inserted at index row0_at
   float* logits;            // [2][B][NQ+1]
@@ -447,8 +468,9 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   if (p.trace && threadIdx.x == 0 && blockIdx.x < TRACE_EVENTS) p.trace[4 * TRACE_EVENTS + blockIdx.x] = gtime();     // CTA start
 
   if (threadIdx.x == 0) {
-    mbar_init(&bars[BAR_W2], 1);
     for (int s = 0; s < W_STAGES; ++s) { mbar_init(&bars[BAR_W_FULL + s], 1); mbar_init(&bars[BAR_W_EMPTY + s], 1); }
+    for (int s = 0; s < A_STAGES; ++s) { mbar_init(&bars[BAR_CJ_FULL + s], 1); mbar_init(&bars[BAR_CJ_EMPTY + s], R_WARPS); }
+    for (int s = 0; s < F_STAGES; ++s) { mbar_init(&bars[BAR_F_FULL + s], 1); mbar_init(&bars[BAR_F_EMPTY + s], G_THREADS / 64); }
     for (int s = 0; s < A_STAGES; ++s) { mbar_init(&bars[BAR_A_FULL + s], R_WARPS + 1); mbar_init(&bars[BAR_A_EMPTY + s], 1); }
     mbar_init(&bars[BAR_ACC_FULL], 1);
     mbar_init(&bars[BAR_H1_READY], 4);
@@ -471,39 +493,82 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   if (warp >= T_WARP) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
   if (warp == T_WARP) {
-    // ================================================================================= TMA producer
+    // ================================================================================= weight producer (W ring)
+    // per tile: nkb stages of W1 k-blocks, then two stages carrying the tile's W2 k-blocks (layer 2)
     if (lane == 0) {
-      mbar_expect_tx(&bars[BAR_W2], 4 * BLK_BYTES);
-      for (int kb = 0; kb < 2; ++kb) {
-        tma_load_2d(smem + OFF_W2 + (0 * 2 + kb) * BLK_BYTES, &map_w2r, &bars[BAR_W2], kb * KB, 0);
-        tma_load_2d(smem + OFF_W2 + (1 * 2 + kb) * BLK_BYTES, &map_w2t, &bars[BAR_W2], kb * KB, 0);
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        Item it;
+        if (!decode_item(p, item, it)) continue;
+        for (int kb = 0; kb < it.nkb + 2; ++kb) {
+          mbar_wait(&bars[BAR_W_EMPTY + stage], phase ^ 1);
+          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES);
+          uint8_t* dst = smem + OFF_W1 + stage * 2 * BLK_BYTES;
+          if (kb < it.nkb) {
+            tma_load_2d(dst, &map_w1r, &bars[BAR_W_FULL + stage], kb * KB, 0);
+            tma_load_2d(dst + BLK_BYTES, &map_w1t, &bars[BAR_W_FULL + stage], kb * KB, 0);
+          } else {
+            tma_load_2d(dst, &map_w2r, &bars[BAR_W_FULL + stage], (kb - it.nkb) * KB, 0);
+            tma_load_2d(dst + BLK_BYTES, &map_w2t, &bars[BAR_W_FULL + stage], (kb - it.nkb) * KB, 0);
+          }
+          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+        }
       }
-      int stage = 0; uint32_t phase = 0;      // the W ring and the A ring advance together (one stage of each per k-block)
+    }
+  } else if (warp == C_WARP) {
+    // ================================================================================= column-block / A-ring producer
+    // hypothesis tiles: the k-block's column block (2 KB of constants + 2 KB of HMMA B fragments) into the CJ ring, and the
+    // 17th arrival on the A stage; row-0 tiles: that arrival carries the two [128 pairs x 64 columns] fp16 residual
+    // blocks TMA writes into the A stage (rows >= B: zero fill)
+    if (lane == 0) {
+      int as = 0; uint32_t aph = 0; int cs = 0; uint32_t cph = 0;
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         Item it;
         if (!decode_item(p, item, it)) continue;
         for (int kb = 0; kb < it.nkb; ++kb) {
-          mbar_wait(&bars[BAR_W_EMPTY + stage], phase ^ 1);
-          mbar_expect_tx(&bars[BAR_W_FULL + stage], 2 * BLK_BYTES + (it.row0 ? 0 : CJK_BYTES));
-          uint8_t* dst = smem + OFF_W1 + stage * 2 * BLK_BYTES;
-          tma_load_2d(dst, &map_w1r, &bars[BAR_W_FULL + stage], kb * KB, 0);
-          tma_load_2d(dst + BLK_BYTES, &map_w1t, &bars[BAR_W_FULL + stage], kb * KB, 0);
-          // the k-block's column block (2 KB of constants + 2 KB of HMMA B fragments) travels with the weights
-          if (!it.row0)
-            bulk_load_1d(smem + OFF_CJ + stage * CJK_BYTES, p.cjk + ((size_t)it.b * (p.NQp / KB) + kb) * CJK_BYTES, CJK_BYTES,
-                         &bars[BAR_W_FULL + stage]);
-          // A ring: the producer is the 17th arriver of every stage; for a row-0 tile its arrival carries the bytes of
-          // the two [128 pairs x 64 columns] fp16 residual blocks that TMA writes into the stage (rows >= B: zero fill)
-          mbar_wait(&bars[BAR_A_EMPTY + stage], phase ^ 1);
-          if (it.row0) {
-            uint8_t* a = smem + OFF_A + stage * 2 * BLK_BYTES;
-            mbar_expect_tx(&bars[BAR_A_FULL + stage], 2 * BLK_BYTES);
-            tma_load_2d(a, &map_x0r, &bars[BAR_A_FULL + stage], kb * KB, it.b);
-            tma_load_2d(a + BLK_BYTES, &map_x0t, &bars[BAR_A_FULL + stage], kb * KB, it.b);
-          } else {
-            mbar_arrive(&bars[BAR_A_FULL + stage]);
+          if (!it.row0) {
+            mbar_wait(&bars[BAR_CJ_EMPTY + cs], cph ^ 1);
+            mbar_expect_tx(&bars[BAR_CJ_FULL + cs], CJK_BYTES);
+            bulk_load_1d(smem + OFF_CJ + cs * CJK_BYTES, p.cjk + ((size_t)it.b * (p.NQp / KB) + kb) * CJK_BYTES, CJK_BYTES,
+                         &bars[BAR_CJ_FULL + cs]);
+            if (++cs == A_STAGES) { cs = 0; cph ^= 1; }
           }
-          if (++stage == W_STAGES) { stage = 0; phase ^= 1; }
+          mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
+          if (it.row0) {
+            uint8_t* a = smem + OFF_A + as * 2 * BLK_BYTES;
+            mbar_expect_tx(&bars[BAR_A_FULL + as], 2 * BLK_BYTES);
+            tma_load_2d(a, &map_x0r, &bars[BAR_A_FULL + as], kb * KB, it.b);
+            tma_load_2d(a + BLK_BYTES, &map_x0t, &bars[BAR_A_FULL + as], kb * KB, it.b);
+          } else {
+            mbar_arrive(&bars[BAR_A_FULL + as]);
+          }
+          if (++as == A_STAGES) { as = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == F_WARP) {
+    // ================================================================================= feature producer (F ring)
+    // The only HBM stream of the kernel.  256 gather threads with register-staged LDG.128 top out at ~3.6 TB/s no matter
+    // how many loads are in flight; cp.async.bulk into a 8 x 8 KB ring reaches 6.2 TB/s with 64 KB in flight (scripts/ubench/stream.cu).  The
+    // producer runs ahead of the consumers across tile boundaries: chunk = F_ROWS hypothesis rows of one branch, order
+    // (chunk 0, rot), (chunk 0, tran), (chunk 1, rot), ...
+    if (lane == 0) {
+      int fs = 0; uint32_t fph = 0;
+      for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
+        Item it;
+        if (!decode_item(p, item, it) || it.row0) continue;
+        const int rows = min(TILE_H, it.m - it.tile * TILE_H);
+        const size_t row0 = (size_t)it.b * p.NQ + (size_t)it.tile * TILE_H;
+        for (int r = 0; r < rows; r += F_ROWS) {
+          const uint32_t bytes = (uint32_t)min(F_ROWS, rows - r) * (C_FEAT * 4);
+#pragma unroll 1
+          for (int br = 0; br < 2; ++br) {
+            mbar_wait_spin(&bars[BAR_F_EMPTY + fs], fph ^ 1);
+            NSAC_TRACE(6, true);
+            mbar_expect_tx(&bars[BAR_F_FULL + fs], bytes);
+            bulk_load_1d(smem + OFF_F + fs * F_BYTES, (br == 0 ? p.feat_rot : p.feat_tran) + (row0 + r) * C_FEAT, bytes, &bars[BAR_F_FULL + fs]);
+            if (++fs == F_STAGES) { fs = 0; fph ^= 1; }
+          }
         }
       }
     }
@@ -511,7 +576,6 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     // ================================================================================= MMA issuer
     if (lane == 0) {
       int ws = 0; uint32_t wph = 0; int as = 0; uint32_t aph = 0; uint32_t tph = 0;   // tph: per-tile barrier parity
-      mbar_wait(&bars[BAR_W2], 0);
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         Item it;
         if (!decode_item(p, item, it)) continue;
@@ -537,25 +601,32 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
         }
         umma_commit(&bars[BAR_ACC_FULL]);
-        // layer 2: A = H1 (fp16 pairs in tensor memory), B = W2 (resident in shared memory), D2 in its own columns.
+        // layer 2: A = H1 (fp16 pairs in tensor memory), B = W2 (two k-blocks through the W ring), D2 in its own columns.
         // H1_READY of this tile also implies that the epilogue warps have finished reading D2 of the previous tile.
         NSAC_TRACE(1, true);
         mbar_wait(&bars[BAR_H1_READY], tph);
         NSAC_TRACE(1, true);
         fence_after();
 #pragma unroll 1
-        for (int br = 0; br < 2; ++br) {
+        for (int kb2 = 0; kb2 < 2; ++kb2) {
+          mbar_wait(&bars[BAR_W_FULL + ws], wph);
+          fence_after();
+          const uint32_t w0 = smem_u32(smem + OFF_W1 + ws * 2 * BLK_BYTES);
 #pragma unroll 1
-          for (int k = 0; k < HID / 16; ++k) {
-            const uint64_t dw = sw128_desc(smem_u32(smem + OFF_W2 + (br * 2 + (k >> 2)) * BLK_BYTES)) + 2 * (k & 3);
-            umma_ts(tmem_base + TM_D2 + br * HID, tmem_base + TM_D + br * HID + k * 8, dw, IDESC, k != 0);
+          for (int br = 0; br < 2; ++br) {
+            const uint64_t dw = sw128_desc(w0 + br * BLK_BYTES);
+#pragma unroll 1
+            for (int k4 = 0; k4 < 4; ++k4)
+              umma_ts(tmem_base + TM_D2 + br * HID, tmem_base + TM_D + br * HID + (kb2 * 4 + k4) * 8, dw + 2 * k4, IDESC, (kb2 | k4) != 0);
           }
+          umma_commit(&bars[BAR_W_EMPTY + ws]);
+          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
         }
         umma_commit(&bars[BAR_ACC2_FULL]);
         tph ^= 1;
       }
     }
-  }   // warps 30, 31: idle (they only donate their registers)
+  }
   } else if (warp >= E_WARP0) {
     // ================================================================================= epilogue warps 24..27
     asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
@@ -649,7 +720,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     // warps only pass their turns.
     const int rw = warp - R_WARP0;                   // 0..15 (these warps keep the 64 registers of the launch)
     const int rb = rw & 7, chalf = rw >> 3, g = lane >> 2, q = lane & 3;
-    int as = 0; uint32_t aph = 0; int ws = 0; uint32_t wph = 0;
+    int as = 0; uint32_t aph = 0; int cs = 0; uint32_t cph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       Item it;
       if (!decode_item(p, item, it)) continue;
@@ -659,62 +730,46 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
           if (++as == A_STAGES) { as = 0; aph ^= 1; }
-          if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
         }
         continue;
       }
-      // ---- hypothesis tile: A fragments of this thread's two rows (g, g + 8 of row block rb), once per tile
+      // ---- hypothesis tile: A fragments of this thread's two rows (g, g + 8 of row block rb), once per tile.  They were
+      // computed by score_prep_kernel for every hypothesis (identity pose beyond m): two 16-byte loads per row, no math
+      // and no dependence on matched_num, instead of two dependent global round trips + ~250 instructions per tile.
       uint32_t afrag[4][4];
+      {
+        const uint4* ar = p.afr + ((size_t)it.b * p.tiles_per_pair * TILE_H + (size_t)it.tile * TILE_H + rb * 16 + g) * 4 + (q == 1 ? 2 : 0);
 #pragma unroll
-      for (int h2 = 0; h2 < 2; ++h2) {
-        // rows beyond m keep the identity pose: their A rows only reach their own (ignored) rows of D
-        const int hidx = it.tile * TILE_H + rb * 16 + g + 8 * h2;       // index into q_h / t_h (hypothesis h = hidx + 1)
-        float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-        if (hidx < it.m) {
-          const float4 qq = *reinterpret_cast<const float4*>(p.q_h + ((size_t)it.b * p.NQ + hidx) * 4);
-          const float* tp = p.t_h + ((size_t)it.b * p.NQ + hidx) * 3;
-          qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
-          tx = tp[0]; ty = tp[1]; tz = tp[2];
+        for (int h2 = 0; h2 < 2; ++h2) {
+          uint4 w01 = __ldg(ar + h2 * 8 * 4), w2 = __ldg(ar + h2 * 8 * 4 + 1);
+          if (q == 3) { w01 = make_uint4(0u, 0u, 0u, 0u); w2 = w01; }
+          afrag[0][h2] = w01.x; afrag[1][h2] = w01.y; afrag[2][h2] = w01.z; afrag[3][h2] = w01.w;
+          afrag[0][2 + h2] = w2.x; afrag[1][2 + h2] = w2.y; afrag[2][2 + h2] = w2.z; afrag[3][2 + h2] = w2.w;
         }
-        float R[9], tr[3];
-        row_constants(qw, qx, qy, qz, tx, ty, tz, R, tr);
-        a_words(R[0], R[1], R[2], q, afrag[0][h2], afrag[0][2 + h2]);
-        a_words(R[3], R[4], R[5], q, afrag[1][h2], afrag[1][2 + h2]);
-        a_words(R[6], R[7], R[8], q, afrag[2][h2], afrag[2][2 + h2]);
-        // t.u = (t / k) . ((k R) n^) = s . n^ with s = (k R)^T (t / k)
-        a_words(fmaf(tr[0], R[0], fmaf(tr[1], R[3], tr[2] * R[6])), fmaf(tr[0], R[1], fmaf(tr[1], R[4], tr[2] * R[7])),
-                fmaf(tr[0], R[2], fmaf(tr[1], R[5], tr[2] * R[8])), q, afrag[3][h2], afrag[3][2 + h2]);
       }
       u64 sum_r[2] = {0ull, 0ull}, sum_t[2] = {0ull, 0ull};
-      // the next tile's poses are two dependent global round trips away (matched_num -> q_h / t_h rows): decode the next
-      // item now and prefetch its rows after the first k-block, so the per-tile preamble does not wait on DRAM
+      // decode the next item now and prefetch its fragment rows after the first k-block
       Item nx;
       nx.row0 = true;
       if (item + (int)gridDim.x < num_items && !decode_item(p, item + gridDim.x, nx)) nx.row0 = true;
       for (int kb = 0; kb < it.nkb; ++kb) {
-        if (kb == 1 && !nx.row0 && q == 0) {
-          const int hidx = nx.tile * TILE_H + rb * 16 + g;
-          if (hidx + 8 < nx.m) {
-            const float* qp = p.q_h + ((size_t)nx.b * p.NQ + hidx) * 4;
-            const float* tp = p.t_h + ((size_t)nx.b * p.NQ + hidx) * 3;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(qp));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(qp + 32));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(tp + 24));
-          }
+        if (kb == 1 && !nx.row0 && q == 0) {        // next tile's fragment rows (64 B each) into L2
+          const uint4* ar = p.afr + ((size_t)nx.b * p.tiles_per_pair * TILE_H + (size_t)nx.tile * TILE_H + rb * 16 + g) * 4;
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ar));
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(ar + 8 * 4));
         }
         NSAC_TRACE(0, threadIdx.x == 0);
         mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
         NSAC_TRACE(0, threadIdx.x == 0);
-        mbar_wait(&bars[BAR_W_FULL + ws], wph);           // column block of this k-block has landed (TMA)
+        mbar_wait(&bars[BAR_CJ_FULL + cs], cph);          // column block of this k-block has landed (TMA)
         NSAC_TRACE(0, threadIdx.x == 0);
-        residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + ws * CJK_BYTES, smem + OFF_A + as * 2 * BLK_BYTES, rb, chalf, lane, kb * KB,
+        residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + cs * CJK_BYTES, smem + OFF_A + as * 2 * BLK_BYTES, rb, chalf, lane, kb * KB,
                                   it.m, sum_r, sum_t);
         fence_proxy_async();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&bars[BAR_A_FULL + as]);
+        if (lane == 0) { mbar_arrive(&bars[BAR_A_FULL + as]); mbar_arrive(&bars[BAR_CJ_EMPTY + cs]); }
         if (++as == A_STAGES) { as = 0; aph ^= 1; }
-        if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
+        if (++cs == A_STAGES) { cs = 0; cph ^= 1; }
       }
       if (SUMS) {   // sum_j of the masked distances (argmin in 'min-cost', :1090-1093): 4 q-lanes x 2 column halves per row
 #pragma unroll
@@ -742,32 +797,15 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     }
   } else {
     // ================================================================================= gather warps 16..23
-    // thread = (branch, row parity, 4 feature channels): 10 float4 loads in flight per thread = 40 KB per SM (Little's
-    // law: 41 GB/s per SM at ~1 us loaded latency; with a 56-register cap ptxas kept only ~4.5 loads in flight and the
-    // whole kernel became gather-bound, s2/s3 captures).  These warps keep the 64 registers of the launch.
+    // consumers of the feature ring (F_WARP): flash-style softmax partials of the tile (local max / sum of exp, the
+    // exp-weighted and the plain sum of its [rows,256] one-plane features); these warps keep the 64 registers of the launch
     const int gt = threadIdx.x - G_WARP0 * 32;       // 0..255
-    const int br = gt >> 7, par = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
+    const int br = gt >> 7, rs = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
     int lbuf = 0; uint32_t lph = 0;
-    // The stream is latency-bound with what fits in registers (s9 timeline: 12 us per 262 KB tile = 22 GB/s per SM at
-    // ~1.5 us loaded DRAM latency), so every tile's rows are pulled into L2 one tile ahead with fire-and-forget
-    // prefetches (no registers held); the demand loads below then pay L2 latency only.
-    auto prefetch_tile = [&](const Item& x) {
-      if (x.row0) return;
-      const int nlines = min(TILE_H, x.m - x.tile * TILE_H) * (C_FEAT * 4 / 128);
-      const char* base = reinterpret_cast<const char*>((br == 0 ? p.feat_rot : p.feat_tran) + ((size_t)x.b * p.NQ + (size_t)x.tile * TILE_H) * C_FEAT);
-      for (int l = gt & 127; l < nlines; l += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(base + (size_t)l * 128));
-    };
-    {
-      Item first;
-      if ((int)blockIdx.x < num_items && decode_item(p, blockIdx.x, first)) prefetch_tile(first);
-    }
+    int fs = br; uint32_t fph = 0;                   // this branch's next stage of the feature ring (stages alternate rot / tran)
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       Item it;
       if (!decode_item(p, item, it)) continue;
-      {
-        Item nx;
-        if (item + (int)gridDim.x < num_items && decode_item(p, item + gridDim.x, nx)) prefetch_tile(nx);
-      }
       NSAC_TRACE(3, threadIdx.x == G_WARP0 * 32);
       mbar_wait(&bars[BAR_LOGIT_READY + lbuf], lph);
       NSAC_TRACE(3, threadIdx.x == G_WARP0 * 32);
@@ -784,7 +822,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       float* ex = s_exp + br * TILE_H;
       float mx;
       {
-        const int r = par * 64 + t64;
+        const int r = rs * 64 + t64;
         const float v = r < rows ? lg[r] : -INFINITY;
         const float wm = warp_max(v);
         float* wmax = s_gpart + (br * 64) * 12 + 9;
@@ -794,49 +832,56 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         ex[r] = r < rows ? __expf(v - mx) : 0.f;
       }
       named_bar_sync(4 + br, 128);
-      const float* f = (br == 0 ? p.feat_rot : p.feat_tran) + ((size_t)b * p.NQ + (size_t)tile * TILE_H) * C_FEAT + c4;
       // packed accumulators: (x,y) and (z,w) of the exp-weighted sum and of the plain sum
       u64 wxy = 0ull, wzw = 0ull, fxy = 0ull, fzw = 0ull;
       float se = 0.f;
-      if (par == 0 && t64 < 32) {            // sum of the tile's softmax numerators, once (one warp per branch)
+      if (rs == 0 && t64 < 32) {             // sum of the tile's softmax numerators, once (one warp per branch)
         const float4 e4 = *reinterpret_cast<const float4*>(ex + t64 * 4);
         se = warp_sum((e4.x + e4.y) + (e4.z + e4.w));
       }
-      int r = par;
-      for (; r + 18 < rows; r += 20) {       // 10 rows of this parity in flight
-        ulonglong2 v[10];
+      // feature ring: this thread = 4 channels x rows rs*8 .. rs*8+7 of every 16-row chunk of its branch
+      constexpr int HR = F_ROWS / 2;
+      for (int r0 = 0; r0 < rows; r0 += F_ROWS) {
+        mbar_wait_spin(&bars[BAR_F_FULL + fs], fph);
+        NSAC_TRACE(7, threadIdx.x == G_WARP0 * 32);
+        const ulonglong2* fr = reinterpret_cast<const ulonglong2*>(smem + OFF_F + fs * F_BYTES) + (rs * HR) * (C_FEAT / 4) + t64;
+        float e[HR];
 #pragma unroll
-        for (int u = 0; u < 10; ++u) v[u] = __ldg(reinterpret_cast<const ulonglong2*>(f + (size_t)(r + 2 * u) * C_FEAT));
-#pragma unroll
-        for (int u = 0; u < 10; ++u) {
-          const u64 e2 = bc2(ex[r + 2 * u]);
-          wxy = ffma2(e2, v[u].x, wxy); wzw = ffma2(e2, v[u].y, wzw);
-          fxy = fadd2(fxy, v[u].x); fzw = fadd2(fzw, v[u].y);
+        for (int i = 0; i < HR; i += 4) {
+          const float4 e4 = *reinterpret_cast<const float4*>(ex + r0 + rs * HR + i);      // 0 beyond `rows`
+          e[i] = e4.x; e[i + 1] = e4.y; e[i + 2] = e4.z; e[i + 3] = e4.w;
         }
+#pragma unroll
+        for (int i = 0; i < HR; ++i) {
+          if (r0 + rs * HR + i < rows) {            // (a partial last chunk leaves stale rows in the stage)
+            const ulonglong2 v = fr[i * (C_FEAT / 4)];
+            const u64 e2 = bc2(e[i]);
+            wxy = ffma2(e2, v.x, wxy); wzw = ffma2(e2, v.y, wzw);
+            fxy = fadd2(fxy, v.x); fzw = fadd2(fzw, v.y);
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&bars[BAR_F_EMPTY + fs]);
+        fs += 2;
+        if (fs >= F_STAGES) { fs -= F_STAGES; fph ^= 1; }
       }
-      for (; r < rows; r += 2) {
-        const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(f + (size_t)r * C_FEAT));
-        const u64 e2 = bc2(ex[r]);
-        wxy = ffma2(e2, v.x, wxy); wzw = ffma2(e2, v.y, wzw);
-        fxy = fadd2(fxy, v.x); fzw = fadd2(fzw, v.y);
-      }
-      float4 ws, fs;
+      float4 ws, fs4;
       upk2(wxy, ws.x, ws.y); upk2(wzw, ws.z, ws.w);
-      upk2(fxy, fs.x, fs.y); upk2(fzw, fs.z, fs.w);
+      upk2(fxy, fs4.x, fs4.y); upk2(fzw, fs4.z, fs4.w);
       float* gp = s_gpart + (br * 64 + t64) * 12;
-      if (par == 1) {
+      if (rs == 1) {
         *reinterpret_cast<float4*>(gp) = ws;
-        *reinterpret_cast<float4*>(gp + 4) = fs;
+        *reinterpret_cast<float4*>(gp + 4) = fs4;
       }
       named_bar_sync(4 + br, 128);
-      if (par == 0) {
+      if (rs == 0) {
         const float4 w1 = *reinterpret_cast<const float4*>(gp), f1 = *reinterpret_cast<const float4*>(gp + 4);
         ws.x += w1.x; ws.y += w1.y; ws.z += w1.z; ws.w += w1.w;
-        fs.x += f1.x; fs.y += f1.y; fs.z += f1.z; fs.w += f1.w;
+        fs4.x += f1.x; fs4.y += f1.y; fs4.z += f1.z; fs4.w += f1.w;
         float* part = p.partials + (((size_t)b * p.tiles_per_pair + tile) * 2 + br) * PART_STRIDE;
         if (t64 == 0) { part[0] = mx; part[1] = se; }
         *reinterpret_cast<float4*>(part + PART_HDR + c4) = ws;
-        *reinterpret_cast<float4*>(part + PART_HDR + C_FEAT + c4) = fs;
+        *reinterpret_cast<float4*>(part + PART_HDR + C_FEAT + c4) = fs4;
       }
       named_bar_sync(4 + br, 128);      // s_exp / s_gpart free for the next tile
       NSAC_TRACE(3, threadIdx.x == G_WARP0 * 32);
@@ -860,13 +905,42 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
 //   sums[.][b][0]              masked distance sums of hypothesis 0 ('min-cost'), fixed summation order
 constexpr int PREP_THREADS = 256;
 __global__ void __launch_bounds__(PREP_THREADS)
-score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__ q0, const float* __restrict__ t0,
-                  const int32_t* __restrict__ matched_num, int B, int NQ, int NQp, uint8_t* __restrict__ cjk,
-                  __half* __restrict__ x0, float* __restrict__ sums) {
+score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__ q_h, const float* __restrict__ t_h,
+                  const float* __restrict__ q0, const float* __restrict__ t0, const int32_t* __restrict__ matched_num, int B, int NQ,
+                  int NQp, int rows_per_pair, uint8_t* __restrict__ cjk, __half* __restrict__ x0, uint4* __restrict__ afr,
+                  float* __restrict__ sums) {
   __shared__ float red[2][PREP_THREADS / 32];
   const int b = blockIdx.x, tid = threadIdx.x, m = matched_num[b];
   float R[9], ts[3];
   row_constants(q0[b * 4 + 0], q0[b * 4 + 1], q0[b * 4 + 2], q0[b * 4 + 3], t0[b * 3 + 0], t0[b * 3 + 1], t0[b * 3 + 2], R, ts);
+  // A fragments of every hypothesis row h = 1 + i (rows beyond m: identity pose; their D rows are never read)
+  for (int i = tid; i < rows_per_pair; i += PREP_THREADS) {
+    float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+    if (i < m) {
+      const float4 qq = *reinterpret_cast<const float4*>(q_h + ((size_t)b * NQ + i) * 4);
+      const float* tp = t_h + ((size_t)b * NQ + i) * 3;
+      qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
+      tx = tp[0]; ty = tp[1]; tz = tp[2];
+    }
+    float Rh[9], th[3];
+    row_constants(qw, qx, qy, qz, tx, ty, tz, Rh, th);
+    // t.u = (t / k) . ((k R) n^) = s . n^ with s = (k R)^T (t / k)
+    const float sv[3] = {fmaf(th[0], Rh[0], fmaf(th[1], Rh[3], th[2] * Rh[6])), fmaf(th[0], Rh[1], fmaf(th[1], Rh[4], th[2] * Rh[7])),
+                         fmaf(th[0], Rh[2], fmaf(th[1], Rh[5], th[2] * Rh[8]))};
+    uint32_t w01[2][4], w2[2][4];
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {        // v = 0: hi words (k-slot groups q = 0, 2), v = 1: lo words (q = 1)
+      a_words(Rh[0], Rh[1], Rh[2], v, w01[v][0], w2[v][0]);
+      a_words(Rh[3], Rh[4], Rh[5], v, w01[v][1], w2[v][1]);
+      a_words(Rh[6], Rh[7], Rh[8], v, w01[v][2], w2[v][2]);
+      a_words(sv[0], sv[1], sv[2], v, w01[v][3], w2[v][3]);
+    }
+    uint4* o = afr + ((size_t)b * rows_per_pair + i) * 4;
+    o[0] = make_uint4(w01[0][0], w01[0][1], w01[0][2], w01[0][3]);
+    o[1] = make_uint4(w2[0][0], w2[0][1], w2[0][2], w2[0][3]);
+    o[2] = make_uint4(w01[1][0], w01[1][1], w01[1][2], w01[1][3]);
+    o[3] = make_uint4(w2[1][0], w2[1][1], w2[1][2], w2[1][3]);
+  }
   float sr = 0.f, st = 0.f;
   for (int j = tid; j < NQp; j += PREP_THREADS) {
     float f[CJ_FIELDS];
@@ -1158,7 +1232,7 @@ inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
 static unsigned long long* g_score_trace = nullptr;
 static int g_score_trace_cta = 0;
 // Debug aid: the next nsac_score_aggregate_tc launches record the role timeline of CTA `cta` into `buf`
-// (6 * 256 uint64 device words, zero-filled by the caller); nullptr switches it off.
+// (8 * 256 uint64 device words, zero-filled by the caller); nullptr switches it off.
 extern "C" int nsac_debug_score_trace(void* buf, int cta) {
   g_score_trace = static_cast<unsigned long long*>(buf);
   g_score_trace_cta = cta;
@@ -1186,7 +1260,8 @@ extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) {
   const size_t per = (size_t)B * (NQ + 1);
   const int tiles = (NQ + TILE_H - 1) / TILE_H;
   return align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float)) +
-         align256((size_t)B * nq_padded(NQ) * 64) + align256((size_t)2 * B * nq_padded(NQ) * sizeof(__half)) + 256;
+         align256((size_t)B * nq_padded(NQ) * 64) + align256((size_t)2 * B * nq_padded(NQ) * sizeof(__half)) +
+         align256((size_t)B * tiles * TILE_H * 64) + 256;
 }
 
 extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
@@ -1218,11 +1293,12 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   float* partials = reinterpret_cast<float*>(ws + align256(4 * per * sizeof(float)));
   uint8_t* cjk = ws + align256(4 * per * sizeof(float)) + align256((size_t)B * tiles * 2 * PART_STRIDE * sizeof(float));
   __half* x0 = reinterpret_cast<__half*>(cjk + align256((size_t)B * NQp * 64));
+  uint4* afr = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(x0) + align256((size_t)2 * B * NQp * sizeof(__half)));
   const float* vecs = reinterpret_cast<const float*>(pk + pack_off_vecs(NQp));
   const int row0_tiles = nsac_cdiv(B, TILE_H);
 
   // column blocks of every (pair, k-block) + hypothesis 0 of every pair
-  score_prep_kernel<<<B, PREP_THREADS, 0, s>>>(geo_local, q0, t0, matched_num, B, NQ, NQp, cjk, x0, sums);
+  score_prep_kernel<<<B, PREP_THREADS, 0, s>>>(geo_local, q_h, t_h, q0, t0, matched_num, B, NQ, NQp, tiles * TILE_H, cjk, x0, afr, sums);
   NSAC_CHECK_LAUNCH("score_prep_kernel");
 
   CUtensorMap m1r, m1t, m2r, m2t, mx0r, mx0t;
@@ -1237,7 +1313,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   TcParams tp;
   tp.trace = g_score_trace; tp.trace_cta = g_score_trace_cta;
   tp.geo_local = geo_local; tp.q_h = q_h; tp.t_h = t_h; tp.q0 = q0; tp.t0 = t0; tp.feat_rot = feat_rot; tp.feat_tran = feat_tran;
-  tp.matched_num = matched_num; tp.vecs = vecs; tp.cjk = cjk;
+  tp.matched_num = matched_num; tp.vecs = vecs; tp.cjk = cjk; tp.afr = afr;
   tp.B = B; tp.NQ = NQ; tp.NQp = NQp; tp.tiles_per_pair = tiles;
   tp.need_sums = out_cam_type == NSAC_CAM_MIN_COST; tp.logits = logits; tp.sums = sums; tp.partials = partials;
   static bool attr = false;

@@ -32,7 +32,7 @@ def once():
 for _ in range(3):
     once()
 torch.cuda.synchronize()
-buf = torch.zeros(6, 256, dtype=torch.int64, device=dev)
+buf = torch.zeros(8, 256, dtype=torch.int64, device=dev)
 _lib.lib().nsac_debug_score_trace(buf.data_ptr(), CTA)
 once()
 torch.cuda.synchronize()
@@ -44,8 +44,8 @@ en = [int(x) - t0_ for x in t[5].tolist() if x > 0]
 print('CTA start (ns): min', min(st), 'max', max(st))
 print('CTA end   (ns):', ' '.join(str(e) for e in en))
 print(f"CTA {CTA} dbg {DBG}")
-names = ["residual", "mma", "epilogue", "gather"]
-for r in range(4):
+names = ["residual", "mma", "epilogue", "gather", "", "", "f-producer", "f-consumer"]
+for r in (0, 1, 2, 3, 6, 7):
     ev = [int(x) - t0_ for x in t[r].tolist() if x > 0]
     print(f"{names[r]:9s} n={len(ev)} first {ev[0] if ev else None} last {ev[-1] if ev else None}")
     print("   t(ns):", " ".join(str(e) for e in ev[:80]))
