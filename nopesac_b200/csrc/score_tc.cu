@@ -898,7 +898,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   }
 }
 
-// One block per pair: the column blocks of the hypothesis tiles and hypothesis 0 (the initial pose) of the pair.
+// Two blocks per pair: the A fragments of its hypothesis rows / the column blocks of its hypothesis tiles and hypothesis 0
+// (the initial pose).
 //   cjk [B][NQp/64][4096 B]    per k-block: column constants -k n1, -k pi1, A, Bc (CJ8 layout) + HMMA B fragments
 //                              [8 groups][32 lanes][2 words] of n^ (fp16 hi / hi / lo k-slots, see hmma16816)
 //   x0  [2][B][NQp] fp16       exp(-d) of hypothesis 0 against every column (0 beyond m): the A operand of the row-0 tiles
@@ -910,11 +911,12 @@ score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__
                   int NQp, int rows_per_pair, uint8_t* __restrict__ cjk, __half* __restrict__ x0, uint4* __restrict__ afr,
                   float* __restrict__ sums) {
   __shared__ float red[2][PREP_THREADS / 32];
-  const int b = blockIdx.x, tid = threadIdx.x, m = matched_num[b];
-  float R[9], ts[3];
-  row_constants(q0[b * 4 + 0], q0[b * 4 + 1], q0[b * 4 + 2], q0[b * 4 + 3], t0[b * 3 + 0], t0[b * 3 + 1], t0[b * 3 + 2], R, ts);
+  // blocks [0, B): the rows of pair b (A fragments); blocks [B, 2B): its columns + hypothesis 0 - two independent load
+  // chains, so they run as separate blocks instead of back to back
+  const bool do_rows = (int)blockIdx.x < B;
+  const int b = do_rows ? blockIdx.x : blockIdx.x - B, tid = threadIdx.x, m = matched_num[b];
   // A fragments of every hypothesis row h = 1 + i (rows beyond m: identity pose; their D rows are never read)
-  for (int i = tid; i < rows_per_pair; i += PREP_THREADS) {
+  for (int i = tid; do_rows && i < rows_per_pair; i += PREP_THREADS) {
     float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
     if (i < m) {
       const float4 qq = *reinterpret_cast<const float4*>(q_h + ((size_t)b * NQ + i) * 4);
@@ -941,6 +943,9 @@ score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__
     o[2] = make_uint4(w01[1][0], w01[1][1], w01[1][2], w01[1][3]);
     o[3] = make_uint4(w2[1][0], w2[1][1], w2[1][2], w2[1][3]);
   }
+  if (do_rows) return;
+  float R[9], ts[3];
+  row_constants(q0[b * 4 + 0], q0[b * 4 + 1], q0[b * 4 + 2], q0[b * 4 + 3], t0[b * 3 + 0], t0[b * 3 + 1], t0[b * 3 + 2], R, ts);
   float sr = 0.f, st = 0.f;
   for (int j = tid; j < NQp; j += PREP_THREADS) {
     float f[CJ_FIELDS];
@@ -1087,33 +1092,43 @@ score_select_tc_kernel(const SelParams p) {
     publish_row(p, b, P);
     return;
   }
-  if (tid < 2) misc[tid] = p.logits[(size_t)tid * p.B * H1n + (size_t)b * H1n];     // hypothesis 0 (row-0 tiles of score_tc_kernel)
-  __syncthreads();
-  // ---- merge the tile partials with hypothesis 0 (log-sum-exp rescale)
+  // ---- merge the tile partials with hypothesis 0 (log-sum-exp rescale).  The kernel is a chain of dependent global
+  // round trips, so every thread issues ALL of its loads right after m is known (headers and hypothesis-0 logits are
+  // the same addresses for the whole block: broadcast) and computes M and S redundantly instead of thread 0 + barriers.
   const int ntile = (m + TILE_H - 1) / TILE_H;
-  if (tid < 2) {
-    const int br = tid;
-    float M = misc[br];                      // every logit here lacks the constant c34 (softmax-invariant)
-    for (int t = 0; t < ntile; ++t) M = fmaxf(M, p.partials[(((size_t)b * p.tiles_per_pair + t) * 2 + br) * PART_STRIDE]);
-    float S = expf(misc[br] - M);
-    for (int t = 0; t < ntile; ++t) {
-      const float* part = p.partials + (((size_t)b * p.tiles_per_pair + t) * 2 + br) * PART_STRIDE;
-      S += expf(part[0] - M) * part[1];
-    }
-    misc[2 + br] = M;
-    misc[4 + br] = S;
+  const float* part0 = p.partials + ((size_t)b * p.tiles_per_pair * 2) * PART_STRIDE;
+  const float l0r = p.logits[(size_t)b * H1n], l0t = p.logits[(size_t)p.B * H1n + (size_t)b * H1n];   // hypothesis 0 (row-0 tiles)
+  const float f0r = p.feat_rot0[(size_t)b * C + tid], f0t = p.feat_tran0[(size_t)b * C + tid];         // tid = channel
+  float Mr_ = l0r, Mt_ = l0t;                  // every logit here lacks the constant c34 (softmax-invariant)
+  for (int t = 0; t < ntile; ++t) {
+    Mr_ = fmaxf(Mr_, part0[(t * 2 + 0) * PART_STRIDE]);
+    Mt_ = fmaxf(Mt_, part0[(t * 2 + 1) * PART_STRIDE]);
   }
-  __syncthreads();
+  float Sr_ = expf(l0r - Mr_), St_ = expf(l0t - Mt_);
+  float ar = 0.f, at = 0.f, wr = 0.f, wt = 0.f;      // aggregated features of channel tid (:1047-1087)
+  for (int t = 0; t < ntile; ++t) {
+    const float* pr = part0 + (t * 2 + 0) * PART_STRIDE;
+    const float* pt = pr + PART_STRIDE;
+    const float er = expf(pr[0] - Mr_), et = expf(pt[0] - Mt_);
+    Sr_ = fmaf(er, pr[1], Sr_);
+    St_ = fmaf(et, pt[1], St_);
+    wr = fmaf(er, pr[PART_HDR + tid], wr);
+    wt = fmaf(et, pt[PART_HDR + tid], wt);
+    ar += pr[PART_HDR + C + tid];
+    at += pt[PART_HDR + C + tid];
+  }
+  if (tid == 0) { misc[0] = l0r; misc[1] = l0t; }
   // scores (softmax over hypotheses 0..m, :1010-1014, :1039-1043) -> global (optional) + kept for max-score
-  const float Mr_ = misc[2], Mt_ = misc[3], Sr_ = misc[4], St_ = misc[5];
   float* lr = p.logits + (size_t)b * H1n;
   float* lt = p.logits + (size_t)p.B * H1n + (size_t)b * H1n;
-  for (int h = tid; h <= m; h += blockDim.x) {
-    const float a = expf(lr[h] - Mr_) / Sr_;
-    const float c = expf(lt[h] - Mt_) / St_;
-    lr[h] = a; lt[h] = c;                     // logits buffer now holds the scores
-    if (p.score_rot) p.score_rot[(size_t)b * H1n + h] = a;
-    if (p.score_tran) p.score_tran[(size_t)b * H1n + h] = c;
+  if (p.score_rot || p.score_tran || (m > 1 && p.out_cam_type == NSAC_CAM_MAX_SCORE)) {
+    for (int h = tid; h <= m; h += blockDim.x) {
+      const float a = expf(lr[h] - Mr_) / Sr_;
+      const float c = expf(lt[h] - Mt_) / St_;
+      lr[h] = a; lt[h] = c;                     // logits buffer now holds the scores
+      if (p.score_rot) p.score_rot[(size_t)b * H1n + h] = a;
+      if (p.score_tran) p.score_tran[(size_t)b * H1n + h] = c;
+    }
   }
   __syncthreads();
   int sel_r = -1, sel_t = -1;
@@ -1125,21 +1140,10 @@ score_select_tc_kernel(const SelParams p) {
     sel_t = block_arg_extreme(lt, m + 1, true, red, redi);
   }
   if (p.sel_idx && tid == 0) { p.sel_idx[b * 2] = sel_r; p.sel_idx[b * 2 + 1] = sel_t; }
-  // ---- aggregated features, one channel per thread (:1047-1087)
   {
     const int c = tid;
-    const float f0r = p.feat_rot0[(size_t)b * C + c], f0t = p.feat_tran0[(size_t)b * C + c];
-    float ar = 0.f, at = 0.f, wr = 0.f, wt = 0.f;
-    for (int t = 0; t < ntile; ++t) {
-      const float* pr = p.partials + (((size_t)b * p.tiles_per_pair + t) * 2 + 0) * PART_STRIDE;
-      const float* pt = pr + PART_STRIDE;
-      wr = fmaf(expf(pr[0] - Mr_), pr[PART_HDR + c], wr);
-      wt = fmaf(expf(pt[0] - Mt_), pt[PART_HDR + c], wt);
-      ar += pr[PART_HDR + C + c];
-      at += pt[PART_HDR + C + c];
-    }
-    wr = (wr + expf(misc[0] - Mr_) * f0r) / Sr_;
-    wt = (wt + expf(misc[1] - Mt_) * f0t) / St_;
+    wr = (wr + expf(l0r - Mr_) * f0r) / Sr_;
+    wt = (wt + expf(l0t - Mt_) * f0t) / St_;
     if (m > 1) {  // the initial pose joins the average only when m > 1 (:1052-1063)
       const float w = 1.f / (float)(m + 1);
       ar = (ar + f0r) * w;
@@ -1298,7 +1302,7 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   const int row0_tiles = nsac_cdiv(B, TILE_H);
 
   // column blocks of every (pair, k-block) + hypothesis 0 of every pair
-  score_prep_kernel<<<B, PREP_THREADS, 0, s>>>(geo_local, q_h, t_h, q0, t0, matched_num, B, NQ, NQp, tiles * TILE_H, cjk, x0, afr, sums);
+  score_prep_kernel<<<2 * B, PREP_THREADS, 0, s>>>(geo_local, q_h, t_h, q0, t0, matched_num, B, NQ, NQp, tiles * TILE_H, cjk, x0, afr, sums);
   NSAC_CHECK_LAUNCH("score_prep_kernel");
 
   CUtensorMap m1r, m1t, m2r, m2t, mx0r, mx0t;
