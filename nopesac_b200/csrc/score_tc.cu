@@ -1,31 +1,27 @@
 // K8 + K9 on the Blackwell tensor pipe — hypothesis scoring and pose selection (camera_head.py:964-1115).
 //
-// Work item = (pair b, tile of 128 one-plane hypotheses h = 1 + 128*tile + r); hypothesis 0 (the initial pose)
-// is a single row and is scored by a small batched kernel.  One persistent CTA per SM, 24 warps in 6 warpgroups
-// (setmaxnreg moves registers from the TMA / MMA / epilogue warps to the residual warps):
-//
-//   warp 0        TMA        W2 (both branches, resident) once; then per (tile, k-block) the two [128 x 64] fp16
-//                            slices of the first score-MLP layer W1 (rot / trans) into a 2-stage ring
-//   warp 1        MMA        layer 1: D_b[128x128] += X_b[128x64] . W1_b^T  (tcgen05.mma kind::f16, A and B from
-//                            shared memory);  layer 2: D_b = H1_b . W2_b^T with H1 read from TENSOR MEMORY (A operand
-//                            written there by the epilogue warps) — the hidden activations never touch shared memory
-//   warps 4-7     epilogue   TMEM -> registers: +b1, ReLU, pack fp16x2 -> tcgen05.st (H1);  then +b2, ReLU and the
-//                            folded Linear(128,64)+Linear(64,1) dot product: one thread owns one hypothesis row, so
-//                            the logit needs no cross-thread reduction
-//   warps 8-15    residuals  the CUDA-core part: thread = (hypothesis row, 8-column chunk).  u = R_h n_j is shared by
-//                            both branches;  rot: exp(-|u - n1_j|);  trans: exp(-|A_j (d_j + t_h.u) u - pi1_j|)
-//                            (closed forms of the reference's warp + normalise, see residual_pair()); results are
-//                            written as fp16 straight into the 128-byte-swizzled K-major A-operand tiles (2-stage
-//                            ring), fence.proxy.async, mbarrier arrive.  The [B,NQ+1,NQ,3] temporaries of the
-//                            reference never exist.
-//   warps 16-23   gather     flash-style softmax partials: local max / sum of exp over the tile's logits and the
-//                            exp-weighted + plain sums of the tile's [128,256] one-plane features — the only HBM
-//                            stream of the kernel (float4 loads, 16 rows in flight), overlapped with the residual
-//                            and tensor work of the NEXT tile
-//
-// A per-pair selection kernel then scores hypothesis 0 (exact fp32), merges the tile partials (log-sum-exp
-// rescale), applies the m == 0 / m == 1 / m > 1 rules (:964, :1052, :1068), the avg / soft / min-cost /
-// max-score selection and the shared pose heads, and writes pose[b, 0:16].
+// Three kernels per call:
+//   score_prep_kernel        per pair: column blocks (residual constants + HMMA B fragments) of every k-block of 64
+//                            matched columns, HMMA A fragments of every hypothesis row, hypothesis 0 (the initial pose)
+//   score_tc_kernel          persistent, one CTA per SM, 32 warps in 8 warpgroups (setmaxnreg), work item = (pair b, tile
+//                            of 128 one-plane hypotheses h = 1 + 128*tile + r) or a row-0 tile (hypothesis 0 of 128 pairs):
+//     warps 0-15   residuals  u = (kR) n^ and t.u on HMMA (fp16 hi/lo k-slots), then per row x column pair 13 packed fp32
+//                             instructions + 4 MUFU.SQRT + 4 MUFU.EX2:  rot: exp(-|u - n1|), trans: exp(-|A (d + t.u) u - pi1|)
+//                             (closed forms of the reference's warp + normalise), written as fp16 straight into the
+//                             128-byte-swizzled K-major A-operand tiles (2-stage ring), fence.proxy.async, mbarrier arrive.
+//                             The [B,NQ+1,NQ,3] temporaries of the reference never exist.
+//     warps 16-23  gather     flash-style softmax partials: local max / sum of exp over the tile's logits and the
+//                             exp-weighted + plain sums of the tile's [128,256] one-plane features, read from the feature ring
+//     warps 24-27  epilogue   TMEM -> registers: +b1, ReLU, fp16x2 -> tcgen05.st (H1, in place);  then +b2, ReLU and the
+//                             folded Linear(128,64)+Linear(64,1) dot product: one thread owns one hypothesis row
+//     warp 28      TMA        W1 k-blocks (rot / trans [128 x 64] fp16 slices), then the tile's two W2 k-blocks (2-stage ring)
+//     warp 29      MMA        layer 1: D_b[128x128] += X_b[128x64] . W1_b^T (tcgen05.mma kind::f16, A and B from shared
+//                             memory);  layer 2: D2_b = H1_b . W2_b^T with H1 read from TENSOR MEMORY
+//     warp 30      TMA        column blocks (CJ ring) + row-0 tiles' A stages
+//     warp 31      TMA        feature ring: the only HBM stream of the kernel
+//   score_select_tc_kernel   per pair: merges the tile partials with hypothesis 0 (log-sum-exp rescale), applies the
+//                            m == 0 / m == 1 / m > 1 rules (:964, :1052, :1068), the avg / soft / min-cost / max-score
+//                            selection and the shared pose heads, and writes pose[b, 0:16].
 //
 // Precision: the score MLPs run single-pass fp16 (11 significant bits for exp(-d) in [0,1] and for the
 // weights) with fp32 accumulation; measured effect on scores <= 4e-5 and on the soft pose <= 3e-5 even with a
@@ -197,9 +193,6 @@ __device__ __forceinline__ uint64_t sw128_desc(uint32_t addr) {
 constexpr uint32_t IDESC = (1u << 4) | ((uint32_t)(HID >> 3) << 17) | ((uint32_t)(TILE_H >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------ residual math
-// Column constants of matched plane pair j (cj[12]): n^ = unit(p0*flip) (0-2), n1 = unit(p1*flip) (3-5),
-// pi1 = p1*flip (6-8), A = d^2/(d+1e-5)^2 (9), Bc = A*d (10), valid (11).
-//
 // Reference (camera_head.py:997-1035 with the warp of :1446-1453): e = R (p0*flip) + t, b = e - t, pi0 = (e.b/(|b|+1e-5)^2) b.
 // With u = R n^ (unit) and d = |p0|: b = d u, e.b = d^2 + d (t.u), so pi0 = A (d + t.u) u; for t = 0 its direction is u.
 //   rot  : exp(-| u - n1 |)                 (F.normalize of both sides)

@@ -1,5 +1,7 @@
-// Micro-benchmark of the residual evaluation (residual_cp of score_tc.cu: one hypothesis row x one column pair) in
-// isolation: cycles per evaluation per SM sub-partition for 1/2/4/8 warps per scheduler, constants in registers.
+// Micro-benchmark of the residual tail (residual_tail of score_tc.cu: everything after u = R n^ for one hypothesis row x one
+// column pair: 13 packed FMA-pipe instructions + 4 MUFU.SQRT + 4 MUFU.EX2 + 2 cvt) in isolation: cycles per evaluation per SM
+// sub-partition for 1/2/4/8 warps per scheduler, constants in registers.  (profiles/ubench_eval_all_fma.txt is the same
+// measurement for the earlier all-FMA evaluation, 25 packed instructions: 66-67 cycles at >= 2 warps per scheduler.)
 #include <cstdio>
 #include "../../nopesac_b200/csrc/score_tc.cu"
 
@@ -7,8 +9,8 @@ __global__ void k_eval(const float* in, uint32_t* out, long long* cyc, int iters
   float R[9], tr[3];
   for (int i = 0; i < 9; ++i) R[i] = in[i] + threadIdx.x * 1e-4f;
   for (int i = 0; i < 3; ++i) tr[i] = in[9 + i];
-  u64 c[CJ_FIELDS];
-  for (int i = 0; i < CJ_FIELDS; ++i) c[i] = pk2(in[12 + i] + (threadIdx.x & 31) * 1e-3f, in[24 + i]);
+  u64 c[CJ8_FIELDS];
+  for (int i = 0; i < CJ8_FIELDS; ++i) c[i] = pk2(in[12 + i] + (threadIdx.x & 31) * 1e-3f, in[24 + i]);
   uint32_t acc = 0;
   u64 s0 = 0, s1 = 0;
   __syncthreads();
@@ -18,7 +20,7 @@ __global__ void k_eval(const float* in, uint32_t* out, long long* cyc, int iters
     for (int i = 0; i < 8; ++i) {
       uint32_t hr, ht;
       R[0] += 1e-6f;
-      residual_cp<false>(R, tr, c, hr, ht, s0, s1);
+      residual_tail<false>(pk2(R[0], R[1]), pk2(R[2], R[3]), pk2(R[4], R[5]), pk2(tr[0], tr[1]), c, 0ull, hr, ht, s0, s1);
       acc ^= hr + ht;
     }
   }
@@ -38,7 +40,7 @@ int main() {
     k_eval<<<148, w * 128>>>(in, out, cyc, 10);
     k_eval<<<148, w * 128>>>(in, out, cyc, iters);
     long long c; cudaMemcpy(&c, cyc, 8, cudaMemcpyDeviceToHost);
-    printf("residual_cp: warps/sched=%d  cycles per evaluation per scheduler = %.1f  (XU floor 64, FMA-pipe floor 50)\n", w,
+    printf("residual_tail: warps/sched=%d  cycles per evaluation per scheduler = %.1f  (XU floor 64, FMA-pipe floor 26)\n", w,
            (double)c / ((double)iters * 8 * w));
   }
   return 0;
