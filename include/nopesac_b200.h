@@ -208,6 +208,10 @@ int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const floa
  * kernel records %globaltimer at every role hand-off (rows: residual, mma, epilogue, gather; rows 4 / 5: start / end of every CTA,
  * rows 6 / 7: feature producer / consumer per chunk).  NULL = off. */
 int nsac_debug_score_trace(void* buf, int cta);
+/* Same for the GEMM engine: CTA 0 of every nsac_gemm_split / nsac_conv3x3_split launch writes 9 timestamps into `buf`
+ * (16 uint64 device words): entry, setup done, first TMA issued, first operands landed, first chunk committed, epilogue
+ * start, epilogue end, after the final barrier, after TMEM dealloc.  NULL = off. */
+int nsac_debug_gemm_trace(void* buf);
 
 /* Assignment pruning with the refined pose (camera_head.py:605-629): keep matches whose warped normal
  * angle < 45 deg and offset distance < 1 m.  pose rows are (t[3], q[4], ...) with stride ldpose. */

@@ -410,8 +410,10 @@ class PlaneCameraHead(nn.Module):
         B = planeParam1.shape[0]
         NQ = self.num_queries
         trans_list, rot_list = [], []
-        output_cameras = {"camera_zero": {"tran": torch.zeros(1, 3, device=device),
-                                          "rot": torch.tensor([[1., 0., 0., 0.]], device=device)}}
+        # (no torch.tensor([...], device=...) here: that is a pageable H2D copy per call and not CUDA-graph capturable)
+        zero_rot = torch.zeros(1, 4, device=device)
+        zero_rot[:, 0] = 1.0
+        output_cameras = {"camera_zero": {"tran": torch.zeros(1, 3, device=device), "rot": zero_rot}}
         out_cam_type = self.inference_out_cam_type if self.cam_ref_on else "initial"
 
         if initial_pose is None:

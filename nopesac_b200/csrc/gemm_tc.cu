@@ -31,10 +31,13 @@
 //   warp 1      MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BLOCK_N,
 //                              K=16) on K-major SW128 descriptors; tcgen05.commit frees ring slots and
 //                              publishes the accumulator; also owns tcgen05.alloc / dealloc
-//   warps 2..5  epilogue       tcgen05.ld (32x32b.x32) of the fp32 accumulator from TMEM (double-buffered so
+//   warps 2..9  epilogue       tcgen05.ld (32x32b.x32) of the fp32 accumulator from TMEM (double-buffered so
 //                              the epilogue of tile i overlaps the MMAs of tile i+1), bias (+ per-pair bias
-//                              rows), activation, then fp32 rows and/or re-split bf16 hi/lo planes for the
-//                              next layer straight from registers
+//                              rows), activation, then fp32 rows and/or re-split fp16 / bf16 hi/lo planes for the
+//                              next layer straight from registers.  Two warps per TMEM lane quadrant (each owns
+//                              half of the columns), packed fp32 math, vector bias loads: one 128x128 tile takes
+//                              3.2 us instead of 10.6 us (nsac_debug_gemm_trace) - the epilogue, not the tensor
+//                              pipe, bounded the engine for K <= ~1300 and put a 12 us floor under every launch
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -45,8 +48,9 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;                 // 64 bf16 = one 128-byte swizzle row
 constexpr int UMMA_K = 16;
-constexpr int NUM_THREADS = 192;            // 6 warps
-constexpr uint32_t SPIN_LIMIT = 2000;      // suspended waits of up to ~10 ms each: ~20 s, then trap instead of hanging
+constexpr int EPI_WARPS = 8;                // two per TMEM lane quadrant: each owns half of the tile's columns
+constexpr int NUM_THREADS = 64 + EPI_WARPS * 32;   // TMA warp + MMA warp + epilogue warps
+constexpr uint32_t SPIN_LIMIT = 1u << 24;  // suspended waits of up to ~1 us each: ~17 s, then trap instead of hanging
 
 constexpr int CHUNK_KB = 4;                 // K-blocks (x64 elements) accumulated inside the tensor core per chunk
 
@@ -85,7 +89,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done) : "r"(addr), "r"(parity), "r"(0x989680u) : "memory");
+        : "=r"(done) : "r"(addr), "r"(parity), "r"(1000u) : "memory");
     if (done) break;
     if (++spins > SPIN_LIMIT) __trap();
   }
@@ -148,14 +152,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int m, int n, bool bf16) {
          ((uint32_t)(m >> 4) << 24);
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == NSAC_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == NSAC_ACT_LEAKY) return v > 0.f ? v : 0.01f * v;
-  return v;
+// Optional timeline of CTA 0 (profiling aid, nsac_debug_gemm_trace): %globaltimer at the role hand-offs of the launch.
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
-
+#define GEMM_TRACE(slot)                                                        \
+  do {                                                                          \
+    if (p.trace && blockIdx.x == 0) p.trace[slot] = gtime();                    \
+  } while (0)
 
 struct GemmParams {
+  unsigned long long* trace;   // nullptr unless tracing: [16] slots
   const float* bias;
   int bias_group_rows;
   int M, N, K, act, passes, fmt;
@@ -184,6 +193,116 @@ __device__ __forceinline__ void split16(float x, int fmt, uint16_t& hi, uint16_t
 
 
 
+
+// ---- packed fp32 (sm_100 FADD2 / FFMA2) for the epilogue: it is a long serial instruction stream on one warp per
+// scheduler, and for K <= ~1300 the tile's MMAs finish before it does (nsac_debug_gemm_trace: 8-10 us per 128x128 tile
+// before this rewrite, i.e. the epilogue - not the tensor pipe - bounded the engine)
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ u64 ffma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 fadd2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// two values -> packed (hi, lo) 16-bit plane words
+template <int FMT>
+__device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  if (FMT == NSAC_SPLIT_F16) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 back = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  } else {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    const float2 back = __bfloat1622float2(h);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(a - back.x, b - back.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+  }
+}
+
+struct EpiOut {
+  float out_scale;
+  const float* brow;      // bias row of this thread's output row (nullptr: no bias)
+  float* out_f32;         // row pointers (nullptr: not requested)
+  uint16_t* out_hi;
+  uint16_t* out_lo;
+  int n_valid;            // valid columns from col0 on (>= 32: full chunk)
+  bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
+};
+
+// 32 accumulator columns -> scale, bias, activation, fp32 store, split-plane store
+template <int ACT, int FMT>
+__device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const EpiOut& o) {
+  float f[32];
+  const u64 sc = pk2(o.out_scale, o.out_scale);
+  const bool full = o.n_valid >= 32 && o.vec_ok;
+#pragma unroll
+  for (int i = 0; i < 32; i += 4) {
+    u64 b01 = 0ull, b23 = 0ull;
+    if (o.brow) {
+      if (full) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + i));
+        b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
+      } else {
+        float b[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) b[k] = i + k < o.n_valid ? __ldg(o.brow + col0 + i + k) : 0.f;
+        b01 = pk2(b[0], b[1]); b23 = pk2(b[2], b[3]);
+      }
+    }
+    upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
+    upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
+  }
+  if (ACT == NSAC_ACT_RELU) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+  } else if (ACT == NSAC_ACT_LEAKY) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.01f * f[i]);      // LeakyReLU(0.01): max(x, 0.01 x)
+  }
+  if (o.out_f32) {
+    float* dst = o.out_f32 + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        if (i < o.n_valid) dst[i] = f[i];
+    }
+  }
+  if (o.out_hi) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int i = 0; i < 32; i += 2) split16x2<FMT>(f[i], f[i + 1], hi[i >> 1], lo[i >> 1]);
+    uint16_t* dh = o.out_hi + col0;
+    uint16_t* dl = o.out_lo + col0;
+    if (full) {
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        *reinterpret_cast<uint4*>(dh + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
+        *reinterpret_cast<uint4*>(dl + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        if (i < o.n_valid) {
+          dh[i] = (i & 1) ? (uint16_t)(hi[i >> 1] >> 16) : (uint16_t)(hi[i >> 1] & 0xffff);
+          dl[i] = (i & 1) ? (uint16_t)(lo[i >> 1] >> 16) : (uint16_t)(lo[i >> 1] & 0xffff);
+        }
+      }
+    }
+  }
+}
+
+template <int FMT>
+__device__ __forceinline__ void finish32_act(const u64 (&acc)[16], int col0, const EpiOut& o, int act) {
+  if (act == NSAC_ACT_RELU) finish32<NSAC_ACT_RELU, FMT>(acc, col0, o);
+  else if (act == NSAC_ACT_LEAKY) finish32<NSAC_ACT_LEAKY, FMT>(acc, col0, o);
+  else finish32<NSAC_ACT_NONE, FMT>(acc, col0, o);
+}
+
 template <int BLOCK_N>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -207,11 +326,12 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   const int num_tiles = tiles_m * tiles_n;
   const int num_kb = p.K / BLOCK_K;
 
+  if (threadIdx.x == 0) GEMM_TRACE(0);
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_a_hi)) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -222,6 +342,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
+  if (threadIdx.x == 0) GEMM_TRACE(1);
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -256,6 +377,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
           tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, &full[stage], kb * BLOCK_K, n0);
           if (p.passes >= 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, &full[stage], kb * BLOCK_K, n0);
+          if (tile == (int)blockIdx.x && kb == 0) GEMM_TRACE(2);
           if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -275,6 +397,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           const int kb1 = kb0 + CHUNK_KB < num_kb ? kb0 + CHUNK_KB : num_kb;
           for (int kb = kb0; kb < kb1; ++kb) {
             mbar_wait(&full[stage], phase);
+            if (tile == (int)blockIdx.x && kb == 0) GEMM_TRACE(3);
             tcgen05_fence_after();
             const uint32_t st = smem_u32(smem + stage * C::STAGE_BYTES);
             const uint64_t a_hi = make_sw128_desc(st), a_lo = make_sw128_desc(st + C::A_BYTES);
@@ -292,36 +415,43 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
           }
           tcgen05_commit(&tmem_full[buf]);                 // chunk complete -> epilogue warps
+          if (tile == (int)blockIdx.x && kb0 == 0) GEMM_TRACE(4);
         }
       }
     }
   } else {
-    // ===================================================================== epilogue warps 2..5
-    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    // ===================================================================== epilogue warps 2..9
+    // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the tile's columns in halves
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
     uint32_t chunk_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
-      float sum[BLOCK_N];
+      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N + half * HALF_N;
+      u64 sum[HALF_N / 2];
 #pragma unroll
-      for (int i = 0; i < BLOCK_N; ++i) sum[i] = 0.f;
+      for (int i = 0; i < HALF_N / 2; ++i) sum[i] = 0ull;
       for (int kb0 = 0; kb0 < num_kb; kb0 += CHUNK_KB, ++chunk_ctr) {
         const uint32_t buf = chunk_ctr & 1, buf_phase = (chunk_ctr >> 1) & 1;
         mbar_wait(&tmem_full[buf], buf_phase);
+        if (tile == (int)blockIdx.x && kb0 == 0 && threadIdx.x == 64) GEMM_TRACE(5);
         tcgen05_fence_after();
-        const uint32_t t_main = tmem_base + lane_base + buf * C::ACC_COLS;
+        const uint32_t t_main = tmem_base + lane_base + buf * C::ACC_COLS + half * HALF_N;
 #pragma unroll
-        for (int c = 0; c < BLOCK_N; c += 32) {
+        for (int c = 0; c < HALF_N; c += 32) {
           uint32_t v[32];
           tmem_ld32(t_main + c, v);
           if (p.passes >= 2) {
             uint32_t u[32];
             tmem_ld32(t_main + BLOCK_N + c, u);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum[c + i] += __uint_as_float(v[i]) + __uint_as_float(u[i]);
+            for (int i = 0; i < 32; i += 2)
+              sum[(c + i) >> 1] = fadd2(sum[(c + i) >> 1], fadd2(pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])),
+                                                                 pk2(__uint_as_float(u[i]), __uint_as_float(u[i + 1]))));
           } else {
 #pragma unroll
-            for (int i = 0; i < 32; ++i) sum[c + i] += __uint_as_float(v[i]);
+            for (int i = 0; i < 32; i += 2)
+              sum[(c + i) >> 1] = fadd2(sum[(c + i) >> 1], pk2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])));
           }
         }
         tcgen05_fence_before();
@@ -338,69 +468,41 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         row_ok = r < p.BW * p.BH && y < p.H && x < p.W;
         row = (img * p.H + y) * p.W + x;
       }
-      const float* brow = nullptr;
-      if (p.bias) brow = p.bias_group_rows > 0 ? p.bias + (size_t)((row_ok ? row : 0) / p.bias_group_rows) * p.N : p.bias;
+      if (row_ok) {
+        EpiOut o;
+        o.out_scale = p.out_scale;
+        o.brow = nullptr;
+        if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
+        o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
+        o.out_hi = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
+        o.out_lo = p.out_lo ? p.out_lo + (size_t)row * p.ld_split : nullptr;
+        o.vec_ok = (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
+                   (!o.out_f32 || (reinterpret_cast<uintptr_t>(o.out_f32) & 15) == 0) &&
+                   (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0);
 #pragma unroll
-      for (int c = 0; c < BLOCK_N; c += 32) {
-        const int col0 = n0 + c;
-        if (row_ok && col0 < p.N) {
-          float f[32];
+        for (int c = 0; c < HALF_N; c += 32) {
+          const int col0 = n0 + c;
+          if (col0 < p.N) {
+            o.n_valid = p.N - col0;
+            u64 acc[16];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            float x = sum[c + i] * p.out_scale;
-            if (brow && col0 + i < p.N) x += __ldg(brow + col0 + i);
-            f[i] = apply_act(x, p.act);
-          }
-          const bool full_chunk = col0 + 32 <= p.N;
-          if (p.out_f32) {
-            float* dst = p.out_f32 + (size_t)row * p.ldo + col0;
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(f[i], f[i + 1], f[i + 2], f[i + 3]);
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                if (col0 + i < p.N) dst[i] = f[i];
-            }
-          }
-          if (p.out_hi) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              uint16_t h0, l0, h1, l1;
-              split16(f[i], p.fmt, h0, l0);
-              split16(f[i + 1], p.fmt, h1, l1);
-              hi[i >> 1] = (uint32_t)h0 | ((uint32_t)h1 << 16);
-              lo[i >> 1] = (uint32_t)l0 | ((uint32_t)l1 << 16);
-            }
-            uint16_t* dh = p.out_hi + (size_t)row * p.ld_split + col0;
-            uint16_t* dl = p.out_lo + (size_t)row * p.ld_split + col0;
-            if (full_chunk) {
-#pragma unroll
-              for (int i = 0; i < 16; i += 4) {
-                *reinterpret_cast<uint4*>(dh + 2 * i) = make_uint4(hi[i], hi[i + 1], hi[i + 2], hi[i + 3]);
-                *reinterpret_cast<uint4*>(dl + 2 * i) = make_uint4(lo[i], lo[i + 1], lo[i + 2], lo[i + 3]);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                if (col0 + i < p.N) {
-                  dh[i] = (i & 1) ? (uint16_t)(hi[i >> 1] >> 16) : (uint16_t)(hi[i >> 1] & 0xffff);
-                  dl[i] = (i & 1) ? (uint16_t)(lo[i >> 1] >> 16) : (uint16_t)(lo[i >> 1] & 0xffff);
-                }
-              }
-            }
+            for (int i = 0; i < 16; ++i) acc[i] = sum[(c >> 1) + i];
+            if (p.fmt == NSAC_SPLIT_F16) finish32_act<NSAC_SPLIT_F16>(acc, col0, o, p.act);
+            else finish32_act<NSAC_SPLIT_BF16>(acc, col0, o, p.act);
           }
         }
       }
     }
   }
+  if (threadIdx.x == 64) GEMM_TRACE(6);
   tcgen05_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) GEMM_TRACE(7);
   if (warp == 1) {
     tcgen05_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS));
   }
+  if (threadIdx.x == 32) GEMM_TRACE(8);
 }
 
 // fp32 [rows, K] * scale -> hi / lo 16-bit planes [rows, ld_split], zero-padded to ld_split columns
@@ -490,6 +592,14 @@ bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int 
 
 // 3x3 / stride 1 / pad 1 convolution as an implicit GEMM: x planes [N,H,W,Cin] (Cin % 64 == 0), weight planes
 // [Cout, 9*Cin] in (ky, kx, cin) order; output rows are NHWC pixels [N*H*W, Cout].
+static unsigned long long* g_gemm_trace = nullptr;
+// Profiling aid: while `buf` (16 uint64 device words) is set, CTA 0 of every GEMM-engine launch records %globaltimer at
+// kernel entry, after setup, first TMA issue, first operands landed, first chunk committed, epilogue start / end, exit.
+extern "C" int nsac_debug_gemm_trace(void* buf) {
+  g_gemm_trace = static_cast<unsigned long long*>(buf);
+  return NSAC_OK;
+}
+
 extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                                   int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
                                   float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
@@ -517,6 +627,7 @@ extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void
     return NSAC_ERR_LAUNCH;
   }
   GemmParams p;
+  p.trace = g_gemm_trace;
   p.bias = bias; p.bias_group_rows = 0; p.M = N * H * W; p.N = Cout; p.K = K; p.act = act; p.passes = passes;
   p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
@@ -555,6 +666,7 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
     return NSAC_ERR_LAUNCH;
   }
   GemmParams p;
+  p.trace = g_gemm_trace;
   p.bias = bias; p.bias_group_rows = bias_group_rows; p.M = M; p.N = N; p.K = K; p.act = act; p.passes = passes;
   p.fmt = fmt; p.out_scale = out_scale;
   p.out_f32 = out_f32; p.ldo = ldo;
