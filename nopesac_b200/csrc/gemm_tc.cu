@@ -62,7 +62,9 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int ACC_COLS = 2 * BLOCK_N;              // one buffer = hi.hi accumulator + lo-terms accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
 
@@ -223,6 +225,8 @@ __device__ __forceinline__ void split16x2(float a, float b, uint32_t& hi, uint32
 
 struct EpiOut {
   float out_scale;
+  float slope;            // activation as max(x, slope * x): 1 = none, 0 = ReLU, 0.01 = LeakyReLU (one code path: the epilogue is
+                          // straight-line unrolled code and six ACT x FMT copies of it thrashed the instruction cache)
   const float* brow;      // bias row of this thread's output row (nullptr: no bias)
   float* out_f32;         // row pointers (nullptr: not requested)
   uint16_t* out_hi;
@@ -232,7 +236,7 @@ struct EpiOut {
 };
 
 // 32 accumulator columns -> scale, bias, activation, fp32 store, split-plane store
-template <int ACT, int FMT>
+template <int FMT>
 __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const EpiOut& o) {
   float f[32];
   const u64 sc = pk2(o.out_scale, o.out_scale);
@@ -254,13 +258,8 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
     upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
     upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
   }
-  if (ACT == NSAC_ACT_RELU) {
 #pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
-  } else if (ACT == NSAC_ACT_LEAKY) {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.01f * f[i]);      // LeakyReLU(0.01): max(x, 0.01 x)
-  }
+  for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
   if (o.out_f32) {
     float* dst = o.out_f32 + col0;
     if (full) {
@@ -296,14 +295,73 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
   }
 }
 
-template <int FMT>
-__device__ __forceinline__ void finish32_act(const u64 (&acc)[16], int col0, const EpiOut& o, int act) {
-  if (act == NSAC_ACT_RELU) finish32<NSAC_ACT_RELU, FMT>(acc, col0, o);
-  else if (act == NSAC_ACT_LEAKY) finish32<NSAC_ACT_LEAKY, FMT>(acc, col0, o);
-  else finish32<NSAC_ACT_NONE, FMT>(acc, col0, o);
+
+// Row-per-lane data -> coalesced global stores.  After the accumulator read every lane holds one output ROW; written
+// straight from registers a 16-byte store instruction touches 32 different 128-byte lines (the LSU then needs ~32 cycles
+// per instruction: 2.8 of the 3.2 us of a tile's epilogue, nsac_debug_gemm_trace).  Each warp therefore transposes
+// 32 rows x 128 (or 64) bytes through its 4 KB of shared memory (16-byte chunks XOR-swizzled by the row: conflict-free
+// both ways) and writes them out as 4 full lines (8 half lines) per instruction.  row_ptr = this lane's own destination
+// (start of its row segment).
+template <int WORDS>      // WORDS = 32: 128-byte row segments, WORDS = 16: 64-byte row segments
+__device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t (&w)[WORDS], uint8_t* row_ptr, int lane) {
+  constexpr int BYTES = WORDS * 4, CPR = BYTES / 16, RPI = 32 / CPR;     // 16-byte chunks per row, rows per store instruction
+  const int swz_w = CPR == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+  for (int c = 0; c < CPR; ++c)
+    *reinterpret_cast<uint4*>(stage + lane * BYTES + ((c ^ swz_w) << 4)) = make_uint4(w[4 * c], w[4 * c + 1], w[4 * c + 2], w[4 * c + 3]);
+  __syncwarp();
+  const int sub = lane / CPR, ch = lane % CPR;
+  const unsigned long long my = reinterpret_cast<unsigned long long>(row_ptr);
+#pragma unroll
+  for (int j = 0; j < 32 / RPI; ++j) {
+    const int row = RPI * j + sub;
+    const int swz_r = CPR == 8 ? (row & 7) : ((row >> 1) & 3);
+    const uint4 x = *reinterpret_cast<const uint4*>(stage + row * BYTES + ((ch ^ swz_r) << 4));
+    uint8_t* dst = reinterpret_cast<uint8_t*>(__shfl_sync(0xffffffffu, my, row));
+    *reinterpret_cast<uint4*>(dst + ch * 16) = x;
+  }
+  __syncwarp();
 }
 
-template <int BLOCK_N>
+// 64 accumulator columns of a full tile part (every lane of the warp has a valid row, all 64 columns valid, aligned):
+// scale, bias, activation, then fp32 rows and / or split planes through the staged stores, 32 columns at a time
+template <int FMT>
+__device__ __forceinline__ void finish64_staged(const u64 (&sum)[32], int col0, const EpiOut& o, uint8_t* stage, int lane) {
+  const u64 sc = pk2(o.out_scale, o.out_scale), sl = pk2(o.slope, o.slope);
+#pragma unroll
+  for (int g = 0; g < 2; ++g) {            // two groups of 32 columns
+    uint32_t f[32];                        // fp32 bit patterns
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+      u64 b01 = 0ull, b23 = 0ull;
+      if (o.brow) {
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + 32 * g + i));
+        b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
+      }
+      float x0, x1, x2, x3;
+      upk2(ffma2(sum[16 * g + (i >> 1)], sc, b01), x0, x1);
+      upk2(ffma2(sum[16 * g + (i >> 1) + 1], sc, b23), x2, x3);
+      {   // activation as max(x, slope * x + 0): the +0 addend makes ReLU of a negative +0, not -0
+        float t0, t1, t2, t3;
+        upk2(ffma2(pk2(x0, x1), sl, 0ull), t0, t1);
+        upk2(ffma2(pk2(x2, x3), sl, 0ull), t2, t3);
+        x0 = fmaxf(x0, t0); x1 = fmaxf(x1, t1); x2 = fmaxf(x2, t2); x3 = fmaxf(x3, t3);
+      }
+      f[i] = __float_as_uint(x0); f[i + 1] = __float_as_uint(x1); f[i + 2] = __float_as_uint(x2); f[i + 3] = __float_as_uint(x3);
+    }
+    if (o.out_f32)                         // 32 fp32 columns = one 128-byte segment per row
+      staged_store<32>(stage, f, reinterpret_cast<uint8_t*>(o.out_f32 + col0 + 32 * g), lane);
+    if (o.out_hi) {                        // 32 16-bit columns = one 64-byte segment per row and plane
+      uint32_t hi[16], lo[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) split16x2<FMT>(__uint_as_float(f[i]), __uint_as_float(f[i + 1]), hi[i >> 1], lo[i >> 1]);
+      staged_store<16>(stage, hi, reinterpret_cast<uint8_t*>(o.out_hi + col0 + 32 * g), lane);
+      staged_store<16>(stage, lo, reinterpret_cast<uint8_t*>(o.out_lo + col0 + 32 * g), lane);
+    }
+  }
+}
+
+template <int BLOCK_N, int FMT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -317,6 +375,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool conv = p.conv_taps == 9;
@@ -385,7 +444,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, p.fmt == NSAC_SPLIT_BF16);
+      const uint32_t idesc = make_idesc(BLOCK_M, BLOCK_N, FMT == NSAC_SPLIT_BF16);
       int stage = 0; uint32_t phase = 0;
       uint32_t chunk_ctr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -458,6 +517,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
+      if (tile == (int)blockIdx.x && threadIdx.x == 64) GEMM_TRACE(9);
       // ---- bias, activation, stores
       int row = m0 + quad * 32 + lane;
       bool row_ok = row < p.M;
@@ -468,10 +528,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         row_ok = r < p.BW * p.BH && y < p.H && x < p.W;
         row = (img * p.H + y) * p.W + x;
       }
+      EpiOut o;
+      o.out_scale = p.out_scale;
+      o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
+      o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
       if (row_ok) {
-        EpiOut o;
-        o.out_scale = p.out_scale;
-        o.brow = nullptr;
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
         o.out_hi = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
@@ -479,6 +540,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         o.vec_ok = (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
                    (!o.out_f32 || (reinterpret_cast<uintptr_t>(o.out_f32) & 15) == 0) &&
                    (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0);
+      }
+      // fast path (warp-uniform): every lane has a valid, aligned row and all 64 columns of this half exist
+      const bool staged = HALF_N == 64 && __all_sync(0xffffffffu, row_ok && o.vec_ok) && n0 + HALF_N <= p.N;
+      if (staged) {
+        uint8_t* stage = out_stage + (warp - 2) * 4096;
+        finish64_staged<FMT>(sum, n0, o, stage, lane);
+      } else if (row_ok) {
 #pragma unroll
         for (int c = 0; c < HALF_N; c += 32) {
           const int col0 = n0 + c;
@@ -487,8 +555,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             u64 acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = sum[(c >> 1) + i];
-            if (p.fmt == NSAC_SPLIT_F16) finish32_act<NSAC_SPLIT_F16>(acc, col0, o, p.act);
-            else finish32_act<NSAC_SPLIT_BF16>(acc, col0, o, p.act);
+            finish32<FMT>(acc, col0, o);
           }
         }
       }
@@ -566,12 +633,16 @@ int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   using C = Cfg<BLOCK_N>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = tiles_m * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_bf16x3_kernel<BLOCK_N><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
+  if (p.fmt == NSAC_SPLIT_BF16)
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
+  else
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
   NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }

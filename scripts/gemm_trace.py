@@ -6,7 +6,7 @@ from nopesac_b200 import ops, _lib
 
 dev = torch.device("cuda:0")
 names = ["entry", "setup done", "first TMA issued", "first operands landed", "first chunk committed", "epilogue start", "epilogue end",
-         "after final barrier", "after dealloc"]
+         "after final barrier", "after dealloc", "accumulators read"]
 for (M, N, K) in [(128, 128, 64), (2048, 256, 256), (2048, 512, 512)]:
     a = ops.Split(torch.randn(M, K, device=dev).half(), torch.randn(M, K, device=dev).half() * 0.01, K)
     w = ops.Split(torch.randn(N, K, device=dev).half(), torch.randn(N, K, device=dev).half() * 0.01, K)
@@ -23,5 +23,5 @@ for (M, N, K) in [(128, 128, 64), (2048, 256, 256), (2048, 512, 512)]:
     t0 = int(bufs[0][0])
     print(f"M={M} N={N} K={K}")
     for i, b in enumerate(bufs):
-        t = [int(x) - t0 for x in b[:9].tolist()]
+        t = [int(x) - t0 for x in b[:10].tolist()]
         print(f"  launch {i}: " + "  ".join(f"{n} {v}" for n, v in zip(names, t)))
