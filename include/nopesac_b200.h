@@ -87,7 +87,9 @@ int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt,
  *                        [Cout, 9*Cin] in (ky, kx, cin) order; BatchNorm(eval) is folded into weights + bias by
  *                        the caller; epilogue as in nsac_gemm_split.  Replaces F.conv2d / cuDNN.
  *   nsac_nchw_to_planes  backbone feature maps [N,C,HW] fp32 -> NHWC planes
- *   nsac_groupnorm_nhwc  GroupNorm(G) (+ReLU) (+ nearest-2x-upsampled skip [N,H/2,W/2,C], camera_modules.py:344-347)
+ *   nsac_groupnorm_nhwc  GroupNorm(G) (+ReLU) (+ nearest-2x-upsampled skip [N,H/2,W/2,C], camera_modules.py:344-347).
+ *                        stats_ws: nsac_groupnorm_ws_bytes(N,H,W,G) bytes of scratch for the coalesced 4-channels-per-group
+ *                        path (statistics kernel + apply kernel); NULL selects the one-kernel path
  *   nsac_maxpool2_planes MaxPool2d(2,2) of an fp32 NHWC map -> planes
  *   nsac_corr_softmax    compute_corr_softmax (camera_head.py:1117-1133): f1,f2 [B,HW,C] -> planes [B*HW, Cp]
  *                        (channel c2 = w2*H + h2, zero padded to Cp)
@@ -97,9 +99,10 @@ int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, con
                        int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
                        float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream);
 int nsac_nchw_to_planes(const float* x, int N, int C, int HW, int fmt, void* hi, void* lo, void* stream);
+size_t nsac_groupnorm_ws_bytes(int N, int H, int W, int G);
 int nsac_groupnorm_nhwc(const float* x, int N, int H, int W, int C, int G, const float* gamma, const float* beta,
                         float eps, int relu, const float* skip_half_res, int fmt, float* out_f32, void* out_hi,
-                        void* out_lo, void* stream);
+                        void* out_lo, void* stats_ws, size_t stats_ws_bytes, void* stream);
 int nsac_maxpool2_planes(const float* x, int N, int H, int W, int C, int fmt, void* hi, void* lo, void* stream);
 int nsac_corr_softmax(const float* f1, const float* f2, int B, int H, int W, int C, int Cp, int fmt, void* hi,
                       void* lo, void* stream);

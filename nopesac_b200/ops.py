@@ -219,9 +219,11 @@ def groupnorm_nhwc(x: torch.Tensor, N: int, H: int, W: int, gamma, beta, groups:
     Cc = x.shape[1]
     out_f32 = torch.empty_like(x) if want_f32 else None
     out_split = _empty_split(x.shape[0], Cc, x.device, fmt) if want_split else None
+    ws_bytes = _lib.lib().nsac_groupnorm_ws_bytes(N, H, W, groups)
+    ws = torch.empty(max(ws_bytes, 16), device=x.device, dtype=torch.uint8)
     st = _lib.lib().nsac_groupnorm_nhwc(_p(x), N, H, W, Cc, groups, _p(gamma), _p(beta), eps, int(relu), _p(skip), fmt,
                                         _p(out_f32), None if out_split is None else _p(out_split.hi),
-                                        None if out_split is None else _p(out_split.lo), _stream())
+                                        None if out_split is None else _p(out_split.lo), _p(ws), ws_bytes, _stream())
     _lib.check(st, "nsac_groupnorm_nhwc")
     _count()
     return out_f32, out_split
