@@ -237,7 +237,7 @@ class PlaneCameraHead(nn.Module):
         if "geo_encoder.split" not in pk:
             with torch.no_grad():
                 for name in ("geo_encoder", "geo_proj_s1", "decoder_rot", "geo_proj_s2", "decoder_tran",
-                             "decoder_rot2", "decoder_tran2"):
+                             "decoder_rot2", "decoder_tran2", "rot_emb_proj", "trans_emb_proj"):
                     pk[name + ".split"] = getattr(self, name).split_weights()
                 for name in ("decoder_rot2", "decoder_tran2"):
                     pk[name + ".w_geo_split"] = ops.split_weight(pk[name + ".w_geo"])
@@ -361,8 +361,13 @@ class PlaneCameraHead(nn.Module):
 
     # ------------------------------------------------------------------ K2: AIM (:685-735)
     def _forward_rec_heads(self, initial_rot, initial_trans):
-        rot_feat = self.rot_emb_proj.run(initial_rot, ops.ACT_RELU)
-        trans_feat = self.trans_emb_proj.run(initial_trans + 1e-10, ops.ACT_RELU)
+        # AIM (:685-735): layer 0 (K = 4 / 3) on the CUDA cores, the five 256-wide layers on the tcgen05 engine (M = batch
+        # size is one tile: 7 us per layer instead of 35 us on the 128x128-tile fp32 kernel, which runs them on two CTAs)
+        pk = self.prepare_tc()
+        P = self.tc_passes
+        rot_feat, _ = self.rot_emb_proj.run_tc(initial_rot, pk["rot_emb_proj.split"], final_act=ops.ACT_RELU, want_f32=True, passes=P)
+        trans_feat, _ = self.trans_emb_proj.run_tc(initial_trans + 1e-10, pk["trans_emb_proj.split"], final_act=ops.ACT_RELU,
+                                                   want_f32=True, passes=P)
         rec_rot, rec_trans = ops.pose_heads(rot_feat, trans_feat, self.rots.weight, self.rots.bias,
                                             self.trans.weight, self.trans.bias)
         return rec_rot, rot_feat, rec_trans, trans_feat

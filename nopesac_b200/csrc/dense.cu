@@ -150,6 +150,7 @@ linear_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict
     }
   }
 }
+
 }  // namespace
 
 extern "C" int nsac_linear(const float* x, int ldx, const float* w, const float* bias,
