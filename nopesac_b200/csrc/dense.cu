@@ -228,8 +228,9 @@ extern "C" int nsac_layernorm(const float* x, int ldx, const float* gamma, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// Multi-head attention over <= a few dozen plane tokens: one CTA per pair, one warp per head,
-// D = 32 = one lane per channel.  K/V of the head staged in shared memory.
+// Multi-head attention over <= a few dozen plane tokens: one CTA per (pair, slice of the queries), one warp per
+// head, D = 32 = one lane per channel.  K/V of the head staged in shared memory (every query slice re-stages them:
+// 64 CTAs of 16 serial queries took 26 us per call; slicing the queries over gridDim.y fills the SMs).
 // ------------------------------------------------------------------------------------------------
 namespace {
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
@@ -242,13 +243,15 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
   float* Ks = sm + (size_t)h * (S * 66 + S);
   float* Vs = Ks + S * 33;
   float* ps = Vs + S * 33;
+#pragma unroll 4
   for (int s = 0; s < S; ++s) {
     Ks[s * 33 + lane] = k[((size_t)b * S + s) * ldkv + h * 32 + lane];
     Vs[s * 33 + lane] = v[((size_t)b * S + s) * ldkv + h * 32 + lane];
   }
   __syncwarp();
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
-  for (int l = 0; l < L; ++l) {
+  const int lq = (L + gridDim.y - 1) / gridDim.y, l_end = min(L, (int)(blockIdx.y + 1) * lq);
+  for (int l = blockIdx.y * lq; l < l_end; ++l) {
     const float qd = q[((size_t)b * L + l) * ldq + h * 32 + lane];
     float mx = -INFINITY;
     for (int s0 = 0; s0 < S; s0 += 32) {
@@ -300,7 +303,10 @@ extern "C" int nsac_attention(const float* q, int ldq, const float* k, const flo
   NSAC_REQUIRE(smem <= 200 * 1024, "nsac_attention: S=%d too large for the shared-memory staging", S);
   if (smem > 48 * 1024)
     NSAC_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  attention_kernel<<<B, H * 32, smem, static_cast<cudaStream_t>(stream)>>>(
+  int slices = (4 * 148 + B - 1) / B;        // ~4 CTAs per SM
+  if (slices > L) slices = L;
+  if (slices < 1) slices = 1;
+  attention_kernel<<<dim3(B, slices), H * 32, smem, static_cast<cudaStream_t>(stream)>>>(
       q, ldq, k, v, ldkv, out, ldo, static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo), ld_split, L, S, H);
   NSAC_CHECK_LAUNCH("nsac_attention");
   return NSAC_OK;
