@@ -556,7 +556,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
           const uint32_t bytes = (uint32_t)min(F_ROWS, rows - r) * (C_FEAT * 4);
 #pragma unroll 1
           for (int br = 0; br < 2; ++br) {
-            mbar_wait_spin(&bars[BAR_F_EMPTY + fs], fph ^ 1);
+            mbar_wait(&bars[BAR_F_EMPTY + fs], fph ^ 1);
             NSAC_TRACE(6, true);
             mbar_expect_tx(&bars[BAR_F_FULL + fs], bytes);
             bulk_load_1d(smem + OFF_F + fs * F_BYTES, (br == 0 ? p.feat_rot : p.feat_tran) + (row0 + r) * C_FEAT, bytes, &bars[BAR_F_FULL + fs]);
@@ -835,7 +835,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       // feature ring: this thread = 4 channels x rows rs*8 .. rs*8+7 of every 16-row chunk of its branch
       constexpr int HR = F_ROWS / 2;
       for (int r0 = 0; r0 < rows; r0 += F_ROWS) {
-        mbar_wait_spin(&bars[BAR_F_FULL + fs], fph);
+        mbar_wait(&bars[BAR_F_FULL + fs], fph);
         NSAC_TRACE(7, threadIdx.x == G_WARP0 * 32);
         const ulonglong2* fr = reinterpret_cast<const ulonglong2*>(smem + OFF_F + fs * F_BYTES) + (rs * HR) * (C_FEAT / 4) + t64;
         float e[HR];
