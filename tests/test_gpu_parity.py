@@ -264,6 +264,57 @@ def test_score_tc_kernel_ragged_batch_vs_exact_kernel():
             assert torch.equal(a["sel_idx"], b["sel_idx"]), cam
 
 
+@pytest.mark.parametrize("B,NQ", [(130, 64), (7, 300), (257, 50)])
+def test_score_tc_kernel_row0_tiles_and_odd_shapes(B, NQ):
+    """Tensor-core scoring path vs the exact CUDA-core path where the work-item list is irregular: more than one row-0 tile
+    with a partial last one (B = 130, 257: hypothesis 0 of 128 pairs per tile), NQ not a multiple of 64 / three hypothesis
+    tiles per pair (NQ = 300 -> NQp = 320), random m per pair including 0 and NQ."""
+    dev = _gpu()
+    from nopesac_b200 import ops
+    head, _, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    pk = head.prepare()
+    g = torch.Generator(device=dev).manual_seed(100 + B)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo = rnd(B, NQ, 6)
+    qh = torch.nn.functional.normalize(rnd(B, NQ, 4), dim=-1)
+    th = rnd(B, NQ, 3) * 0.3
+    q0 = torch.nn.functional.normalize(rnd(B, 4), dim=-1)
+    t0 = rnd(B, 3) * 0.3
+    fr, ft, fr0, ft0 = rnd(B, NQ, 256) * 0.3, rnd(B, NQ, 256) * 0.3, rnd(B, 256) * 0.3, rnd(B, 256) * 0.3
+    mnum = torch.randint(0, NQ + 1, (B,), device=dev, generator=g, dtype=torch.int32)
+    mnum[0], mnum[-1] = NQ, 0
+    if B > 2:
+        mnum[1] = 1
+    valid = torch.arange(NQ, device=dev)[None, :] < mnum[:, None]
+    geo = geo * valid[:, :, None]            # padded rows are zero in the real pipeline
+    for cam in ("soft", "avg-all", "min-cost", "max-score"):
+        out = {}
+        for precision in ("fp32", "fp16"):
+            out[precision] = ops.score_aggregate(geo, qh, th, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
+                                                 pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
+                                                 head.trans.bias, out_cam_type=cam, precision=precision)
+        torch.cuda.synchronize()
+        a, b = out["fp32"], out["fp16"]
+        assert util.maxdiff(a["score_rot"], b["score_rot"]) <= 1e-4 and util.maxdiff(a["score_tran"], b["score_tran"]) <= 1e-4, cam
+        assert torch.equal(a["pose"][:, 14], mnum.float()) and torch.equal(b["pose"][:, 14], mnum.float())
+        lin = [0, 1, 2, 7, 8, 9, 10, 11, 12, 13]      # translations (linear in the features) and the score-free average pose
+        assert util.maxdiff(a["pose"][:, lin], b["pose"][:, lin]) <= 1e-4, (cam, util.maxdiff(a["pose"][:, lin], b["pose"][:, lin]))
+        # The soft quaternion is normalize(W_rots . sum_h s_h f_h + b): with RANDOM features the sum nearly cancels, so the
+        # normalisation divides by a small norm and amplifies the (<= 2e-5) score differences of the fp16 score MLPs.  The
+        # bar is therefore set on the un-normalised vector: |dq| * |u| <= 1e-4 (|u| from the exact path's scores, in torch).
+        with torch.no_grad():
+            H = NQ + 1
+            feats = torch.cat([fr0[:, None], fr], 1)                                   # hypothesis 0 first
+            live = torch.arange(H, device=dev)[None, :] <= mnum[:, None]
+            agg = ((a["score_rot"] * live)[:, :, None] * feats).sum(1)
+            u = agg @ head.rots.weight.T + head.rots.bias
+            norm = u.norm(dim=1).clamp(max=1.0)
+        dq = (a["pose"][:, 3:7] - b["pose"][:, 3:7]).abs().max(dim=1).values
+        assert float((dq * norm).max()) <= 1e-4, (cam, float((dq * norm).max()), float(dq.max()))
+        if cam == "min-cost":      # distances are fp32 on both paths: same argmin
+            assert torch.equal(a["sel_idx"], b["sel_idx"]), cam
+
+
 def test_linear_kernel_against_torch():
     """nsac_linear vs torch fp64 on odd shapes (K = 3, 8; N = 3; strided in/out; grouped bias)."""
     dev = _gpu()
