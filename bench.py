@@ -248,6 +248,16 @@ def main():
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
 
+    # pose error of this rank's pairs against the planted ground truth (reference formulas, mp3d_evaluation.py:382-425,
+    # computed on the device by nopesac_b200.evaluation): reported, not a target - the weights are random
+    pose_err = None
+    if rank == 0:
+        from nopesac_b200 import evaluation
+        rows = head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp)[5]["pose"]
+        pm = evaluation.camera_metrics(rows, dbatch.gt_tran, dbatch.gt_quat)
+        pose_err = {"T_median_m": pm["T median err"], "T_mean_m": pm["T mean err"], "R_median_deg": pm["R median err"],
+                    "R_mean_deg": pm["R mean err"], "pairs": B, "note": "random-init weights vs planted GT: reported, not a target"}
+
     if args.only_value:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -369,6 +379,7 @@ def main():
         "gpu_launches": launches,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
+        "pose_err": pose_err,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

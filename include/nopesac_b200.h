@@ -222,6 +222,13 @@ int nsac_prune_assignment(const float* assign, const float* planes1, const float
                           const float* pose, int ldpose, int B, int n1, int n2, float* assign_out,
                           void* stream);
 
+/* Camera-pose evaluation (evaluation/mp3d_evaluation.py:382-425 `_eval_camera_reg`, :463-465
+ * `angle_error_vec`): per-pair translation error |t - t_gt|_2 and rotation error 2 acos(clip(|q.q_gt|,-1,1)) 180/pi of the
+ * result rows (t[3], q[4], ... with stride ldpose), plus stats[8] = {T mean, R mean, #T<1.0, #T<0.5, #T<0.2, #R<30, #R<15,
+ * #R<10}.  Medians need the sorted errors: nopesac_b200/evaluation.py. */
+int nsac_camera_errors(const float* pose, int ldpose, const float* gt_tran, const float* gt_rot, int B, float* err_t,
+                       float* err_r, float* stats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

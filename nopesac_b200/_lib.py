@@ -64,6 +64,7 @@ _SIGNATURES = {
                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nsac_debug_score_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "nsac_debug_gemm_trace": (C.c_int, [C.c_void_p]),
+    "nsac_camera_errors": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_void_p]),
     "nsac_prune_assignment": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, c_float_p, C.c_void_p]),
 }
