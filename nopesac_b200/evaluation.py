@@ -8,7 +8,9 @@ result rows (the unit that is exchanged between GPUs); only the 10 scalars come 
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict
+import os
+import pickle
+from typing import Dict, List
 
 import torch
 
@@ -76,3 +78,57 @@ class CameraEvaluator:
         if not self._rows:
             return {}
         return camera_metrics(torch.cat(self._rows).contiguous(), torch.cat(self._gt_t), torch.cat(self._gt_q))
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Result files (mp3d_evaluation.py:259-313 `get_optimized_dict`, :336-342, :852-860 `save_dict`): the per-pair records that
+# the reference's `eval.py --evaluate camera` reads back from `continuous.pkl` / `NopeSAC_instances_predictions.pth`.
+# ---------------------------------------------------------------------------------------------------------------------
+def prediction_records(results: List[dict], gt_tran, gt_rot) -> List[dict]:
+    """`PlaneTR_NopeSAC.inference` results (one dict per pair) + ground truth -> the evaluator's prediction records
+    (mp3d_evaluation.py:184-258 `process`): every `camera*` key becomes {"pred": {tran, rot}, "gts": {tran, rot}},
+    assignments and per-view plane parameters move to the host.  One device->host copy per tensor, at the end."""
+    recs = []
+    for i, r in enumerate(results):
+        gts = {"tran": _np(gt_tran[i]), "rot": _np(gt_rot[i])}
+        rec = {"0": dict(r["0"]), "1": dict(r["1"])}
+        for key, value in r.items():
+            if "camera" in key and isinstance(value, dict) and "tran" in value:
+                rec[key] = {"pred": {"tran": _np(value["tran"]), "rot": _np(value["rot"])}, "gts": gts}
+            elif "assignment" in key:
+                rec[key] = value.detach().cpu() if isinstance(value, torch.Tensor) else value
+        recs.append(rec)
+    return recs
+
+
+def _np(x):
+    return x.detach().cpu().numpy() if isinstance(x, torch.Tensor) else x
+
+
+def optimized_dict(predictions: List[dict]) -> Dict[int, dict]:
+    """mp3d_evaluation.py:259-313: the `continuous.pkl` payload."""
+    out = {}
+    for idx, prediction in enumerate(predictions):
+        best_assignment = prediction["pred_assignment"].numpy()
+        camera = prediction["camera"]
+        aux = {key: {"position": prediction[key]["pred"]["tran"], "rotation": prediction[key]["pred"]["rot"]}
+               for key in prediction if "camera" in key}
+        del aux          # the reference builds it and drops it too (:274-280)
+        out[idx] = {
+            "n_corr": best_assignment.sum(),
+            "cost": 0.1,
+            "best_camera": {"position": camera["pred"]["tran"], "rotation": camera["pred"]["rot"]},
+            "gt_camera": {"position": camera["gts"]["tran"], "rotation": camera["gts"]["rot"]},
+            "best_assignment": best_assignment,
+            "plane_param_override": {"0": _np(prediction["0"]["pred_plane"]), "1": _np(prediction["1"]["pred_plane"])},
+            "image_ids": {"0": prediction["0"]["image_id"], "1": prediction["1"]["image_id"]},
+        }
+    return out
+
+
+def save_results(predictions: List[dict], output_dir: str):
+    """Writes `NopeSAC_instances_predictions.pth` and `continuous.pkl` like MP3DEvaluator.evaluate (:331-342)."""
+    os.makedirs(output_dir, exist_ok=True)
+    torch.save(predictions, os.path.join(output_dir, "NopeSAC_instances_predictions.pth"))
+    with open(os.path.join(output_dir, "continuous.pkl"), "wb") as f:
+        pickle.dump(optimized_dict(predictions).copy(), f)

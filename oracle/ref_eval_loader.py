@@ -54,3 +54,12 @@ def load():
         return self._results
 
     return ns["angle_error_vec"], eval_camera_reg
+
+
+def load_get_optimized_dict():
+    """The reference's `MP3DEvaluator.get_optimized_dict` (mp3d_evaluation.py:259-313) as a plain function of the predictions."""
+    import textwrap
+    src = _extract(["get_optimized_dict"])["get_optimized_dict"]
+    ns = {"np": np}
+    exec(compile(textwrap.dedent(src), _FILE, "exec"), ns)
+    return lambda predictions: ns["get_optimized_dict"](types.SimpleNamespace(), predictions)
