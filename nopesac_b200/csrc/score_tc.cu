@@ -41,10 +41,10 @@ constexpr int W_STAGES = 2, A_STAGES = 2;
 constexpr int BLK_BYTES = TILE_H * KB * 2;           // 16 KB: one [128 x 64] fp16 operand block
 // warp roles, aligned to warpgroups of 4 warps so that setmaxnreg can move registers between the roles
 // (launch: 1024 threads x 64 registers = the whole register file):
-//   WG0-1 = warps 0-7   gather              56 regs   | WG2-5 = warps 8-23   residuals (16)      72 regs
+//   WG0-1 = warps 0-7   gather              40 regs   | WG2-5 = warps 8-23   residuals (16)      80 regs
 //   WG6   = warps 24-27 epilogue            72 regs   | WG7   = warps 28-31  W / MMA / column / feature producers  40 regs
 // setmaxnreg.inc can only draw on what the CTA's own warps released with setmaxnreg.dec (an inc that is not covered
-// deadlocks): released 128*24 + 256*8 = 5120 = claimed 128*8 + 512*8.
+// deadlocks): released 128*24 + 256*24 = 9216 = claimed 128*8 + 512*16.
 // Four residual warps per scheduler: the FMA-pipe phase (packed FFMA2-class instructions, 2 issue cycles each) of one
 // warp overlaps the MUFU phase (8 SQRT/EX2 per row x column pair, 8 cycles each) of another - with two warps per
 // scheduler (r1e/s1 captures) the two pipes alternated instead of overlapping and neither was more than 38 % busy.
@@ -709,7 +709,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     // from 4 HMMAs per 8 columns (residual_kblock_mma), the rest (13 packed FMA-pipe instructions + 4 MUFU.SQRT + 4
     // MUFU.EX2 + 2 cvt per row x column pair) runs on the CUDA cores.  Row-0 tiles: the A stages are filled by TMA, these
     // warps only pass their turns.
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 72;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     const int rw = warp - R_WARP0;                   // 0..15
     const int rb = rw & 7, chalf = rw >> 3, g = lane >> 2, q = lane & 3;
     int as = 0; uint32_t aph = 0; int cs = 0; uint32_t cph = 0;
@@ -791,7 +791,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     // ================================================================================= gather warps 0..7
     // consumers of the feature ring (F_WARP): flash-style softmax partials of the tile (local max / sum of exp, the
     // exp-weighted and the plain sum of its [rows,256] one-plane features)
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     const int gt = threadIdx.x - G_WARP0 * 32;       // 0..255
     const int br = gt >> 7, rs = (gt >> 6) & 1, t64 = gt & 63, c4 = t64 * 4;
     int lbuf = 0; uint32_t lph = 0;
