@@ -9,7 +9,6 @@ from tests import util
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 512
 NQ = int(sys.argv[2]) if len(sys.argv) > 2 else 256
 CTA = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-DBG = int(sys.argv[4]) if len(sys.argv) > 4 else 0   # ablation bits: 1 no MUFU, 2 no feature stream, 4 no epilogue math, 8 no A stores
 dev = torch.device("cuda:0")
 head, _, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
 g = torch.Generator(device=dev).manual_seed(3)
@@ -43,7 +42,7 @@ st = [int(x) - t0_ for x in t[4].tolist() if x > 0]
 en = [int(x) - t0_ for x in t[5].tolist() if x > 0]
 print('CTA start (ns): min', min(st), 'max', max(st))
 print('CTA end   (ns):', ' '.join(str(e) for e in en))
-print(f"CTA {CTA} dbg {DBG}")
+print(f"CTA {CTA}")
 names = ["residual", "mma", "epilogue", "gather", "", "", "f-producer", "f-consumer"]
 for r in (0, 1, 2, 3, 6, 7):
     ev = [int(x) - t0_ for x in t[r].tolist() if x > 0]
