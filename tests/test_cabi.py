@@ -54,3 +54,12 @@ def test_product_never_imports_oracle():
                     txt = f.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{fn} imports oracle"
                 assert "ref_loader" not in txt and "/root/reference" not in txt, f"{fn} references the reference tree"
+
+
+def test_evaluation_fails_loudly_without_cuda_tensors():
+    """Row f3 host mirror: no CPU path — CPU tensors are refused before anything is launched."""
+    from nopesac_b200 import evaluation
+    with pytest.raises(RuntimeError, match="CUDA"):
+        evaluation.camera_metrics(torch.zeros(2, 16), torch.zeros(2, 3), torch.zeros(2, 4))
+    assert evaluation.CameraEvaluator().evaluate() == {}
+    assert evaluation.METRIC_KEYS[0] == "T median err" and len(evaluation.METRIC_KEYS) == 10
