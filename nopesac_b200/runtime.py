@@ -102,3 +102,45 @@ class PairPipeline:
         if pending is not None:
             self.done[pending].synchronize()
             yield self.host_out[pending]
+
+
+class GraphedCameraHead:
+    """The camera-head forward captured once in a CUDA graph and replayed (CUDA graphs instead of a tracing compiler).
+
+    The forward is a fixed sequence of ~380 short launches for a given batch shape (no host synchronisation, no
+    data-dependent shapes), so the whole step can be replayed with one graph launch: the matcher's tiny kernels are
+    host-enqueue-bound when launched eagerly (profiles/r1h_step_stages.json: 15.8 ms eager vs 15.3 ms replayed).
+
+        runner = GraphedCameraHead(head, matching_head, batch, hyp_pairs=hp)   # batch: device tensors (static buffers)
+        rows = runner()                   # replays; result rows [B,16] live in a static buffer
+        runner.load(new_batch)            # device-to-device copy into the static input buffers, then runner()
+
+    The inputs are static buffers owned by the runner (the tensors given at construction are used as those buffers)."""
+
+    def __init__(self, head, matching_head, batch: Dict, hyp_pairs: Optional[torch.Tensor] = None, warmup: int = 2):
+        self.batch = batch
+        self._call = lambda: head(batch["feats1"], batch["feats2"], batch["planes1"], batch["planes2"], batch["app1"], batch["app2"],
+                                  matching_net=matching_head, hyp_pairs=hyp_pairs)[5]["pose"]
+        dev = batch["planes1"].device
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):          # warm-up off the capture: weight packs, kernel attributes, allocator pools
+            for _ in range(max(1, warmup)):
+                self._call()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.rows = self._call()
+
+    def load(self, batch: Dict):
+        """Copies a new batch (same shapes) into the static input buffers on the current stream."""
+        for k, v in batch.items():
+            if isinstance(v, dict):
+                for kk, vv in v.items():
+                    self.batch[k][kk].copy_(vv, non_blocking=True)
+            else:
+                self.batch[k].copy_(v, non_blocking=True)
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.rows
