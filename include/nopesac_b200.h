@@ -229,6 +229,27 @@ int nsac_prune_assignment(const float* assign, const float* planes1, const float
 int nsac_camera_errors(const float* pose, int ldpose, const float* gt_tran, const float* gt_rot, int B, float* err_t,
                        float* err_r, float* stats, void* stream);
 
+/* Plane-list extraction from the PlaneTRHead outputs, the step before the path (SURVEY.md row f1:
+ * meta_arch/siamese_planeTR.py:625-803 `_postprocess_planeHeadMask`, batched, no host round trip).
+ *   pred_logits [B,NQ,2], pred_params [B,NQ,3], mask_logits [B,NQ,h,w], query_feat [B,NQ,C]   (fp32, contiguous)
+ *   H x W = output size, exactly 2x or 4x the mask resolution (the reference: 120x160 -> 480x640), NQ <= 127.
+ *   thresholds: cfg.TEST.PLANE_SCORE_THRESHOLD / MASK_PROB_THRESHOLD (compared in fp32 like torch does) and OVERLAP_THRESHOLD
+ *   (the reference compares a Python float ratio, hence double).
+ * Outputs, padded to NQ rows per image, kept planes first in query order:
+ *   count [B]; flags [B] (bit 0: no query passed the plane test -> best p0 forced (:657-661); bit 1: no plane passed the
+ *   overlap rule -> the un-thresholded region of the max-overlap plane (:741-790); bit 2: forced plane had an empty mask ->
+ *   pixel (0,0) set (:699-702)); ori_idx [B,NQ] (-1 = padding) = pred_plane_oriIdxs; planes [B,NQ,3] = pred_plane;
+ *   feats [B,NQ,C] = pred_plane_feats; scores [B,NQ]; centers [B,NQ,2] = pred_plane_ins_center; bboxes [B,NQ,4] = (x,y,w,h)
+ *   of pycocotools toBbox; areas [B,NQ]; seg [B,H,W] uint8 label map, 255 = no plane, pred_plane_masks[j] == (seg == j).
+ * workspace: nsac_plane_post_workspace_bytes(B,NQ,H,W) bytes, 256-byte aligned; seg 16-byte aligned. */
+size_t nsac_plane_post_workspace_bytes(int B, int NQ, int H, int W);
+int nsac_plane_postprocess(const float* pred_logits, const float* pred_params, const float* mask_logits,
+                           const float* query_feat, int B, int NQ, int C, int h, int w, int H, int W,
+                           float plane_score_thr, float mask_prob_thr, double overlap_thr, int32_t* count,
+                           int32_t* flags, int32_t* ori_idx, float* planes, float* feats, float* scores,
+                           float* centers, float* bboxes, int32_t* areas, uint8_t* seg, void* workspace,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -65,6 +65,9 @@ _SIGNATURES = {
     "nsac_debug_score_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "nsac_debug_gemm_trace": (C.c_int, [C.c_void_p]),
     "nsac_camera_errors": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "nsac_plane_post_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
+    "nsac_plane_postprocess": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p] + [C.c_int] * 7 +
+                               [C.c_float, C.c_float, C.c_double] + [C.c_void_p] * 12),
     "nsac_prune_assignment": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, c_float_p, C.c_void_p]),
 }

@@ -26,6 +26,7 @@ from torch import nn
 from .camera_head import build_camera_head
 from .compat import Registry, ShapeSpec
 from .matching_head import build_matching_head
+from .plane_postprocess import PlaneLists, postprocess_plane_head_mask
 
 __all__ = ["META_ARCH_REGISTRY", "PlaneTR_NopeSAC", "build_model"]
 
@@ -53,6 +54,10 @@ class PlaneTR_NopeSAC(nn.Module):
         self.embedding_on = cfg.MODEL.EMBEDDING_ON
         self.camera_on = cfg.MODEL.CAMERA_ON
         self.camera_refine_on = cfg.MODEL.CAMERA_HEAD.REFINE_ON
+        self.num_queries = cfg.MODEL.SEM_SEG_HEAD.NUM_OBJECT_QUERIES
+        self.overlap_threshold = cfg.TEST.OVERLAP_THRESHOLD                  # siamese_planeTR.py:92-94
+        self.plane_score_threshold = cfg.TEST.PLANE_SCORE_THRESHOLD
+        self.mask_prob_threshold = cfg.TEST.MASK_PROB_THRESHOLD
         # camCls kmeans pickles (siamese_planeTR.py:119-128) are loaded by the reference but never used in
         # forward, and cannot be unpickled without sklearn 0.21 / spherecluster: deliberately skipped.
         self.matching_head = build_matching_head(cfg) if self.embedding_on else None
@@ -74,6 +79,23 @@ class PlaneTR_NopeSAC(nn.Module):
         if missing:
             raise KeyError(f"reference checkpoint lacks hot-path keys: {missing[:5]} ...")
         return sorted(set(state_dict) - set(mine))
+
+    def plane_lists(self, planeTR_outputs: Dict[str, torch.Tensor], query_feat: torch.Tensor, height: int = 480,
+                    width: int = 640) -> PlaneLists:
+        """Row f1, batched and sync-free: PlaneTRHead outputs -> device-resident plane lists (csrc/planes.cu)."""
+        return postprocess_plane_head_mask(planeTR_outputs, query_feat, height, width, self.plane_score_threshold,
+                                           self.mask_prob_threshold, self.overlap_threshold)
+
+    def _postprocess_planeHeadMask(self, planeTR_outputs, pred_depth, batched_inputs, image_sizes, query_feat_in,
+                                   mask_threshold=0.5, nms=False):
+        """The reference's method (siamese_planeTR.py:625-803), same arguments and per-image result dicts; all images of the
+        call must share one output size (the reference asserts batch size 1, :454).  One host sync (the plane counts)."""
+        sizes = {(bi.get("height", sz[0]), bi.get("width", sz[1])) for bi, sz in zip(batched_inputs, image_sizes)}
+        if len(sizes) != 1:
+            raise ValueError(f"_postprocess_planeHeadMask: images of one call must share one output size, got {sorted(sizes)}")
+        height, width = next(iter(sizes))
+        lists = self.plane_lists(planeTR_outputs, query_feat_in, height, width)
+        return lists.to_reference_results(batched_inputs, with_rle=True)
 
     @staticmethod
     def _stack_views(batched_inputs, view: str, device):

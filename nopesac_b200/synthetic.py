@@ -195,3 +195,81 @@ def make_weights(shapes, seed: int = 40):
             t = (torch.rand(shape, generator=g) * 2 - 1) * bound
         out[name] = t
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Row f1: synthetic PlaneTRHead outputs (the inputs of `_postprocess_planeHeadMask`, siamese_planeTR.py:625-803)
+# ---------------------------------------------------------------------------------------------------------------------
+PLANE_HEAD_CASES = ("regular", "zero", "zero_empty", "fallback_empty", "fallback_overlap", "noise")
+
+
+def make_plane_head_outputs(image_idx: int, num_queries: int = 50, mask_h: int = 120, mask_w: int = 160,
+                            channels: int = 256, case: str = "regular", planes: Optional[int] = None):
+    """One image's `pred_logits [NQ,2]`, `pred_params [NQ,3]`, `pred_mask_logits [NQ,h,w]`, `query_feat [NQ,C]` (CPU fp32,
+    seeded by the image index).  Plane queries get smooth blob-shaped mask logits that tile the image; the cases drive the
+    branches of the reference's post-processing:
+      regular           several confident planes (+ two decoys: a duplicate that loses every pixel, a low-overlap one)
+      zero              no query passes the plane-score test            -> `zero_flag` (:657-661)
+      zero_empty        as above and its thresholded mask is empty      -> pixel (0,0) is set (:699-702)
+      fallback_empty    one plane, thresholded mask empty               -> `len(instances) == 0` branch (:741-790)
+      fallback_overlap  one plane, overlap below OVERLAP_THRESHOLD      -> same branch, non-trivial overlap
+      noise             noisy patchwork masks (ragged regions, many near-ties between planes)
+    """
+    assert case in PLANE_HEAD_CASES
+    g = torch.Generator().manual_seed(77000 + image_idx)
+    nq = num_queries
+    ys = torch.arange(mask_h, dtype=torch.float32).view(-1, 1) / mask_h
+    xs = torch.arange(mask_w, dtype=torch.float32).view(1, -1) / mask_w
+    logits = torch.empty(nq, 2)
+    logits[:, 0] = -3.0 + 0.5 * torch.randn(nq, generator=g)
+    logits[:, 1] = 3.0 + 0.5 * torch.randn(nq, generator=g)
+    masks = -4.0 + 0.5 * torch.randn(nq, mask_h, mask_w, generator=g)
+    params = torch.randn(nq, 3, generator=g)
+    feats = torch.randn(nq, channels, generator=g)
+    if planes is None:
+        planes = 4 + int(torch.randint(0, 13, (1,), generator=g))
+    planes = min(planes, nq)
+    order = torch.randperm(nq, generator=g)
+
+    def blob(scale=14.0, sharp=40.0):
+        cy, cx = torch.rand(2, generator=g).tolist()
+        rad = 0.10 + 0.12 * float(torch.rand(1, generator=g))
+        d2 = ((ys - cy) ** 2 + (xs - cx) ** 2) / (rad * rad)
+        return scale - sharp * d2 / 4.0 + 0.3 * torch.randn(mask_h, mask_w, generator=g)
+
+    def patches():
+        coarse = 4.0 * torch.randn(1, 1, mask_h // 8, mask_w // 8, generator=g)
+        up = torch.nn.functional.interpolate(coarse, size=(mask_h, mask_w), mode="bilinear", align_corners=False)[0, 0]
+        return up + 1.5 * torch.randn(mask_h, mask_w, generator=g)
+
+    if case in ("regular", "noise"):
+        for k in range(planes):
+            q = int(order[k])
+            logits[q, 0] = 2.0 + 2.0 * float(torch.rand(1, generator=g))
+            logits[q, 1] = -1.0 + 0.5 * float(torch.randn(1, generator=g))
+            masks[q] = blob() if case == "regular" else patches()
+        if case == "regular" and planes + 2 <= nq:
+            dup, weak = int(order[planes]), int(order[planes + 1])
+            logits[dup] = torch.tensor([0.6, -0.6])           # passes the score test, loses every pixel to its twin
+            masks[dup] = masks[int(order[0])] - 1.0
+            logits[weak] = torch.tensor([0.3, -0.3])          # score ~0.65: most of its area falls below the mask threshold
+            masks[weak] = blob(scale=1.2, sharp=2.0)
+    elif case in ("zero", "zero_empty"):
+        q = int(order[0])
+        logits[q] = torch.tensor([0.1, 0.0])                  # best p0 ~0.52 < PLANE_SCORE_THRESHOLD
+        masks[q] = blob() if case == "zero" else -3.0 + 0.2 * torch.randn(mask_h, mask_w, generator=g)
+    elif case == "fallback_empty":
+        q = int(order[0])
+        logits[q] = torch.tensor([0.25, -0.25])               # score ~0.62
+        masks[q] = 0.7 + 0.1 * torch.randn(mask_h, mask_w, generator=g)      # prob ~0.67: 0.62 * 0.67 < 0.5 everywhere
+    elif case == "fallback_overlap":
+        q = int(order[0])
+        logits[q] = torch.tensor([0.4, -0.4])                 # score ~0.69
+        masks[q] = blob(scale=1.5, sharp=3.0)                 # prob mostly 0.5 .. 0.8: area(0.69 p > 0.5) << area(p >= 0.5)
+    return {"pred_logits": logits, "pred_params": params, "pred_mask_logits": masks, "query_feat": feats}
+
+
+def make_plane_head_batch(first_image: int, num_images: int, cases=("regular",), **kw):
+    """Stacked `[B, ...]` tensors of `make_plane_head_outputs` (case i = cases[i % len(cases)])."""
+    items = [make_plane_head_outputs(first_image + i, case=cases[i % len(cases)], **kw) for i in range(num_images)]
+    return {k: torch.stack([it[k] for it in items]).contiguous() for k in items[0]}

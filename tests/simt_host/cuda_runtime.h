@@ -1,0 +1,116 @@
+// TEST INFRASTRUCTURE — a stand-in for <cuda_runtime.h> that lets g++ compile the plain-SIMT kernels of nopesac_b200/csrc
+// (no TMA / tcgen05 / inline PTX) and run them on the host: one OS thread per CUDA thread, blocks one after another,
+// __syncthreads = a barrier over the block, warp intrinsics = a barrier over the 32 threads of a warp plus a scratch line,
+// atomics = GCC __atomic builtins.  `tests/simt_host/run.py` rewrites `k<<<grid, block, smem, stream>>>(args)` into
+// `SIMT_LAUNCH(grid, block, k(args))`.  The point: the container has no GPU, so the kernel SOURCE is executed here against the
+// oracle before a GPU ever sees it (tests/test_simt_host_planes.py).  Floating point: compiled with -ffp-contract=off so
+// that only the explicit __fmaf_rn calls fuse; expf is glibc's (<= 1 ulp, like CUDA's, but not bit-identical).
+#pragma once
+#include <pthread.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <cmath>
+#include <functional>
+#include <thread>
+#include <vector>
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __noinline__
+#define __launch_bounds__(...)
+#define __shared__ static
+#define __align__(n) __attribute__((aligned(n)))
+
+struct uint3 { unsigned x, y, z; };
+struct dim3 {
+  unsigned x, y, z;
+  dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint4 { unsigned x, y, z, w; };
+
+typedef void* cudaStream_t;
+typedef int cudaError_t;
+enum { cudaSuccess = 0 };
+inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+inline const char* cudaGetErrorString(cudaError_t) { return "simt_host"; }
+
+namespace simt {
+struct Block {
+  pthread_barrier_t all;
+  std::vector<pthread_barrier_t> warp;
+  std::vector<unsigned long long> scratch;   // 32 words per warp
+};
+extern thread_local Block* cur;
+extern thread_local unsigned linear_tid;
+}  // namespace simt
+
+extern thread_local uint3 threadIdx, blockIdx;
+extern thread_local dim3 blockDim, gridDim;
+
+inline void __syncthreads() { pthread_barrier_wait(&simt::cur->all); }
+
+namespace simt {
+// every lane publishes one word, all lanes read the 32 words
+inline void exchange(unsigned long long mine, unsigned long long out[32]) {
+  const unsigned w = linear_tid >> 5, l = linear_tid & 31;
+  cur->scratch[w * 32 + l] = mine;
+  pthread_barrier_wait(&cur->warp[w]);
+  for (int i = 0; i < 32; ++i) out[i] = cur->scratch[w * 32 + i];
+  pthread_barrier_wait(&cur->warp[w]);
+}
+}  // namespace simt
+
+inline unsigned __ballot_sync(unsigned, int pred) {
+  unsigned long long v[32];
+  simt::exchange(pred ? 1ull : 0ull, v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (unsigned)(v[i] & 1ull) << i;
+  return r;
+}
+inline unsigned __reduce_add_sync(unsigned, unsigned x) {
+  unsigned long long v[32];
+  simt::exchange(x, v);
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r += (unsigned)v[i];
+  return r;
+}
+inline float __shfl_xor_sync(unsigned, float x, int o) {
+  unsigned long long v[32];
+  unsigned bits;
+  memcpy(&bits, &x, 4);
+  simt::exchange(bits, v);
+  bits = (unsigned)v[(simt::linear_tid & 31) ^ o];
+  memcpy(&x, &bits, 4);
+  return x;
+}
+inline int __popc(unsigned x) { return __builtin_popcount(x); }
+
+template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <typename T> inline T atomicMin(T* p, T v) {
+  T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+template <typename T> inline T atomicMax(T* p, T v) {
+  T old = __atomic_load_n(p, __ATOMIC_RELAXED);
+  while (v > old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+  return old;
+}
+
+template <typename T> inline T __ldg(const T* p) { return *p; }
+inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __double2float_rn(double d) { return (float)d; }
+inline int max(int a, int b) { return a > b ? a : b; }
+inline int min(int a, int b) { return a < b ? a : b; }
+
+namespace simt {
+void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+}
+#define SIMT_LAUNCH(grid, block, call) simt::launch((grid), (block), [&]() { call; })

@@ -1,0 +1,50 @@
+// TEST INFRASTRUCTURE — runtime half of tests/simt_host/cuda_runtime.h (block scheduler, thread-local indices, error string).
+#include <cuda_runtime.h>
+#include <stdarg.h>
+
+thread_local uint3 threadIdx, blockIdx;
+thread_local dim3 blockDim, gridDim;
+namespace simt {
+thread_local Block* cur = nullptr;
+thread_local unsigned linear_tid = 0;
+
+void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+  const unsigned n = block.x * block.y * block.z;
+  if (n % 32 != 0) {
+    fprintf(stderr, "simt_host: block of %u threads is not a multiple of 32\n", n);
+    abort();
+  }
+  Block blk;
+  pthread_barrier_init(&blk.all, nullptr, n);
+  blk.warp.resize(n / 32);
+  for (auto& w : blk.warp) pthread_barrier_init(&w, nullptr, 32);
+  blk.scratch.assign(n, 0ull);
+  std::vector<std::thread> threads(n);
+  for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+      for (unsigned bx = 0; bx < grid.x; ++bx) {
+        for (unsigned t = 0; t < n; ++t)
+          threads[t] = std::thread([&, t, bx, by, bz]() {
+            cur = &blk;
+            linear_tid = t;
+            threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+            blockIdx = uint3{bx, by, bz};
+            blockDim = block;
+            gridDim = grid;
+            body();
+          });
+        for (auto& th : threads) th.join();
+      }
+  pthread_barrier_destroy(&blk.all);
+  for (auto& w : blk.warp) pthread_barrier_destroy(&w);
+}
+}  // namespace simt
+
+static thread_local char g_err[512];
+void nsac_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+}
+extern "C" const char* simt_last_error() { return g_err; }
