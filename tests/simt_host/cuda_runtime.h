@@ -2,7 +2,7 @@
 // (no TMA / tcgen05 / inline PTX) and run them on the host: one OS thread per CUDA thread, blocks one after another,
 // __syncthreads = a barrier over the block, warp intrinsics = a barrier over the 32 threads of a warp plus a scratch line,
 // atomics = GCC __atomic builtins.  `tests/simt_host/run.py` rewrites `k<<<grid, block, smem, stream>>>(args)` into
-// `SIMT_LAUNCH(grid, block, k(args))`.  The point: the container has no GPU, so the kernel SOURCE is executed here against the
+// `SIMT_LAUNCH(grid, block, smem, k(args))` and `extern __shared__ T x[];` into a pointer to the block's buffer.  The point: the container has no GPU, so the kernel SOURCE is executed here against the
 // oracle before a GPU ever sees it (tests/test_simt_host_planes.py).  Floating point: compiled with -ffp-contract=off so
 // that only the explicit __fmaf_rn calls fuse; expf is glibc's (<= 1 ulp, like CUDA's, but not bit-identical).
 #pragma once
@@ -32,11 +32,17 @@ struct dim3 {
   dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
 struct uint4 { unsigned x, y, z, w; };
+struct __attribute__((aligned(16))) float4 { float x, y, z, w; };
+struct __attribute__((aligned(8))) float2 { float x, y; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
+inline float2 make_float2(float x, float y) { return float2{x, y}; }
 
 typedef void* cudaStream_t;
 typedef int cudaError_t;
 enum { cudaSuccess = 0 };
+enum { cudaFuncAttributeMaxDynamicSharedMemorySize = 8 };
 inline cudaError_t cudaGetLastError() { return cudaSuccess; }
+template <typename F> inline cudaError_t cudaFuncSetAttribute(F, int, int) { return cudaSuccess; }
 inline const char* cudaGetErrorString(cudaError_t) { return "simt_host"; }
 
 namespace simt {
@@ -44,6 +50,7 @@ struct Block {
   pthread_barrier_t all;
   std::vector<pthread_barrier_t> warp;
   std::vector<unsigned long long> scratch;   // 32 words per warp
+  unsigned char* dyn_smem;                   // `extern __shared__` storage of the running block (16-byte aligned)
 };
 extern thread_local Block* cur;
 extern thread_local unsigned linear_tid;
@@ -88,6 +95,16 @@ inline float __shfl_xor_sync(unsigned, float x, int o) {
   memcpy(&x, &bits, 4);
   return x;
 }
+inline float __shfl_sync(unsigned, float x, int src) {
+  unsigned long long v[32];
+  unsigned bits;
+  memcpy(&bits, &x, 4);
+  simt::exchange(bits, v);
+  bits = (unsigned)v[src & 31];
+  memcpy(&x, &bits, 4);
+  return x;
+}
+inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&simt::cur->warp[simt::linear_tid >> 5]); }
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -107,10 +124,14 @@ inline float __fmaf_rn(float a, float b, float c) { return fmaf(a, b, c); }
 inline float __fmul_rn(float a, float b) { return a * b; }
 inline float __fadd_rn(float a, float b) { return a + b; }
 inline float __double2float_rn(double d) { return (float)d; }
+inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+inline float __expf(float x) { return expf(x); }
+inline float __fdividef(float a, float b) { return a / b; }
 inline int max(int a, int b) { return a > b ? a : b; }
 inline int min(int a, int b) { return a < b ? a : b; }
 
 namespace simt {
-void launch(dim3 grid, dim3 block, const std::function<void()>& body);
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body);
+inline unsigned char* dyn_smem() { return cur->dyn_smem; }
 }
-#define SIMT_LAUNCH(grid, block, call) simt::launch((grid), (block), [&]() { call; })
+#define SIMT_LAUNCH(grid, block, smem, call) simt::launch((grid), (block), (size_t)(smem), [&]() { call; })

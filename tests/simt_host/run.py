@@ -31,37 +31,59 @@ def _split_top_level(s: str):
 
 
 def rewrite_launches(src: str) -> str:
-    """`kernel<<<grid, block, smem, stream>>>(args);` -> `SIMT_LAUNCH(grid, block, kernel(args));`"""
+    """`kernel<<<grid, block, smem, stream>>>(args);` -> `SIMT_LAUNCH(grid, block, smem, kernel(args));`"""
     pat = re.compile(r"(\w+(?:<[\w\s,]*>)?)\s*<<<(.*?)>>>\s*\((.*?)\);", re.S)
 
     def sub(m):
         cfg = _split_top_level(m.group(2))
-        return f"SIMT_LAUNCH({cfg[0]}, {cfg[1]}, {m.group(1)}({m.group(3)}));"
+        smem = cfg[2] if len(cfg) > 2 else "0"
+        return f"SIMT_LAUNCH({cfg[0]}, {cfg[1]}, {smem}, {m.group(1)}({m.group(3)}));"
 
     out, n = pat.subn(sub, src)
     if n == 0:
         raise RuntimeError("no kernel launch found")
+    # `extern __shared__ [__align__(16)] T name[];` -> pointer to the running block's dynamic shared memory
+    out = re.sub(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?([\w ]+?)\s+(\w+)\[\];",
+                 lambda m: f"{m.group(1)}* {m.group(2)} = reinterpret_cast<{m.group(1)}*>(simt::dyn_smem());", out)
     return out
 
 
-def build(cu_name: str) -> ctypes.CDLL:
-    with open(os.path.join(CSRC, cu_name)) as f:
-        src = rewrite_launches(f.read())
-    with open(os.path.join(HERE, "cuda_runtime.h")) as f, open(os.path.join(HERE, "simt_runtime.cpp")) as g:
-        key = hashlib.sha1((src + f.read() + g.read()).encode()).hexdigest()[:16]
+def build(cu_names) -> ctypes.CDLL:
+    """One host library from one or several csrc/*.cu files (a str or a list of names)."""
+    if isinstance(cu_names, str):
+        cu_names = [cu_names]
+    srcs = {}
+    for name in cu_names:
+        with open(os.path.join(CSRC, name)) as f:
+            srcs[name] = rewrite_launches(f.read())
+    h = hashlib.sha1()
+    for name in sorted(srcs):
+        h.update(srcs[name].encode())
+    for dep in ("cuda_runtime.h", "cuda_fp16.h", "simt_runtime.cpp"):
+        with open(os.path.join(HERE, dep), "rb") as f:
+            h.update(f.read())
+    with open(os.path.join(CSRC, "common.cuh"), "rb") as f:
+        h.update(f.read())
+    key = h.hexdigest()[:16]
     out_dir = os.path.join(tempfile.gettempdir(), "nsac_simt_host")
     os.makedirs(out_dir, exist_ok=True)
-    lib = os.path.join(out_dir, f"{os.path.splitext(cu_name)[0]}_{key}.so")
+    lib = os.path.join(out_dir, f"simt_{key}.so")
     if not os.path.exists(lib):
-        gen = os.path.join(out_dir, f"{os.path.splitext(cu_name)[0]}_{key}.cpp")
-        with open(gen, "w") as f:
-            f.write(src)
-        # the generated file sits outside csrc/: -I csrc for "common.cuh", which includes "../../include/nopesac_b200.h"
+        gens = []
+        for name, src in srcs.items():
+            gen = os.path.join(out_dir, f"{os.path.splitext(name)[0]}_{key}.cpp")
+            with open(gen, "w") as f:
+                f.write(src)
+            gens.append(gen)
+        # the generated files sit outside csrc/: -I csrc for "common.cuh", which includes "../../include/nopesac_b200.h"
         # relative to ITS OWN directory, so the real header is used.
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w", "-x", "c++",
-               "-I", HERE, "-I", CSRC, gen, os.path.join(HERE, "simt_runtime.cpp"), "-o", lib + ".tmp"]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w",
+               "-I", HERE, "-I", CSRC] + gens + [os.path.join(HERE, "simt_runtime.cpp"), "-o", lib + ".tmp"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("simt_host build failed:\n" + res.stderr[-4000:])
         os.replace(lib + ".tmp", lib)
     return ctypes.CDLL(lib)
+
+
+SIMT_SOURCES = ["dense.cu", "geo.cu", "matcher.cu", "score.cu", "evaluate.cu", "planes.cu"]   # no TMA / tcgen05 / inline PTX

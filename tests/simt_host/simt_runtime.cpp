@@ -8,7 +8,7 @@ namespace simt {
 thread_local Block* cur = nullptr;
 thread_local unsigned linear_tid = 0;
 
-void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
+void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<void()>& body) {
   const unsigned n = block.x * block.y * block.z;
   if (n % 32 != 0) {
     fprintf(stderr, "simt_host: block of %u threads is not a multiple of 32\n", n);
@@ -19,6 +19,8 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
   blk.warp.resize(n / 32);
   for (auto& w : blk.warp) pthread_barrier_init(&w, nullptr, 32);
   blk.scratch.assign(n, 0ull);
+  std::vector<unsigned char> smem(dyn_smem_bytes + 1024, 0xCD);       // garbage-filled like real shared memory
+  blk.dyn_smem = smem.data() + ((1024 - (uintptr_t)smem.data() % 1024) % 1024);
   std::vector<std::thread> threads(n);
   for (unsigned bz = 0; bz < grid.z; ++bz)
     for (unsigned by = 0; by < grid.y; ++by)
@@ -41,7 +43,7 @@ void launch(dim3 grid, dim3 block, const std::function<void()>& body) {
 }  // namespace simt
 
 static thread_local char g_err[512];
-void nsac_set_error(const char* fmt, ...) {
+__attribute__((weak)) void nsac_set_error(const char* fmt, ...) {   // dense.cu brings its own when it is part of the build
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof g_err, fmt, ap);

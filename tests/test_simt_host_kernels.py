@@ -1,0 +1,180 @@
+"""CPU: the SOURCE of the plain-SIMT kernels (csrc/geo.cu, matcher.cu, score.cu, dense.cu, evaluate.cu — no TMA / tcgen05 /
+inline PTX) compiled for the host (tests/simt_host: one OS thread per CUDA thread) and driven through the product's own
+Python wrappers (`nopesac_b200.ops`, with the library handle, the CUDA-tensor check and the stream getter swapped by the test
+fixture) against the oracle.  The build container has no GPU: this is where the kernel logic of the exact-fp32 stages is
+executed before a GPU sees it; the same comparisons run on the device in tests/test_gpu_parity.py.  The tensor-core kernels
+(gemm_tc.cu, score_tc.cu, pixel.cu's engine calls) cannot run here and stay GPU-only."""
+import ctypes as C
+import math
+import os
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests", "simt_host"))
+
+import run as simt_run  # noqa: E402
+
+from nopesac_b200 import _lib, ops, synthetic  # noqa: E402
+from oracle import restate  # noqa: E402
+from tests import util  # noqa: E402
+
+
+@pytest.fixture()
+def host_ops(monkeypatch):
+    L = simt_run.build(simt_run.SIMT_SOURCES)
+    for name, (res, args) in _lib._SIGNATURES.items():
+        if hasattr(L, name):
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+    monkeypatch.setattr(_lib, "_lib", L)
+
+    def chk(t, name, dtype=torch.float32):
+        if t.dtype != dtype:
+            raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
+        return t
+
+    monkeypatch.setattr(ops, "_chk", chk)
+    monkeypatch.setattr(ops, "_stream", lambda: None)
+    return ops
+
+
+def test_geo_sequence_source_on_host(host_ops):
+    """K6 (camera_head.py:1352-1425, 568-569, 937-957): nonzero order, matched_num, geo_local, sig exact; geo_global 2e-5."""
+    for negk in (False, True):
+        sd, msd = util.make_weights(50)
+        b = synthetic.make_batch(3, 1, 16, negative_k=negk)
+        ip = util.initial_pose_for(3)
+        with torch.no_grad():
+            o = restate.inference_joint(sd, msd, None, None, b.planes1, b.planes2, b.app1, b.app2, num_queries=50, initial_pose=ip)
+        t0, q0 = o["camera_initRec"]
+        gl, gg, sig, geo8, mnum, pidx = host_ops.geo_sequence(b.planes1, b.planes2, o["assignment_before"], t0, q0, 50)
+        m = o["matched_num"]
+        assert int(mnum[0]) == m
+        assert torch.equal(pidx[0, :m].long(), torch.nonzero(o["assignment_before"][0]))
+        assert bool((pidx[0, m:] == -1).all())
+        assert torch.equal(gl[0], o["geo_local"])
+        assert util.maxdiff(gg[0], o["geo_global"]) <= 2e-5
+        assert torch.equal(sig[0], o["sig_seq"][:, 0])
+        if negk:
+            assert float(sig[0].min()) == -1.0
+
+
+def test_geo_sequence_explicit_hypothesis_list_on_host(host_ops):
+    """H > P^2 / H < P^2 explicit lists (the BASELINE stress shape) + a batch of 3 pairs."""
+    P, NQ = 8, 40
+    for H in (20, 40):
+        hyp = synthetic.all_pairs_hypotheses(P, H)
+        b = synthetic.make_batch(11, 3, P)
+        t0 = torch.stack([util.initial_pose_for(i)[0][0] for i in range(3)])
+        q0 = torch.stack([util.initial_pose_for(i)[1][0] for i in range(3)])
+        gl, gg, sig, geo8, mnum, pidx = host_ops.geo_sequence(b.planes1, b.planes2, None, t0, q0, NQ, hyp_pairs=hyp.to(torch.int32))
+        for i in range(3):
+            want_l, want_g, want_sig = restate.geo_sequences(b.planes1[i], b.planes2[i], hyp.long(), NQ, t0[i:i + 1], q0[i:i + 1])[:3]
+            assert int(mnum[i]) == H
+            assert torch.equal(gl[i], want_l) and util.maxdiff(gg[i], want_g) <= 2e-5
+            assert torch.equal(sig[i], want_sig.reshape(-1))
+
+
+def test_match_sinkhorn_assign_source_on_host(host_ops):
+    """K5 + a8 (matching_head.py:75-128, 228-306; camera_modules.py:15-34): exp(log_scores_padded) 1e-4, assignment exact;
+    ragged n1 != n2, an all-dustbin case (threshold 0.999)."""
+    g = torch.Generator().manual_seed(5)
+    for (n1, n2, thr) in ((16, 16, 0.2), (5, 9, 0.2), (7, 3, 0.999)):
+        b = synthetic.make_batch(21, 1, max(n1, n2))
+        p1, p2 = b.planes1[:, :n1].contiguous(), b.planes2[:, :n2].contiguous()
+        base = torch.randn(1, max(n1, n2), 256, generator=g)
+        d1 = (base[:, :n1] * 1.2).contiguous()
+        d2 = (base[:, torch.randperm(max(n1, n2), generator=g)[:n2]] * 1.2 + 0.1 * torch.randn(1, n2, 256, generator=g)).contiguous()
+        cam = torch.cat([b.gt_tran, b.gt_rot], dim=1)
+        bin_score = torch.tensor(1.0)
+        off, nrm = restate.match_penalties(p1, p2, cam)
+        s = torch.einsum("bnd,bmd->bnm", d1, d2) / 16.0 - off / 4.0 - nrm / 8.0
+        want = restate.log_optimal_transport(s, bin_score, 200)
+        want_a = restate.get_assignment_matrix(want, thr)
+        lsp, assign = host_ops.match_sinkhorn_assign(d1, d2, p1, p2, cam, bin_score, 4.0, 8.0, 200, thr)
+        assert util.maxdiff(lsp.exp(), want.exp()) <= 1e-4, (n1, n2)
+        assert torch.equal(assign, want_a), (n1, n2)
+        if thr > 0.9:
+            assert float(assign.sum()) == 0.0
+
+
+def test_prune_assignment_source_on_host(host_ops):
+    b = synthetic.make_batch(31, 2, 16)
+    assign = (torch.rand(2, 16, 16, generator=torch.Generator().manual_seed(1)) < 0.3).float()
+    pose = torch.zeros(2, 16)
+    pose[:, 0:3], pose[:, 3:7] = b.gt_tran, b.gt_rot
+    got = host_ops.prune_assignment(assign, b.planes1, b.planes2, pose)
+    want = restate.prune_assignment(assign, b.planes1, b.planes2, b.gt_rot, b.gt_tran)
+    assert torch.equal(got, want)
+    assert 0 < float(got.sum()) < float(assign.sum())
+
+
+def test_score_aggregate_exact_source_on_host(host_ops):
+    """K8 + K9 exact-fp32 path (camera_head.py:964-1115) on the oracle's own per-hypothesis features: poses / scores 1e-5,
+    argmin / argmax selections exact, l2 diagnostic, all four INFERENCE_OUT_CAM_TYPEs, and the m = 0 / m = 1 rules."""
+    nq = 32
+    sd, msd = util.make_weights(nq)
+    for n_hyp in (20, 1, 0):
+        b = synthetic.make_batch(3, 1, 8)
+        ip = util.initial_pose_for(3)
+        hyp = synthetic.all_pairs_hypotheses(8, max(n_hyp, 1))
+        with torch.no_grad():
+            o = restate.inference_joint(sd, msd, None, None, b.planes1, b.planes2, b.app1, b.app2, num_queries=nq, hyp_pairs=hyp, initial_pose=ip)
+            t0, q0 = o["camera_initRec"]
+            _, rf0 = restate.rot_rec_head(sd, o["camera_init"][1])
+            _, tf0 = restate.trans_rec_head(sd, o["camera_init"][0])
+            fr, ft = restate.hypothesis_features(sd, o["geo_global"][None], o["sig_seq"][None], rf0, tf0)
+            qh = torch.nn.functional.normalize(restate.linear(sd, "rots", fr), dim=-1)
+            th = restate.linear(sd, "trans", ft)
+        m = o["matched_num"] if n_hyp else 0
+        geo_local = o["geo_local"].clone()
+        geo_local[m:] = 0
+        mlp = lambda p, r: tuple(sd[k].contiguous() for k in (f"{p}.layers.0.weight", f"{p}.layers.0.bias", f"{p}.layers.1.weight",
+                                                               f"{p}.layers.1.bias", f"{p}.layers.2.weight", f"{p}.layers.2.bias",
+                                                               f"{r}.weight", f"{r}.bias"))
+        for cam in ("soft", "avg-all", "min-cost", "max-score"):
+            with torch.no_grad():
+                want = restate.score_and_select(sd, fr, ft, rf0, tf0, geo_local[None], m, q0, t0, cam)
+            res = host_ops.score_aggregate(geo_local[None].contiguous(), qh[None].contiguous(), th[None].contiguous(), q0, t0,
+                                           fr[None].contiguous(), ft[None].contiguous(), rf0, tf0, torch.tensor([m], dtype=torch.int32),
+                                           mlp("normal_score_proj", "rot_score_reg"), mlp("param_score_proj", "trans_score_reg"),
+                                           sd["rots.weight"], sd["rots.bias"], sd["trans.weight"], sd["trans.bias"],
+                                           out_cam_type=cam, want_diag=True, precision="fp32")
+            pose, tag = res["pose"][0], f"{cam} m={m}"
+            assert util.maxdiff(pose[0:3], want["pred_trans"][0]) <= 1e-5 and util.maxdiff(pose[3:7], want["pred_rot"][0]) <= 1e-5, tag
+            assert int(pose[14]) == m, tag
+            if m > 0:
+                assert util.maxdiff(pose[7:10], want["pred_trans_avg"][0]) <= 1e-5 and util.maxdiff(pose[10:14], want["pred_rot_avg"][0]) <= 1e-5, tag
+            if m > 1:
+                assert util.maxdiff(res["score_rot"][0, :m + 1], want["score_soft_rot"][0, :, 0]) <= 1e-5, tag
+                assert util.maxdiff(res["score_tran"][0, :m + 1], want["score_soft_offset"][0, :, 0]) <= 1e-5, tag
+                if cam in ("min-cost", "max-score"):
+                    assert res["sel_idx"][0].tolist() == [want["sel_rot"], want["sel_tran"]], tag
+                assert torch.allclose(res["diag"][0, 0, :m + 1, :m], want["l2_dist"][0], rtol=1e-5, atol=1e-5), tag
+
+
+def test_dense_kernels_source_on_host(host_ops):
+    """nsac_linear (bias / grouped bias / activations / strided views), nsac_layernorm (+ residual), nsac_attention, nsac_pose_heads."""
+    g = torch.Generator().manual_seed(2)
+    for (M, N, K, act) in ((5, 7, 3, 0), (33, 256, 8, 1), (64, 65, 130, 2), (1, 4, 256, 0)):
+        x, w, bias = torch.randn(M, K, generator=g), torch.randn(N, K, generator=g), torch.randn(N, generator=g)
+        want = torch.nn.functional.linear(x, w, bias)
+        want = {0: want, 1: want.relu(), 2: torch.nn.functional.leaky_relu(want, 0.01)}[act]
+        assert util.maxdiff(host_ops.linear(x, w, bias, act), want) <= 2e-5 * max(1.0, float(want.abs().max())), (M, N, K, act)
+    x, res_in = torch.randn(10, 256, generator=g), torch.randn(10, 256, generator=g)
+    gamma, beta = torch.randn(256, generator=g), torch.randn(256, generator=g)
+    want = res_in + torch.nn.functional.layer_norm(x, (256,), gamma, beta)
+    assert util.maxdiff(host_ops.layernorm(x, gamma, beta, res=res_in), want) <= 1e-5
+    B, Lq, S, H, D = 2, 5, 9, 8, 32
+    q, k, v = (torch.randn(B, n, H * D, generator=g) for n in (Lq, S, S))
+    A = torch.softmax(torch.einsum("nlhd,nshd->nlsh", q.view(B, Lq, H, D), k.view(B, S, H, D)) / math.sqrt(D), dim=2)
+    want = torch.einsum("nlsh,nshd->nlhd", A, v.view(B, S, H, D)).reshape(B, Lq, H * D)
+    assert util.maxdiff(host_ops.attention(q, k, v, B, Lq, S, H, D), want) <= 1e-5
+    fr, ft = torch.randn(6, 256, generator=g), torch.randn(6, 256, generator=g)
+    wr, br, wt, bt = torch.randn(4, 256, generator=g) * 0.1, torch.randn(4, generator=g), torch.randn(3, 256, generator=g) * 0.1, torch.randn(3, generator=g)
+    qo, to = host_ops.pose_heads(fr, ft, wr, br, wt, bt)
+    assert util.maxdiff(qo, torch.nn.functional.normalize(torch.nn.functional.linear(fr, wr, br), dim=-1)) <= 1e-5
+    assert util.maxdiff(to, torch.nn.functional.linear(ft, wt, bt)) <= 1e-5
