@@ -88,7 +88,7 @@ def test_match_sinkhorn_assign_source_on_host(host_ops):
         base = torch.randn(1, max(n1, n2), 256, generator=g)
         d1 = (base[:, :n1] * 1.2).contiguous()
         d2 = (base[:, torch.randperm(max(n1, n2), generator=g)[:n2]] * 1.2 + 0.1 * torch.randn(1, n2, 256, generator=g)).contiguous()
-        cam = torch.cat([b.gt_tran, b.gt_rot], dim=1)
+        cam = torch.cat([b.gt_tran, b.gt_quat], dim=1)
         bin_score = torch.tensor(1.0)
         off, nrm = restate.match_penalties(p1, p2, cam)
         s = torch.einsum("bnd,bmd->bnm", d1, d2) / 16.0 - off / 4.0 - nrm / 8.0
@@ -105,9 +105,9 @@ def test_prune_assignment_source_on_host(host_ops):
     b = synthetic.make_batch(31, 2, 16)
     assign = (torch.rand(2, 16, 16, generator=torch.Generator().manual_seed(1)) < 0.3).float()
     pose = torch.zeros(2, 16)
-    pose[:, 0:3], pose[:, 3:7] = b.gt_tran, b.gt_rot
+    pose[:, 0:3], pose[:, 3:7] = b.gt_tran, b.gt_quat
     got = host_ops.prune_assignment(assign, b.planes1, b.planes2, pose)
-    want = restate.prune_assignment(assign, b.planes1, b.planes2, b.gt_rot, b.gt_tran)
+    want = restate.prune_assignment(assign, b.planes1, b.planes2, b.gt_quat, b.gt_tran)
     assert torch.equal(got, want)
     assert 0 < float(got.sum()) < float(assign.sum())
 
@@ -172,9 +172,35 @@ def test_dense_kernels_source_on_host(host_ops):
     q, k, v = (torch.randn(B, n, H * D, generator=g) for n in (Lq, S, S))
     A = torch.softmax(torch.einsum("nlhd,nshd->nlsh", q.view(B, Lq, H, D), k.view(B, S, H, D)) / math.sqrt(D), dim=2)
     want = torch.einsum("nlsh,nshd->nlhd", A, v.view(B, S, H, D)).reshape(B, Lq, H * D)
-    assert util.maxdiff(host_ops.attention(q, k, v, B, Lq, S, H, D), want) <= 1e-5
+    got = host_ops.attention(q.view(B * Lq, H * D), k.view(B * S, H * D), v.view(B * S, H * D), B, Lq, S, H, D)
+    assert util.maxdiff(got, want.reshape(B * Lq, H * D)) <= 1e-5
     fr, ft = torch.randn(6, 256, generator=g), torch.randn(6, 256, generator=g)
     wr, br, wt, bt = torch.randn(4, 256, generator=g) * 0.1, torch.randn(4, generator=g), torch.randn(3, 256, generator=g) * 0.1, torch.randn(3, generator=g)
     qo, to = host_ops.pose_heads(fr, ft, wr, br, wt, bt)
     assert util.maxdiff(qo, torch.nn.functional.normalize(torch.nn.functional.linear(fr, wr, br), dim=-1)) <= 1e-5
     assert util.maxdiff(to, torch.nn.functional.linear(ft, wt, bt)) <= 1e-5
+
+
+def test_camera_errors_source_on_host(host_ops):
+    """Row f3 kernel (mp3d_evaluation.py:382-425, 463-465) against the evaluation oracle and the golden fixture."""
+    import json
+    import numpy as np
+    from oracle import eval_restate
+    L = _lib._lib
+    with open(os.path.join(ROOT, "tests", "golden", "camera_eval.json")) as f:
+        cases = json.load(f)
+    for c in cases:
+        n = c["n"]
+        arr = lambda k: np.ascontiguousarray(np.asarray(c[k], dtype=np.float32))
+        rows = np.zeros((n, 16), np.float32)
+        rows[:, 0:3], rows[:, 3:7] = arr("pred_tran"), arr("pred_rot")
+        gt_t, gt_q = arr("gt_tran"), arr("gt_rot")
+        et, er, stats = np.empty(n, np.float32), np.empty(n, np.float32), np.empty(8, np.float32)
+        p = lambda a: C.c_void_p(a.ctypes.data)
+        assert L.nsac_camera_errors(p(rows), 16, p(gt_t), p(gt_q), n, p(et), p(er), p(stats), None) == 0
+        assert np.abs(et - np.linalg.norm(gt_t - rows[:, 0:3], axis=1)).max() <= 1e-5
+        assert np.abs(er - eval_restate.angle_error_vec(rows[:, 3:7], gt_q)).max() <= 5e-2
+        want = c["metrics"]
+        assert abs(stats[0] - want["T mean err"]) <= 1e-5 and abs(stats[1] - want["R mean err"]) <= 2e-3
+        for i, k in enumerate(("T err < 1.0", "T err < 0.5", "T err < 0.2", "R err < 30", "R err < 15", "R err < 10")):
+            assert abs(float(stats[2 + i]) / n * 100 - want[k]) <= 1e-9, (n, k)
