@@ -120,6 +120,12 @@ int nsac_layernorm(const float* x, int ldx, const float* gamma, const float* bet
 int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out,
                    int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S, int H, int D,
                    void* stream);
+/* Ragged batches (batch elements with different token counts, padded to S rows each): only the first kv_count[b]
+ * (int32 [B], device; clamped to [1,S]; NULL = S) keys / values of batch element b take part in the softmax — the
+ * all-valid case of the reference's masks (gnn.py:31-34 `kv_mask`).  Query rows beyond a count produce values nobody reads. */
+int nsac_attention_ragged(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out,
+                          int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S, int H, int D,
+                          const int32_t* kv_count, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Matching tail (matching_head.py:75-99, 113-128, 228-234, 259-306 + camera_modules.py:15-34):
@@ -134,6 +140,17 @@ int nsac_match_sinkhorn_assign(const float* desc1, const float* desc2, const flo
                                float offset_mult, float normal_mult, int iters, float threshold,
                                int B, int n1, int n2, int C, float* log_scores_padded, float* assign,
                                void* stream);
+/* Ragged batches: pair b has count1[b] x count2[b] planes (int32 [B], device; clamped to [1,n]; NULL = n1 / n2) stored
+ * in the first rows of the padded [B,n1,..] / [B,n2,..] inputs.  Each pair solves ITS OWN (count1+1) x (count2+1) transport
+ * problem (dustbins, marginals and normalisation of the un-padded pair — what the reference computes one pair at a time, and
+ * what its masked variant `log_optimal_transport_withMask`, matching_head.py:259-306, yields on the valid block); the result
+ * sits in the top-left corner of log_scores_padded[b] ([n1+1, n2+1], the rest -inf) and of assign[b] ([n1, n2], the rest 0). */
+int nsac_match_sinkhorn_assign_ragged(const float* desc1, const float* desc2, const float* planes1,
+                                      const float* planes2, const float* cam, const float* bin_score,
+                                      float offset_mult, float normal_mult, int iters, float threshold,
+                                      int B, int n1, int n2, int C, const int32_t* count1,
+                                      const int32_t* count2, float* log_scores_padded, float* assign,
+                                      void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Geo sequences (camera_head.py:1352-1425 called three times at :513-517, :555-569) + the 8-vector of

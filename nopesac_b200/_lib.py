@@ -44,6 +44,12 @@ _SIGNATURES = {
     "nsac_attention": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
                                  C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                  C.c_void_p]),
+    "nsac_attention_ragged": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        c_int_p, C.c_void_p]),
+    "nsac_match_sinkhorn_assign_ragged": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
+                                                    C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
+                                                    C.c_int, C.c_int, c_int_p, c_int_p, c_float_p, c_float_p, C.c_void_p]),
     "nsac_match_sinkhorn_assign": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, c_float_p, c_float_p,
                                              C.c_float, C.c_float, C.c_int, C.c_float, C.c_int, C.c_int,
                                              C.c_int, C.c_int, c_float_p, c_float_p, C.c_void_p]),

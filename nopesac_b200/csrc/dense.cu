@@ -236,17 +236,19 @@ namespace {
 __global__ void attention_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k,
                                  const float* __restrict__ v, int ldkv, float* __restrict__ out, int ldo,
                                  uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int ld_split,
-                                 int L, int S, int H) {
+                                 int L, int S_pad, int H, const int32_t* __restrict__ kv_count) {
   extern __shared__ float sm[];  // per warp: K [S][33], V [S][33], p [S]
   const int b = blockIdx.x, h = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (h >= H) return;
-  float* Ks = sm + (size_t)h * (S * 66 + S);
-  float* Vs = Ks + S * 33;
-  float* ps = Vs + S * 33;
+  float* Ks = sm + (size_t)h * (S_pad * 66 + S_pad);
+  float* Vs = Ks + S_pad * 33;
+  float* ps = Vs + S_pad * 33;
+  // ragged batches: only the first kv_count[b] source tokens of this batch element exist (row stride stays S_pad)
+  const int S = kv_count ? min(max(kv_count[b], 1), S_pad) : S_pad;
 #pragma unroll 4
   for (int s = 0; s < S; ++s) {
-    Ks[s * 33 + lane] = k[((size_t)b * S + s) * ldkv + h * 32 + lane];
-    Vs[s * 33 + lane] = v[((size_t)b * S + s) * ldkv + h * 32 + lane];
+    Ks[s * 33 + lane] = k[((size_t)b * S_pad + s) * ldkv + h * 32 + lane];
+    Vs[s * 33 + lane] = v[((size_t)b * S_pad + s) * ldkv + h * 32 + lane];
   }
   __syncwarp();
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
@@ -292,9 +294,9 @@ __global__ void attention_kernel(const float* __restrict__ q, int ldq, const flo
 }
 }  // namespace
 
-extern "C" int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv,
-                              float* out, int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S,
-                              int H, int D, void* stream) {
+extern "C" int nsac_attention_ragged(const float* q, int ldq, const float* k, const float* v, int ldkv,
+                                     float* out, int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S,
+                                     int H, int D, const int32_t* kv_count, void* stream) {
   NSAC_REQUIRE(q && k && v && (out || (out_hi && out_lo)), "nsac_attention: null pointer");
   NSAC_REQUIRE(D == 32, "nsac_attention: head dim must be 32 (got %d)", D);
   NSAC_REQUIRE(H >= 1 && H <= 32 && L >= 0 && S >= 1, "nsac_attention: bad shape");
@@ -307,9 +309,16 @@ extern "C" int nsac_attention(const float* q, int ldq, const float* k, const flo
   if (slices > L) slices = L;
   if (slices < 1) slices = 1;
   attention_kernel<<<dim3(B, slices), H * 32, smem, static_cast<cudaStream_t>(stream)>>>(
-      q, ldq, k, v, ldkv, out, ldo, static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo), ld_split, L, S, H);
+      q, ldq, k, v, ldkv, out, ldo, static_cast<uint16_t*>(out_hi), static_cast<uint16_t*>(out_lo), ld_split, L, S, H,
+      kv_count);
   NSAC_CHECK_LAUNCH("nsac_attention");
   return NSAC_OK;
+}
+
+extern "C" int nsac_attention(const float* q, int ldq, const float* k, const float* v, int ldkv,
+                              float* out, int ldo, void* out_hi, void* out_lo, int ld_split, int B, int L, int S,
+                              int H, int D, void* stream) {
+  return nsac_attention_ragged(q, ldq, k, v, ldkv, out, ldo, out_hi, out_lo, ld_split, B, L, S, H, D, nullptr, stream);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -64,10 +64,15 @@ __host__ __device__ inline int geo_floats(int n1, int n2) { return n2 * 4 + n1 *
 __global__ void match_sinkhorn_assign_kernel(
     const float* __restrict__ desc1, const float* __restrict__ desc2, const float* __restrict__ planes1,
     const float* __restrict__ planes2, const float* __restrict__ cam, const float* __restrict__ bin_score,
-    float offset_mult, float normal_mult, int iters, float threshold, int n1, int n2, int C,
+    float offset_mult, float normal_mult, int iters, float threshold, int n1_pad, int n2_pad, int C,
+    const int32_t* __restrict__ count1, const int32_t* __restrict__ count2,
     float* __restrict__ lsp_out, float* __restrict__ assign_out) {
   extern __shared__ float sm[];
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+  // ragged batches: pair b has count1[b] x count2[b] planes in the top-left corner of the padded [n1_pad, n2_pad] layout;
+  // its transport problem, dustbins and normalisation are those of the un-padded pair (the reference runs one pair at a time)
+  const int n1 = count1 ? min(max(count1[b], 1), n1_pad) : n1_pad;
+  const int n2 = count2 ? min(max(count2[b], 1), n2_pad) : n2_pad;
   const int R = n1 + 1, Cc = n2 + 1;
   const int ld = (Cc & 1) ? Cc : Cc + 1;  // odd stride: conflict-free row- and column-walks
   float* p = sm;
@@ -79,10 +84,10 @@ __global__ void match_sinkhorn_assign_kernel(
   float* max0 = p; p += n1;
   PlaneGeo g = carve_geo(p, n1, n2);
 
-  desc1 += (size_t)b * n1 * C;
-  desc2 += (size_t)b * n2 * C;
-  planes1 += (size_t)b * n1 * 3;
-  planes2 += (size_t)b * n2 * 3;
+  desc1 += (size_t)b * n1_pad * C;
+  desc2 += (size_t)b * n2_pad * C;
+  planes1 += (size_t)b * n1_pad * 3;
+  planes2 += (size_t)b * n2_pad * 3;
   cam += (size_t)b * 7;
 
   plane_geometry(planes1, planes2, cam, cam + 3, n1, n2, g);
@@ -134,11 +139,15 @@ __global__ void match_sinkhorn_assign_kernel(
     __syncthreads();
   }
   // Z + u + v - norm  (:234, :304)
-  float* lsp = lsp_out + (size_t)b * R * Cc;
-  for (int e = tid; e < R * Cc; e += blockDim.x) {
-    const int i = e / Cc, j = e - i * Cc;
-    const float val = Z[i * ld + j] + u[i] + v[j] - norm;
-    Z[i * ld + j] = val;
+  const int Rp = n1_pad + 1, Cp = n2_pad + 1;
+  float* lsp = lsp_out + (size_t)b * Rp * Cp;
+  for (int e = tid; e < Rp * Cp; e += blockDim.x) {
+    const int i = e / Cp, j = e - i * Cp;
+    float val = -INFINITY;                       // outside the pair's (n1+1) x (n2+1) block: probability 0
+    if (i < R && j < Cc) {
+      val = Z[i * ld + j] + u[i] + v[j] - norm;
+      Z[i * ld + j] = val;
+    }
     lsp[e] = val;
   }
   __syncthreads();
@@ -164,12 +173,16 @@ __global__ void match_sinkhorn_assign_kernel(
     idx1[j] = bi;
   }
   __syncthreads();
-  float* A = assign_out + (size_t)b * n1 * n2;
-  for (int e = tid; e < n1 * n2; e += blockDim.x) {
-    const int i = e / n2, j = e - i * n2;
-    const bool mutual = idx1[idx0[i]] == i;
-    const bool valid = mutual && (expf(max0[i]) > threshold);
-    A[e] = (valid && idx0[i] == j) ? 1.f : 0.f;
+  float* A = assign_out + (size_t)b * n1_pad * n2_pad;
+  for (int e = tid; e < n1_pad * n2_pad; e += blockDim.x) {
+    const int i = e / n2_pad, j = e - i * n2_pad;
+    bool one = false;
+    if (i < n1 && j < n2) {
+      const bool mutual = idx1[idx0[i]] == i;
+      const bool valid = mutual && (expf(max0[i]) > threshold);
+      one = valid && idx0[i] == j;
+    }
+    A[e] = one ? 1.f : 0.f;
   }
 }
 
@@ -194,11 +207,12 @@ __global__ void prune_assignment_kernel(const float* __restrict__ assign, const 
 }
 }  // namespace
 
-extern "C" int nsac_match_sinkhorn_assign(const float* desc1, const float* desc2, const float* planes1,
-                                          const float* planes2, const float* cam, const float* bin_score,
-                                          float offset_mult, float normal_mult, int iters, float threshold,
-                                          int B, int n1, int n2, int C, float* log_scores_padded,
-                                          float* assign, void* stream) {
+extern "C" int nsac_match_sinkhorn_assign_ragged(const float* desc1, const float* desc2, const float* planes1,
+                                                 const float* planes2, const float* cam, const float* bin_score,
+                                                 float offset_mult, float normal_mult, int iters, float threshold,
+                                                 int B, int n1, int n2, int C, const int32_t* count1,
+                                                 const int32_t* count2, float* log_scores_padded, float* assign,
+                                                 void* stream) {
   NSAC_REQUIRE(desc1 && desc2 && planes1 && planes2 && cam && bin_score && log_scores_padded && assign,
                "nsac_match_sinkhorn_assign: null pointer");
   NSAC_REQUIRE(B >= 0 && n1 >= 1 && n2 >= 1 && C >= 1 && iters >= 0, "nsac_match_sinkhorn_assign: bad shape");
@@ -213,9 +227,18 @@ extern "C" int nsac_match_sinkhorn_assign(const float* desc1, const float* desc2
   if (threads < 128) threads = 128;
   match_sinkhorn_assign_kernel<<<B, threads, smem, static_cast<cudaStream_t>(stream)>>>(
       desc1, desc2, planes1, planes2, cam, bin_score, offset_mult, normal_mult, iters, threshold, n1, n2, C,
-      log_scores_padded, assign);
+      count1, count2, log_scores_padded, assign);
   NSAC_CHECK_LAUNCH("nsac_match_sinkhorn_assign");
   return NSAC_OK;
+}
+
+extern "C" int nsac_match_sinkhorn_assign(const float* desc1, const float* desc2, const float* planes1,
+                                          const float* planes2, const float* cam, const float* bin_score,
+                                          float offset_mult, float normal_mult, int iters, float threshold,
+                                          int B, int n1, int n2, int C, float* log_scores_padded,
+                                          float* assign, void* stream) {
+  return nsac_match_sinkhorn_assign_ragged(desc1, desc2, planes1, planes2, cam, bin_score, offset_mult, normal_mult, iters,
+                                           threshold, B, n1, n2, C, nullptr, nullptr, log_scores_padded, assign, stream);
 }
 
 extern "C" int nsac_prune_assignment(const float* assign, const float* planes1, const float* planes2,

@@ -281,23 +281,33 @@ def layernorm(x, gamma, beta, res=None, out=None, out_split: Optional[Split] = N
     return out
 
 
-def attention(q, k, v, B, L, S, H=8, D=32, out=None, out_split: Optional[Split] = None, want_f32: bool = True):
-    """q [B*L, H*D] (row stride ldq), k/v [B*S, H*D] (same row stride) -> [B*L, H*D] fp32 and / or planes."""
+def attention(q, k, v, B, L, S, H=8, D=32, out=None, out_split: Optional[Split] = None, want_f32: bool = True,
+              kv_count: Optional[torch.Tensor] = None):
+    """q [B*L, H*D] (row stride ldq), k/v [B*S, H*D] (same row stride) -> [B*L, H*D] fp32 and / or planes.
+    `kv_count` (int32 [B]): ragged batch — only the first kv_count[b] source tokens of batch element b are attended to."""
     _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
     assert k.stride(0) == v.stride(0)
     if out is None and want_f32:
         out = torch.empty(B * L, H * D, device=q.device, dtype=torch.float32)
-    st = _lib.lib().nsac_attention(_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), 0 if out is None else out.stride(0),
-                                   None if out_split is None else _p(out_split.hi),
-                                   None if out_split is None else _p(out_split.lo),
-                                   0 if out_split is None else out_split.hi.stride(0), B, L, S, H, D, _stream())
+    tail = (None if out_split is None else _p(out_split.hi), None if out_split is None else _p(out_split.lo),
+            0 if out_split is None else out_split.hi.stride(0), B, L, S, H, D)
+    head = (_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), 0 if out is None else out.stride(0))
+    if kv_count is None:
+        st = _lib.lib().nsac_attention(*head, *tail, _stream())
+    else:
+        kv_count = _c(kv_count, "kv_count", torch.int32)
+        assert kv_count.numel() == B
+        st = _lib.lib().nsac_attention_ragged(*head, *tail, _p(kv_count), _stream())
     _lib.check(st, "nsac_attention")
     _count()
     return out if out is not None else out_split
 
 
 def match_sinkhorn_assign(desc1, desc2, planes1, planes2, cam, bin_score, offset_mult=4.0, normal_mult=8.0,
-                          iters=200, threshold=0.2):
+                          iters=200, threshold=0.2, count1: Optional[torch.Tensor] = None,
+                          count2: Optional[torch.Tensor] = None):
+    """-> (log_scores_padded [B,n1+1,n2+1], assign [B,n1,n2]).  `count1` / `count2` (int32 [B]): ragged batch — pair b has
+    count1[b] x count2[b] planes in the first rows of the padded inputs; its result is the top-left block (rest -inf / 0)."""
     desc1, desc2 = _c(desc1, "desc1"), _c(desc2, "desc2")
     planes1, planes2, cam = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(cam, "cam")
     bin_score = _c(bin_score.reshape(1), "bin_score")
@@ -305,9 +315,15 @@ def match_sinkhorn_assign(desc1, desc2, planes1, planes2, cam, bin_score, offset
     n2 = desc2.shape[1]
     lsp = torch.empty(B, n1 + 1, n2 + 1, device=desc1.device, dtype=torch.float32)
     assign = torch.empty(B, n1, n2, device=desc1.device, dtype=torch.float32)
-    st = _lib.lib().nsac_match_sinkhorn_assign(_p(desc1), _p(desc2), _p(planes1), _p(planes2), _p(cam), _p(bin_score),
-                                               offset_mult, normal_mult, iters, threshold, B, n1, n2, Cd,
-                                               _p(lsp), _p(assign), _stream())
+    args = (_p(desc1), _p(desc2), _p(planes1), _p(planes2), _p(cam), _p(bin_score), offset_mult, normal_mult, iters, threshold,
+            B, n1, n2, Cd)
+    if count1 is None and count2 is None:
+        st = _lib.lib().nsac_match_sinkhorn_assign(*args, _p(lsp), _p(assign), _stream())
+    else:
+        count1 = None if count1 is None else _c(count1, "count1", torch.int32)
+        count2 = None if count2 is None else _c(count2, "count2", torch.int32)
+        assert (count1 is None or count1.numel() == B) and (count2 is None or count2.numel() == B)
+        st = _lib.lib().nsac_match_sinkhorn_assign_ragged(*args, _p(count1), _p(count2), _p(lsp), _p(assign), _stream())
     _lib.check(st, "nsac_match_sinkhorn_assign")
     _count()
     return lsp, assign

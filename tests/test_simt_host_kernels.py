@@ -204,3 +204,53 @@ def test_camera_errors_source_on_host(host_ops):
         assert abs(stats[0] - want["T mean err"]) <= 1e-5 and abs(stats[1] - want["R mean err"]) <= 2e-3
         for i, k in enumerate(("T err < 1.0", "T err < 0.5", "T err < 0.2", "R err < 30", "R err < 15", "R err < 10")):
             assert abs(float(stats[2 + i]) / n * 100 - want[k]) <= 1e-9, (n, k)
+
+
+def test_ragged_attention_source_on_host(host_ops):
+    """nsac_attention_ragged: batch element b attends to its first kv_count[b] source tokens only == attention on the slice."""
+    g = torch.Generator().manual_seed(4)
+    B, Lq, S, H, D = 3, 6, 9, 8, 32
+    q, k, v = (torch.randn(B, n, H * D, generator=g) for n in (Lq, S, S))
+    cnt = torch.tensor([9, 4, 1], dtype=torch.int32)
+    k[1, 4:], v[1, 4:], k[2, 1:], v[2, 1:] = 1e30, float("nan"), -1e30, float("nan")      # padding must never be touched
+    got = host_ops.attention(q.view(B * Lq, H * D), k.view(B * S, H * D), v.view(B * S, H * D), B, Lq, S, H, D, kv_count=cnt).view(B, Lq, H * D)
+    for b in range(B):
+        n = int(cnt[b])
+        A = torch.softmax(torch.einsum("lhd,shd->lsh", q[b].view(Lq, H, D), k[b, :n].view(n, H, D)) / math.sqrt(D), dim=1)
+        want = torch.einsum("lsh,shd->lhd", A, v[b, :n].view(n, H, D)).reshape(Lq, H * D)
+        assert util.maxdiff(got[b], want) <= 1e-5, b
+    full = host_ops.attention(q.view(B * Lq, H * D)[:Lq], k.view(B * S, H * D)[:S], v.view(B * S, H * D)[:S], 1, Lq, S, H, D)
+    assert torch.equal(full, got[0])                       # count == S is the unmasked kernel, bit for bit
+
+
+def test_ragged_match_sinkhorn_assign_source_on_host(host_ops):
+    """nsac_match_sinkhorn_assign_ragged: every pair of a padded batch == the un-padded single-pair call (bit for bit) and the
+    oracle on the slices; padding of the outputs is -inf / 0; NaN padding of the inputs is never read."""
+    g = torch.Generator().manual_seed(9)
+    P = 12
+    counts = [(12, 12), (5, 9), (7, 3), (1, 4)]
+    B = len(counts)
+    b = synthetic.make_batch(40, B, P)
+    base = torch.randn(B, P, 256, generator=g)
+    d1 = base * 1.2
+    d2 = torch.stack([base[i, torch.randperm(P, generator=g)] for i in range(B)]) * 1.2 + 0.1 * torch.randn(B, P, 256, generator=g)
+    p1, p2 = b.planes1.clone(), b.planes2.clone()
+    for i, (a, c) in enumerate(counts):
+        d1[i, a:], p1[i, a:], d2[i, c:], p2[i, c:] = float("nan"), float("nan"), float("nan"), float("nan")
+    cam = torch.cat([b.gt_tran, b.gt_quat], dim=1)
+    bin_score = torch.tensor(1.0)
+    c1 = torch.tensor([a for a, _ in counts], dtype=torch.int32)
+    c2 = torch.tensor([c for _, c in counts], dtype=torch.int32)
+    lsp, assign = host_ops.match_sinkhorn_assign(d1, d2, p1, p2, cam, bin_score, 4.0, 8.0, 200, 0.2, count1=c1, count2=c2)
+    for i, (a, c) in enumerate(counts):
+        s1, s2 = (d1[i:i + 1, :a].contiguous(), d2[i:i + 1, :c].contiguous())
+        q1, q2 = p1[i:i + 1, :a].contiguous(), p2[i:i + 1, :c].contiguous()
+        one_lsp, one_assign = host_ops.match_sinkhorn_assign(s1, s2, q1, q2, cam[i:i + 1].contiguous(), bin_score, 4.0, 8.0, 200, 0.2)
+        assert torch.equal(lsp[i, :a + 1, :c + 1], one_lsp[0]) and torch.equal(assign[i, :a, :c], one_assign[0]), i
+        assert bool(torch.isinf(lsp[i, a + 1:]).all()) and bool(torch.isinf(lsp[i, :, c + 1:]).all())
+        assert float(assign[i, a:].abs().sum()) == 0.0 and float(assign[i, :, c:].abs().sum()) == 0.0
+        off, nrm = restate.match_penalties(q1, q2, cam[i:i + 1])
+        s = torch.einsum("bnd,bmd->bnm", s1, s2) / 16.0 - off / 4.0 - nrm / 8.0
+        want = restate.log_optimal_transport(s, bin_score, 200)
+        assert util.maxdiff(one_lsp.exp(), want.exp()) <= 1e-4, i
+        assert torch.equal(one_assign, restate.get_assignment_matrix(want, 0.2)), i
