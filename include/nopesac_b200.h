@@ -258,7 +258,7 @@ int nsac_camera_errors(const float* pose, int ldpose, const float* gt_tran, cons
  *   pixel (0,0) set (:699-702)); ori_idx [B,NQ] (-1 = padding) = pred_plane_oriIdxs; planes [B,NQ,3] = pred_plane;
  *   feats [B,NQ,C] = pred_plane_feats; scores [B,NQ]; centers [B,NQ,2] = pred_plane_ins_center; bboxes [B,NQ,4] = (x,y,w,h)
  *   of pycocotools toBbox; areas [B,NQ]; seg [B,H,W] uint8 label map, 255 = no plane, pred_plane_masks[j] == (seg == j).
- * workspace: nsac_plane_post_workspace_bytes(B,NQ,H,W) bytes, 256-byte aligned; seg 16-byte aligned. */
+ * workspace: nsac_plane_post_workspace_bytes(B,NQ,H,W) bytes; workspace and seg 16-byte aligned. */
 size_t nsac_plane_post_workspace_bytes(int B, int NQ, int H, int W);
 int nsac_plane_postprocess(const float* pred_logits, const float* pred_params, const float* mask_logits,
                            const float* query_feat, int B, int NQ, int C, int h, int w, int H, int W,

@@ -400,17 +400,24 @@ class PlaneCameraHead(nn.Module):
     # ------------------------------------------------------------------ forward
     def forward(self, features1, features2, planeParam1, planeParam2, planeApp1=None, planeApp2=None,
                 gt_pose=None, gt_corr_matrix=None, batched_inputs=None, ite=0, matching_net=None,
-                hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None):
+                hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None,
+                plane_count1=None, plane_count2=None):
         if self.training:
             raise NotImplementedError("nopesac_b200.PlaneCameraHead is inference-only")
         return self.inference_Joint(features1, features2, planeParam1, planeParam2, planeApp1, planeApp2,
                                     matching_net=matching_net, hyp_pairs=hyp_pairs, initial_pose=initial_pose,
-                                    want_diag=want_diag, assignment_override=assignment_override, result_exchange=result_exchange)
+                                    want_diag=want_diag, assignment_override=assignment_override, result_exchange=result_exchange,
+                                    plane_count1=plane_count1, plane_count2=plane_count2)
 
     @torch.no_grad()
     def inference_Joint(self, cam_feats1, cam_feats2, planeParam1, planeParam2, planeApp1, planeApp2,
                         gt_corr_matrix=None, batched_inputs=None, gt_pose=None, matching_net=None,
-                        hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None):
+                        hyp_pairs=None, initial_pose=None, want_diag=False, assignment_override=None, result_exchange=None,
+                        plane_count1=None, plane_count2=None):
+        """`plane_count1` / `plane_count2` (int32 [B], device): ragged batch — pair b has that many planes in the first rows
+        of the padded planeParam / planeApp tensors (what `nopesac_b200.plane_postprocess.PlaneLists` hands over: `.planes`,
+        `.feats`, `.count`); every per-pair output equals the un-padded single-pair call, assignment matrices are zero and
+        log-scores -inf outside the pair's block."""
         device = planeParam1.device
         B = planeParam1.shape[0]
         NQ = self.num_queries
@@ -450,7 +457,8 @@ class PlaneCameraHead(nn.Module):
             raise RuntimeError("matching_net must be a nopesac_b200.MatchingHead")
         cam = torch.cat([t0, q0], dim=-1)
         log_scores_padded, assignment = matching_net.match(planeApp1, planeApp2, cam, planeParam1, planeParam2,
-                                                           match_threshold=self.matching_score_threshold)
+                                                           match_threshold=self.matching_score_threshold,
+                                                           plane_count1=plane_count1, plane_count2=plane_count2)
         output_planeAss = {"pred_assignment_beforeRef0": assignment.clone()}
         if out_cam_type == "initial":
             output_planeAss["pred_assignment"] = assignment.clone()

@@ -444,7 +444,7 @@ extern "C" int nsac_plane_postprocess(const float* pred_logits, const float* pre
   NSAC_REQUIRE((H == 4 * h && W == 4 * w) || (H == 2 * h && W == 2 * w),
                "nsac_plane_postprocess: output %dx%d must be 2x or 4x the mask resolution %dx%d", H, W, h, w);
   NSAC_REQUIRE(H <= 65536 && W <= 65536 && (size_t)H * W <= ((size_t)1 << 23), "nsac_plane_postprocess: image %dx%d too large", H, W);
-  NSAC_REQUIRE(((uintptr_t)workspace & 255) == 0 && ((uintptr_t)seg & 15) == 0, "nsac_plane_postprocess: workspace / seg misaligned");
+  NSAC_REQUIRE(((uintptr_t)workspace & 15) == 0 && ((uintptr_t)seg & 15) == 0, "nsac_plane_postprocess: workspace / seg must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PlaneWorkspace ws;
   carve(ws, workspace, B, NQ, H, W);

@@ -117,7 +117,7 @@ class MatchingHead(nn.Module):
         return pk
 
     @staticmethod
-    def _layer(w, ws, X, Xp, xs, ss, B, L, S, self_attn: bool, P: int):
+    def _layer(w, ws, X, Xp, xs, ss, B, L, S, self_attn: bool, P: int, kv_count=None):
         """X [rows,512] fp32 and Xp (its fp16 hi/lo planes): columns 0:256 hold the token features, 256:512 the
         message slot, so cat[x, message] (gnn.py:93) is free.  xs / ss = row ranges of the query / source stream.
         All six linears run on the tcgen05 engine; attention and LayerNorm emit the operand planes directly."""
@@ -130,14 +130,14 @@ class MatchingHead(nn.Module):
             kv, _ = ops.gemm_tc(Xp.rows_view(ss[0], ss[1]).cols(0, 256), ws["kv"], passes=P)
             k, v = kv[:, :256], kv[:, 256:]
         msgp = ops.Split.empty(x.shape[0], 256, x.device)
-        ops.attention(q, k, v, B, L, S, out_split=msgp, want_f32=False)
+        ops.attention(q, k, v, B, L, S, out_split=msgp, want_f32=False, kv_count=kv_count)
         msg, _ = ops.gemm_tc(msgp, ws["merge"], passes=P)
         ops.layernorm(msg, w["n1w"], w["n1b"], out=x[:, 256:], out_split=xp.cols(256, 512))     # message slot
         _, hp = ops.gemm_tc(xp, ws["mlp0"], act=ops.ACT_RELU, passes=P, want_f32=False, want_split=True)
         msg, _ = ops.gemm_tc(hp, ws["mlp2"], passes=P)
         ops.layernorm(msg, w["n2w"], w["n2b"], res=x[:, :256], out=x[:, :256], out_split=xp.cols(0, 256))  # x + norm2(.)
 
-    def _descriptors(self, planeApp1, planeApp2):
+    def _descriptors(self, planeApp1, planeApp2, count1=None, count2=None):
         pk = self.prepare_tc()
         P = self.tc_passes
         B, n1, _ = planeApp1.shape
@@ -151,28 +151,35 @@ class MatchingHead(nn.Module):
         s0, s1 = (0, R0), (R0, R0 + R1)
         for w, ws, name in zip(pk["layers"], pk["tc"], self.gnn.layer_names):
             if name == "self":
-                self._layer(w, ws, X, Xp, s0, s0, B, n1, n1, True, P)
-                self._layer(w, ws, X, Xp, s1, s1, B, n2, n2, True, P)
+                self._layer(w, ws, X, Xp, s0, s0, B, n1, n1, True, P, count1)
+                self._layer(w, ws, X, Xp, s1, s1, B, n2, n2, True, P, count2)
             else:
-                self._layer(w, ws, X, Xp, s0, s1, B, n1, n2, False, P)
-                self._layer(w, ws, X, Xp, s1, s0, B, n2, n1, False, P)     # sees the UPDATED feat0 (gnn.py:133-134)
+                self._layer(w, ws, X, Xp, s0, s1, B, n1, n2, False, P, count2)
+                self._layer(w, ws, X, Xp, s1, s0, B, n2, n1, False, P, count1)     # sees the UPDATED feat0 (gnn.py:133-134)
         desc, _ = ops.gemm_tc(Xp.cols(0, 256), pk["desc_ws"], pk["desc_b"], passes=P)
         return desc[:R0].view(B, n1, 256), desc[R0:].view(B, n2, 256)
 
     # ------------------------------------------------------------------ public
     @torch.no_grad()
     def match(self, planeApp1, planeApp2, matcher_inputCam, parameters1_local, parameters2_local,
-              match_threshold=None, normal_decay=1.0, offset_deacy=1.0):
-        """-> (log_scores_padded [B,n1+1,n2+1], assignment [B,n1,n2])."""
+              match_threshold=None, normal_decay=1.0, offset_deacy=1.0, plane_count1=None, plane_count2=None):
+        """-> (log_scores_padded [B,n1+1,n2+1], assignment [B,n1,n2]).
+        Ragged batches: `plane_count1` / `plane_count2` (int32 [B] on the device, e.g. `PlaneLists.count`) say how many of the
+        padded n1 / n2 rows of pair b are planes; padded tokens are never attended to (the all-valid case of the reference's
+        `kv_mask`, gnn.py:31-34) and every pair solves its own transport problem — results in the top-left block, the rest
+        -inf / 0.  No host synchronisation."""
         if matcher_inputCam is None:
             raise NotImplementedError("matcher_inputCam=None is a training-only branch of the reference")
         if normal_decay != 1.0 or offset_deacy != 1.0:
             raise NotImplementedError("decay factors other than 1.0 are never used by the reference (camera_head.py:490-497)")
-        d1, d2 = self._descriptors(planeApp1.float(), planeApp2.float())
+        if (plane_count1 is None) != (plane_count2 is None):
+            raise ValueError("plane_count1 and plane_count2 go together")
+        d1, d2 = self._descriptors(planeApp1.float(), planeApp2.float(), plane_count1, plane_count2)
         thr = self.match_threshold if match_threshold is None else match_threshold
         return ops.match_sinkhorn_assign(d1, d2, parameters1_local, parameters2_local, matcher_inputCam,
                                          self.bin_score.detach(), float(self.offset_multiplier),
-                                         float(self.normal_multiplier), self.sinkhorn_iterations, float(thr))
+                                         float(self.normal_multiplier), self.sinkhorn_iterations, float(thr),
+                                         count1=plane_count1, count2=plane_count2)
 
     def forward(self, planeApp1, planeApp2, matcher_inputCam, parameters1_local, parameters2_local,
                 indices1=None, indices2=None, gt_corr_matrix=None, suffix="", normal_decay=1.0, offset_deacy=1.0):

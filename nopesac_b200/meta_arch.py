@@ -97,6 +97,24 @@ class PlaneTR_NopeSAC(nn.Module):
         lists = self.plane_lists(planeTR_outputs, query_feat_in, height, width)
         return lists.to_reference_results(batched_inputs, with_rle=True)
 
+    @torch.no_grad()
+    def inference_from_plane_heads(self, planeTR_outputs1, query_feat1, planeTR_outputs2, query_feat2, cam_feats1, cam_feats2,
+                                   height: int = 480, width: int = 640, max_planes: int = None, **head_kwargs):
+        """Rows f1 + a2..a15 without a host round trip: the PlaneTRHead outputs of both views of B pairs -> plane lists
+        (`plane_lists`) -> camera head on the padded lists with per-pair plane counts (`plane_count1/2`).  This replaces
+        `inference_single`'s post-processing + the `.unsqueeze(0).to(device)` hand-off of siamese_planeTR.py:364-383, which
+        goes through the host for every plane.  `max_planes` (a caller-side bound on planes per view, e.g. 20) trims the padded
+        lists from NUM_OBJECT_QUERIES rows to that many — counts are clamped to it — so the matcher does not work on padding.
+        Returns (head outputs 6-tuple, PlaneLists view 1, PlaneLists view 2); everything stays on the device."""
+        l1 = self.plane_lists(planeTR_outputs1, query_feat1, height, width)
+        l2 = self.plane_lists(planeTR_outputs2, query_feat2, height, width)
+        P = self.num_queries if max_planes is None else min(int(max_planes), self.num_queries)
+        c1, c2 = l1.count.clamp(max=P), l2.count.clamp(max=P)
+        out = self.camera_head_list[0](cam_feats1, cam_feats2, l1.planes[:, :P].contiguous(), l2.planes[:, :P].contiguous(),
+                                       planeApp1=l1.feats[:, :P].contiguous(), planeApp2=l2.feats[:, :P].contiguous(),
+                                       matching_net=self.matching_head, plane_count1=c1, plane_count2=c2, **head_kwargs)
+        return out, l1, l2
+
     @staticmethod
     def _stack_views(batched_inputs, view: str, device):
         planes = torch.stack([bi[view]["pred_plane"].reshape(-1, 3) for bi in batched_inputs]).to(device).float()

@@ -81,10 +81,8 @@ def postprocess_plane_head_mask(planeTR_outputs: Dict[str, torch.Tensor], query_
     """Batched `_postprocess_planeHeadMask`: `planeTR_outputs` = {'pred_logits' [B,NQ,2], 'pred_params' [B,NQ,3],
     'pred_mask_logits' [B,NQ,h,w]}, `query_feat` [B,NQ,C]; CUDA fp32."""
     logits, params, masks = planeTR_outputs["pred_logits"], planeTR_outputs["pred_params"], planeTR_outputs["pred_mask_logits"]
-    for t in (logits, params, masks, query_feat):
-        if not t.is_cuda:
-            raise RuntimeError("nopesac_b200.plane_postprocess: tensors must live on a CUDA device (there is no CPU fallback)")
-    logits, params, masks, query_feat = (t.detach().to(torch.float32).contiguous() for t in (logits, params, masks, query_feat))
+    logits, params, masks, query_feat = (ops._chk(t.detach(), n).contiguous() for t, n in (
+        (logits, "pred_logits"), (params, "pred_params"), (masks, "pred_mask_logits"), (query_feat, "query_feat")))
     B, NQ = logits.shape[:2]
     h, w = masks.shape[-2:]
     Cf = query_feat.shape[-1]
@@ -105,7 +103,7 @@ def postprocess_plane_head_mask(planeTR_outputs: Dict[str, torch.Tensor], query_
                                   float(plane_score_threshold), float(mask_prob_threshold), float(overlap_threshold),
                                   _ptr(out.count), _ptr(out.flags), _ptr(out.ori_idx), _ptr(out.planes), _ptr(out.feats),
                                   _ptr(out.scores), _ptr(out.centers), _ptr(out.bboxes), _ptr(out.areas), _ptr(out.seg), _ptr(ws),
-                                  C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+                                  ops._stream())
     _lib.check(st, "nsac_plane_postprocess")
     ops._count(4)
     return out

@@ -48,8 +48,9 @@ def rewrite_launches(src: str) -> str:
     return out
 
 
-def build(cu_names) -> ctypes.CDLL:
-    """One host library from one or several csrc/*.cu files (a str or a list of names)."""
+def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
+    """One host library from one or several csrc/*.cu files (a str or a list of names) plus test-side .cpp files of this
+    directory (`extra_cpp`, e.g. the tensor-engine stand-ins)."""
     if isinstance(cu_names, str):
         cu_names = [cu_names]
     srcs = {}
@@ -59,7 +60,7 @@ def build(cu_names) -> ctypes.CDLL:
     h = hashlib.sha1()
     for name in sorted(srcs):
         h.update(srcs[name].encode())
-    for dep in ("cuda_runtime.h", "cuda_fp16.h", "simt_runtime.cpp"):
+    for dep in ("cuda_runtime.h", "cuda_fp16.h", "simt_runtime.cpp") + tuple(extra_cpp):
         with open(os.path.join(HERE, dep), "rb") as f:
             h.update(f.read())
     with open(os.path.join(CSRC, "common.cuh"), "rb") as f:
@@ -77,8 +78,9 @@ def build(cu_names) -> ctypes.CDLL:
             gens.append(gen)
         # the generated files sit outside csrc/: -I csrc for "common.cuh", which includes "../../include/nopesac_b200.h"
         # relative to ITS OWN directory, so the real header is used.
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-w",
-               "-I", HERE, "-I", CSRC] + gens + [os.path.join(HERE, "simt_runtime.cpp"), "-o", lib + ".tmp"]
+        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fopenmp", "-ffp-contract=off", "-w",
+               "-I", HERE, "-I", CSRC] + gens + [os.path.join(HERE, c) for c in ("simt_runtime.cpp",) + tuple(extra_cpp)] + \
+              ["-o", lib + ".tmp"]
         res = subprocess.run(cmd, capture_output=True, text=True)
         if res.returncode != 0:
             raise RuntimeError("simt_host build failed:\n" + res.stderr[-4000:])

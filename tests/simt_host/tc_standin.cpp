@@ -1,0 +1,121 @@
+// TEST INFRASTRUCTURE — functional stand-ins for the entry points whose kernels cannot run on the host (tcgen05 / TMA):
+// same C ABI and contract as include/nopesac_b200.h, plain C++ arithmetic.  They exist so that the product's Python glue
+// (PlaneCameraHead / MatchingHead) can be executed end to end on CPU tensors in the `-m "not gpu"` suite, with the plain-SIMT
+// kernels running from their real source (tests/simt_host/cuda_runtime.h).  They are NOT the product and prove nothing about
+// the tensor-core kernels themselves (tests/test_gpu_gemm_tc.py, tests/test_gpu_parity.py do that on the device).
+//   nsac_split16 / nsac_gemm_split   16-bit hi/lo planes, products of planes summed in double (at least as accurate as the
+//                                    TMEM accumulation), epilogue act(out_scale * acc + bias), optional re-split
+//   nsac_score_pack* / nsac_score_aggregate_tc   routed to the exact-fp32 nsac_score_aggregate (csrc/score.cu, real source)
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/nopesac_b200.h"
+
+void nsac_set_error(const char* fmt, ...);
+
+namespace {
+float plane_to_float(uint16_t v, int fmt) {
+  if (fmt == NSAC_SPLIT_F16) {
+    _Float16 h;
+    memcpy(&h, &v, 2);
+    return (float)h;
+  }
+  uint32_t bits = (uint32_t)v << 16;
+  float f;
+  memcpy(&f, &bits, 4);
+  return f;
+}
+uint16_t float_to_plane(float x, int fmt) {
+  uint16_t v;
+  if (fmt == NSAC_SPLIT_F16) {
+    _Float16 h = (_Float16)x;
+    memcpy(&v, &h, 2);
+    return v;
+  }
+  uint32_t bits;
+  memcpy(&bits, &x, 4);
+  if ((bits & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((bits >> 16) | 0x40);          // NaN
+  bits += 0x7fffu + ((bits >> 16) & 1u);                                                    // round to nearest even
+  return (uint16_t)(bits >> 16);
+}
+void split16(float x, int fmt, uint16_t& hi, uint16_t& lo) {
+  hi = float_to_plane(x, fmt);
+  lo = float_to_plane(x - plane_to_float(hi, fmt), fmt);
+}
+}  // namespace
+
+extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo, int ld_split,
+                            void*) {
+  if (!x || !hi || !lo || rows < 0 || K < 1 || ldx < K || ld_split < K) {
+    nsac_set_error("nsac_split16 (stand-in): bad arguments");
+    return NSAC_ERR_ARG;
+  }
+  uint16_t *h = static_cast<uint16_t*>(hi), *l = static_cast<uint16_t*>(lo);
+  for (int r = 0; r < rows; ++r)
+    for (int c = 0; c < ld_split; ++c) split16(c < K ? x[(size_t)r * ldx + c] * scale : 0.f, fmt, h[(size_t)r * ld_split + c], l[(size_t)r * ld_split + c]);
+  return NSAC_OK;
+}
+
+extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                               const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
+                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
+  if (!a_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 2 && !a_lo) || (passes >= 3 && !w_lo) || K % 64 != 0 || lda < K ||
+      ldw < K || (!out_f32 && !out_hi) || (out_hi && !out_lo)) {
+    nsac_set_error("nsac_gemm_split (stand-in): bad arguments");
+    return NSAC_ERR_ARG;
+  }
+  const uint16_t *ah = static_cast<const uint16_t*>(a_hi), *al = static_cast<const uint16_t*>(a_lo);
+  const uint16_t *wh = static_cast<const uint16_t*>(w_hi), *wl = static_cast<const uint16_t*>(w_lo);
+  std::vector<double> WH((size_t)N * K), WL((size_t)N * K, 0.0);
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) {
+      WH[(size_t)n * K + k] = plane_to_float(wh[(size_t)n * ldw + k], fmt);
+      if (passes >= 3) WL[(size_t)n * K + k] = plane_to_float(wl[(size_t)n * ldw + k], fmt);
+    }
+  const float slope = act == NSAC_ACT_RELU ? 0.f : (act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
+  std::vector<double> AH(K), AL(K);
+#pragma omp parallel for firstprivate(AH, AL)
+  for (int m = 0; m < M; ++m) {
+    for (int k = 0; k < K; ++k) {
+      AH[k] = plane_to_float(ah[(size_t)m * lda + k], fmt);
+      AL[k] = passes >= 2 ? plane_to_float(al[(size_t)m * lda + k], fmt) : 0.0;
+    }
+    const float* brow = bias ? (bias_group_rows > 0 ? bias + (size_t)(m / bias_group_rows) * N : bias) : nullptr;
+    for (int n = 0; n < N; ++n) {
+      const double *w0 = &WH[(size_t)n * K], *w1 = &WL[(size_t)n * K];
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc += (AH[k] + AL[k]) * w0[k] + AH[k] * w1[k];              // hi.hi + lo.hi + hi.lo
+      if (passes >= 4)
+        for (int k = 0; k < K; ++k) acc += AL[k] * w1[k];
+      float v = out_scale * (float)acc + (brow ? brow[n] : 0.f);
+      v = fmaxf(v, slope * v + 0.f);
+      if (out_f32) out_f32[(size_t)m * ldo + n] = v;
+      if (out_hi) split16(v, fmt, static_cast<uint16_t*>(out_hi)[(size_t)m * ld_split + n], static_cast<uint16_t*>(out_lo)[(size_t)m * ld_split + n]);
+    }
+  }
+  return NSAC_OK;
+}
+
+// ---- scoring on the "tensor pipe": the exact CUDA-core twin does the work
+extern "C" size_t nsac_score_pack_bytes(int) { return 2 * sizeof(nsac_score_mlp); }
+extern "C" int nsac_score_pack(const nsac_score_mlp* rot_mlp, const nsac_score_mlp* tran_mlp, int, void* pack, void*) {
+  memcpy(pack, rot_mlp, sizeof(nsac_score_mlp));
+  memcpy(static_cast<char*>(pack) + sizeof(nsac_score_mlp), tran_mlp, sizeof(nsac_score_mlp));
+  return NSAC_OK;
+}
+extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) { return nsac_score_workspace_bytes(B, NQ); }
+extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0, const float* t0,
+                                       const float* feat_rot, const float* feat_tran, const float* feat_rot0,
+                                       const float* feat_tran0, const int32_t* matched_num, const void* pack, const float* w_rots,
+                                       const float* b_rots, const float* w_trans, const float* b_trans, int B, int NQ,
+                                       int out_cam_type, float* pose, float* score_rot, float* score_tran, int32_t* sel_idx,
+                                       void* workspace, float* const*, int, int, void* stream) {
+  const nsac_score_mlp* mlps = static_cast<const nsac_score_mlp*>(pack);
+  return nsac_score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num, &mlps[0], &mlps[1],
+                              w_rots, b_rots, w_trans, b_trans, B, NQ, out_cam_type, pose, score_rot, score_tran, sel_idx, nullptr,
+                              workspace, stream);
+}

@@ -114,7 +114,7 @@ def test_product_rle_matches_oracle_rle():
 def test_plane_postprocess_refuses_cpu_tensors():
     from nopesac_b200 import plane_postprocess
     it = synthetic.make_plane_head_outputs(0, num_queries=8, mask_h=8, mask_w=8, channels=4)
-    with pytest.raises(RuntimeError, match="no CPU fallback"):
+    with pytest.raises(RuntimeError, match="no CPU path"):
         plane_postprocess.postprocess_plane_head_mask({k: it[k][None] for k in ("pred_logits", "pred_params", "pred_mask_logits")},
                                                       it["query_feat"][None], 32, 32)
 

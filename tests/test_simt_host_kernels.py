@@ -15,30 +15,15 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "simt_host"))
 
-import run as simt_run  # noqa: E402
 
 from nopesac_b200 import _lib, ops, synthetic  # noqa: E402
 from oracle import restate  # noqa: E402
-from tests import util  # noqa: E402
+from tests import host_fixture, util  # noqa: E402
 
 
 @pytest.fixture()
 def host_ops(monkeypatch):
-    L = simt_run.build(simt_run.SIMT_SOURCES)
-    for name, (res, args) in _lib._SIGNATURES.items():
-        if hasattr(L, name):
-            fn = getattr(L, name)
-            fn.restype, fn.argtypes = res, args
-    monkeypatch.setattr(_lib, "_lib", L)
-
-    def chk(t, name, dtype=torch.float32):
-        if t.dtype != dtype:
-            raise RuntimeError(f"{name}: expected {dtype}, got {t.dtype}")
-        return t
-
-    monkeypatch.setattr(ops, "_chk", chk)
-    monkeypatch.setattr(ops, "_stream", lambda: None)
-    return ops
+    return host_fixture.install(monkeypatch, with_tensor_standins=False)
 
 
 def test_geo_sequence_source_on_host(host_ops):
