@@ -159,6 +159,31 @@ def run_reference_arm(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------
+def measure_plane_lists(dev, images: int, iters: int = 10):
+    """nsac_plane_postprocess on `images` synthetic PlaneTRHead outputs of the inference_mp3d shape (50 queries, 120x160 mask
+    logits -> 480x640): ms per call with CUDA events on the launch stream, inputs (> 126 MB for 64+ images) exceed L2."""
+    from nopesac_b200 import plane_postprocess, synthetic
+    base = synthetic.make_plane_head_batch(300, 8, cases=("regular",))
+    rep = (images + 7) // 8
+    batch = {k: v.repeat(rep, *([1] * (v.dim() - 1)))[:images].contiguous().to(dev) for k, v in base.items()}
+    outs = {k: batch[k] for k in ("pred_logits", "pred_params", "pred_mask_logits")}
+    for _ in range(3):
+        res = plane_postprocess.postprocess_plane_head_mask(outs, batch["query_feat"], 480, 640)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        res = plane_postprocess.postprocess_plane_head_mask(outs, batch["query_feat"], 480, 640)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    nq, h, w = batch["pred_mask_logits"].shape[1:]
+    alg = images * (4 * nq * h * w + 3 * 480 * 640)
+    return {"images": images, "ms_per_call": ms, "images_per_s": images / ms * 1e3, "planes_per_image": float(res.count.float().mean()),
+            "algorithmic_bytes": alg, "achieved_gbs": alg / ms / 1e6,
+            "note": "row f1, both views of this rank's pairs; outside the timed region of `value`"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -366,6 +391,15 @@ def main():
                         "sample": f"{args.cpu_pairs} pairs of the same workload after 1 warm-up pair, per-pair loop at "
                                   f"batch size 1 (oracle/restate.py), {dt:.1f} s"}
 
+    # row f1 (the step before the path): plane lists of both views of this rank's pairs from synthetic PlaneTRHead outputs,
+    # timed separately (NOT part of `value`, whose stage set S4 starts at the backbone / plane-head outputs).  Reported only.
+    plane_lists = None
+    if rank == 0:
+        try:
+            plane_lists = measure_plane_lists(dev, 2 * B)
+        except Exception as e:   # never let the side measurement take the bench line down
+            plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -380,6 +414,7 @@ def main():
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "pose_err": pose_err,
+        "plane_lists": plane_lists,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
