@@ -13,8 +13,8 @@ of scope this round: its per-view outputs enter throug
 
 and `forward` returns the reference's per-pair result dicts (:411-431): every `camera*` key with
 {"tran","rot"} and the `pred_assignment*` matrices (as device tensors; `.cpu().numpy()` packing of
-:384-399 is left to the caller so that no host sync happens inside).  Pairs of one call must have the
-same number of planes per view (pad upstream, or call per group).
+:384-399 is left to the caller so that no host sync happens inside).  Pairs of one call may have different
+numbers of planes: they are zero-padded to the largest count and the kernels get the per-pair counts (ragged batch).
 """
 from __future__ import annotations
 
@@ -117,13 +117,28 @@ class PlaneTR_NopeSAC(nn.Module):
 
     @staticmethod
     def _stack_views(batched_inputs, view: str, device):
-        planes = torch.stack([bi[view]["pred_plane"].reshape(-1, 3) for bi in batched_inputs]).to(device).float()
-        feats = torch.stack([bi[view]["pred_plane_feats"].reshape(-1, 256) for bi in batched_inputs]).to(device).float()
+        """Per-view inputs of B pairs -> padded [B,Pmax,3] / [B,Pmax,256] tensors + plane counts (None if all pairs have the
+        same number of planes in this view) + stacked camera feature maps.  Plane counts come from tensor SHAPES (host-side
+        metadata): no device synchronisation."""
+        planes = [bi[view]["pred_plane"].reshape(-1, 3) for bi in batched_inputs]
+        feats = [bi[view]["pred_plane_feats"].reshape(-1, 256) for bi in batched_inputs]
+        ns = [p.shape[0] for p in planes]
+        if any(f.shape[0] != n for f, n in zip(feats, ns)) or min(ns) < 1:
+            raise ValueError(f"view {view}: pred_plane / pred_plane_feats disagree or are empty (planes per pair: {ns})")
+        count = None
+        if len(set(ns)) > 1:
+            pmax = max(ns)
+            pad = lambda t, n: torch.cat([t, t.new_zeros(pmax - n, t.shape[1])]) if n < pmax else t
+            planes = [pad(p, n) for p, n in zip(planes, ns)]
+            feats = [pad(f, n) for f, n in zip(feats, ns)]
+            count = torch.tensor(ns, dtype=torch.int32).to(device, non_blocking=True)
+        planes = torch.stack(planes).to(device).float()
+        feats = torch.stack(feats).to(device).float()
         cam = {}
         for k in batched_inputs[0][view]["cam_feats"]:
             cam[k] = torch.stack([bi[view]["cam_feats"][k].reshape(bi[view]["cam_feats"][k].shape[-3:])
                                   for bi in batched_inputs]).to(device).float()
-        return planes, feats, cam
+        return planes, feats, cam, count
 
     @torch.no_grad()
     def forward(self, batched_inputs: List[dict]):
@@ -137,11 +152,16 @@ class PlaneTR_NopeSAC(nn.Module):
             zero = {"camera": {"tran": torch.zeros(3), "rot": torch.tensor([1., 0., 0., 0.])}}
             return [dict(zero) for _ in range(B)]
         dev = self.device
-        p1, a1, f1 = self._stack_views(batched_inputs, "0", dev)
-        p2, a2, f2 = self._stack_views(batched_inputs, "1", dev)
+        p1, a1, f1, c1 = self._stack_views(batched_inputs, "0", dev)
+        p2, a2, f2, c2 = self._stack_views(batched_inputs, "1", dev)
+        if (c1 is None) != (c2 is None):           # ragged in one view only: the other view's counts are all Pmax
+            full = lambda p: torch.full((B,), p.shape[1], dtype=torch.int32, device=dev)
+            c1, c2 = (full(p1) if c1 is None else c1), (full(p2) if c2 is None else c2)
         cams, _, _, _, planeAss, _ = self.camera_head_list[0](
             f1, f2, p1, p2, planeApp1=a1, planeApp2=a2, batched_inputs=batched_inputs,
-            matching_net=self.matching_head)
+            matching_net=self.matching_head, plane_count1=c1, plane_count2=c2)
+        n1s = [bi["0"]["pred_plane"].reshape(-1, 3).shape[0] for bi in batched_inputs]
+        n2s = [bi["1"]["pred_plane"].reshape(-1, 3).shape[0] for bi in batched_inputs]
         results = []
         for i in range(B):
             r = {"0": batched_inputs[i]["0"], "1": batched_inputs[i]["1"], "pred_aff": None,
@@ -150,6 +170,6 @@ class PlaneTR_NopeSAC(nn.Module):
                 j = i if value["tran"].shape[0] == B else 0      # camera_zero is [1,3] regardless of B
                 r[key] = {"tran": value["tran"][j], "rot": value["rot"][j]}
             for key, value in planeAss.items():
-                r[key] = value[i]
+                r[key] = value[i, :n1s[i], :n2s[i]]        # the pair's own [n1, n2] block of the padded batch
             results.append(r)
         return results

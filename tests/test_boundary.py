@@ -99,3 +99,24 @@ def test_weight_packs_are_invalidated_on_load():
     head.load_state_dict(hs)
     assert head._packed is None
     assert torch.equal(head.prepare()["decoder_rot2.w_geo"], hs["decoder_rot2.layers.0.weight"][:, 256:])
+
+
+def test_stack_views_pads_ragged_pairs_and_reports_counts():
+    """Host logic of PlaneTR_NopeSAC.inference for pairs with different plane counts: zero padding to the largest count,
+    int32 counts (None when the view is not ragged), feature maps stacked."""
+    import torch
+    g = torch.Generator().manual_seed(0)
+    mk = lambda n: {"pred_plane": torch.randn(n, 3, generator=g), "pred_plane_feats": torch.randn(1, n, 256, generator=g),
+                    "cam_feats": {"res5": torch.randn(1, 8, 2, 3, generator=g)}}
+    bis = [{"0": mk(4), "1": mk(5)}, {"0": mk(2), "1": mk(5)}, {"0": mk(7), "1": mk(5)}]
+    p, f, cam, cnt = PlaneTR_NopeSAC._stack_views(bis, "0", torch.device("cpu"))
+    assert p.shape == (3, 7, 3) and f.shape == (3, 7, 256) and cnt.dtype == torch.int32 and cnt.tolist() == [4, 2, 7]
+    assert torch.equal(p[1, :2], bis[1]["0"]["pred_plane"]) and float(p[1, 2:].abs().sum()) == 0.0
+    assert torch.equal(f[0, :4], bis[0]["0"]["pred_plane_feats"][0]) and float(f[0, 4:].abs().sum()) == 0.0
+    assert cam["res5"].shape == (3, 8, 2, 3)
+    p, f, cam, cnt = PlaneTR_NopeSAC._stack_views(bis, "1", torch.device("cpu"))
+    assert p.shape == (3, 5, 3) and cnt is None
+    import pytest
+    bad = [{"0": {"pred_plane": torch.zeros(0, 3), "pred_plane_feats": torch.zeros(0, 256), "cam_feats": {}}}]
+    with pytest.raises(ValueError):
+        PlaneTR_NopeSAC._stack_views(bad, "0", torch.device("cpu"))

@@ -86,3 +86,32 @@ def test_plane_lists_feed_the_camera_head_without_host_round_trip():
         assert util.maxdiff(cams["camera"]["tran"][i], one[0]["camera"]["tran"][0]) <= util.ABS_TOL, i
         assert util.maxdiff(cams["camera"]["rot"][i], one[0]["camera"]["rot"][0]) <= util.ABS_TOL, i
         assert int(pro["matched_num"][i]) == int(one[5]["matched_num"][0])
+
+
+def test_meta_arch_inference_accepts_pairs_with_different_plane_counts():
+    """`PlaneTR_NopeSAC.inference` (the reference's call, siamese_planeTR.py:338-450) on a batch whose pairs have different
+    plane counts == the same model called pair by pair (the only way the reference can be called)."""
+    dev = _gpu()
+    from nopesac_b200 import config, meta_arch, synthetic
+    NQ = 50
+    model = meta_arch.PlaneTR_NopeSAC(config.inference_cfg(NQ)).to(dev)
+    sd, msd = util.make_weights(NQ)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    counts = [(16, 16), (6, 11), (9, 4)]
+    b = synthetic.make_batch(5, len(counts), 16, with_features=True)
+    bis = []
+    for i, (n1, n2) in enumerate(counts):
+        view = lambda planes, app, feats, n: {"pred_plane": planes[i, :n], "pred_plane_feats": app[i:i + 1, :n],
+                                             "cam_feats": {k: v[i:i + 1] for k, v in feats.items()}}
+        bis.append({"0": view(b.planes1, b.app1, b.feats1, n1), "1": view(b.planes2, b.app2, b.feats2, n2)})
+    batched = model(bis)
+    torch.cuda.synchronize()
+    for i, (n1, n2) in enumerate(counts):
+        single = model([bis[i]])[0]
+        assert batched[i]["pred_assignment"].shape == (n1, n2)
+        for key in ("pred_assignment_beforeRef0", "pred_assignment_afterRef0", "pred_assignment"):
+            assert torch.equal(batched[i][key], single[key]), (i, key)
+        for key in ("camera_init", "camera_initRec", "camera_avgRef0", "camera_softRef0", "camera"):
+            assert util.maxdiff(batched[i][key]["tran"], single[key]["tran"]) <= util.ABS_TOL, (i, key)
+            assert util.maxdiff(batched[i][key]["rot"], single[key]["rot"]) <= util.ABS_TOL, (i, key)
