@@ -65,6 +65,10 @@ def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
             h.update(f.read())
     with open(os.path.join(CSRC, "common.cuh"), "rb") as f:
         h.update(f.read())
+    # NSAC_SIMT_SANITIZE=address|thread: instrumented build; run python under LD_PRELOAD=$(gcc -print-file-name=libasan.so)
+    # (or libtsan.so) — scripts/simt_sanitize.sh
+    san = os.environ.get("NSAC_SIMT_SANITIZE", "")
+    h.update(san.encode())
     key = h.hexdigest()[:16]
     out_dir = os.path.join(tempfile.gettempdir(), "nsac_simt_host")
     os.makedirs(out_dir, exist_ok=True)
@@ -78,7 +82,8 @@ def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
             gens.append(gen)
         # the generated files sit outside csrc/: -I csrc for "common.cuh", which includes "../../include/nopesac_b200.h"
         # relative to ITS OWN directory, so the real header is used.
-        cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-fopenmp", "-ffp-contract=off", "-w",
+        opt = ["-O1", "-g", f"-fsanitize={san}", "-fno-omit-frame-pointer"] if san else ["-O2"]
+        cmd = ["g++"] + opt + ["-std=c++17", "-fPIC", "-shared", "-pthread", "-fopenmp", "-ffp-contract=off", "-w",
                "-I", HERE, "-I", CSRC] + gens + [os.path.join(HERE, c) for c in ("simt_runtime.cpp",) + tuple(extra_cpp)] + \
               ["-o", lib + ".tmp"]
         res = subprocess.run(cmd, capture_output=True, text=True)
