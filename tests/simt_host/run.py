@@ -60,7 +60,7 @@ def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
     h = hashlib.sha1()
     for name in sorted(srcs):
         h.update(srcs[name].encode())
-    for dep in ("cuda_runtime.h", "cuda_fp16.h", "simt_runtime.cpp") + tuple(extra_cpp):
+    for dep in ("cuda_runtime.h", "cuda_fp16.h", "cuda_bf16.h", "simt_runtime.cpp") + tuple(extra_cpp):
         with open(os.path.join(HERE, dep), "rb") as f:
             h.update(f.read())
     with open(os.path.join(CSRC, "common.cuh"), "rb") as f:
@@ -93,4 +93,4 @@ def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
     return ctypes.CDLL(lib)
 
 
-SIMT_SOURCES = ["dense.cu", "geo.cu", "matcher.cu", "score.cu", "evaluate.cu", "planes.cu"]   # no TMA / tcgen05 / inline PTX
+SIMT_SOURCES = ["dense.cu", "geo.cu", "matcher.cu", "score.cu", "evaluate.cu", "planes.cu", "pixel.cu"]   # no TMA / tcgen05 / inline PTX

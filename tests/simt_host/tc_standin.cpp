@@ -3,7 +3,7 @@
 // (PlaneCameraHead / MatchingHead) can be executed end to end on CPU tensors in the `-m "not gpu"` suite, with the plain-SIMT
 // kernels running from their real source (tests/simt_host/cuda_runtime.h).  They are NOT the product and prove nothing about
 // the tensor-core kernels themselves (tests/test_gpu_gemm_tc.py, tests/test_gpu_parity.py do that on the device).
-//   nsac_split16 / nsac_gemm_split   16-bit hi/lo planes, products of planes summed in double (at least as accurate as the
+//   nsac_split16 / nsac_gemm_split / nsac_conv3x3_split   16-bit hi/lo planes, products of planes summed in double (at least as accurate as the
 //                                    TMEM accumulation), epilogue act(out_scale * acc + bias), optional re-split
 //   nsac_score_pack* / nsac_score_aggregate_tc   routed to the exact-fp32 nsac_score_aggregate (csrc/score.cu, real source)
 #include <math.h>
@@ -95,6 +95,52 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
       v = fmaxf(v, slope * v + 0.f);
       if (out_f32) out_f32[(size_t)m * ldo + n] = v;
       if (out_hi) split16(v, fmt, static_cast<uint16_t*>(out_hi)[(size_t)m * ld_split + n], static_cast<uint16_t*>(out_lo)[(size_t)m * ld_split + n]);
+    }
+  }
+  return NSAC_OK;
+}
+
+// 3x3 / stride 1 / pad 1 convolution over NHWC planes as the same hi/lo-plane product (weights [Cout, 9*Cin], (ky,kx,cin) order)
+extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int N,
+                                  int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale, float* out_f32,
+                                  int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
+  if (!x_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 2 && !x_lo) || (passes >= 3 && !w_lo) || Cin % 64 != 0 ||
+      (!out_f32 && !out_hi) || (out_hi && !out_lo)) {
+    nsac_set_error("nsac_conv3x3_split (stand-in): bad arguments");
+    return NSAC_ERR_ARG;
+  }
+  const int K = 9 * Cin;
+  const uint16_t *xh = static_cast<const uint16_t*>(x_hi), *xl = static_cast<const uint16_t*>(x_lo);
+  const uint16_t *wh = static_cast<const uint16_t*>(w_hi), *wl = static_cast<const uint16_t*>(w_lo);
+  std::vector<double> WH((size_t)Cout * K), WL((size_t)Cout * K, 0.0);
+  for (size_t i = 0; i < (size_t)Cout * K; ++i) {
+    WH[i] = plane_to_float(wh[i], fmt);
+    if (passes >= 3) WL[i] = plane_to_float(wl[i], fmt);
+  }
+  const float slope = act == NSAC_ACT_RELU ? 0.f : (act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
+  std::vector<double> AH(K), AL(K);
+#pragma omp parallel for firstprivate(AH, AL)
+  for (int m = 0; m < N * H * W; ++m) {
+    const int n = m / (H * W), y = (m / W) % H, x = m % W;
+    for (int t = 0; t < 9; ++t) {
+      const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+      const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
+      const size_t src = (((size_t)n * H + yy) * W + xx) * Cin;
+      for (int c = 0; c < Cin; ++c) {
+        AH[t * Cin + c] = in ? plane_to_float(xh[src + c], fmt) : 0.0;
+        AL[t * Cin + c] = (in && passes >= 2) ? plane_to_float(xl[src + c], fmt) : 0.0;
+      }
+    }
+    for (int co = 0; co < Cout; ++co) {
+      const double *w0 = &WH[(size_t)co * K], *w1 = &WL[(size_t)co * K];
+      double acc = 0.0;
+      for (int k = 0; k < K; ++k) acc += (AH[k] + AL[k]) * w0[k] + AH[k] * w1[k];
+      if (passes >= 4)
+        for (int k = 0; k < K; ++k) acc += AL[k] * w1[k];
+      float v = out_scale * (float)acc + (bias ? bias[co] : 0.f);
+      v = fmaxf(v, slope * v + 0.f);
+      if (out_f32) out_f32[(size_t)m * ldo + co] = v;
+      if (out_hi) split16(v, fmt, static_cast<uint16_t*>(out_hi)[(size_t)m * ld_split + co], static_cast<uint16_t*>(out_lo)[(size_t)m * ld_split + co]);
     }
   }
   return NSAC_OK;

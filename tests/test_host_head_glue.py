@@ -17,8 +17,13 @@ from tests.test_gpu_parity import _check_against, _selection_from_reference
 import os
 
 _ALL = [n for n in util.golden_names() if not util.load_golden(n)["case"]["feats"] and util.load_golden(n)["case"]["NQ"] <= 64]
+# NSAC_HOST_GLUE_PIXEL=1 adds the fixtures WITH backbone feature maps: the pixel pose CNN (K1) then runs on the host too (its glue
+# kernels from source, the convolutions through the stand-in) — the whole `inference_Joint`, minutes per pair.
+_PIXEL = [n for n in util.golden_names() if util.load_golden(n)["case"]["feats"] and util.load_golden(n)["case"]["NQ"] <= 64]
 _FAST = ["c1_nq32_p8", "ragged_nq50_p5x9", "maxscore_nq50_p16"]
 NO_FEATS = _ALL if os.environ.get("NSAC_HOST_GLUE_ALL") == "1" else [n for n in _FAST if n in _ALL]
+if os.environ.get("NSAC_HOST_GLUE_PIXEL") == "1":
+    NO_FEATS = _PIXEL
 MAX_PAIRS = None if os.environ.get("NSAC_HOST_GLUE_ALL") == "1" else 1
 
 
@@ -32,11 +37,16 @@ def _run_host_case(case, pair_indices, want_diag=False, **kw):
     bs = [util.case_batch(case, pi) for pi in pair_indices]
     cat = lambda f: torch.cat([f(b) for b in bs], 0)
     p1, p2, a1, a2 = cat(lambda b: b.planes1), cat(lambda b: b.planes2), cat(lambda b: b.app1), cat(lambda b: b.app2)
-    poses = [util.initial_pose_for(pi) for pi in pair_indices]
-    ip = (torch.cat([p[0] for p in poses]), torch.cat([p[1] for p in poses]))
+    f1 = f2 = ip = None
+    if case["feats"]:
+        f1 = {k: torch.cat([b.feats1[k] for b in bs], 0) for k in bs[0].feats1}
+        f2 = {k: torch.cat([b.feats2[k] for b in bs], 0) for k in bs[0].feats2}
+    else:
+        poses = [util.initial_pose_for(pi) for pi in pair_indices]
+        ip = (torch.cat([p[0] for p in poses]), torch.cat([p[1] for p in poses]))
     hp = util.case_hyp_pairs(case)
     hp = None if hp is None else hp.to(torch.int32)
-    return head(None, None, p1, p2, a1, a2, matching_net=match, hyp_pairs=hp, initial_pose=ip, want_diag=want_diag, **kw)
+    return head(f1, f2, p1, p2, a1, a2, matching_net=match, hyp_pairs=hp, initial_pose=ip, want_diag=want_diag, **kw)
 
 
 @pytest.mark.parametrize("name", NO_FEATS)
