@@ -21,22 +21,25 @@ void launch(dim3 grid, dim3 block, size_t dyn_smem_bytes, const std::function<vo
   blk.scratch.assign(n, 0ull);
   std::vector<unsigned char> smem(dyn_smem_bytes + 1024, 0xCD);       // garbage-filled like real shared memory
   blk.dyn_smem = smem.data() + ((1024 - (uintptr_t)smem.data() % 1024) % 1024);
+  // one OS thread per CUDA thread of a block, created once per launch; the blocks of the grid run one after another on this
+  // team (a barrier between blocks: static / dynamic shared memory is reused)
   std::vector<std::thread> threads(n);
-  for (unsigned bz = 0; bz < grid.z; ++bz)
-    for (unsigned by = 0; by < grid.y; ++by)
-      for (unsigned bx = 0; bx < grid.x; ++bx) {
-        for (unsigned t = 0; t < n; ++t)
-          threads[t] = std::thread([&, t, bx, by, bz]() {
-            cur = &blk;
-            linear_tid = t;
-            threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+  for (unsigned t = 0; t < n; ++t)
+    threads[t] = std::thread([&, t]() {
+      cur = &blk;
+      linear_tid = t;
+      threadIdx = uint3{t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
+      blockDim = block;
+      gridDim = grid;
+      for (unsigned bz = 0; bz < grid.z; ++bz)
+        for (unsigned by = 0; by < grid.y; ++by)
+          for (unsigned bx = 0; bx < grid.x; ++bx) {
             blockIdx = uint3{bx, by, bz};
-            blockDim = block;
-            gridDim = grid;
             body();
-          });
-        for (auto& th : threads) th.join();
-      }
+            pthread_barrier_wait(&blk.all);
+          }
+    });
+  for (auto& th : threads) th.join();
   pthread_barrier_destroy(&blk.all);
   for (auto& w : blk.warp) pthread_barrier_destroy(&w);
 }

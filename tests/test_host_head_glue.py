@@ -1,29 +1,26 @@
-"""CPU: the product's Python glue — `PlaneCameraHead.inference_Joint` + `MatchingHead.match` (everything downstream of the
-pixel CNN) — executed end to end on CPU tensors against the golden fixtures generated from the live reference and the oracle.
+"""CPU: the product's Python glue — `PlaneCameraHead.inference_Joint` (pixel pose CNN included) + `MatchingHead.match` —
+executed end to end on CPU tensors against the golden fixtures generated from the live reference and the oracle.
 The plain-SIMT kernels run from their real source on the host (tests/simt_host); the tensor-engine entry points are functional
 stand-ins (tests/simt_host/tc_standin.cpp: hi/lo-plane GEMM in double, scoring routed to the exact-fp32 kernel).  What this
 covers in a container without a GPU: weight packing, plane formats, row ranges / column slices of the GNN token buffer, geo
 sequences, hypothesis features, per-pair m rules, result layout — the same `_check_against` bar as tests/test_gpu_parity.py.
-What it does NOT cover: the tcgen05 kernels and the pixel CNN (GPU tests)."""
+What it does NOT cover: the tcgen05 kernels themselves (GPU tests)."""
 import pytest
 import torch
 
 from tests import host_fixture, util
 from tests.test_gpu_parity import _check_against, _selection_from_reference
 
-# The host execution is slow (every warp shuffle of the attention kernel is two 32-thread barriers): three fixtures, first pair
-# of each — the smallest reference case (c1), ragged plane counts n1 != n2, and an index-selection mode.  NSAC_HOST_GLUE_ALL=1
-# runs every fixture without feature maps and NQ <= 64 (about 8 minutes).
+# The host execution is slow (every warp shuffle is two 32-thread barriers): by default three fixtures, first pair of each —
+# c1_nq32_p8 = BASELINE.json configs[0], the reference's own CPU case, WITH backbone feature maps (the pixel pose CNN K1 runs on
+# the host too: its glue kernels from source, the convolutions through the stand-in, i.e. the whole `inference_Joint`), ragged
+# plane counts n1 != n2, and an index-selection mode.  NSAC_HOST_GLUE_ALL=1 runs every fixture with NQ <= 64, all pairs
+# (about ten minutes).
 import os
 
-_ALL = [n for n in util.golden_names() if not util.load_golden(n)["case"]["feats"] and util.load_golden(n)["case"]["NQ"] <= 64]
-# NSAC_HOST_GLUE_PIXEL=1 adds the fixtures WITH backbone feature maps: the pixel pose CNN (K1) then runs on the host too (its glue
-# kernels from source, the convolutions through the stand-in) — the whole `inference_Joint`, minutes per pair.
-_PIXEL = [n for n in util.golden_names() if util.load_golden(n)["case"]["feats"] and util.load_golden(n)["case"]["NQ"] <= 64]
+_ALL = [n for n in util.golden_names() if util.load_golden(n)["case"]["NQ"] <= 64]
 _FAST = ["c1_nq32_p8", "ragged_nq50_p5x9", "maxscore_nq50_p16"]
 NO_FEATS = _ALL if os.environ.get("NSAC_HOST_GLUE_ALL") == "1" else [n for n in _FAST if n in _ALL]
-if os.environ.get("NSAC_HOST_GLUE_PIXEL") == "1":
-    NO_FEATS = _PIXEL
 MAX_PAIRS = None if os.environ.get("NSAC_HOST_GLUE_ALL") == "1" else 1
 
 
