@@ -267,6 +267,26 @@ int nsac_plane_postprocess(const float* pred_logits, const float* pred_params, c
                            float* centers, float* bboxes, int32_t* areas, uint8_t* seg, void* workspace,
                            void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ResNet-50 backbone glue (detectron2 build_resnet_backbone, Base.yaml:2-12 — plain ResNet, stride in the
+ * 3x3, FrozenBN).  The convolutions themselves run on the tensor-core engine (nsac_gemm_split / nsac_conv3x3_split /
+ * nsac_im2col3x3_planes); activations are NHWC rows [N*H*W, C].
+ *   nsac_stem_im2col_planes  image [N,3,H,W] fp32 NCHW, (x - mean) / std per channel (PIXEL_MEAN / PIXEL_STD; HOST pointers to
+ *                            3 floats) fused with the im2col of the 7x7 / stride 2 / pad 3 stem convolution -> planes
+ *                            [N*Ho*Wo, 192], Ho = (H-1)/2+1: columns (ky,kx,c), 147 used, the rest zero
+ *   nsac_maxpool3x3s2_nhwc   MaxPool2d(3, stride 2, pad 1) of an fp32 NHWC map -> fp32 and / or planes [N*Ho*Wo, C]
+ *   nsac_subsample2_planes   every second pixel (even y, even x) of NHWC planes: the input of a stride-2 1x1 convolution
+ *   nsac_add_relu_nhwc       relu(a + b) over `count` fp32 elements (count % 4 == 0) -> fp32 and / or planes (bottleneck output)
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_stem_im2col_planes(const float* img, int N, int H, int W, const float* mean3_host, const float* std3_host,
+                            int fmt, void* hi, void* lo, void* stream);
+int nsac_maxpool3x3s2_nhwc(const float* x, int N, int H, int W, int C, int fmt, float* out_f32, void* hi, void* lo,
+                           void* stream);
+int nsac_subsample2_planes(const void* hi, const void* lo, int N, int H, int W, int C, void* out_hi, void* out_lo,
+                           void* stream);
+int nsac_add_relu_nhwc(const float* a, const float* b, size_t count, int fmt, float* out_f32, void* hi, void* lo,
+                       void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,6 +71,13 @@ _SIGNATURES = {
     "nsac_debug_score_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "nsac_debug_gemm_trace": (C.c_int, [C.c_void_p]),
     "nsac_camera_errors": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_void_p]),
+    "nsac_stem_im2col_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsac_maxpool3x3s2_nhwc": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "nsac_subsample2_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                         C.c_void_p]),
+    "nsac_add_relu_nhwc": (C.c_int, [c_float_p, c_float_p, C.c_size_t, C.c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsac_plane_post_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "nsac_plane_postprocess": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p] + [C.c_int] * 7 +
                                [C.c_float, C.c_float, C.c_double] + [C.c_void_p] * 12),

@@ -265,6 +265,66 @@ def im2col3x3_planes(x: torch.Tensor, N: int, H: int, W: int, stride: int, fmt: 
     return out, Ho, Wo
 
 
+# ---------------------------------------------------------------------------------------------------
+# ResNet-50 backbone glue (row f2; csrc/backbone.cu)
+# ---------------------------------------------------------------------------------------------------
+def stem_im2col_planes(img: torch.Tensor, mean, std, fmt: int = SPLIT_F16):
+    """[N,3,H,W] fp32 -> ((img - mean) / std) im2col planes of the 7x7 / stride 2 / pad 3 stem conv: (Split [N*Ho*Wo, 192] with
+    K = 147 in (ky,kx,c) order, Ho, Wo).  mean / std: 3 Python floats each (cfg.MODEL.PIXEL_MEAN / PIXEL_STD)."""
+    img = _c(img, "img")
+    N, Cc, H, W = img.shape
+    assert Cc == 3
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = _empty_split(N * Ho * Wo, 192, img.device, fmt)
+    out.K = 147
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    st = _lib.lib().nsac_stem_im2col_planes(_p(img), N, H, W, m3, s3, fmt, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_stem_im2col_planes")
+    _count()
+    return out, Ho, Wo
+
+
+def maxpool3x3s2_nhwc(x: torch.Tensor, N: int, H: int, W: int, fmt: int = SPLIT_F16, want_f32: bool = True, want_split: bool = True):
+    """MaxPool2d(3, 2, 1) of an fp32 NHWC map [N*H*W, C] -> (fp32 [N*Ho*Wo, C] or None, Split or None, Ho, Wo)."""
+    x = _c(x, "x")
+    Cc = x.shape[1]
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = torch.empty(N * Ho * Wo, Cc, device=x.device, dtype=torch.float32) if want_f32 else None
+    sp = _empty_split(N * Ho * Wo, Cc, x.device, fmt) if want_split else None
+    st = _lib.lib().nsac_maxpool3x3s2_nhwc(_p(x), N, H, W, Cc, fmt, _p(out), None if sp is None else _p(sp.hi),
+                                           None if sp is None else _p(sp.lo), _stream())
+    _lib.check(st, "nsac_maxpool3x3s2_nhwc")
+    _count()
+    return out, sp, Ho, Wo
+
+
+def subsample2_planes(x: Split, N: int, H: int, W: int):
+    """Every second pixel of contiguous NHWC planes [N*H*W, C] -> (Split [N*Ho*Wo, C], Ho, Wo)."""
+    Cc = x.hi.shape[1]
+    assert x.hi.is_contiguous() and x.lo.is_contiguous() and x.rows == N * H * W and Cc % 8 == 0
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    out = Split(torch.empty(N * Ho * Wo, Cc, device=x.hi.device, dtype=x.hi.dtype),
+                torch.empty(N * Ho * Wo, Cc, device=x.hi.device, dtype=x.hi.dtype), x.K, x.fmt, x.scale)
+    st = _lib.lib().nsac_subsample2_planes(_p(x.hi), _p(x.lo), N, H, W, Cc, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_subsample2_planes")
+    _count()
+    return out, Ho, Wo
+
+
+def add_relu_nhwc(a: torch.Tensor, b: torch.Tensor, fmt: int = SPLIT_F16, want_f32: bool = True, want_split: bool = True):
+    """relu(a + b) of two contiguous fp32 [rows, C] maps (C % 64 == 0 for the planes) -> (fp32 or None, Split or None)."""
+    a, b = _c(a, "a"), _c(b, "b")
+    assert a.shape == b.shape and a.dim() == 2 and (not want_split or a.shape[1] % 64 == 0)
+    out = torch.empty_like(a) if want_f32 else None
+    sp = Split(torch.empty(a.shape, device=a.device, dtype=_SPLIT_DTYPE[fmt]), torch.empty(a.shape, device=a.device, dtype=_SPLIT_DTYPE[fmt]),
+               a.shape[1], fmt) if want_split else None
+    st = _lib.lib().nsac_add_relu_nhwc(_p(a), _p(b), a.numel(), fmt, _p(out), None if sp is None else _p(sp.hi),
+                                       None if sp is None else _p(sp.lo), _stream())
+    _lib.check(st, "nsac_add_relu_nhwc")
+    _count()
+    return out, sp
+
+
 def layernorm(x, gamma, beta, res=None, out=None, out_split: Optional[Split] = None):
     """out = (res or 0) + LayerNorm(x); optionally also written as fp16 hi/lo planes (`out_split` view)."""
     _chk(x, "x")

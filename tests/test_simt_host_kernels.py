@@ -23,7 +23,7 @@ from tests import host_fixture, util  # noqa: E402
 
 @pytest.fixture()
 def host_ops(monkeypatch):
-    return host_fixture.install(monkeypatch, with_tensor_standins=False)
+    return host_fixture.install(monkeypatch, with_tensor_standins=True)    # stand-ins only for ops.split() in helper code
 
 
 def test_geo_sequence_source_on_host(host_ops):
@@ -239,3 +239,58 @@ def test_ragged_match_sinkhorn_assign_source_on_host(host_ops):
         want = restate.log_optimal_transport(s, bin_score, 200)
         assert util.maxdiff(one_lsp.exp(), want.exp()) <= 1e-4, i
         assert torch.equal(one_assign, restate.get_assignment_matrix(want, 0.2)), i
+
+
+def test_entry_points_reject_bad_arguments_with_a_message(host_ops):
+    """SURVEY.md §8b 'Errors': every export returns a negative status and sets nsac_last_error() instead of crashing — checked
+    on the host build of the same sources (argument validation happens before any launch)."""
+    L = _lib._lib
+    L.nsac_last_error.restype = C.c_char_p
+    err = lambda: L.nsac_last_error().decode()
+    z = torch.zeros(64)
+    p = lambda t: C.c_void_p(t.data_ptr())
+    assert L.nsac_linear(None, 4, None, None, 0, None, 4, 4, 4, 4, 0, None) == -1 and "null pointer" in err()
+    assert L.nsac_attention(p(z), 256, p(z), p(z), 256, p(z), 256, None, None, 0, 1, 1, 1, 8, 16, None) == -1 and "head dim must be 32" in err()
+    assert L.nsac_match_sinkhorn_assign(p(z), p(z), p(z), p(z), p(z), p(z), 4.0, 8.0, 200, 0.2, 1, 0, 3, 256, p(z), p(z), None) == -1
+    assert "bad shape" in err()
+    assert L.nsac_match_sinkhorn_assign(p(z), p(z), p(z), p(z), p(z), p(z), 4.0, 8.0, 200, 0.2, 1, 2000, 3, 256, p(z), p(z), None) == -1
+    assert "1023 planes" in err()
+    assert L.nsac_prune_assignment(p(z), p(z), p(z), p(z), 3, 1, 2, 2, p(z), None) == -1 and "bad shape" in err()
+    assert L.nsac_camera_errors(p(z), 3, p(z), p(z), 1, p(z), p(z), p(z), None) == -1 and "bad shape" in err()
+    assert L.nsac_geo_sequence(None, None, None, None, 0, None, None, 1, 2, 2, 8, None, None, None, None, None, None, None) == -1
+    assert L.nsac_plane_post_workspace_bytes(1, 0, 480, 640) == 0
+    # a successful call afterwards is unaffected by the stale message
+    x, w = torch.randn(3, 4), torch.randn(5, 4)
+    assert util.maxdiff(host_ops.linear(x, w), x @ w.T) <= 1e-6
+
+
+def test_backbone_glue_kernels_source_on_host(host_ops):
+    """csrc/backbone.cu (row f2): stem normalisation + 7x7/2 im2col, MaxPool2d(3,2,1), stride-2 subsampling, relu(a + b) against
+    PyTorch; odd and even sizes."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(6)
+    nhwc = lambda x: x.permute(0, 2, 3, 1).reshape(-1, x.shape[1]).contiguous()
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    for (N, H, W) in ((2, 16, 24), (1, 15, 21)):
+        img = torch.rand(N, 3, H, W, generator=g) * 255
+        cols, Ho, Wo = host_ops.stem_im2col_planes(img, mean, std)
+        norm = (img - torch.tensor(mean).view(1, 3, 1, 1)) / torch.tensor(std).view(1, 3, 1, 1)
+        ref = F.unfold(norm, 7, padding=3, stride=2)                                  # [N, 3*49, L], rows (c, ky, kx)
+        assert (Ho, Wo) == ((H - 1) // 2 + 1, (W - 1) // 2 + 1) and ref.shape[2] == Ho * Wo
+        ref = ref.reshape(N, 3, 49, Ho * Wo).permute(0, 3, 2, 1).reshape(N * Ho * Wo, 147)      # (ky,kx,c) order
+        assert util.maxdiff(cols.float(), ref) <= 2e-6
+        assert float((cols.hi[:, 147:].float().abs() + cols.lo[:, 147:].float().abs()).max()) == 0.0
+        w = torch.randn(64, 3, 7, 7, generator=g)
+        conv = F.conv2d(norm.double(), w.double(), stride=2, padding=3)
+        assert util.maxdiff(cols.float().double() @ w.permute(0, 2, 3, 1).reshape(64, 147).double().T, nhwc(conv)) <= 1e-4
+        x = torch.randn(N, 64, H, W, generator=g)
+        out, sp, Hp, Wp = host_ops.maxpool3x3s2_nhwc(nhwc(x), N, H, W)
+        ref = F.max_pool2d(x, 3, 2, 1)
+        assert ref.shape[2:] == (Hp, Wp) and torch.equal(out, nhwc(ref)) and util.maxdiff(sp.float(), out) <= 1e-6
+        xp = host_ops.split(nhwc(x))
+        sub, Hs, Ws = host_ops.subsample2_planes(xp, N, H, W)
+        assert (Hs, Ws) == ((H - 1) // 2 + 1, (W - 1) // 2 + 1)
+        assert util.maxdiff(sub.float(), nhwc(x[:, :, ::2, ::2])) <= 1e-6
+        a, b = nhwc(x), nhwc(torch.randn(N, 64, H, W, generator=g))
+        o, op_ = host_ops.add_relu_nhwc(a, b)
+        assert torch.equal(o, torch.relu(a + b)) and util.maxdiff(op_.float(), o) <= 1e-6
