@@ -184,6 +184,39 @@ def measure_plane_lists(dev, images: int, iters: int = 10):
             "note": "row f1, both views of this rank's pairs; outside the timed region of `value`"}
 
 
+def measure_from_rgb(dev, B: int, head, match, dbatch, hp, iters: int = 3):
+    """pairs/s of RGB -> ResNet-50 (random init, both views = 2B images of 480x640) -> camera head, inputs resident in HBM,
+    CUDA events on the launch stream after 2 warm-ups."""
+    from nopesac_b200 import backbone, config
+    net = backbone.build_backbone(config.inference_cfg())
+    with torch.no_grad():                              # random init: damp the residual branches so res5 stays O(1) like a trained net
+        for name, buf in net.named_buffers():
+            if name.endswith("conv3.norm.weight"):
+                buf.mul_(0.3)
+    net = net.to(dev)
+    g = torch.Generator(device=dev).manual_seed(1)
+    images = torch.rand(2 * B, 3, 480, 640, device=dev, generator=g) * 255
+
+    def step():
+        feats = net(images)
+        f1 = {k: v[:B] for k, v in feats.items()}
+        f2 = {k: v[B:] for k, v in feats.items()}
+        return head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp)
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    return {"value": B / ms * 1e3, "unit": "pairs/s", "ms_per_step": ms, "pairs": B, "stage_set": "S5' = ResNet-50 backbone (random init) + "
+            "camera head from RGB, synthetic plane lists", "note": "first version of the backbone (residual add unfused); reported, not the headline"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -400,6 +433,15 @@ def main():
         except Exception as e:   # never let the side measurement take the bench line down
             plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    # row f2: the same step started at RGB (ResNet-50 backbone of both views + camera head) — the stage set S5' of DESIGN.md
+    # §5.  Reported beside `value` (whose stage set S4 starts at the backbone feature maps), never instead of it.
+    from_rgb = None
+    if rank == 0:
+        try:
+            from_rgb = measure_from_rgb(dev, B, head, match, dbatch, hp)
+        except Exception as e:   # never let the side measurement take the bench line down
+            from_rgb = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -415,6 +457,7 @@ def main():
         "cpu_baseline": cpu_baseline,
         "pose_err": pose_err,
         "plane_lists": plane_lists,
+        "from_rgb": from_rgb,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -23,6 +23,7 @@ from typing import Dict, List
 import torch
 from torch import nn
 
+from .backbone import build_backbone
 from .camera_head import build_camera_head
 from .compat import Registry, ShapeSpec
 from .matching_head import build_matching_head
@@ -47,9 +48,12 @@ def build_model(cfg):
 
 @META_ARCH_REGISTRY.register()
 class PlaneTR_NopeSAC(nn.Module):
-    def __init__(self, cfg):
+    def __init__(self, cfg, with_backbone: bool = False):
+        """`with_backbone=True` also builds `self.backbone` (row f2: the R-50 of `build_backbone(cfg)`, siamese_planeTR.py
+        `__init__`; `backbone.*` checkpoint keys then load too) so that `inference_from_images` starts at RGB."""
         super().__init__()
         self.cfg = cfg
+        self.backbone = build_backbone(cfg) if with_backbone else None
         self.mask_on = cfg.MODEL.MASK_ON
         self.embedding_on = cfg.MODEL.EMBEDDING_ON
         self.camera_on = cfg.MODEL.CAMERA_ON
@@ -74,7 +78,8 @@ class PlaneTR_NopeSAC(nn.Module):
         """Loads the hot-path keys of a full reference checkpoint; returns the keys that were ignored
         (backbone / sem_seg_head / criterion)."""
         mine = {k: v for k, v in state_dict.items()
-                if k.startswith("matching_head.") or k.startswith("camera_head_list.0.")}
+                if k.startswith("matching_head.") or k.startswith("camera_head_list.0.") or
+                (self.backbone is not None and k.startswith("backbone."))}
         missing, unexpected = self.load_state_dict(mine, strict=False)
         if missing:
             raise KeyError(f"reference checkpoint lacks hot-path keys: {missing[:5]} ...")
@@ -96,6 +101,21 @@ class PlaneTR_NopeSAC(nn.Module):
         height, width = next(iter(sizes))
         lists = self.plane_lists(planeTR_outputs, query_feat_in, height, width)
         return lists.to_reference_results(batched_inputs, with_rle=True)
+
+    @torch.no_grad()
+    def inference_from_images(self, images1: torch.Tensor, images2: torch.Tensor, planeParam1, planeParam2, planeApp1, planeApp2,
+                              **head_kwargs):
+        """RGB -> backbone -> camera head (rows f2 + a2..a15): `images*` [B,3,H,W] fp32 in 0..255 (normalisation is fused into
+        the stem), both views go through the backbone as one batch of 2B images, `res3..res5` feed the pixel pose CNN, the
+        plane lists come from the caller (PlaneTRHead is not built here).  Returns the camera head's 6-tuple."""
+        if self.backbone is None:
+            raise RuntimeError("PlaneTR_NopeSAC was built without a backbone (with_backbone=True)")
+        B = images1.shape[0]
+        feats = self.backbone(torch.cat([images1, images2], 0))
+        f1 = {k: v[:B] for k, v in feats.items()}
+        f2 = {k: v[B:] for k, v in feats.items()}
+        return self.camera_head_list[0](f1, f2, planeParam1, planeParam2, planeApp1=planeApp1, planeApp2=planeApp2,
+                                        matching_net=self.matching_head, **head_kwargs)
 
     @torch.no_grad()
     def inference_from_plane_heads(self, planeTR_outputs1, query_feat1, planeTR_outputs2, query_feat2, cam_feats1, cam_feats2,

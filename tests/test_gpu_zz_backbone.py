@@ -1,0 +1,89 @@
+"""GPU: the ResNet-50 backbone (row f2) on the tensor-core engine against the backbone oracle (= torchvision's resnet50,
+tests/test_oracle_backbone.py), and RGB -> backbone -> camera head.  Named to run last: the backbone's glue kernels and its
+whole Python composition were executed on the host against the same oracle (tests/test_simt_host_kernels.py,
+tests/test_host_head_glue.py); these tests put the real tcgen05 GEMM / implicit-GEMM convolution underneath.
+Bar: 1e-4 of the stage's largest activation (3-pass fp16 hi/lo planes ~ fp32 through 53 convolutions)."""
+import pytest
+import torch
+
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+def _gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+def _seeded_state(seed=8):
+    from oracle import backbone_restate as br
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shape in br.state_shapes().items():
+        if k.endswith("running_var"):
+            sd[k] = torch.rand(shape, generator=g) + 0.5
+        elif k.endswith("norm.weight"):
+            sd[k] = torch.rand(shape, generator=g) * 0.5 + 0.5
+        elif k.endswith("norm.bias") or k.endswith("running_mean"):
+            sd[k] = torch.randn(shape, generator=g) * 0.1
+        else:
+            sd[k] = torch.randn(shape, generator=g) * (2.0 / (shape[0] * shape[2] * shape[3])) ** 0.5
+    return sd
+
+
+@pytest.mark.parametrize("N,H,W", [(2, 64, 96), (1, 480, 640), (3, 120, 200)])
+def test_resnet50_backbone_matches_oracle(N, H, W):
+    dev = _gpu()
+    from nopesac_b200 import backbone, config
+    from oracle import backbone_restate as br
+    cfg = config.inference_cfg()
+    net = backbone.build_backbone(cfg)
+    sd = _seeded_state()
+    net.load_state_dict(sd)
+    net = net.to(dev)
+    images = torch.rand(N, 3, H, W, generator=torch.Generator().manual_seed(N + H)) * 255
+    got = net(images.to(dev))
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want = br.resnet50(sd, br.normalize(images, cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        rel = util.maxdiff(got[k], want[k]) / float(want[k].abs().max())
+        assert rel <= 1e-4, (k, rel)
+
+
+def test_rgb_to_camera_head():
+    """`PlaneTR_NopeSAC(cfg, with_backbone=True).inference_from_images`: the head fed by this backbone == the head fed by the
+    oracle backbone's feature maps (poses 1e-4, assignments exact)."""
+    dev = _gpu()
+    from nopesac_b200 import config, meta_arch, synthetic
+    from oracle import backbone_restate as br
+    NQ = 50
+    cfg = config.inference_cfg(NQ)
+    model = meta_arch.PlaneTR_NopeSAC(cfg, with_backbone=True)
+    sd, msd = util.make_weights(NQ)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    bsd = _seeded_state(9)
+    for k in [k for k in bsd if k.endswith("conv3.norm.weight")]:
+        bsd[k] = bsd[k] * 0.3                      # keeps the res5 activations O(1) like a trained network's
+    model.backbone.load_state_dict(bsd)
+    model = model.to(dev)
+    B = 2
+    b = synthetic.make_batch(7, B, 16)
+    g = torch.Generator().manual_seed(5)
+    im1, im2 = torch.rand(B, 3, 480, 640, generator=g) * 255, torch.rand(B, 3, 480, 640, generator=g) * 255
+    bd = b.to(dev)
+    got = model.inference_from_images(im1.to(dev), im2.to(dev), bd.planes1, bd.planes2, bd.app1, bd.app2)
+    with torch.no_grad():
+        f1 = br.resnet50(bsd, br.normalize(im1, cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+        f2 = br.resnet50(bsd, br.normalize(im2, cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+    want = model.camera_head_list[0]({k: v.to(dev) for k, v in f1.items()}, {k: v.to(dev) for k, v in f2.items()}, bd.planes1, bd.planes2,
+                                     planeApp1=bd.app1, planeApp2=bd.app2, matching_net=model.matching_head)
+    torch.cuda.synchronize()
+    assert torch.equal(got[4]["pred_assignment_beforeRef0"], want[4]["pred_assignment_beforeRef0"])
+    for key in ("camera_init", "camera"):
+        assert util.maxdiff(got[0][key]["tran"], want[0][key]["tran"]) <= util.ABS_TOL, key
+        assert util.maxdiff(got[0][key]["rot"], want[0][key]["rot"]) <= util.ABS_TOL, key

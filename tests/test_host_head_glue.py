@@ -127,3 +127,37 @@ def test_plane_lists_to_camera_head_glue_on_host(host_ops):
         ass_i = {k: v[i:i + 1, :n1, :n2] for k, v in ass.items()}
         pro_i = {k: v[i:i + 1] for k, v in pro.items() if torch.is_tensor(v) and v.shape[0] == B}
         _check_against(util.oracle_to_flat(o), cams_i, [lsp[0][i:i + 1, :n1 + 1, :n2 + 1]], ass_i, pro_i, 0, f"plane-list pair {i} ({n1}x{n2})")
+
+
+def test_resnet50_backbone_glue_on_host_matches_oracle(host_ops):
+    """Row f2: `ResNet50Backbone.forward` (stem normalisation + im2col, 53 convolutions as GEMMs on hi/lo planes with FrozenBN
+    folded, max-pool, stride-2 paths, residual adds) on CPU tensors against the backbone oracle (= torchvision's resnet50,
+    tests/test_oracle_backbone.py) at a reduced input size; parameter names / shapes are detectron2's."""
+    from nopesac_b200 import backbone, config
+    from oracle import backbone_restate as br
+    cfg = config.inference_cfg(device="cpu")
+    net = backbone.build_backbone(cfg)
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == br.state_shapes()
+    g = torch.Generator().manual_seed(8)
+    sd = {}
+    for k, shape in br.state_shapes().items():
+        if k.endswith("running_var"):
+            sd[k] = torch.rand(shape, generator=g) + 0.5
+        elif k.endswith("norm.weight"):
+            sd[k] = torch.rand(shape, generator=g) * 0.5 + 0.5
+        elif k.endswith("norm.bias") or k.endswith("running_mean"):
+            sd[k] = torch.randn(shape, generator=g) * 0.1
+        else:
+            fan_out = shape[0] * shape[2] * shape[3]
+            sd[k] = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
+    net.load_state_dict(sd)
+    images = torch.rand(2, 3, 64, 96, generator=g) * 255
+    got = net(images)
+    with torch.no_grad():
+        want = br.resnet50(sd, br.normalize(images, cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+    assert list(got) == ["res2", "res3", "res4", "res5"]
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        rel = util.maxdiff(got[k], want[k]) / float(want[k].abs().max())
+        assert rel <= 1e-4, (k, rel)
+    assert {k: (v.channels, v.stride) for k, v in net.output_shape().items()} == {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5": (2048, 32)}
