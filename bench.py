@@ -217,6 +217,38 @@ def measure_from_rgb(dev, B: int, head, match, dbatch, hp, iters: int = 3):
             "camera head from RGB, synthetic plane lists", "note": "first version of the backbone (residual add unfused); reported, not the headline"}
 
 
+def run_side_measurement(which: str, B: int, timeout_s: int):
+    """`python bench.py --side <which> --pairs B` in a child process; returns its JSON dict or {"error": ...}."""
+    try:
+        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--side", which, "--pairs", str(B)], capture_output=True,
+                             text=True, timeout=timeout_s, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
+        for ln in reversed(res.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                return json.loads(ln)
+        return {"error": f"child exited {res.returncode}: {(res.stderr or res.stdout)[-160:]}"}
+    except subprocess.TimeoutExpired:
+        return {"error": f"timed out after {timeout_s} s"}
+    except Exception as e:  # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"[:200]}
+
+
+def side_main(args):
+    """Child-process entry of the side measurements (own CUDA context)."""
+    from nopesac_b200 import synthetic
+    from tests import util
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    B = args.pairs
+    if args.side == "from_rgb":
+        head, match, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+        hp = synthetic.all_pairs_hypotheses(PLANES, NQ).to(dev, torch.int32)
+        dbatch = synthetic.make_batch(0, B, PLANES).to(dev)
+        out = measure_from_rgb(dev, B, head, match, dbatch, hp)
+    else:
+        out = measure_plane_lists(dev, 2 * B)
+    print(json.dumps(out), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,7 +259,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: skip the e2e / roofline / cpu legs")
     ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs timed by the cpu_baseline leg")
+    ap.add_argument("--side", default=None, choices=["from_rgb", "plane_lists"], help="internal: one side measurement, one JSON dict")
     args = ap.parse_args()
+    if args.side:
+        side_main(args)
+        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -434,13 +470,12 @@ def main():
             plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     # row f2: the same step started at RGB (ResNet-50 backbone of both views + camera head) — the stage set S5' of DESIGN.md
-    # §5.  Reported beside `value` (whose stage set S4 starts at the backbone feature maps), never instead of it.
+    # §5.  Reported beside `value` (whose stage set S4 starts at the backbone feature maps), never instead of it.  This path has
+    # not met a GPU before this run, so it is measured in a CHILD process with a timeout: a hang or a sticky CUDA error there
+    # cannot take this line down.
     from_rgb = None
-    if rank == 0:
-        try:
-            from_rgb = measure_from_rgb(dev, B, head, match, dbatch, hp)
-        except Exception as e:   # never let the side measurement take the bench line down
-            from_rgb = {"error": f"{type(e).__name__}: {e}"[:200]}
+    if rank == 0 and world == 1:
+        from_rgb = run_side_measurement("from_rgb", B, timeout_s=240)
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,

@@ -8,7 +8,7 @@ import torch
 
 from tests import util
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]   # code that has not met a GPU yet: never hang the run
 
 
 def _gpu():
