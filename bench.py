@@ -352,6 +352,38 @@ def main():
         pose_err = {"T_median_m": pm["T median err"], "T_mean_m": pm["T mean err"], "R_median_deg": pm["R median err"],
                     "R_mean_deg": pm["R mean err"], "pairs": B, "note": "random-init weights vs planted GT: reported, not a target"}
 
+    # ------------------------------------------------------------------ multi-GPU: the exchanged rows are the right rows
+    # (replaces the reference's pickled comm.gather, mp3d_evaluation.py:317-318; SURVEY.md §4 "all-gather equality vs
+    # single-rank concatenation").  One extra step outside the timed region: (1) the rows the fused NVLink exchange left in
+    # this rank's buffer == one NCCL all-gather of every rank's local rows, bit for bit, on EVERY rank; (2) the LAST rank
+    # recomputes rank 0's shard from rank 0's seeds on its own GPU and compares it with rows [0, B) it received.
+    exchange_check = None
+    if world > 1:
+        out = head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp,
+                   result_exchange=exchange)
+        local_rows = out[5]["pose"].contiguous()
+        got = exchange.finish().clone() if exchange is not None else None
+        ref = torch.empty(world * B, 16, device=dev)
+        dist.all_gather_into_tensor(ref, local_rows)
+        if got is None:
+            got = ref
+        same = bool(torch.equal(got, ref)) and bool(torch.equal(ref[rank * B:(rank + 1) * B], local_rows))
+        rec_equal, rec_diff = True, 0.0
+        if rank == world - 1:
+            h0 = synthetic.make_batch(0, B, PLANES).to(dev)
+            g1, g2 = synthetic.device_features(B, dev, seed=7)
+            r0 = head(g1, g2, h0.planes1, h0.planes2, h0.app1, h0.app2, matching_net=match, hyp_pairs=hp)[5]["pose"]
+            rec_equal = bool(torch.equal(r0, got[:B]))
+            rec_diff = float((r0 - got[:B]).abs().max())
+            del g1, g2
+        flags = torch.tensor([1.0 if same else 0.0, 1.0 if rec_equal else 0.0, -rec_diff], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+        exchange_check = {"exchange_verified": bool(flags[0].item() == 1.0), "ranks": world,
+                          "rows": [world * B, 16], "what": "rows left by the exchange == NCCL all-gather of the local rows (torch.equal, "
+                          "every rank) and each rank's own shard sits at its block offset",
+                          "recompute_of_rank0_shard_on_last_rank": {"bit_equal": bool(flags[1].item() == 1.0),
+                                                                    "max_abs_diff": float(-flags[2].item())}}
+
     if args.only_value:
         if rank == 0:
             print(json.dumps({"metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world,
@@ -488,6 +520,8 @@ def main():
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps, "note": "pinned host inputs; H2D of step i+1 overlaps the kernels of step i"},
         "gpu_launches": launches,
+        "exchange_verified": None if exchange_check is None else exchange_check["exchange_verified"],
+        "exchange_check": exchange_check,
         "roofline": roofline,
         "cpu_baseline": cpu_baseline,
         "pose_err": pose_err,

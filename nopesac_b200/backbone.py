@@ -109,7 +109,9 @@ class ResNet50Backbone(nn.Module):
 
     def prepare(self):
         """FrozenBN folded into the weights, (ky,kx,cin)-ordered fp16 hi/lo planes + fp32 bias per convolution."""
-        if self._packed is None:
+        ver = ops.weights_version(self)
+        if self._packed is None or self._packed_version != ver:
+            self._packed_version = ver
             with torch.no_grad():
                 def pack(cb: _ConvBN):
                     w, b = cb.folded()

@@ -214,7 +214,9 @@ class PlaneCameraHead(nn.Module):
         return super()._apply(fn, *a, **k)
 
     def prepare(self):
-        if self._packed is None:
+        ver = ops.weights_version(self)
+        if self._packed is None or self._packed_version != ver:
+            self._packed_version = ver
             with torch.no_grad():
                 pk = {}
                 if self.cam_ref_on:
@@ -466,6 +468,8 @@ class PlaneCameraHead(nn.Module):
             return output_cameras, trans_list, rot_list, [log_scores_padded], output_planeAss, None
 
         # ------------------------------------------------------------ geo sequences (:513-569)
+        if assignment_override is not None and tuple(assignment_override.shape) != tuple(assignment.shape):
+            raise ValueError(f"assignment_override must be [B,n1,n2] = {tuple(assignment.shape)}, got {tuple(assignment_override.shape)}")
         geo_local, geo_global, sig, geo8, matched_num, pair_idx = ops.geo_sequence(
             planeParam1, planeParam2, assignment if assignment_override is None else assignment_override,
             t0, q0, NQ, hyp_pairs=hyp_pairs)
@@ -475,12 +479,18 @@ class PlaneCameraHead(nn.Module):
         q_h, t_h = ops.pose_heads(fused_rot, fused_tran, self.rots.weight, self.rots.bias,
                                   self.trans.weight, self.trans.bias)
         pk = self.prepare_tc()
+        # 'max-score' picks argmax of the scores themselves: a discrete decision, so it takes the exact-fp32 scoring path
+        # (the single-pass fp16 score MLPs of the tensor-core path move scores by up to ~4e-5 and could flip a near-tie)
+        precision = "fp32" if out_cam_type == "max-score" else "fp16"
+        if precision == "fp32" and result_exchange is not None:
+            raise NotImplementedError("INFERENCE_OUT_CAM_TYPE='max-score' runs the exact-fp32 scoring kernels, which have no fused "
+                                      "result exchange: gather the rows with nopesac_b200.dist.gather_results instead")
         res = ops.score_aggregate(geo_local, q_h.view(B, NQ, 4), t_h.view(B, NQ, 3), q0, t0,
                                   fused_rot.view(B, NQ, 256), fused_tran.view(B, NQ, 256), rot_feat0, trans_feat0,
                                   matched_num, pk["normal_score_proj"], pk["param_score_proj"],
                                   self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
                                   out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
-                                  pack=pk["score_pack"], exchange=result_exchange)
+                                  precision=precision, pack=pk["score_pack"], exchange=result_exchange)
         pose = res["pose"]
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]

@@ -18,8 +18,8 @@ __global__ void geo_sequence_kernel(const float* __restrict__ planes1, const flo
   const int b = blockIdx.x, tid = threadIdx.x;
   if (hyp_pairs) {
     for (int k = tid; k < H; k += blockDim.x) {
-      pairs[2 * k] = hyp_pairs[2 * k];
-      pairs[2 * k + 1] = hyp_pairs[2 * k + 1];
+      pairs[2 * k] = min(max(hyp_pairs[2 * k], 0), n1 - 1);          // caller-supplied indices: clamped, never out of bounds
+      pairs[2 * k + 1] = min(max(hyp_pairs[2 * k + 1], 0), n2 - 1);
     }
     if (tid == 0) s_m = H;
   } else if (tid < 32) {

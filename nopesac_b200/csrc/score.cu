@@ -251,7 +251,7 @@ __device__ int block_arg_extreme(const float* vals, int n, bool want_max, float*
       if (i == 0x7fffffff) continue;
       if ((want_max ? v > best : v < best) || (v == best && i < bi)) { best = v; bi = i; }
     }
-    redi[0] = bi;
+    redi[0] = bi == 0x7fffffff ? 0 : bi;      // no finite candidate (all NaN): hypothesis 0, never an out-of-range index
   }
   __syncthreads();
   const int r = redi[0];

@@ -1031,7 +1031,7 @@ __device__ int block_arg_extreme(const float* vals, int n, bool want_max, float*
       if (i == 0x7fffffff) continue;
       if ((want_max ? v > best : v < best) || (v == best && i < bi)) { best = v; bi = i; }
     }
-    redi[0] = bi;
+    redi[0] = bi == 0x7fffffff ? 0 : bi;      // no finite candidate (all NaN): hypothesis 0, never an out-of-range index
   }
   __syncthreads();
   const int r = redi[0];
@@ -1114,6 +1114,8 @@ score_select_tc_kernel(const SelParams p) {
   // scores (softmax over hypotheses 0..m, :1010-1014, :1039-1043) -> global (optional) + kept for max-score
   float* lr = p.logits + (size_t)b * H1n;
   float* lt = p.logits + (size_t)p.B * H1n + (size_t)b * H1n;
+  // every thread has read the hypothesis-0 logits (l0r / l0t above) before thread 0 overwrites lr[0] / lt[0] with scores
+  __syncthreads();
   if (p.score_rot || p.score_tran || (m > 1 && p.out_cam_type == NSAC_CAM_MAX_SCORE)) {
     for (int h = tid; h <= m; h += blockDim.x) {
       const float a = expf(lr[h] - Mr_) / Sr_;

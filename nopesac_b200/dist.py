@@ -46,10 +46,15 @@ def gather_results(local_rows: torch.Tensor, num_pairs: int, group=None) -> torc
 
 
 class FusedResultExchange:
-    """Result exchange fused into the last kernel of the path: every rank owns a [world*B_local, 16] buffer in
+    """Result exchange fused into the last kernel of the path: every rank owns a [2, world*B_local, 16] buffer in
     symmetric (NVLink peer-mapped) memory; the selection kernel that finishes a pair stores its 64-byte row into the
     corresponding row of EVERY rank's buffer (plain st.global on peer mappings), so no all-gather collective runs —
-    only one cross-rank barrier (`finish()`) before the rows are read.  `rows` is this rank's complete copy.
+    only one cross-rank barrier (`finish()`) before the rows are read.
+
+    Double-buffered by step parity: step i writes slot i & 1.  A fast rank's stores of step i+1 therefore go to the OTHER
+    slot while a slow rank still reads step i; slot i & 1 is only written again in step i+2, which a rank can start only
+    after the barrier of step i+1 — and every rank enqueues that barrier after its own read-out of step i (same stream).
+    So the rows returned by `finish()` stay valid until the `finish()` after next, by protocol, not by timing.
 
     Needs one process per GPU with an initialised NCCL process group and NVLink / P2P access between the GPUs."""
 
@@ -58,15 +63,31 @@ class FusedResultExchange:
         group = group if group is not None else dist.group.WORLD
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
-        self.row_offset = self.rank * pairs_per_rank
-        self.rows = symm_mem.empty((self.world * pairs_per_rank, RESULT_WIDTH), dtype=torch.float32, device=device)
-        self.rows.zero_()
-        self.handle = symm_mem.rendezvous(self.rows, group)
+        self.pairs_per_rank = pairs_per_rank
+        self.slot_rows = self.world * pairs_per_rank
+        self.step = 0
+        self.buf = symm_mem.empty((2 * self.slot_rows, RESULT_WIDTH), dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
         self.peer_ptrs_dev = int(self.handle.buffer_ptrs_dev)     # device array of `world` float* (one per rank)
         torch.cuda.synchronize(device)
         dist.barrier(group)
 
+    @property
+    def row_offset(self) -> int:
+        """First row (in every rank's buffer) of this rank's shard in the slot of the current step."""
+        return (self.step & 1) * self.slot_rows + self.rank * self.pairs_per_rank
+
+    @property
+    def rows(self) -> torch.Tensor:
+        """The current step's slot: this rank's complete [world*B_local, 16] copy once `finish()` has run."""
+        s = (self.step & 1) * self.slot_rows
+        return self.buf[s:s + self.slot_rows]
+
     def finish(self) -> torch.Tensor:
-        """Cross-rank barrier on the current stream: afterwards `rows` holds the rows of all ranks."""
+        """Cross-rank barrier on the current stream: afterwards the returned slot holds the rows of all ranks (valid until
+        the `finish()` after next).  Advances to the other slot."""
         self.handle.barrier(channel=0)
-        return self.rows
+        out = self.rows
+        self.step += 1
+        return out

@@ -82,7 +82,9 @@ class MatchingHead(nn.Module):
 
     def prepare(self):
         """Fused QKV / KV weight matrices (built once; invalidated by load_state_dict / .to())."""
-        if self._packed is None:
+        ver = ops.weights_version(self)
+        if self._packed is None or self._packed_version != ver:
+            self._packed_version = ver
             with torch.no_grad():
                 pk = []
                 for lyr in self.gnn.layers:

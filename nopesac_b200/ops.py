@@ -50,6 +50,18 @@ def _c(t: torch.Tensor, name: str, dtype=torch.float32):
     return _chk(t, name, dtype).contiguous()
 
 
+def weights_version(module) -> int:
+    """Sum of the in-place version counters of a module's parameters and buffers: changes whenever any of them is
+    modified in place (`p.data.copy_()`, `p.mul_()`, BN running-stat edits ...), so packed weight copies keyed on it
+    can never go stale silently."""
+    v = 0
+    for t in module.parameters():
+        v += t._version
+    for t in module.buffers():
+        v += t._version
+    return v
+
+
 def linear(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE,
            out: Optional[torch.Tensor] = None, bias_group_rows: int = 0) -> torch.Tensor:
     """out[M,N] = act(x[M,K] @ w[N,K]^T + bias).  `x` / `out` may be column slices of wider row-major

@@ -75,7 +75,10 @@ class PairPipeline:
         self.done[slot].record(cur)
 
     def run(self, host_batches: Iterable[Dict]) -> Iterator[torch.Tensor]:
-        """Yields the pinned [B,16] result rows of every batch, in order."""
+        """Yields the pinned [B,16] result rows of every batch, in order.
+
+        The yielded tensor is one of TWO reused pinned buffers: it is overwritten two steps later.  Consume it inside the
+        loop body, or `.clone()` it — `list(pipe.run(...))` keeps references to buffers that are rewritten."""
         it = iter(host_batches)
         try:
             nxt = next(it)

@@ -19,14 +19,20 @@ poses = [util.initial_pose_for(200 + rank * B + i) for i in range(B)]
 ip = (torch.cat([p[0] for p in poses]).to(dev), torch.cat([p[1] for p in poses]).to(dev))
 ex = FusedResultExchange(B, dev)
 ok = True
-for it in range(3):
-    out = head(None, None, b.planes1, b.planes2, b.app1, b.app2, matching_net=match, initial_pose=ip, result_exchange=ex)
-    rows = ex.finish().clone()
+prev_rows = prev_ref = None
+for it in range(6):
+    # different inputs every step (so a stale slot cannot pass), a deliberately late rank on odd steps
+    bb = synthetic.make_batch(1000 * it + rank * B, B, P).to(dev)
+    if it % 2 == 1 and rank == world - 1:
+        torch.cuda._sleep(20_000_000)          # ~10 ms of device time: the other ranks run ahead into the next step
+    out = head(None, None, bb.planes1, bb.planes2, bb.app1, bb.app2, matching_net=match, initial_pose=ip, result_exchange=ex)
+    rows = ex.finish()                          # NOT cloned: the slot must stay valid through the next step (double buffer)
     ref = gather_results(out[5]["pose"].contiguous(), world * B)
     torch.cuda.synchronize()
-    same = bool(torch.equal(rows, ref))
-    ok = ok and same
-    dist.barrier()
+    ok = ok and bool(torch.equal(rows, ref))
+    if prev_rows is not None:                   # the previous step's slot is untouched by this step's peer stores
+        ok = ok and bool(torch.equal(prev_rows, prev_ref))
+    prev_rows, prev_ref = rows, ref
 flag = torch.tensor([1 if ok else 0], device=dev)
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
