@@ -3,21 +3,24 @@
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
-A "step" = one pass of the hot path (PlaneCameraHead.inference_Joint incl. the matching head: pixel pose
-network -> AIM -> GNN + Sinkhorn matcher -> geo sequences -> hypothesis generation -> scoring -> soft
-aggregation -> assignment pruning; stage set S4 of SURVEY.md §8d) over one batch of synthetic pairs.
-Workload at every N: BASELINE.json configs[1] per GPU — 64 pairs, 16 planes/view, NUM_OBJECT_QUERIES = 256 with
-all 16x16 candidate plane pairs as one-plane hypotheses (257 hypotheses x 256 residual columns per pair),
-backbone feature maps of a 480x640 input.  N > 1 (torchrun): pairs are sharded 64/GPU (weak scaling) and
-every step ends with ONE NCCL all-gather of the [64,16] per-pair results — the only collective of the path.
+A "step" = one pass of the path over one batch of synthetic pairs, from RGB (stage set S5 of SURVEY.md §8d, BASELINE.json
+configs[1]): uint8 480x640 images of both views -> ResNet-50 backbone (random init) -> PlaneCameraHead.inference_Joint incl.
+the matching head (pixel pose network -> AIM -> GNN + Sinkhorn matcher -> geo sequences -> hypothesis generation -> scoring ->
+soft aggregation -> assignment pruning).  Per GPU: 64 pairs, 16 planes/view, NUM_OBJECT_QUERIES = 256 with all 16x16
+candidate plane pairs as one-plane hypotheses (257 hypotheses x 256 residual columns per pair).  The plane lists (what
+PlaneTRHead + post-processing produce) are synthetic inputs.  N > 1 (torchrun): pairs are sharded 64/GPU (weak scaling), the
+[64,16] result rows are exchanged by the fused NVLink store of the selection kernel (or one NCCL all-gather) — the only
+exchange of the path — and the gathered rows are verified after the timed loop (`exchange_verified`).
 
-value    pairs/s with all inputs resident in HBM (inputs 2.2 GB/GPU >> 126 MB L2: no flush needed).
-e2e      pairs/s through the same public call with HOST (pinned) inputs: H2D of the step's inputs and D2H of the
-         [B,16] result inside the timed region.
-roofline the hypothesis-scoring kernel (nsac_score_aggregate) timed alone with CUDA events on a launch that
-         moves > 256 MB (B=512, m=NQ=256), algorithmic bytes of SURVEY.md §8d over measured HBM copy bandwidth.
-cpu_baseline / --impl reference: the CPU oracle port (oracle/restate.py — the reference is Python and cannot
-         travel to the GPU box) on the host cores, per-pair loop at batch size 1 like the reference.
+value    pairs/s, inputs resident in HBM; an L2 flush (256 MB write) separates the timed steps.
+e2e      pairs/s through the same public call with HOST (pinned) inputs: H2D of the step's uint8 images + plane lists and D2H of
+         the [B,16] result rows inside the timed region.
+roofline the hypothesis-scoring call (nsac_score_aggregate_tc) timed alone with CUDA events on a launch that moves > 256 MB
+         (B=512, m=NQ=256), algorithmic bytes of SURVEY.md §8d over the measured HBM copy bandwidth.  `score_sweep` repeats it
+         for BASELINE.json configs[4] (32/128/512/2048 hypotheses) with both bounds; `roofline_tensor` times the GEMM engine
+         (most of the step) on its three shape classes against the measured bf16 peak.
+cpu_baseline / --impl reference: the CPU oracle port (oracle/backbone_restate.py + oracle/restate.py — the reference is Python
+         and cannot travel to the GPU box) on the host cores, per-pair loop at batch size 1 like the reference, same stage set.
 """
 from __future__ import annotations
 
@@ -39,9 +42,11 @@ import torch  # noqa: E402
 PAIRS_PER_GPU = 64
 PLANES = 16
 NQ = 256
-WORKLOAD = ("camera head S4 (pixel pose net + AIM + GNN/Sinkhorn matcher + 256 one-plane hypotheses + scoring + soft "
-            "aggregation + pruning), 64 synthetic 480x640 pairs/GPU, 16 planes/view, NUM_OBJECT_QUERIES=256 (all 16x16 "
-            "plane pairs as hypotheses), fp32, random-init weights, from backbone feature maps")
+IMG_H, IMG_W = 480, 640
+WORKLOAD = ("full model from RGB, stage set S5: ResNet-50 backbone (random init, FrozenBN) on both uint8 480x640 views + camera "
+            "head (pixel pose net + AIM + GNN/Sinkhorn matcher + 256 one-plane hypotheses + scoring + soft aggregation + "
+            "pruning), 64 synthetic pairs/GPU, 16 planes/view, NUM_OBJECT_QUERIES=256 (all 16x16 plane pairs as hypotheses), "
+            "fp32-grade arithmetic (3-pass fp16 hi/lo tensor-core GEMMs), random-init weights, synthetic plane lists")
 METRIC = "image-pairs/sec (480x640, 16 planes x 256 hyp)"
 
 
@@ -50,6 +55,12 @@ def score_algorithmic_bytes(B, m, nq):
     per_pair = 24 * m + 2076 * (m + 1) + 68
     weights = 8 * (nq * 128 + 128 + 128 * 128 + 128 + 128 * 64 + 64 + 64 + 1)
     return B * per_pair + weights
+
+
+def score_algorithmic_flops(B, m, nq):
+    """SURVEY.md §8(d) "Algorithmic FLOPs": residuals ~2*45*(m+1)*m, both score MLPs 2*2*(m+1)*(nq*128 + 128^2 + 128*64 + 64),
+    aggregation 2*2*C*(m+1)."""
+    return B * (2 * 45 * (m + 1) * m + 4 * (m + 1) * (nq * 128 + 128 * 128 + 128 * 64 + 64) + 4 * 256 * (m + 1))
 
 
 class ClockSampler:
@@ -102,31 +113,45 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return {"hbm": float(d["hbm_gbs"]), "tf_burst": float(d["bf16_tflops"]), "tf_sustained": float(d["bf16_tflops_sustained"]),
+                "src": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback (B200_PROFILING.md)"}
 
 
 # ---------------------------------------------------------------------------------------------------
+def backbone_state():
+    """Seeded random-init R-50 state shared by both arms (shapes from the product's own module)."""
+    from nopesac_b200 import backbone, synthetic
+    shapes = {k: tuple(v.shape) for k, v in backbone.ResNet50Backbone().state_dict().items()}
+    return synthetic.make_backbone_weights(shapes, seed=8)
+
+
 def cpu_reference_pairs_per_s(num_pairs: int, threads: int, warm: int = 1):
-    """The oracle port on the host: per-pair loop at bs=1 (the only mode the reference supports), same
-    workload shape, same weights."""
+    """The oracle port on the host, same stage set S5: per-pair loop at bs=1 (the only mode the reference supports) — R-50 on
+    both views (oracle/backbone_restate.py), then the camera head (oracle/restate.py) — same workload shape, same weights."""
+    from oracle import backbone_restate as br
     from oracle import restate
-    from nopesac_b200 import synthetic
+    from nopesac_b200 import config, synthetic
     from tests import util
     torch.set_num_threads(threads)
+    cfg = config.inference_cfg(NQ)
     sd, msd = util.make_weights(NQ)
+    bsd = backbone_state()
     hp = synthetic.all_pairs_hypotheses(PLANES, NQ)
-    batches = [synthetic.make_batch(1000 + i, 1, PLANES, with_features=True) for i in range(num_pairs + warm)]
+    batches = [synthetic.make_batch(1000 + i, 1, PLANES) for i in range(num_pairs + warm)]
+    images = [synthetic.make_images(5000 + i, 2, IMG_H, IMG_W) for i in range(num_pairs + warm)]
 
-    def one(b):
+    def one(b, im):
         with torch.no_grad():
-            return restate.inference_joint(sd, msd, b.feats1, b.feats2, b.planes1, b.planes2, b.app1, b.app2,
-                                           num_queries=NQ, hyp_pairs=hp)
-    for b in batches[:warm]:
-        one(b)
+            f = br.resnet50(bsd, br.normalize(im.float(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+            f1 = {k: v[0:1] for k, v in f.items()}
+            f2 = {k: v[1:2] for k, v in f.items()}
+            return restate.inference_joint(sd, msd, f1, f2, b.planes1, b.planes2, b.app1, b.app2, num_queries=NQ, hyp_pairs=hp)
+    for b, im in zip(batches[:warm], images[:warm]):
+        one(b, im)
     t0 = time.perf_counter()
-    for b in batches[warm:]:
-        one(b)
+    for b, im in zip(batches[warm:], images[warm:]):
+        one(b, im)
     dt = time.perf_counter() - t0
     return num_pairs / dt, dt
 
@@ -135,7 +160,7 @@ def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 4
+    sample = 2
     vals = []
     for _ in range(args.warmup if args.warmup < 2 else 1):
         cpu_reference_pairs_per_s(1, threads, warm=1)
@@ -145,12 +170,13 @@ def run_reference_arm(args, rank, world):
         vals.append(v)
     wall = time.perf_counter() - t_all
     value = statistics.mean(vals)
-    desc = f"{sample} pairs/step x {args.steps} steps of the same workload, per-pair loop at batch size 1"
+    desc = f"{sample} pairs/step x {args.steps} steps of the same workload (S5: R-50 on both views + camera head), per-pair loop at batch size 1"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sample / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "pairs_per_step": sample, "device": "cpu"},
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": PAIRS_PER_GPU, "planes_per_view": PLANES, "num_object_queries": NQ,
+                   "stage_set": "S5", "pairs_per_step": sample, "device": "cpu"},
         "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "wall_s": wall,
@@ -184,69 +210,102 @@ def measure_plane_lists(dev, images: int, iters: int = 10):
             "note": "row f1, both views of this rank's pairs; outside the timed region of `value`"}
 
 
-def measure_from_rgb(dev, B: int, head, match, dbatch, hp, iters: int = 3):
-    """pairs/s of RGB -> ResNet-50 (random init, both views = 2B images of 480x640) -> camera head, inputs resident in HBM,
-    CUDA events on the launch stream after 2 warm-ups."""
-    from nopesac_b200 import backbone, config
-    net = backbone.build_backbone(config.inference_cfg())
-    with torch.no_grad():                              # random init: damp the residual branches so res5 stays O(1) like a trained net
-        for name, buf in net.named_buffers():
-            if name.endswith("conv3.norm.weight"):
-                buf.mul_(0.3)
-    net = net.to(dev)
-    g = torch.Generator(device=dev).manual_seed(1)
-    images = torch.rand(2 * B, 3, 480, 640, device=dev, generator=g) * 255
-
-    def step():
-        feats = net(images)
-        f1 = {k: v[:B] for k, v in feats.items()}
-        f2 = {k: v[B:] for k, v in feats.items()}
-        return head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp)
-
-    for _ in range(2):
-        step()
+def graph_timed(fn, reps: int, flush=None):
+    """ms per call of `fn` (a short chain of kernel launches): captured once in a CUDA graph, replays timed with CUDA events on the
+    replay stream (launched eagerly from Python the host side is slower than such kernels).  `flush`: tensor zeroed before
+    every replay (inputs that fit in L2), outside the timed events."""
+    for _ in range(3):
+        fn()
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(iters):
-        step()
-    e1.record()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        fn()
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        fn()
+    graph.replay()
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / iters
-    return {"value": B / ms * 1e3, "unit": "pairs/s", "ms_per_step": ms, "pairs": B, "stage_set": "S5' = ResNet-50 backbone (random init) + "
-            "camera head from RGB, synthetic plane lists", "note": "first version of the backbone (residual add unfused); reported, not the headline"}
+    times = []
+    for _ in range(reps):
+        if flush is not None:
+            flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        graph.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    return statistics.mean(times)
 
 
-def run_side_measurement(which: str, B: int, timeout_s: int):
-    """`python bench.py --side <which> --pairs B` in a child process; returns its JSON dict or {"error": ...}."""
-    try:
-        res = subprocess.run([sys.executable, os.path.abspath(__file__), "--side", which, "--pairs", str(B)], capture_output=True,
-                             text=True, timeout=timeout_s, env={**os.environ, "WORLD_SIZE": "1", "RANK": "0", "LOCAL_RANK": "0"})
-        for ln in reversed(res.stdout.strip().splitlines()):
-            if ln.startswith("{"):
-                return json.loads(ln)
-        return {"error": f"child exited {res.returncode}: {(res.stderr or res.stdout)[-160:]}"}
-    except subprocess.TimeoutExpired:
-        return {"error": f"timed out after {timeout_s} s"}
-    except Exception as e:  # noqa: BLE001
-        return {"error": f"{type(e).__name__}: {e}"[:200]}
-
-
-def side_main(args):
-    """Child-process entry of the side measurements (own CUDA context)."""
-    from nopesac_b200 import synthetic
+def score_case(dev, B, nq, head=None):
+    """Inputs + closure of one nsac_score_aggregate_tc call (K8+K9) with m = nq valid hypotheses per pair."""
+    from nopesac_b200 import ops
     from tests import util
-    dev = torch.device("cuda", 0)
-    torch.cuda.set_device(dev)
-    B = args.pairs
-    if args.side == "from_rgb":
-        head, match, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
-        hp = synthetic.all_pairs_hypotheses(PLANES, NQ).to(dev, torch.int32)
-        dbatch = synthetic.make_batch(0, B, PLANES).to(dev)
-        out = measure_from_rgb(dev, B, head, match, dbatch, hp)
-    else:
-        out = measure_plane_lists(dev, 2 * B)
-    print(json.dumps(out), flush=True)
+    if head is None:
+        head, _, _, _ = util.build_cuda_heads(nq, "soft", 0.2, dev)
+    g = torch.Generator(device=dev).manual_seed(3)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo_local = rnd(B, nq, 6)
+    q_h = torch.nn.functional.normalize(rnd(B, nq, 4), dim=-1)
+    t_h = rnd(B, nq, 3) * 0.3
+    q0 = torch.nn.functional.normalize(rnd(B, 4), dim=-1)
+    t0 = rnd(B, 3) * 0.3
+    fr, ft = rnd(B, nq, 256), rnd(B, nq, 256)
+    fr0, ft0 = rnd(B, 256), rnd(B, 256)
+    mnum = torch.full((B,), nq, device=dev, dtype=torch.int32)
+    pk = head.prepare_tc()
+
+    def once():
+        return ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
+                                   pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
+                                   head.trans.bias, out_cam_type="soft", want_scores=False, pack=pk["score_pack"])
+    return once
+
+
+def measure_gemm_engine(dev, peaks):
+    """The GEMM engine (nsac_gemm_split / nsac_conv3x3_split, 3 MMA passes on fp16 hi/lo planes) on its three shape classes,
+    CUDA events around back-to-back launches on the launch stream; tensor-pipe work = 3 x 2MNK."""
+    from nopesac_b200 import ops
+    g = torch.Generator(device=dev).manual_seed(0)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    out = []
+
+    def timed(fn, flops, name, reps=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        tf = 3 * flops / ms / 1e9
+        out.append({"shape": name, "us": ms * 1e3, "tflops_tensor": tf, "tflops_fp32_equivalent": tf / 3,
+                    "frac_of_bf16_sustained": tf / peaks["tf_sustained"]})
+
+    M, N, K = PAIRS_PER_GPU * NQ, 1024, 1024
+    a, w = ops.split(rnd(M, K)), ops.split(rnd(N, K) * 0.03)
+    o = ops.Split.empty(M, N, dev)
+    timed(lambda: ops.gemm_tc(a, w, None, ops.ACT_RELU, want_f32=False, out_split=o), 2.0 * M * N * K,
+          f"K7 hypothesis-generation layer {M}x{N}x{K}")
+    Ni, H, W, C = 2 * PAIRS_PER_GPU, 60, 80, 256
+    x, wc = ops.split(rnd(Ni * H * W, C)), ops.split(rnd(C, 9 * C) * 0.02)
+    timed(lambda: ops.conv3x3_tc(x, Ni, H, W, wc, None, ops.ACT_LEAKY, want_f32=False, want_split=True),
+          2.0 * Ni * H * W * C * 9 * C, f"K1 3x3 convolution {Ni}x{H}x{W} {C}->{C} (implicit GEMM)")
+    M, N, K = 2 * PAIRS_PER_GPU * PLANES, 256, 256
+    a2, w2 = ops.split(rnd(M, K)), ops.split(rnd(N, K) * 0.06)
+    timed(lambda: ops.gemm_tc(a2, w2), 2.0 * M * N * K, f"K4 GNN linear {M}x{N}x{K} (launch-bound)", reps=50)
+    best = max(out, key=lambda r: r["tflops_tensor"])
+    return {"kernel": "gemm_bf16x3_kernel (tcgen05 / TMA / TMEM; 3 MMA passes hi.hi + lo.hi + hi.lo on fp16 planes ~ fp32)",
+            "bound": "tensor", "achieved": best["tflops_tensor"], "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
+            "frac": best["tflops_tensor"] / peaks["tf_sustained"], "peak_source": peaks["src"] + " bf16_tflops_sustained",
+            "precision": "3-pass fp16 (tensor work = 3 x 2MNK; fp32-equivalent throughput = achieved / 3)", "traffic": None,
+            "shapes": out, "timing": "CUDA events around back-to-back launches on the launch stream"}
 
 
 def main():
@@ -258,12 +317,8 @@ def main():
     ap.add_argument("--pairs", type=int, default=PAIRS_PER_GPU, help="pairs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-value", action="store_true", help="profiling runs: skip the e2e / roofline / cpu legs")
-    ap.add_argument("--cpu-pairs", type=int, default=8, help="pairs timed by the cpu_baseline leg")
-    ap.add_argument("--side", default=None, choices=["from_rgb", "plane_lists"], help="internal: one side measurement, one JSON dict")
+    ap.add_argument("--cpu-pairs", type=int, default=4, help="pairs timed by the cpu_baseline leg")
     args = ap.parse_args()
-    if args.side:
-        side_main(args)
-        return
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
@@ -274,7 +329,7 @@ def main():
         return
 
     import torch.distributed as dist
-    from nopesac_b200 import ops, synthetic
+    from nopesac_b200 import config, meta_arch, ops, synthetic
     from tests import util   # seeded weights (shapes from tests/golden/state_shapes.json)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
@@ -284,11 +339,21 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     B = args.pairs
 
-    head, match, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    # the reference's META_ARCH with its backbone (configs/Base.yaml:2-12) + camera head + matching head, seeded random weights
+    cfg = config.inference_cfg(NQ, "soft", 0.2)
+    model = meta_arch.PlaneTR_NopeSAC(cfg, with_backbone=True)
+    sd, msd = util.make_weights(NQ)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    model.backbone.load_state_dict(backbone_state())
+    model = model.to(dev)
+    head, match = model.camera_head_list[0], model.matching_head
+
     hp = synthetic.all_pairs_hypotheses(PLANES, NQ).to(dev, torch.int32)
-    host = synthetic.make_batch(rank * B, B, PLANES)                 # planes / appearance: seeded on the host
-    f1, f2 = synthetic.device_features(B, dev, seed=7 + rank)       # 2.2 GB of feature maps: drawn on the device
+    host = synthetic.make_batch(rank * B, B, PLANES)                          # planes / appearance: seeded on the host
+    host_images = synthetic.make_images(7000 + rank, 2 * B, IMG_H, IMG_W)     # uint8 [2B,3,480,640]: first views, then second views
     dbatch = host.to(dev)
+    images = host_images.to(dev)
     gathered = torch.empty(world * B, 16, device=dev) if world > 1 else None
     exchange, exchange_kind = None, "single GPU: no exchange"
     if world > 1:
@@ -298,14 +363,17 @@ def main():
                 from nopesac_b200.dist import FusedResultExchange
                 exchange = FusedResultExchange(B, dev)
                 exchange_kind = ("fused: the selection kernel stores each result row into every rank's buffer over NVLink "
-                                 "peer memory (symmetric memory) + one cross-rank barrier per step; no collective")
+                                 "peer memory (symmetric memory, double-buffered by step parity) + one cross-rank barrier per "
+                                 "step; no collective")
             except Exception as e:  # noqa: BLE001  (no P2P / symmetric memory on this box)
                 exchange = None
                 exchange_kind += f" (fused exchange unavailable: {type(e).__name__})"
 
-    def step(p1, p2, a1, a2, fa, fb):
-        out = head(fa, fb, p1, p2, a1, a2, matching_net=match, hyp_pairs=hp, result_exchange=exchange)
-        pose = out[5]["pose"]
+    def forward(img, p1, p2, a1, a2, ex=None):
+        return model.inference_from_images(img, None, p1, p2, a1, a2, hyp_pairs=hp, result_exchange=ex)
+
+    def step(img, p1, p2, a1, a2):
+        pose = forward(img, p1, p2, a1, a2, exchange)[5]["pose"]
         if exchange is not None:
             return exchange.finish()
         if world > 1:
@@ -319,8 +387,9 @@ def main():
         torch.cuda.synchronize()
 
     # ------------------------------------------------------------------ value: inputs resident in HBM
+    flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)        # > 126 MB L2
     for _ in range(args.warmup):
-        step(dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, f1, f2)
+        step(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -330,7 +399,8 @@ def main():
     barrier()
     e0.record()
     for _ in range(args.steps):
-        step(dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, f1, f2)
+        flush.zero_()
+        step(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -342,16 +412,6 @@ def main():
     ms_total = float(t.item())
     value = world * B * args.steps / (ms_total / 1e3)
 
-    # pose error of this rank's pairs against the planted ground truth (reference formulas, mp3d_evaluation.py:382-425,
-    # computed on the device by nopesac_b200.evaluation): reported, not a target - the weights are random
-    pose_err = None
-    if rank == 0:
-        from nopesac_b200 import evaluation
-        rows = head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp)[5]["pose"]
-        pm = evaluation.camera_metrics(rows, dbatch.gt_tran, dbatch.gt_quat)
-        pose_err = {"T_median_m": pm["T median err"], "T_mean_m": pm["T mean err"], "R_median_deg": pm["R median err"],
-                    "R_mean_deg": pm["R mean err"], "pairs": B, "note": "random-init weights vs planted GT: reported, not a target"}
-
     # ------------------------------------------------------------------ multi-GPU: the exchanged rows are the right rows
     # (replaces the reference's pickled comm.gather, mp3d_evaluation.py:317-318; SURVEY.md §4 "all-gather equality vs
     # single-rank concatenation").  One extra step outside the timed region: (1) the rows the fused NVLink exchange left in
@@ -359,8 +419,7 @@ def main():
     # recomputes rank 0's shard from rank 0's seeds on its own GPU and compares it with rows [0, B) it received.
     exchange_check = None
     if world > 1:
-        out = head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp,
-                   result_exchange=exchange)
+        out = forward(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, exchange)
         local_rows = out[5]["pose"].contiguous()
         got = exchange.finish().clone() if exchange is not None else None
         ref = torch.empty(world * B, 16, device=dev)
@@ -371,11 +430,11 @@ def main():
         rec_equal, rec_diff = True, 0.0
         if rank == world - 1:
             h0 = synthetic.make_batch(0, B, PLANES).to(dev)
-            g1, g2 = synthetic.device_features(B, dev, seed=7)
-            r0 = head(g1, g2, h0.planes1, h0.planes2, h0.app1, h0.app2, matching_net=match, hyp_pairs=hp)[5]["pose"]
+            im0 = synthetic.make_images(7000, 2 * B, IMG_H, IMG_W).to(dev)
+            r0 = forward(im0, h0.planes1, h0.planes2, h0.app1, h0.app2)[5]["pose"]
             rec_equal = bool(torch.equal(r0, got[:B]))
             rec_diff = float((r0 - got[:B]).abs().max())
-            del g1, g2
+            del im0
         flags = torch.tensor([1.0 if same else 0.0, 1.0 if rec_equal else 0.0, -rec_diff], device=dev)
         dist.all_reduce(flags, op=dist.ReduceOp.MIN)
         exchange_check = {"exchange_verified": bool(flags[0].item() == 1.0), "ranks": world,
@@ -383,6 +442,16 @@ def main():
                           "every rank) and each rank's own shard sits at its block offset",
                           "recompute_of_rank0_shard_on_last_rank": {"bit_equal": bool(flags[1].item() == 1.0),
                                                                     "max_abs_diff": float(-flags[2].item())}}
+
+    # pose error of this rank's pairs against the planted ground truth (reference formulas, mp3d_evaluation.py:382-425,
+    # computed on the device by nopesac_b200.evaluation): reported, not a target - the weights are random
+    pose_err = None
+    if rank == 0:
+        from nopesac_b200 import evaluation
+        rows = forward(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2)[5]["pose"]
+        pm = evaluation.camera_metrics(rows, dbatch.gt_tran, dbatch.gt_quat)
+        pose_err = {"T_median_m": pm["T median err"], "T_mean_m": pm["T mean err"], "R_median_deg": pm["R median err"],
+                    "R_mean_deg": pm["R mean err"], "pairs": B, "note": "random-init weights vs planted GT: reported, not a target"}
 
     if args.only_value:
         if rank == 0:
@@ -393,12 +462,11 @@ def main():
         return
 
     # ------------------------------------------------------------------ e2e: host (pinned) inputs
-    # Same public call, inputs in pinned host memory: every step copies its 2.2 GB of inputs H2D and reads the
-    # [B,16] result rows back; nopesac_b200.runtime.PairPipeline overlaps the copy of step i+1 with the kernels of
-    # step i (two device slots, copy stream + events).
+    # Same public call, inputs in pinned host memory: every step copies its uint8 images (2 x 64 x 3 x 480 x 640 = 118 MB) and
+    # plane lists H2D and reads the [B,16] result rows back; nopesac_b200.runtime.PairPipeline overlaps the copy of step i+1
+    # with the kernels of step i (two device slots, copy stream + events).
     from nopesac_b200.runtime import PairPipeline, batch_bytes, pin_batch
-    hbatch = pin_batch({"planes1": host.planes1, "planes2": host.planes2, "app1": host.app1, "app2": host.app2,
-                        "feats1": {k: v.cpu() for k, v in f1.items()}, "feats2": {k: v.cpu() for k, v in f2.items()}})
+    hbatch = pin_batch({"images": host_images, "planes1": host.planes1, "planes2": host.planes2, "app1": host.app1, "app2": host.app2})
     h2d = batch_bytes(hbatch)
     d2h = (world * B if world > 1 else B) * 16 * 4
     post = None
@@ -408,7 +476,8 @@ def main():
                 return exchange.finish()
             dist.all_gather_into_tensor(gathered, rows)
             return gathered
-    pipe = PairPipeline(head, match, dev, hyp_pairs=hp, post=post, result_exchange=exchange)
+    pipe = PairPipeline(head, match, dev, post=post,
+                        compute=lambda d: forward(d["images"], d["planes1"], d["planes2"], d["app1"], d["app2"], exchange)[5]["pose"])
     e2e_steps = max(3, min(args.steps, 6))
     for _ in pipe.run([hbatch] * 2):
         pass
@@ -429,48 +498,32 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ------------------------------------------------------------------ roofline: scoring kernel alone
-    peak, peak_src = measured_peaks()
-    RB, m = 512, NQ
-    g = torch.Generator(device=dev).manual_seed(3)
-    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
-    geo_local = rnd(RB, NQ, 6)
-    q_h = torch.nn.functional.normalize(rnd(RB, NQ, 4), dim=-1)
-    t_h = rnd(RB, NQ, 3) * 0.3
-    q0 = torch.nn.functional.normalize(rnd(RB, 4), dim=-1)
-    t0 = rnd(RB, 3) * 0.3
-    fr, ft = rnd(RB, NQ, 256), rnd(RB, NQ, 256)
-    fr0, ft0 = rnd(RB, 256), rnd(RB, 256)
-    mnum = torch.full((RB,), m, device=dev, dtype=torch.int32)
-    pk = head.prepare_tc()
+    # ------------------------------------------------------------------ S4 for continuity with round 1 (camera head from feature maps)
+    s4 = None
+    try:
+        f1, f2 = synthetic.device_features(B, dev, seed=7)
+        run4 = lambda: head(f1, f2, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2, matching_net=match, hyp_pairs=hp)
+        for _ in range(3):
+            run4()
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(5):
+            run4()
+        e1.record()
+        torch.cuda.synchronize()
+        ms4 = e0.elapsed_time(e1) / 5
+        s4 = {"value": B / ms4 * 1e3, "unit": "pairs/s", "ms_per_step": ms4, "stage_set": "S4: camera head from fp32 NCHW backbone "
+              "feature maps (round 1's headline configuration), inputs 2.2 GB/GPU resident in HBM"}
+        del f1, f2
+    except Exception as e:  # noqa: BLE001
+        s4 = {"error": f"{type(e).__name__}: {e}"[:200]}
 
-    def score_once():
-        return ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
-                                   pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
-                                   head.trans.bias, out_cam_type="soft", want_scores=False, pack=pk["score_pack"])
-    for _ in range(3):
-        score_once()
-    torch.cuda.synchronize()
-    # One scoring call = 3 short kernels (prep, tiles, selection).  Launched eagerly from Python the host side (ctypes +
-    # tensor allocation) is slower than the GPU, so the call is captured once in a CUDA graph and the replays are timed
-    # with CUDA events on the replay stream: kernel time, not Python time.
-    side = torch.cuda.Stream()
-    side.wait_stream(torch.cuda.current_stream())
-    with torch.cuda.stream(side):
-        score_once()
-    torch.cuda.current_stream().wait_stream(side)
-    graph = torch.cuda.CUDAGraph()
-    with torch.cuda.graph(graph):
-        score_once()
-    graph.replay()
-    torch.cuda.synchronize()
-    reps = 20
-    e0.record()
-    for _ in range(reps):
-        graph.replay()        # 276 MB of inputs per launch > L2: no flush needed
-    e1.record()
-    torch.cuda.synchronize()
-    score_ms = e0.elapsed_time(e1) / reps
+    # ------------------------------------------------------------------ roofline: scoring kernel alone
+    peaks = measured_peaks()
+    RB, m = 512, NQ
+    score_once = score_case(dev, RB, NQ, head)
+    # One scoring call = 3 short kernels (prep, tiles, selection) chained by programmatic dependent launch.
+    score_ms = graph_timed(score_once, 20)                 # 276 MB of inputs per launch > L2: no flush needed
     alg = score_algorithmic_bytes(RB, m, NQ)
     achieved = alg / (score_ms / 1e3) / 1e9
     traffic = None
@@ -480,53 +533,68 @@ def main():
     except (OSError, ValueError):
         pass
     roofline = {"kernel": "nsac_score_aggregate_tc (K8+K9: prep + tile + selection kernels), B=512, m=NQ=256", "bound": "hbm",
-                "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": alg, "ms_per_launch": score_ms,
+                "achieved": achieved, "peak": peaks["hbm"], "peak_source": peaks["src"] + " hbm_gbs", "unit": "GB/s",
+                "frac": achieved / peaks["hbm"], "traffic": traffic, "algorithmic_bytes_per_launch": alg, "ms_per_launch": score_ms,
                 "timing": "CUDA-graph replays of one call, CUDA events on the replay stream"}
+    del score_once
+
+    # BASELINE.json configs[4]: hypothesis-count sweep at B = 64, 16 planes/view — both bounds (bytes grow O(H),
+    # scoring work O(H^2); the HBM bound is meaningful up to H ~ 256)
+    sweep = []
+    for nq in (32, 128, 256, 512, 2048):
+        try:
+            once = score_case(dev, 64, nq, head if nq == NQ else None)
+            ab, af = score_algorithmic_bytes(64, nq, nq), score_algorithmic_flops(64, nq, nq)
+            ms_s = graph_timed(once, 10, flush if ab < (200 << 20) else None)
+            sweep.append({"hypotheses": nq, "pairs": 64, "us_per_call": ms_s * 1e3, "algorithmic_bytes": ab,
+                          "achieved_gbs": ab / ms_s / 1e6, "frac_of_hbm": ab / ms_s / 1e6 / peaks["hbm"],
+                          "algorithmic_flops": af, "achieved_tflops": af / ms_s / 1e9,
+                          "frac_of_bf16_burst": af / ms_s / 1e9 / peaks["tf_burst"], "flop_per_byte": af / ab})
+            del once
+        except Exception as e:  # noqa: BLE001
+            sweep.append({"hypotheses": nq, "error": f"{type(e).__name__}: {e}"[:160]})
+
+    try:
+        roofline_tensor = measure_gemm_engine(dev, peaks)
+    except Exception as e:  # noqa: BLE001
+        roofline_tensor = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     cpu_baseline = None
     if not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, dt = cpu_reference_pairs_per_s(args.cpu_pairs, threads)
         cpu_baseline = {"value": v, "unit": "pairs/s", "cores": threads, "kind": "port",
-                        "sample": f"{args.cpu_pairs} pairs of the same workload after 1 warm-up pair, per-pair loop at "
-                                  f"batch size 1 (oracle/restate.py), {dt:.1f} s"}
+                        "sample": f"{args.cpu_pairs} pairs of the same workload (S5) after 1 warm-up pair, per-pair loop at "
+                                  f"batch size 1 (oracle/backbone_restate.py + oracle/restate.py), {dt:.1f} s"}
 
     # row f1 (the step before the path): plane lists of both views of this rank's pairs from synthetic PlaneTRHead outputs,
-    # timed separately (NOT part of `value`, whose stage set S4 starts at the backbone / plane-head outputs).  Reported only.
-    plane_lists = None
-    if rank == 0:
-        try:
-            plane_lists = measure_plane_lists(dev, 2 * B)
-        except Exception as e:   # never let the side measurement take the bench line down
-            plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
-
-    # row f2: the same step started at RGB (ResNet-50 backbone of both views + camera head) — the stage set S5' of DESIGN.md
-    # §5.  Reported beside `value` (whose stage set S4 starts at the backbone feature maps), never instead of it.  This path has
-    # not met a GPU before this run, so it is measured in a CHILD process with a timeout: a hang or a sticky CUDA error there
-    # cannot take this line down.
-    from_rgb = None
-    if rank == 0 and world == 1:
-        from_rgb = run_side_measurement("from_rgb", B, timeout_s=240)
+    # timed separately (NOT part of `value`, whose plane lists are inputs).  Reported only.
+    try:
+        plane_lists = measure_plane_lists(dev, 2 * B)
+    except Exception as e:   # never let the side measurement take the bench line down
+        plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
 
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": B, "planes_per_view": PLANES, "num_object_queries": NQ,
-                   "stage_set": "S4", "l2": "inputs (2.2 GB/GPU) exceed the 126 MB L2; no flush",
+                   "stage_set": "S5", "l2": "256 MB L2 flush (buffer write) before every timed step, inside the timed region",
                    "parallelism": f"pairs sharded over {world} GPU(s), 64/GPU; result exchange = {exchange_kind}"},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "pairs/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps, "note": "pinned host inputs; H2D of step i+1 overlaps the kernels of step i"},
+                "steps": e2e_steps, "note": "pinned host inputs (uint8 RGB of both views + plane lists); H2D of step i+1 overlaps the "
+                "kernels of step i"},
         "gpu_launches": launches,
         "exchange_verified": None if exchange_check is None else exchange_check["exchange_verified"],
         "exchange_check": exchange_check,
         "roofline": roofline,
+        "roofline_tensor": roofline_tensor,
+        "score_sweep": sweep,
         "cpu_baseline": cpu_baseline,
         "pose_err": pose_err,
+        "from_feature_maps": s4,
         "plane_lists": plane_lists,
-        "from_rgb": from_rgb,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

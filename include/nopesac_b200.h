@@ -78,6 +78,14 @@ int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_h
                     void* stream);
 int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,
                  int ld_split, void* stream);
+/* nsac_gemm_split with a residual input given as hi/lo planes [M, ld_res] (same fmt): out = act(out_scale * acc + bias +
+ * (res_hi + res_lo)) — the `out += shortcut; relu(out)` of a bottleneck block (detectron2 BottleneckBlock.forward, the backbone
+ * Base.yaml:2-12 builds) inside the producing GEMM's epilogue.  In both entry points a_lo == NULL means "A has no lo plane"
+ * (exactly representable in 16 bits): the lo.hi pass and its loads are skipped. */
+int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                             const float* bias, int M, int N, int K, int act, int passes, int fmt, float out_scale,
+                             const void* res_hi, const void* res_lo, int ld_res, float* out_f32, int ldo, void* out_hi,
+                             void* out_lo, int ld_split, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Pixel pose-regression network K1 (camera_head.py:642-683; camera_modules.py:36-48, 246-348) on the tensor-core
@@ -286,6 +294,17 @@ int nsac_subsample2_planes(const void* hi, const void* lo, int N, int H, int W, 
                            void* stream);
 int nsac_add_relu_nhwc(const float* a, const float* b, size_t count, int fmt, float* out_f32, void* hi, void* lo,
                        void* stream);
+/*   nsac_stem_im2col_u8        image [N,3,H,W] UINT8 (what preprocess_image receives, siamese_planeTR.py:534-542) -> ONE fp16 plane
+ *                              [N*Ho*Wo, 192] of raw pixel values (exact; no lo plane), out-of-image taps = 0.  The normalisation is
+ *                              folded into the stem weights by the caller (w / std, bias - sum w mean / std).
+ *   nsac_stem_border_fix       exact fp32 recomputation (zero padding of the NORMALISED image, + bias, ReLU) of the stem outputs
+ *                              [N*Ho*Wo, 64] whose 7x7 window leaves the image; w_folded [64,147] (ky,kx,c) for normalised input
+ *   nsac_im2col3x3_from_planes 3x3 / pad 1 / stride 1|2 im2col NHWC planes -> planes [N*Ho*Wo, 9*C] (16-byte copies) */
+int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream);
+int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, const float* bias, int N, int H, int W,
+                         const float* mean3_host, const float* std3_host, float* out, void* stream);
+int nsac_im2col3x3_from_planes(const void* hi, const void* lo, int N, int H, int W, int C, int stride, void* out_hi,
+                               void* out_lo, void* stream);
 
 #ifdef __cplusplus
 }

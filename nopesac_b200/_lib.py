@@ -23,6 +23,9 @@ _SIGNATURES = {
     "nsac_gemm_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p, C.c_int,
                                   C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
                                   C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_gemm_split_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p,
+                                           C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                           C.c_int, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nsac_split16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p]),
     "nsac_conv3x3_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
@@ -78,6 +81,11 @@ _SIGNATURES = {
     "nsac_subsample2_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                          C.c_void_p]),
     "nsac_add_relu_nhwc": (C.c_int, [c_float_p, c_float_p, C.c_size_t, C.c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nsac_stem_im2col_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsac_stem_border_fix": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), c_float_p, C.c_void_p]),
+    "nsac_im2col3x3_from_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                             C.c_void_p, C.c_void_p]),
     "nsac_plane_post_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "nsac_plane_postprocess": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p] + [C.c_int] * 7 +
                                [C.c_float, C.c_float, C.c_double] + [C.c_void_p] * 12),
@@ -95,11 +103,12 @@ def exported_symbols():
 def lib() -> C.CDLL:
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        path = os.environ.get("NSAC_B200_LIB", LIB_PATH)      # development aid: A/B a kernel variant built elsewhere (scripts/)
+        if not os.path.exists(path):
             raise RuntimeError(
-                f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                f"{path} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nopesac_b200 has no CPU / eager fallback).")
-        L = C.CDLL(LIB_PATH)
+        L = C.CDLL(path)
         for name, (res, args) in _SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

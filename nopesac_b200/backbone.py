@@ -7,10 +7,13 @@ same registry name, same parameter / buffer names (`stem.conv1.weight`, `stem.co
 `(x - PIXEL_MEAN) / PIXEL_STD` of `preprocess_image` (siamese_planeTR.py `preprocess_image`, Base.yaml:6-7).
 
 Every convolution is a GEMM on NHWC 16-bit hi/lo planes (3 passes ~ fp32): 1x1 -> `nsac_gemm_split`, 3x3 stride 1 ->
-`nsac_conv3x3_split` (implicit GEMM, 4-D TMA gather), 3x3 stride 2 -> `nsac_im2col3x3_planes` + GEMM, stem 7x7/2 ->
-`nsac_stem_im2col_planes` + GEMM; FrozenBN is folded into weights and bias, ReLU runs in the GEMM epilogue; max-pool,
-stride-2 subsampling of the shortcut input and relu(out + shortcut) are the byte movers of csrc/backbone.cu.  No cuDNN, no
-CPU path.  First version: the residual add is a separate kernel (fusing it into the GEMM epilogue is the next step).
+`nsac_conv3x3_split` (implicit GEMM, 4-D TMA gather), 3x3 stride 2 -> `nsac_im2col3x3_from_planes` + GEMM, stem 7x7/2 -> im2col +
+GEMM; FrozenBN is folded into weights and bias, ReLU runs in the GEMM epilogue, and `relu(out + shortcut)` of every bottleneck
+block runs in the epilogue of its last GEMM (`nsac_gemm_split_residual`): activations exist only as hi/lo planes between layers
+(r1 went through fp32 NHWC + a separate add kernel: 11 of 62 ms).  uint8 images (what the reference's loader delivers) take the
+fast stem: one exact fp16 plane of raw pixels, normalisation folded into the weights, borders recomputed exactly
+(`nsac_stem_im2col_u8` / `nsac_stem_border_fix`).  `forward(..., planes=True)` hands the NHWC planes straight to the camera
+head's pixel network (`PlaneFeatures`), skipping the NCHW fp32 round trip.  No cuDNN, no CPU path.
 """
 from __future__ import annotations
 
@@ -22,7 +25,7 @@ from torch import nn
 from . import ops
 from .compat import Registry, ShapeSpec
 
-__all__ = ["BACKBONE_REGISTRY", "ResNet50Backbone", "build_resnet_backbone", "build_backbone"]
+__all__ = ["BACKBONE_REGISTRY", "ResNet50Backbone", "PlaneFeatures", "build_resnet_backbone", "build_backbone"]
 
 BACKBONE_REGISTRY = Registry("BACKBONE")
 STAGES = (("res2", 3, 64, 256, 1), ("res3", 4, 128, 512, 2), ("res4", 6, 256, 1024, 2), ("res5", 3, 512, 2048, 2))
@@ -117,6 +120,13 @@ class ResNet50Backbone(nn.Module):
                     w, b = cb.folded()
                     return ops.split_weight(w), b          # planes are zero-padded to a multiple of 64 columns (stem: 147 -> 192)
                 pk = {"stem": pack(self.stem.conv1)}
+                # 8-bit image path: conv(w, (p - mean) / std) = conv(w / std, p) - sum w mean / std (interior pixels)
+                wf, bf = self.stem.conv1.folded()                                   # [64, 147] in (ky, kx, c) order
+                istd = (1.0 / torch.tensor(self.pixel_std, dtype=torch.float64, device=wf.device)).repeat(49)
+                mean = torch.tensor(self.pixel_mean, dtype=torch.float64, device=wf.device).repeat(49)
+                w8 = wf.double() * istd
+                pk["stem.u8"] = (ops.split_weight(w8.float().contiguous()), (bf.double() - (w8 * mean).sum(1)).float().contiguous())
+                pk["stem.f32"] = (wf.float().contiguous(), bf.float().contiguous())
                 for name, *_ in STAGES:
                     for i, blk in enumerate(getattr(self, name)):
                         for c in ("conv1", "conv2", "conv3") + (("shortcut",) if hasattr(blk, "shortcut") else ()):
@@ -125,46 +135,73 @@ class ResNet50Backbone(nn.Module):
         return self._packed
 
     # ------------------------------------------------------------------ forward
-    def _block(self, pk, key, blk, x_f32, xp, N, H, W):
+    def _block(self, pk, key, blk, xp, N, H, W):
+        """One bottleneck block on planes: conv1 (1x1) -> conv2 (3x3, stride here) -> conv3 (1x1) + shortcut + ReLU in its epilogue."""
         P = self.tc_passes
         w1, b1 = pk[key + ".conv1"]
         w2, b2 = pk[key + ".conv2"]
         w3, b3 = pk[key + ".conv3"]
         Ho, Wo = H, W
+        _, y1p = ops.gemm_tc(xp, w1, b1, ops.ACT_RELU, P, want_f32=False, want_split=True)
         if blk.stride == 1:
-            _, y1p = ops.gemm_tc(xp, w1, b1, ops.ACT_RELU, P, want_f32=False, want_split=True)
             _, y2p = ops.conv3x3_tc(y1p, N, H, W, w2, b2, ops.ACT_RELU, P, want_f32=False, want_split=True)
         else:
-            y1, _ = ops.gemm_tc(xp, w1, b1, ops.ACT_RELU, P)
-            cols, Ho, Wo = ops.im2col3x3_planes(y1, N, H, W, blk.stride)
+            cols, Ho, Wo = ops.im2col3x3_from_planes(y1p, N, H, W, blk.stride)
             _, y2p = ops.gemm_tc(cols, w2, b2, ops.ACT_RELU, P, want_f32=False, want_split=True)
-        y3, _ = ops.gemm_tc(y2p, w3, b3, ops.ACT_NONE, P)
         if hasattr(blk, "shortcut"):
             ws, bs = pk[key + ".shortcut"]
             src = xp if blk.stride == 1 else ops.subsample2_planes(xp, N, H, W)[0]
-            sc, _ = ops.gemm_tc(src, ws, bs, ops.ACT_NONE, P)
+            _, sc = ops.gemm_tc(src, ws, bs, ops.ACT_NONE, P, want_f32=False, want_split=True)
         else:
-            sc = x_f32
-        x_f32, xp = ops.add_relu_nhwc(y3, sc)
-        return x_f32, xp, Ho, Wo
+            sc = xp
+        _, out = ops.gemm_tc(y2p, w3, b3, ops.ACT_RELU, P, want_f32=False, want_split=True, residual=sc)
+        return out, Ho, Wo
+
+    def _stem(self, pk, images):
+        N = images.shape[0]
+        if images.dtype == torch.uint8:
+            # raw pixels are exact in fp16: one plane, normalisation folded into the weights; borders recomputed exactly
+            cols, H, W = ops.stem_im2col_u8(images)
+            ws, bs = pk["stem.u8"]
+            x, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU, self.tc_passes)
+            wf, bf = pk["stem.f32"]
+            ops.stem_border_fix(images, wf, bf, self.pixel_mean, self.pixel_std, x)
+        else:
+            cols, H, W = ops.stem_im2col_planes(images.float(), self.pixel_mean, self.pixel_std)
+            ws, bs = pk["stem"]
+            x, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU, self.tc_passes)
+        _, xp, H, W = ops.maxpool3x3s2_nhwc(x, N, H, W, want_f32=False)
+        return xp, H, W
 
     @torch.no_grad()
-    def forward(self, images: torch.Tensor, nhwc: bool = False) -> Dict[str, torch.Tensor]:
-        """images: [N,3,H,W] fp32, NOT normalised (0..255, cfg.INPUT.FORMAT order) -> {'res2'..'res5'}: [N,C,h,w] fp32 (or the
-        NHWC rows [N*h*w, C] the kernels produce, with `nhwc=True`)."""
+    def forward(self, images: torch.Tensor, nhwc: bool = False, planes: bool = False):
+        """images: [N,3,H,W], NOT normalised (0..255, cfg.INPUT.FORMAT order), uint8 (fast stem) or float ->
+        {'res2'..'res5'}: [N,C,h,w] fp32 like the reference's backbone; `nhwc=True`: the NHWC rows [N*h*w, C] fp32;
+        `planes=True`: a `PlaneFeatures` (NHWC hi/lo planes, the engine's own format) for `PlaneCameraHead`."""
         pk = self.prepare()
         N = images.shape[0]
-        cols, H, W = ops.stem_im2col_planes(images.float(), self.pixel_mean, self.pixel_std)
-        ws, bs = pk["stem"]
-        x, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU, self.tc_passes)
-        x_f32, xp, H, W = ops.maxpool3x3s2_nhwc(x, N, H, W)
-        out = {}
+        xp, H, W = self._stem(pk, images)
+        out = PlaneFeatures(N) if planes else {}
         for name, *_ in STAGES:
             for i, blk in enumerate(getattr(self, name)):
-                x_f32, xp, H, W = self._block(pk, f"{name}.{i}", blk, x_f32, xp, N, H, W)
+                xp, H, W = self._block(pk, f"{name}.{i}", blk, xp, N, H, W)
             if name in self._out_features:
-                out[name] = x_f32 if nhwc else x_f32.view(N, H, W, -1).permute(0, 3, 1, 2).contiguous()
+                if planes:
+                    out[name] = (xp, H, W)
+                else:
+                    x_f32 = xp.float()
+                    out[name] = x_f32 if nhwc else x_f32.view(N, H, W, -1).permute(0, 3, 1, 2).contiguous()
         return out
+
+
+class PlaneFeatures(dict):
+    """Backbone output in the tensor-core engine's own format: name -> (ops.Split NHWC planes [N*h*w, C], h, w) for a batch of
+    `N` images.  `PlaneCameraHead` takes it as `features1` (with `features2=None`): images [0, N/2) are the first views,
+    [N/2, N) the second views — exactly the stacking its pixel network builds from two NCHW dicts."""
+
+    def __init__(self, num_images: int):
+        super().__init__()
+        self.num_images = num_images
 
 
 @BACKBONE_REGISTRY.register()

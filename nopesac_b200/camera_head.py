@@ -303,11 +303,15 @@ class PlaneCameraHead(nn.Module):
         if not hasattr(pd.layer_3, "norm"):
             raise NotImplementedError("SEM_SEG_HEAD.NORM must be 'GN' (as in every reference config)")
         P = self.tc_passes
-        B = features1["res5"].shape[0]
+        from .backbone import PlaneFeatures
+        stacked = isinstance(features1, PlaneFeatures)      # both views already stacked as NHWC planes (backbone.forward(planes=True))
+        B = features1.num_images // 2 if stacked else features1["res5"].shape[0]
         N = 2 * B
         LEAKY = ops.ACT_LEAKY
 
         def planes(name):
+            if stacked:
+                return features1[name]
             f1, f2 = features1[name], features2[name]
             _, C, H, W = f1.shape
             out = ops.Split(torch.empty(N * H * W, C, device=f1.device, dtype=torch.float16),

@@ -117,6 +117,109 @@ add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t
   }
 }
 
+// ---- 8-bit image path of the stem (what the reference's data loader delivers: uint8 RGB, siamese_planeTR.py:534-542) ---------
+// Raw pixel values 0..255 are exact in fp16, so the im2col matrix needs ONE plane (no lo plane) and the GEMM two passes
+// (hi.hi + hi.lo); the normalisation (x - mean) / std is folded into the weights (w / std) and the bias (- sum w mean / std).
+// Out-of-image taps are written as 0, which is only right in normalised space: the <= 2 output rows / columns per border whose
+// window leaves the image are recomputed exactly by stem_border_fix_kernel afterwards.
+// One CTA = one output row (n, yo): its 7 x 3 input rows are staged in shared memory with coalesced loads, then every thread
+// emits 16-byte chunks (8 consecutive k of one output pixel).
+constexpr int STEM_U8_MAXW = 2048;     // widest image row that fits the staging buffer (7 rows x 3 channels x (W + 6) bytes <= 43 KB)
+__global__ void __launch_bounds__(256)
+stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int Wo, uint16_t* __restrict__ out) {
+  extern __shared__ uint8_t rows[];                    // [7][3][W + 6], x index shifted by +3, zero outside the image
+  const int n = blockIdx.x / Ho, yo = blockIdx.x % Ho, Wp = W + 6;
+  for (int i = threadIdx.x; i < 21 * Wp; i += blockDim.x) {
+    const int xs = i % Wp, rc = i / Wp, ky = rc / 3, c = rc % 3;
+    const int y = 2 * yo + ky - 3, x = xs - 3;
+    rows[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + (((size_t)n * 3 + c) * H + y) * W + x) : (uint8_t)0;
+  }
+  __syncthreads();
+  const size_t row0 = ((size_t)n * Ho + yo) * Wo;
+  for (int i = threadIdx.x; i < Wo * (STEM_KP / 8); i += blockDim.x) {
+    const int xo = i / (STEM_KP / 8), k0 = (i % (STEM_KP / 8)) * 8;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      uint32_t pair = 0;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int k = k0 + j + e;
+        float v = 0.f;
+        if (k < STEM_K) {
+          const int c = k % 3, tap = k / 3, ky = tap / 7, kx = tap - ky * 7;
+          v = (float)rows[(ky * 3 + c) * Wp + 2 * xo + kx];
+        }
+        pair |= (uint32_t)__half_as_ushort(__float2half_rn(v)) << (16 * e);
+      }
+      w[j >> 1] = pair;
+    }
+    *reinterpret_cast<uint4*>(out + (row0 + xo) * STEM_KP + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+
+// Exact fp32 recomputation of the stem outputs whose 7x7 window leaves the image (zero padding applies to the NORMALISED
+// image): out[row, co] = relu(bias[co] + sum_k w[co, k] * (p - mean_c) / std_c over the in-image taps).  w: folded weights
+// [64, 147] in (ky, kx, c) order for normalised input.  One warp per border pixel, lane = 2 output channels.
+__global__ void __launch_bounds__(256)
+stem_border_fix_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias, int N, int H,
+                       int W, int Ho, int Wo, float m0, float m1, float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  // border pixels of one image: rows yo < 2 or yo >= Ho - 2 (all xo), plus columns xo < 2 or xo >= Wo - 2 of the other rows
+  const int top = Ho < 4 ? Ho : 4, side_rows = Ho - top, per_img = top * Wo + side_rows * 4;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N * per_img) return;
+  const int n = warp / per_img, r = warp % per_img;
+  int yo, xo;
+  if (r < top * Wo) {
+    const int t = r / Wo;
+    yo = t < 2 ? t : Ho - 4 + t;          // t = 0,1 -> rows 0,1; t = 2,3 -> rows Ho-2, Ho-1
+    xo = r % Wo;
+  } else {
+    const int q = r - top * Wo, t = q & 3;
+    yo = 2 + (q >> 2);
+    xo = t < 2 ? t : Wo - 4 + t;
+  }
+  if (yo < 0 || yo >= Ho || xo < 0 || xo >= Wo) return;
+  const float mean[3] = {m0, m1, m2}, istd[3] = {1.f / s0, 1.f / s1, 1.f / s2};
+  float a0 = 0.f, a1 = 0.f;
+  for (int k = 0; k < STEM_K; ++k) {
+    const int c = k % 3, tap = k / 3, ky = tap / 7, kx = tap - ky * 7;
+    const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
+    if (y < 0 || y >= H || x < 0 || x >= W) continue;
+    const float v = ((float)__ldg(img + (((size_t)n * 3 + c) * H + y) * W + x) - mean[c]) * istd[c];
+    a0 = fmaf(__ldg(w + (size_t)(2 * lane) * STEM_K + k), v, a0);
+    a1 = fmaf(__ldg(w + (size_t)(2 * lane + 1) * STEM_K + k), v, a1);
+  }
+  float* o = out + (((size_t)n * Ho + yo) * Wo + xo) * 64 + 2 * lane;
+  *reinterpret_cast<float2*>(o) = make_float2(fmaxf(a0 + __ldg(bias + 2 * lane), 0.f), fmaxf(a1 + __ldg(bias + 2 * lane + 1), 0.f));
+}
+
+// 3x3 / pad 1 / stride s im2col from NHWC planes to planes [N*Ho*Wo, 9*C] in (ky, kx, c) order: 16-byte copies of both planes
+// (one thread = 8 channels of one tap of one output pixel); the strided 3x3 convolutions of res3.0 / res4.0 / res5.0.
+__global__ void __launch_bounds__(256)
+im2col3x3_from_planes_kernel(const uint16_t* __restrict__ hi, const uint16_t* __restrict__ lo, int N, int H, int W, int C, int stride,
+                             int Ho, int Wo, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo) {
+  const int C8 = C >> 3;
+  const size_t total = (size_t)N * Ho * Wo * 9 * C8;
+  for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(idx % C8);
+    size_t t = idx / C8;
+    const int tap = (int)(t % 9);
+    const size_t pix = t / 9;
+    const int xo = (int)(pix % Wo), yo = (int)((pix / Wo) % Ho), n = (int)(pix / ((size_t)Wo * Ho));
+    const int y = yo * stride + tap / 3 - 1, x = xo * stride + tap % 3 - 1;
+    uint4 vh = make_uint4(0u, 0u, 0u, 0u), vl = vh;
+    if (y >= 0 && y < H && x >= 0 && x < W) {
+      const size_t src = (((size_t)n * H + y) * W + x) * C + c8 * 8;
+      vh = __ldg(reinterpret_cast<const uint4*>(hi + src));
+      vl = __ldg(reinterpret_cast<const uint4*>(lo + src));
+    }
+    const size_t dst = (pix * 9 + tap) * C + c8 * 8;
+    *reinterpret_cast<uint4*>(out_hi + dst) = vh;
+    *reinterpret_cast<uint4*>(out_lo + dst) = vl;
+  }
+}
+
 inline int grid_for(size_t total) {
   size_t blocks = (total + 255) / 256;
   const size_t cap = (size_t)148 * 16;          // a few waves of the 148 SMs, grid-stride beyond that
@@ -175,5 +278,45 @@ extern "C" int nsac_add_relu_nhwc(const float* a, const float* b, size_t count, 
                                                                                       static_cast<uint16_t*>(hi),
                                                                                       static_cast<uint16_t*>(lo));
   NSAC_CHECK_LAUNCH("nsac_add_relu_nhwc");
+  return NSAC_OK;
+}
+
+extern "C" int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream) {
+  NSAC_REQUIRE(img && out_hi, "nsac_stem_im2col_u8: null pointer");
+  NSAC_REQUIRE(N >= 0 && H >= 7 && W >= 7 && W <= STEM_U8_MAXW, "nsac_stem_im2col_u8: bad shape N=%d H=%d W=%d", N, H, W);
+  if (N == 0) return NSAC_OK;
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const size_t smem = (size_t)21 * (W + 6);
+  stem_im2col_u8_kernel<<<N * Ho, 256, smem, static_cast<cudaStream_t>(stream)>>>(img, H, W, Ho, Wo, static_cast<uint16_t*>(out_hi));
+  NSAC_CHECK_LAUNCH("nsac_stem_im2col_u8");
+  return NSAC_OK;
+}
+
+extern "C" int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, const float* bias, int N, int H, int W,
+                                    const float* mean3_host, const float* std3_host, float* out, void* stream) {
+  NSAC_REQUIRE(img && w_folded && bias && mean3_host && std3_host && out, "nsac_stem_border_fix: null pointer");
+  NSAC_REQUIRE(N >= 0 && H >= 7 && W >= 7, "nsac_stem_border_fix: bad shape N=%d H=%d W=%d", N, H, W);
+  NSAC_REQUIRE(std3_host[0] != 0.f && std3_host[1] != 0.f && std3_host[2] != 0.f, "nsac_stem_border_fix: zero PIXEL_STD");
+  if (N == 0) return NSAC_OK;
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const int top = Ho < 4 ? Ho : 4, per_img = top * Wo + (Ho - top) * 4;
+  const size_t warps = (size_t)N * per_img;
+  stem_border_fix_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      img, w_folded, bias, N, H, W, Ho, Wo, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2], out);
+  NSAC_CHECK_LAUNCH("nsac_stem_border_fix");
+  return NSAC_OK;
+}
+
+extern "C" int nsac_im2col3x3_from_planes(const void* hi, const void* lo, int N, int H, int W, int C, int stride, void* out_hi,
+                                          void* out_lo, void* stream) {
+  NSAC_REQUIRE(hi && lo && out_hi && out_lo, "nsac_im2col3x3_from_planes: null pointer");
+  NSAC_REQUIRE(N >= 0 && H >= 1 && W >= 1 && C >= 8 && C % 8 == 0 && (stride == 1 || stride == 2),
+               "nsac_im2col3x3_from_planes: bad shape (C %% 8 == 0, stride 1 or 2)");
+  if (N == 0) return NSAC_OK;
+  const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
+  im2col3x3_from_planes_kernel<<<grid_for((size_t)N * Ho * Wo * 9 * (C / 8)), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      static_cast<const uint16_t*>(hi), static_cast<const uint16_t*>(lo), N, H, W, C, stride, Ho, Wo, static_cast<uint16_t*>(out_hi),
+      static_cast<uint16_t*>(out_lo));
+  NSAC_CHECK_LAUNCH("nsac_im2col3x3_from_planes");
   return NSAC_OK;
 }

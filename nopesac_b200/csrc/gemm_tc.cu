@@ -178,6 +178,12 @@ struct GemmParams {
   uint16_t* out_hi;
   uint16_t* out_lo;
   int ld_split;
+  // optional residual input (16-bit hi/lo planes, same format as the operands): out = act(acc * scale + bias + (res_hi + res_lo))
+  const uint16_t* res_hi;
+  const uint16_t* res_lo;
+  int ld_res;
+  int a_lo_zero;            // the A operand has no lo plane (exactly representable in 16 bits, e.g. raw 8-bit pixels): the
+                            // lo.hi pass and its TMA loads are skipped, passes = 3 then means hi.hi + hi.lo
 };
 
 // x -> (hi, lo) 16-bit planes in the requested format
@@ -233,7 +239,16 @@ struct EpiOut {
   uint16_t* out_lo;
   int n_valid;            // valid columns from col0 on (>= 32: full chunk)
   bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
+  const uint16_t* res_hi; // residual row pointers (nullptr: none)
+  const uint16_t* res_lo;
 };
+
+// packed 16-bit plane word -> two floats
+template <int FMT>
+__device__ __forceinline__ float2 unsplit16x2(uint32_t w) {
+  if (FMT == NSAC_SPLIT_F16) return __half22float2(*reinterpret_cast<const __half2*>(&w));
+  return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w));
+}
 
 // 32 accumulator columns -> scale, bias, activation, fp32 store, split-plane store
 template <int FMT>
@@ -257,6 +272,15 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
     }
     upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
     upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
+  }
+  if (o.res_hi) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+      if (i < o.n_valid) {
+        uint16_t h = __ldg(o.res_hi + col0 + i), l = __ldg(o.res_lo + col0 + i);
+        f[i] += FMT == NSAC_SPLIT_F16 ? __half2float(__ushort_as_half(h)) + __half2float(__ushort_as_half(l))
+                                      : __bfloat162float(__ushort_as_bfloat16(h)) + __bfloat162float(__ushort_as_bfloat16(l));
+      }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
@@ -323,6 +347,31 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t (&w)
   __syncwarp();
 }
 
+// The mirror image for the residual input: coalesced 16-byte global loads (4 or 8 full row segments per instruction) into the
+// warp's staging buffer, then every lane reads its own row.  row_ptr = this lane's own source row segment.
+template <int WORDS>
+__device__ __forceinline__ void staged_load(uint8_t* stage, uint32_t (&w)[WORDS], const uint8_t* row_ptr, int lane) {
+  constexpr int BYTES = WORDS * 4, CPR = BYTES / 16, RPI = 32 / CPR;
+  const int sub = lane / CPR, ch = lane % CPR;
+  const unsigned long long my = reinterpret_cast<unsigned long long>(row_ptr);
+#pragma unroll
+  for (int j = 0; j < 32 / RPI; ++j) {
+    const int row = RPI * j + sub;
+    const int swz_r = CPR == 8 ? (row & 7) : ((row >> 1) & 3);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, my, row));
+    const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + ch * 16));
+    *reinterpret_cast<uint4*>(stage + row * BYTES + ((ch ^ swz_r) << 4)) = x;
+  }
+  __syncwarp();
+  const int swz_w = CPR == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+  for (int c = 0; c < CPR; ++c) {
+    const uint4 x = *reinterpret_cast<const uint4*>(stage + lane * BYTES + ((c ^ swz_w) << 4));
+    w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+  }
+  __syncwarp();
+}
+
 // 64 accumulator columns of a full tile part (every lane of the warp has a valid row, all 64 columns valid, aligned):
 // scale, bias, activation, then fp32 rows and / or split planes through the staged stores, 32 columns at a time
 template <int FMT>
@@ -331,12 +380,23 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[32], int col0, 
 #pragma unroll
   for (int g = 0; g < 2; ++g) {            // two groups of 32 columns
     uint32_t f[32];                        // fp32 bit patterns
+    uint32_t rh[16], rl[16];               // residual planes of these 32 columns (hi + lo = the fp32 value)
+    if (o.res_hi) {
+      staged_load<16>(stage, rh, reinterpret_cast<const uint8_t*>(o.res_hi + col0 + 32 * g), lane);
+      staged_load<16>(stage, rl, reinterpret_cast<const uint8_t*>(o.res_lo + col0 + 32 * g), lane);
+    }
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       u64 b01 = 0ull, b23 = 0ull;
       if (o.brow) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + 32 * g + i));
         b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
+      }
+      if (o.res_hi) {                      // bias + residual first (exact: hi + lo reproduces the fp32 activation)
+        const float2 h0 = unsplit16x2<FMT>(rh[i >> 1]), l0 = unsplit16x2<FMT>(rl[i >> 1]);
+        const float2 h1 = unsplit16x2<FMT>(rh[(i >> 1) + 1]), l1 = unsplit16x2<FMT>(rl[(i >> 1) + 1]);
+        b01 = fadd2(b01, fadd2(pk2(h0.x, h0.y), pk2(l0.x, l0.y)));
+        b23 = fadd2(b23, fadd2(pk2(h1.x, h1.y), pk2(l1.x, l1.y)));
       }
       float x0, x1, x2, x3;
       upk2(ffma2(sum[16 * g + (i >> 1)], sc, b01), x0, x1);
@@ -408,7 +468,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t a_bytes = conv ? (uint32_t)(p.BW * p.BH * BLOCK_K * 2) : (uint32_t)C::A_BYTES;   // box bytes
-      const uint32_t tx = (p.passes >= 2 ? 2 * a_bytes : a_bytes) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
+      const bool load_alo = p.passes >= 2 && !p.a_lo_zero;
+      const uint32_t tx = (load_alo ? 2 * a_bytes : a_bytes) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int tm = tile % tiles_m;
         const int m0 = tm * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
@@ -429,10 +490,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
             tma_load_4d(st, &map_a_hi, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
-            if (p.passes >= 2) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+            if (load_alo) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
           } else {
             tma_load_2d(st, &map_a_hi, &full[stage], kb * BLOCK_K, m0);
-            if (p.passes >= 2) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
+            if (load_alo) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
           }
           tma_load_2d(st + 2 * C::A_BYTES, &map_w_hi, &full[stage], kb * BLOCK_K, n0);
           if (p.passes >= 3) tma_load_2d(st + 2 * C::A_BYTES + C::W_BYTES, &map_w_lo, &full[stage], kb * BLOCK_K, n0);
@@ -466,9 +527,10 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
               const uint64_t koff = (uint64_t)((k * UMMA_K * 2) >> 4);   // advance the start address inside the swizzle row
               const uint32_t first = (kb == kb0 && k == 0) ? 0u : 1u;
               umma_bf16(d_main, a_hi + koff, w_hi + koff, idesc, first);
-              if (p.passes >= 2) umma_bf16(d_lo, a_lo + koff, w_hi + koff, idesc, first);
-              if (p.passes >= 3) umma_bf16(d_lo, a_hi + koff, w_lo + koff, idesc, 1);
-              if (p.passes >= 4) umma_bf16(d_lo, a_lo + koff, w_lo + koff, idesc, 1);
+              uint32_t lo_first = first;
+              if (p.passes >= 2 && !p.a_lo_zero) { umma_bf16(d_lo, a_lo + koff, w_hi + koff, idesc, first); lo_first = 1u; }
+              if (p.passes >= 3) umma_bf16(d_lo, a_hi + koff, w_lo + koff, idesc, lo_first);
+              if (p.passes >= 4 && !p.a_lo_zero) umma_bf16(d_lo, a_lo + koff, w_lo + koff, idesc, 1);
             }
             tcgen05_commit(&empty[stage]);                 // slot reusable once these MMAs retire
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -500,7 +562,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         for (int c = 0; c < HALF_N; c += 32) {
           uint32_t v[32];
           tmem_ld32(t_main + c, v);
-          if (p.passes >= 2) {
+          if (p.passes >= 3 || (p.passes >= 2 && !p.a_lo_zero)) {
             uint32_t u[32];
             tmem_ld32(t_main + BLOCK_N + c, u);
 #pragma unroll
@@ -532,6 +594,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       o.out_scale = p.out_scale;
       o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
       o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
+      o.res_hi = nullptr; o.res_lo = nullptr;
+      if (row_ok && p.res_hi) {
+        o.res_hi = p.res_hi + (size_t)row * p.ld_res;
+        o.res_lo = p.res_lo + (size_t)row * p.ld_res;
+      }
       if (row_ok) {
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
@@ -539,7 +606,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         o.out_lo = p.out_lo ? p.out_lo + (size_t)row * p.ld_split : nullptr;
         o.vec_ok = (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
                    (!o.out_f32 || (reinterpret_cast<uintptr_t>(o.out_f32) & 15) == 0) &&
-                   (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0);
+                   (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0) &&
+                   (!o.res_hi || ((reinterpret_cast<uintptr_t>(o.res_hi) | reinterpret_cast<uintptr_t>(o.res_lo)) & 15) == 0);
       }
       // fast path (warp-uniform): every lane has a valid, aligned row and all 64 columns of this half exist
       const bool staged = HALF_N == 64 && __all_sync(0xffffffffu, row_ok && o.vec_ok) && n0 + HALF_N <= p.N;
@@ -702,18 +770,22 @@ extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void
   p.bias = bias; p.bias_group_rows = 0; p.M = N * H * W; p.N = Cout; p.K = K; p.act = act; p.passes = passes;
   p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
+  p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0;
   p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
   return launch_gemm<128>(mah, mal, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
 }
 
-extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
-                               int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
-                               int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
-                               void* out_lo, int ld_split, void* stream) {
+static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                           int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
+                           int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
+                           void* out_lo, int ld_split, const void* res_hi, const void* res_lo, int ld_res, void* stream) {
+  NSAC_REQUIRE(!res_hi || (res_lo && ld_res >= N && ld_res % 8 == 0 && (reinterpret_cast<uintptr_t>(res_hi) & 15) == 0 &&
+                           (reinterpret_cast<uintptr_t>(res_lo) & 15) == 0),
+               "nsac_gemm_split_residual: residual needs both planes, 16-byte alignment and ld_res %% 8 == 0");
   NSAC_REQUIRE(a_hi && w_hi, "nsac_gemm_split: null operand");
   NSAC_REQUIRE(passes >= 1 && passes <= 4, "nsac_gemm_split: passes must be 1..4");
-  NSAC_REQUIRE((passes < 2 || a_lo) && (passes < 3 || w_lo), "nsac_gemm_split: missing lo plane for %d passes", passes);
+  NSAC_REQUIRE(passes < 3 || w_lo, "nsac_gemm_split: missing W lo plane for %d passes", passes);     // a_lo == nullptr: A has no lo plane
   NSAC_REQUIRE(M >= 0 && N >= 8 && K >= BLOCK_K && K % BLOCK_K == 0, "nsac_gemm_split: need K %% 64 == 0 (M=%d N=%d K=%d)", M, N, K);
   NSAC_REQUIRE(lda >= K && ldw >= K && lda % 8 == 0 && ldw % 8 == 0, "nsac_gemm_split: lda/ldw must be >= K and multiples of 8");
   NSAC_REQUIRE(out_f32 || out_hi, "nsac_gemm_split: no output requested");
@@ -742,9 +814,30 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
   p.fmt = fmt; p.out_scale = out_scale;
   p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
+  p.res_hi = static_cast<const uint16_t*>(res_hi); p.res_lo = static_cast<const uint16_t*>(res_lo); p.ld_res = ld_res;
+  p.a_lo_zero = a_lo == nullptr ? 1 : 0;
   p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return launch_gemm<128>(mah, mal, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+}
+
+extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                               int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
+                               int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
+                               void* out_lo, int ld_split, void* stream) {
+  return gemm_split_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, bias_group_rows, M, N, K, act, passes, fmt, out_scale, out_f32, ldo,
+                         out_hi, out_lo, ld_split, nullptr, nullptr, 0, stream);
+}
+
+// nsac_gemm_split + a residual input given as hi/lo planes [M, ld_res]: out = act(A.W^T * scale + bias + residual) - the
+// `out += shortcut; relu` of a bottleneck block (detectron2 BottleneckBlock.forward) inside the producing GEMM's epilogue.
+extern "C" int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                                        int ldw, const float* bias, int M, int N, int K, int act, int passes, int fmt,
+                                        float out_scale, const void* res_hi, const void* res_lo, int ld_res, float* out_f32,
+                                        int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+  NSAC_REQUIRE(res_hi && res_lo, "nsac_gemm_split_residual: null residual planes");
+  return gemm_split_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, 0, M, N, K, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                         ld_split, res_hi, res_lo, ld_res, stream);
 }
 
 extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,

@@ -31,6 +31,10 @@
 #include <cuda_fp16.h>
 #include "common.cuh"
 
+#ifndef NSAC_SCORE_L2PREFETCH
+#define NSAC_SCORE_L2PREFETCH 0
+#endif
+
 namespace {
 
 constexpr int TILE_H = 128;        // hypotheses per tile (UMMA M)
@@ -141,6 +145,14 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
+// L2 prefetch of a contiguous global range (no shared-memory destination, no barrier): decouples the HBM stream from the
+// shared-memory ring, which can only run 64 KB ahead of its consumers
+__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
+}
+// programmatic dependent launch: let the next kernel of the stream start its prologue / wait for the previous one's results
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -294,10 +306,10 @@ __device__ __forceinline__ void row_constants(float qw, float qx, float qy, floa
 // i.e. hi.hi + lo.hi + hi.lo (the dropped lo.lo term is < 4e-7 absolute).  Thread (g = lane / 4, q = lane % 4) owns the
 // k-slots (2q, 2q+1 | 2q+8, 2q+9) of rows g, g+8 (A) / column g (B) and receives rows g, g+8 x columns 2q, 2q+1 (D):
 // exactly one packed column pair per row.
-__device__ __forceinline__ void hmma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+__device__ __forceinline__ void hmma16816(float (&d)[4], const uint4& a, uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%10,%10,%10,%10};"
                : "=f"(d[0]), "=f"(d[1]), "=f"(d[2]), "=f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1), "f"(0.f));
+               : "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b0), "r"(b1), "f"(0.f));
 }
 __device__ __forceinline__ uint32_t h_bits(float x) { return (uint32_t)__half_as_ushort(__float2half_rn(x)); }
 // this thread's two A words (k-slots 2q,2q+1 and 2q+8,2q+9) of one row for the 3-vector v
@@ -314,38 +326,50 @@ constexpr int CJ8_FIELDS = 8;         // per column: -k n1 (0-2), -k pi1 (3-5), 
                                       // warp reads with one LDS.128 are 64 contiguous bytes (one wavefront; the [pair][field] layout
                                       // cost 8 wavefronts per load and the shared-memory pipe became the bottleneck, s7 timeline)
 
-// everything after u: one row x one column pair
-template <bool SUMS>
-__device__ __forceinline__ void residual_tail(u64 ux, u64 uy, u64 uz, u64 tu, const u64 (&c)[CJ8_FIELDS], u64 valid, uint32_t& hr,
-                                              uint32_t& ht, u64& sum_r, u64& sum_t) {
+// everything after u, first half (FMA pipe): squared distances of one row x one column pair
+__device__ __forceinline__ void residual_dist2(u64 ux, u64 uy, u64 uz, u64 tu, const u64 (&c)[CJ8_FIELDS], u64& dr2, u64& dt2) {
   const u64 ax = fadd2(ux, c[0]), ay = fadd2(uy, c[1]), az = fadd2(uz, c[2]);
-  const u64 dr2 = ffma2(ax, ax, ffma2(ay, ay, fmul2(az, az)));
+  dr2 = ffma2(ax, ax, ffma2(ay, ay, fmul2(az, az)));
   const u64 g = ffma2(tu, c[6], c[7]);
   const u64 wx = ffma2(g, ux, c[3]), wy = ffma2(g, uy, c[4]), wz = ffma2(g, uz, c[5]);
-  const u64 dt2 = ffma2(wx, wx, ffma2(wy, wy, fmul2(wz, wz)));
+  dt2 = ffma2(wx, wx, ffma2(wy, wy, fmul2(wz, wz)));
+}
+// second half (MUFU pipe): 4 SQRT + 4 EX2 + 2 cvt.  The MUFU instructions are `asm volatile` like the HMMAs, so their order
+// relative to the NEXT group's HMMAs is the source order (see residual_kblock_mma).
+__device__ __forceinline__ float vsqrt(float x) { float r; asm volatile("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float vexp2n(float x) { float r; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-x)); return r; }
+template <bool SUMS>
+__device__ __forceinline__ void residual_finish(u64 dr2, u64 dt2, u64 valid, uint32_t& hr, uint32_t& ht, u64& sum_r, u64& sum_t) {
   float r0, r1, t0, t1;
   upk2(dr2, r0, r1);
   upk2(dt2, t0, t1);
-  r0 = fast_sqrt(r0); r1 = fast_sqrt(r1); t0 = fast_sqrt(t0); t1 = fast_sqrt(t1);
+  r0 = vsqrt(r0); r1 = vsqrt(r1); t0 = vsqrt(t0); t1 = vsqrt(t1);
   if (SUMS) {   // masked distance sums (in log2 units; rescaled by the caller)
     sum_r = ffma2(valid, pk2(r0, r1), sum_r);
     sum_t = ffma2(valid, pk2(t0, t1), sum_t);
   }
-  hr = cvt_h2<false>(fast_exp2(-r0), fast_exp2(-r1));
-  ht = cvt_h2<false>(fast_exp2(-t0), fast_exp2(-t1));
+  hr = cvt_h2<false>(vexp2n(r0), vexp2n(r1));
+  ht = cvt_h2<false>(vexp2n(t0), vexp2n(t1));
 }
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) { asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 
 // One warp's share of a k-block of a hypothesis tile: 16 rows (row block rb) x 32 columns (column half chalf) = 4 groups
 // of 8 columns; per group 4 HMMAs (u_x, u_y, u_z, t.u) and two row x column-pair tails per thread.
+// Software-pipelined by hand: the HMMAs + FMA-pipe half of group g+1 are issued BEFORE the MUFU half of group g (both are
+// volatile asm, so ptxas keeps that order), i.e. the 16 MUFU instructions of a group (128 cycles of the XU pipe) run under
+// the next group's shared-memory loads, HMMA latency and packed-FMA chain instead of after them (r1j SASS: every group was
+// one serial LDS -> HMMA -> FMA -> MUFU -> STS chain, 52 % of the MUFU floor).
+// `sts0` = shared-window address of this thread's word in the rot A tile for group 0, row g: the 128-byte swizzle is
+// ((chalf*4 + grp) ^ (row & 7)) << 4 and row & 7 == g for both rows, so group grp is sts0 ^ (grp << 4), row g+8 is +1024,
+// the trans tile +BLK_BYTES.
 template <bool SUMS>
-__device__ __forceinline__ void residual_kblock_mma(const uint32_t (&afrag)[4][4], const uint8_t* __restrict__ cjk, uint8_t* a_rot,
-                                                    int rb, int chalf, int lane, int col0, int m, u64 (&sum_r)[2], u64 (&sum_t)[2]) {
-  uint8_t* a_tran = a_rot + BLK_BYTES;
-  const int g = lane >> 2, q = lane & 3;
+__device__ __forceinline__ void residual_kblock_mma(const uint4 (&afrag)[4], const uint8_t* __restrict__ cjk, uint32_t sts0,
+                                                    int chalf, int lane, int col0, int m, u64 (&sum_r)[2], u64 (&sum_t)[2]) {
+  const int q = lane & 3;
   const uint2* bfr = reinterpret_cast<const uint2*>(cjk + 2048) + (chalf * 4) * 32 + lane;
   const ulonglong2* c8 = reinterpret_cast<const ulonglong2*>(cjk) + (chalf * 4) * 16 + q;
-#pragma unroll
-  for (int grp = 0; grp < 4; ++grp) {
+  u64 dr2[2][2], dt2[2][2];          // [pipeline slot][row half]
+  auto front = [&](int grp, u64 (&r2)[2], u64 (&t2)[2]) {
     const uint2 b = bfr[grp * 32];
     float dx[4], dy[4], dz[4], dt[4];
     hmma16816(dx, afrag[0], b.x, b.y);
@@ -358,21 +382,31 @@ __device__ __forceinline__ void residual_kblock_mma(const uint32_t (&afrag)[4][4
       const ulonglong2 v = c8[(grp * 4 + i) * 4];
       c[2 * i] = v.x; c[2 * i + 1] = v.y;
     }
+#pragma unroll
+    for (int h2 = 0; h2 < 2; ++h2)
+      residual_dist2(pk2(dx[2 * h2], dx[2 * h2 + 1]), pk2(dy[2 * h2], dy[2 * h2 + 1]), pk2(dz[2 * h2], dz[2 * h2 + 1]),
+                     pk2(dt[2 * h2], dt[2 * h2 + 1]), c, r2[h2], t2[h2]);
+  };
+  auto back = [&](int grp, const u64 (&r2)[2], const u64 (&t2)[2]) {
     u64 valid = 0ull;
     if (SUMS) {
       const int j = col0 + chalf * 32 + grp * 8 + 2 * q;
       valid = pk2(j < m ? 1.f : 0.f, j + 1 < m ? 1.f : 0.f);
     }
+    const uint32_t a = sts0 ^ (uint32_t)(grp << 4);
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2) {
       uint32_t hr, ht;
-      residual_tail<SUMS>(pk2(dx[2 * h2], dx[2 * h2 + 1]), pk2(dy[2 * h2], dy[2 * h2 + 1]), pk2(dz[2 * h2], dz[2 * h2 + 1]),
-                          pk2(dt[2 * h2], dt[2 * h2 + 1]), c, valid, hr, ht, sum_r[h2], sum_t[h2]);
-      const int row = rb * 16 + g + 8 * h2;
-      const uint32_t off = (uint32_t)row * 128u + (uint32_t)(((chalf * 4 + grp) ^ (row & 7)) << 4) + (uint32_t)(q << 2);   // 128-byte swizzle
-      *reinterpret_cast<uint32_t*>(a_rot + off) = hr;
-      *reinterpret_cast<uint32_t*>(a_tran + off) = ht;
+      residual_finish<SUMS>(r2[h2], t2[h2], valid, hr, ht, sum_r[h2], sum_t[h2]);
+      sts32(a + h2 * 1024, hr);
+      sts32(a + h2 * 1024 + BLK_BYTES, ht);
     }
+  };
+  front(0, dr2[0], dt2[0]);
+#pragma unroll
+  for (int grp = 0; grp < 4; ++grp) {
+    if (grp + 1 < 4) front(grp + 1, dr2[(grp + 1) & 1], dt2[(grp + 1) & 1]);
+    back(grp, dr2[grp & 1], dt2[grp & 1]);
   }
 }
 
@@ -404,7 +438,7 @@ struct TcParams {
   const int32_t* matched_num;
   const float* vecs;        // packed: b1[2][128], b2[2][128], w34[2][128]
   const uint8_t* cjk;       // [B][NQp/64][4096 B] per k-block: column constants + HMMA B fragments of the hypothesis tiles
-  const uint4* afr;         // [B][tiles*128][4] HMMA A fragments of every hypothesis row: hi (w01[4 comps], w2[4]), lo (w01[4], w2[4])
+  const uint4* afr;         // [B][tiles*64 row pairs (g, g+8)][hi | lo][4 comps] uint4 = the HMMA A operand {a0,a1,a2,a3} as is
   int B, NQ, NQp, tiles_per_pair, need_sums;
   int num_items, row0_tiles, row0_at;     // item list = B*tiles_per_pair hypothesis tiles + row0_tiles inserted at index row0_at
   float* logits;            // [2][B][NQ+1]
@@ -478,6 +512,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
   __syncthreads();
   fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Everything above (barriers, tensor memory, the weight vectors) is independent of score_prep_kernel: with programmatic
+  // dependent launch it overlaps the prep kernel's tail.  From here on its outputs (cjk, afr, x0) are read.
+  pdl_wait();
+  pdl_launch_dependents();          // the selection kernel may be scheduled as soon as SMs free up (it waits for this grid)
 
   // setmaxnreg: ONE instruction per warpgroup (all 4 warps must execute the same one), inside the warpgroup's own
   // branch so that the register limit is unambiguous on every control path
@@ -545,8 +583,28 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     // (chunk 0, rot), (chunk 0, tran), (chunk 1, rot), ...
     if (lane == 0) {
       int fs = 0; uint32_t fph = 0;
+#if NSAC_SCORE_L2PREFETCH
+      // Experiment (r2b, rejected): pulling the NEXT tile's rows into L2 one item ahead (cp.async.bulk.prefetch.L2) so that HBM
+      // streams during the first tile's scoring.  Measured: DRAM reads 286 -> 393 MB per launch (prefetched lines are evicted
+      // or fetched twice) and the kernel got 10 us slower; the ring fills were no faster from L2.  Kept behind the macro.
+      auto prefetch_item = [&](int item) {
+        Item nx;
+        if (item >= num_items || !decode_item(p, item, nx) || nx.row0) return;
+        const uint32_t bytes = (uint32_t)min(TILE_H, nx.m - nx.tile * TILE_H) * (C_FEAT * 4);
+        const size_t off = ((size_t)nx.b * p.NQ + (size_t)nx.tile * TILE_H) * C_FEAT;
+        for (uint32_t o = 0; o < bytes; o += 32768u) {
+          const uint32_t n = min(32768u, bytes - o);
+          l2_prefetch(reinterpret_cast<const uint8_t*>(p.feat_rot + off) + o, n);
+          l2_prefetch(reinterpret_cast<const uint8_t*>(p.feat_tran + off) + o, n);
+        }
+      };
+      prefetch_item(blockIdx.x);
+#else
+      auto prefetch_item = [&](int) {};
+#endif
       for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
         Item it;
+        prefetch_item(item + gridDim.x);
         if (!decode_item(p, item, it) || it.row0) continue;
         const int rows = min(TILE_H, it.m - it.tile * TILE_H);
         const size_t row0 = (size_t)it.b * p.NQ + (size_t)it.tile * TILE_H;
@@ -712,6 +770,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     asm volatile("setmaxnreg.inc.sync.aligned.u32 80;");
     const int rw = warp - R_WARP0;                   // 0..15
     const int rb = rw & 7, chalf = rw >> 3, g = lane >> 2, q = lane & 3;
+    // this thread's word of row rb*16 + g, group 0 of its column half, in A stage 0 (128-byte swizzle; see residual_kblock_mma)
+    const uint32_t sts_base = smem_u32(smem + OFF_A) + (uint32_t)(rb * 16 + g) * 128u + (uint32_t)(((chalf * 4) ^ g) << 4) + (uint32_t)(q << 2);
     int as = 0; uint32_t aph = 0; int cs = 0; uint32_t cph = 0;
     for (int item = blockIdx.x; item < num_items; item += gridDim.x) {
       Item it;
@@ -728,16 +788,11 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       // ---- hypothesis tile: A fragments of this thread's two rows (g, g + 8 of row block rb), once per tile.  They were
       // computed by score_prep_kernel for every hypothesis (identity pose beyond m): two 16-byte loads per row, no math
       // and no dependence on matched_num, instead of two dependent global round trips + ~250 instructions per tile.
-      uint32_t afrag[4][4];
+      uint4 afrag[4];       // one HMMA A operand (a0..a3) per component: u_x, u_y, u_z, t.u
       {
-        const uint4* ar = p.afr + ((size_t)it.b * p.tiles_per_pair * TILE_H + (size_t)it.tile * TILE_H + rb * 16 + g) * 4 + (q == 1 ? 2 : 0);
+        const uint4* ar = p.afr + (((size_t)it.b * p.tiles_per_pair + it.tile) * (TILE_H / 2) + rb * 8 + g) * 8 + (q == 1 ? 4 : 0);
 #pragma unroll
-        for (int h2 = 0; h2 < 2; ++h2) {
-          uint4 w01 = __ldg(ar + h2 * 8 * 4), w2 = __ldg(ar + h2 * 8 * 4 + 1);
-          if (q == 3) { w01 = make_uint4(0u, 0u, 0u, 0u); w2 = w01; }
-          afrag[0][h2] = w01.x; afrag[1][h2] = w01.y; afrag[2][h2] = w01.z; afrag[3][h2] = w01.w;
-          afrag[0][2 + h2] = w2.x; afrag[1][2 + h2] = w2.y; afrag[2][2 + h2] = w2.z; afrag[3][2 + h2] = w2.w;
-        }
+        for (int c = 0; c < 4; ++c) afrag[c] = q == 3 ? make_uint4(0u, 0u, 0u, 0u) : __ldg(ar + c);
       }
       u64 sum_r[2] = {0ull, 0ull}, sum_t[2] = {0ull, 0ull};
       // decode the next item now and prefetch its fragment rows after the first k-block
@@ -745,17 +800,16 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       nx.row0 = true;
       if (item + (int)gridDim.x < num_items && !decode_item(p, item + gridDim.x, nx)) nx.row0 = true;
       for (int kb = 0; kb < it.nkb; ++kb) {
-        if (kb == 1 && !nx.row0 && q == 0) {        // next tile's fragment rows (64 B each) into L2
-          const uint4* ar = p.afr + ((size_t)nx.b * p.tiles_per_pair * TILE_H + (size_t)nx.tile * TILE_H + rb * 16 + g) * 4;
+        if (kb == 1 && !nx.row0 && q == 0) {        // next tile's fragments of this row pair (128 B) into L2
+          const uint4* ar = p.afr + (((size_t)nx.b * p.tiles_per_pair + nx.tile) * (TILE_H / 2) + rb * 8 + g) * 8;
           asm volatile("prefetch.global.L2 [%0];" ::"l"(ar));
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(ar + 8 * 4));
         }
         NSAC_TRACE(0, threadIdx.x == R_WARP0 * 32);
         mbar_wait(&bars[BAR_A_EMPTY + as], aph ^ 1);
         NSAC_TRACE(0, threadIdx.x == R_WARP0 * 32);
         mbar_wait(&bars[BAR_CJ_FULL + cs], cph);          // column block of this k-block has landed (TMA)
         NSAC_TRACE(0, threadIdx.x == R_WARP0 * 32);
-        residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + cs * CJK_BYTES, smem + OFF_A + as * 2 * BLK_BYTES, rb, chalf, lane, kb * KB,
+        residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + cs * CJK_BYTES, sts_base + (uint32_t)(as * 2 * BLK_BYTES), chalf, lane, kb * KB,
                                   it.m, sum_r, sum_t);
         fence_proxy_async();
         __syncwarp();
@@ -904,37 +958,45 @@ score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__
                   int NQp, int rows_per_pair, uint8_t* __restrict__ cjk, __half* __restrict__ x0, uint4* __restrict__ afr,
                   float* __restrict__ sums) {
   __shared__ float red[2][PREP_THREADS / 32];
+  pdl_launch_dependents();          // the tile kernel's prologue (barriers, tensor memory) may overlap this kernel
   // blocks [0, B): the rows of pair b (A fragments); blocks [B, 2B): its columns + hypothesis 0 - two independent load
   // chains, so they run as separate blocks instead of back to back
   const bool do_rows = (int)blockIdx.x < B;
   const int b = do_rows ? blockIdx.x : blockIdx.x - B, tid = threadIdx.x, m = matched_num[b];
-  // A fragments of every hypothesis row h = 1 + i (rows beyond m: identity pose; their D rows are never read)
-  for (int i = tid; do_rows && i < rows_per_pair; i += PREP_THREADS) {
-    float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
-    if (i < m) {
-      const float4 qq = *reinterpret_cast<const float4*>(q_h + ((size_t)b * NQ + i) * 4);
-      const float* tp = t_h + ((size_t)b * NQ + i) * 3;
-      qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
-      tx = tp[0]; ty = tp[1]; tz = tp[2];
-    }
-    float Rh[9], th[3];
-    row_constants(qw, qx, qy, qz, tx, ty, tz, Rh, th);
-    // t.u = (t / k) . ((k R) n^) = s . n^ with s = (k R)^T (t / k)
-    const float sv[3] = {fmaf(th[0], Rh[0], fmaf(th[1], Rh[3], th[2] * Rh[6])), fmaf(th[0], Rh[1], fmaf(th[1], Rh[4], th[2] * Rh[7])),
-                         fmaf(th[0], Rh[2], fmaf(th[1], Rh[5], th[2] * Rh[8]))};
-    uint32_t w01[2][4], w2[2][4];
+  // A fragments of every hypothesis row h = 1 + i (rows beyond m: identity pose; their D rows are never read).  One thread per
+  // row PAIR (g, g + 8) of a 16-row block: the pair's fragments are stored as the four HMMA A operands {a0 = row g k-slots
+  // 2q,2q+1 | a1 = row g+8 | a2 = row g k-slots 2q+8,2q+9 | a3 = row g+8}, hi words (lanes q = 0, 2) then lo words (q = 1), so the
+  // residual warps load them straight into the operand registers.
+  for (int pi = tid; do_rows && pi < rows_per_pair / 2; pi += PREP_THREADS) {
+    uint32_t w01[2][2][4], w2[2][2][4];          // [row of the pair][hi / lo][component]
 #pragma unroll
-    for (int v = 0; v < 2; ++v) {        // v = 0: hi words (k-slot groups q = 0, 2), v = 1: lo words (q = 1)
-      a_words(Rh[0], Rh[1], Rh[2], v, w01[v][0], w2[v][0]);
-      a_words(Rh[3], Rh[4], Rh[5], v, w01[v][1], w2[v][1]);
-      a_words(Rh[6], Rh[7], Rh[8], v, w01[v][2], w2[v][2]);
-      a_words(sv[0], sv[1], sv[2], v, w01[v][3], w2[v][3]);
+    for (int rr = 0; rr < 2; ++rr) {
+      const int i = (pi >> 3) * 16 + (pi & 7) + 8 * rr;
+      float qw = 1.f, qx = 0.f, qy = 0.f, qz = 0.f, tx = 0.f, ty = 0.f, tz = 0.f;
+      if (i < m) {
+        const float4 qq = *reinterpret_cast<const float4*>(q_h + ((size_t)b * NQ + i) * 4);
+        const float* tp = t_h + ((size_t)b * NQ + i) * 3;
+        qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
+        tx = tp[0]; ty = tp[1]; tz = tp[2];
+      }
+      float Rh[9], th[3];
+      row_constants(qw, qx, qy, qz, tx, ty, tz, Rh, th);
+      // t.u = (t / k) . ((k R) n^) = s . n^ with s = (k R)^T (t / k)
+      const float sv[3] = {fmaf(th[0], Rh[0], fmaf(th[1], Rh[3], th[2] * Rh[6])), fmaf(th[0], Rh[1], fmaf(th[1], Rh[4], th[2] * Rh[7])),
+                           fmaf(th[0], Rh[2], fmaf(th[1], Rh[5], th[2] * Rh[8]))};
+#pragma unroll
+      for (int v = 0; v < 2; ++v) {        // v = 0: hi words (k-slot groups q = 0, 2), v = 1: lo words (q = 1)
+        a_words(Rh[0], Rh[1], Rh[2], v, w01[rr][v][0], w2[rr][v][0]);
+        a_words(Rh[3], Rh[4], Rh[5], v, w01[rr][v][1], w2[rr][v][1]);
+        a_words(Rh[6], Rh[7], Rh[8], v, w01[rr][v][2], w2[rr][v][2]);
+        a_words(sv[0], sv[1], sv[2], v, w01[rr][v][3], w2[rr][v][3]);
+      }
     }
-    uint4* o = afr + ((size_t)b * rows_per_pair + i) * 4;
-    o[0] = make_uint4(w01[0][0], w01[0][1], w01[0][2], w01[0][3]);
-    o[1] = make_uint4(w2[0][0], w2[0][1], w2[0][2], w2[0][3]);
-    o[2] = make_uint4(w01[1][0], w01[1][1], w01[1][2], w01[1][3]);
-    o[3] = make_uint4(w2[1][0], w2[1][1], w2[1][2], w2[1][3]);
+    uint4* o = afr + ((size_t)b * (rows_per_pair / 2) + pi) * 8;
+#pragma unroll
+    for (int v = 0; v < 2; ++v)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[v * 4 + c] = make_uint4(w01[0][v][c], w01[1][v][c], w2[0][v][c], w2[1][v][c]);
   }
   if (do_rows) return;
   float R[9], ts[3];
@@ -1075,6 +1137,7 @@ score_select_tc_kernel(const SelParams p) {
 
   const int m = p.matched_num[b];
   float* P = p.pose + (size_t)b * 16;
+  pdl_wait();                       // launched early (programmatic dependent launch): the tile kernel's results from here on
   if (p.score_rot) for (int h = tid; h < H1n; h += blockDim.x) p.score_rot[(size_t)b * H1n + h] = 0.f;
   if (p.score_tran) for (int h = tid; h < H1n; h += blockDim.x) p.score_tran[(size_t)b * H1n + h] = 0.f;
   if (p.sel_idx && tid < 2) p.sel_idx[b * 2 + tid] = -1;
@@ -1328,10 +1391,19 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   const int rem = items % grid;
   tp.num_items = items; tp.row0_tiles = row0_tiles;
   tp.row0_at = (rem != 0 && rem + row0_tiles <= grid) ? rem : 0;
+  // prep -> tiles -> selection are chained by programmatic dependent launch: each kernel may start while its predecessor
+  // drains and blocks in griddepcontrol.wait before it touches the predecessor's results (captured as programmatic edges
+  // in a CUDA graph)
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+  cfg.attrs = pdl_attr; cfg.numAttrs = 1;
   if (tp.need_sums)
-    score_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, mx0r, mx0t, tp);
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<true>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
   else
-    score_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(m1r, m1t, m2r, m2t, mx0r, mx0t, tp);
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<false>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
   NSAC_CHECK_LAUNCH("score_tc_kernel");
 
   SelParams sp;
@@ -1342,7 +1414,8 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   sp.score_tran = score_tran; sp.sel_idx = sel_idx;
   sp.peer_rows = peer_rows; sp.num_peers = num_peers; sp.row_offset = row_offset;
   const size_t sel_smem = sizeof(float) * (4 * C_FEAT + SEL_THREADS + 16 + 8) + sizeof(int) * SEL_THREADS;
-  score_select_tc_kernel<<<B, SEL_THREADS, sel_smem, s>>>(sp);
+  cfg.gridDim = dim3(B); cfg.blockDim = dim3(SEL_THREADS); cfg.dynamicSmemBytes = sel_smem;
+  NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_select_tc_kernel, sp));
   NSAC_CHECK_LAUNCH("score_select_tc_kernel");
   return NSAC_OK;
 }

@@ -105,16 +105,15 @@ class PlaneTR_NopeSAC(nn.Module):
     @torch.no_grad()
     def inference_from_images(self, images1: torch.Tensor, images2: torch.Tensor, planeParam1, planeParam2, planeApp1, planeApp2,
                               **head_kwargs):
-        """RGB -> backbone -> camera head (rows f2 + a2..a15): `images*` [B,3,H,W] fp32 in 0..255 (normalisation is fused into
-        the stem), both views go through the backbone as one batch of 2B images, `res3..res5` feed the pixel pose CNN, the
+        """RGB -> backbone -> camera head (rows f2 + a2..a15): `images*` [B,3,H,W] uint8 (fast stem) or float in 0..255
+        (normalisation is fused into the stem), both views go through the backbone as one batch of 2B images, `res3..res5` feed the pixel pose CNN, the
         plane lists come from the caller (PlaneTRHead is not built here).  Returns the camera head's 6-tuple."""
         if self.backbone is None:
             raise RuntimeError("PlaneTR_NopeSAC was built without a backbone (with_backbone=True)")
-        B = images1.shape[0]
-        feats = self.backbone(torch.cat([images1, images2], 0))
-        f1 = {k: v[:B] for k, v in feats.items()}
-        f2 = {k: v[B:] for k, v in feats.items()}
-        return self.camera_head_list[0](f1, f2, planeParam1, planeParam2, planeApp1=planeApp1, planeApp2=planeApp2,
+        # `images2 is None`: `images1` already holds both views stacked, [2B,3,H,W] = first views then second views
+        images = images1 if images2 is None else torch.cat([images1, images2], 0)
+        feats = self.backbone(images, planes=True)     # NHWC hi/lo planes, views stacked: no NCHW round trip
+        return self.camera_head_list[0](feats, None, planeParam1, planeParam2, planeApp1=planeApp1, planeApp2=planeApp2,
                                         matching_net=self.matching_head, **head_kwargs)
 
     @torch.no_grad()

@@ -118,7 +118,8 @@ class Split:
                      K, fmt)
 
     def float(self) -> torch.Tensor:
-        return (self.hi[:, :self.K].float() + self.lo[:, :self.K].float()) / self.scale
+        lo = 0.0 if self.lo is None else self.lo[:, :self.K].float()
+        return (self.hi[:, :self.K].float() + lo) / self.scale
 
 
 def split(x: torch.Tensor, fmt: int = SPLIT_F16, scale: float = 1.0) -> Split:
@@ -150,8 +151,10 @@ def split_weight(w: torch.Tensor, fmt: int = SPLIT_F16) -> Split:
 
 def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = ACT_NONE, passes: int = 3,
             want_f32: bool = True, want_split: bool = False, out_f32: Optional[torch.Tensor] = None,
-            out_split: Optional[Split] = None, bias_group_rows: int = 0):
-    """tcgen05 split-precision GEMM: act(a @ w^T + bias) -> (fp32 [M,N] or None, Split or None)."""
+            out_split: Optional[Split] = None, bias_group_rows: int = 0, residual: Optional[Split] = None):
+    """tcgen05 split-precision GEMM: act(a @ w^T + bias [+ residual]) -> (fp32 [M,N] or None, Split or None).
+    `a.lo is None`: A is exact in one 16-bit plane (the lo.hi pass is skipped).  `residual`: planes [M,N] added before the
+    activation (the shortcut of a bottleneck block, fused into the epilogue)."""
     M, N = a.rows, w.rows
     assert a.K == w.K, f"gemm_tc: K mismatch {a.K} vs {w.K}"
     assert a.fmt == w.fmt, "gemm_tc: operand plane formats differ"
@@ -170,6 +173,16 @@ def gemm_tc(a: Split, w: Split, bias: Optional[torch.Tensor] = None, act: int = 
         assert bias.is_contiguous() and bias.shape[-1] == N
     ldo = 0 if out_f32 is None else (out_f32.stride(0) if M > 1 else max(N, out_f32.stride(0)))
     lds = 0 if out_split is None else out_split.hi.stride(0)
+    if residual is not None:
+        assert bias_group_rows == 0 and residual.fmt == a.fmt and residual.scale == 1.0 and residual.rows == M and residual.K == N
+        st = _lib.lib().nsac_gemm_split_residual(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), _p(bias),
+                                                 M, N, K, act, passes, a.fmt, 1.0 / (a.scale * w.scale), _p(residual.hi),
+                                                 _p(residual.lo), residual.hi.stride(0), _p(out_f32), ldo,
+                                                 None if out_split is None else _p(out_split.hi),
+                                                 None if out_split is None else _p(out_split.lo), lds, _stream())
+        _lib.check(st, "nsac_gemm_split_residual")
+        _count()
+        return out_f32, out_split
     st = _lib.lib().nsac_gemm_split(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), _p(bias),
                                     bias_group_rows, M, N, K, act, passes, a.fmt, 1.0 / (a.scale * w.scale),
                                     _p(out_f32), ldo, None if out_split is None else _p(out_split.hi),
@@ -292,6 +305,47 @@ def stem_im2col_planes(img: torch.Tensor, mean, std, fmt: int = SPLIT_F16):
     m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
     st = _lib.lib().nsac_stem_im2col_planes(_p(img), N, H, W, m3, s3, fmt, _p(out.hi), _p(out.lo), _stream())
     _lib.check(st, "nsac_stem_im2col_planes")
+    _count()
+    return out, Ho, Wo
+
+
+def stem_im2col_u8(img: torch.Tensor):
+    """[N,3,H,W] uint8 -> (Split with ONE fp16 plane [N*Ho*Wo, 192] of raw pixel values (K = 147 in (ky,kx,c) order, `lo` is
+    None: exact), Ho, Wo).  Out-of-image taps are 0 — see stem_border_fix."""
+    img = _c(img, "img", torch.uint8)
+    N, Cc, H, W = img.shape
+    assert Cc == 3
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    hi = torch.empty(N * Ho * Wo, 192, device=img.device, dtype=torch.float16)
+    st = _lib.lib().nsac_stem_im2col_u8(_p(img), N, H, W, _p(hi), _stream())
+    _lib.check(st, "nsac_stem_im2col_u8")
+    _count()
+    return Split(hi, None, 147), Ho, Wo
+
+
+def stem_border_fix(img: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor, mean, std, out: torch.Tensor):
+    """Recomputes in exact fp32 the rows of the stem output `out` [N*Ho*Wo, 64] whose 7x7 window leaves the image (the zero
+    padding applies to the normalised image); w_folded [64,147] fp32, (ky,kx,c) order, for normalised input."""
+    img = _c(img, "img", torch.uint8)
+    _chk(w_folded, "w_folded"); _chk(bias, "bias"); _chk(out, "out")
+    N, _, H, W = img.shape
+    assert w_folded.is_contiguous() and tuple(w_folded.shape) == (64, 147) and out.is_contiguous() and out.shape[1] == 64
+    m3, s3 = (C.c_float * 3)(*[float(v) for v in mean]), (C.c_float * 3)(*[float(v) for v in std])
+    st = _lib.lib().nsac_stem_border_fix(_p(img), _p(w_folded), _p(bias), N, H, W, m3, s3, _p(out), _stream())
+    _lib.check(st, "nsac_stem_border_fix")
+    _count()
+    return out
+
+
+def im2col3x3_from_planes(x: Split, N: int, H: int, W: int, stride: int):
+    """3x3 / pad 1 im2col of contiguous NHWC planes [N*H*W, C] -> (Split [N*Ho*Wo, 9*C], Ho, Wo): 16-byte copies."""
+    Cc = x.hi.shape[1]
+    assert x.hi.is_contiguous() and x.lo.is_contiguous() and x.rows == N * H * W and Cc % 8 == 0 and (9 * Cc) % 64 == 0
+    Ho, Wo = (H - 1) // stride + 1, (W - 1) // stride + 1
+    out = Split(torch.empty(N * Ho * Wo, 9 * Cc, device=x.hi.device, dtype=x.hi.dtype),
+                torch.empty(N * Ho * Wo, 9 * Cc, device=x.hi.device, dtype=x.hi.dtype), 9 * Cc, x.fmt, x.scale)
+    st = _lib.lib().nsac_im2col3x3_from_planes(_p(x.hi), _p(x.lo), N, H, W, Cc, stride, _p(out.hi), _p(out.lo), _stream())
+    _lib.check(st, "nsac_im2col3x3_from_planes")
     _count()
     return out, Ho, Wo
 

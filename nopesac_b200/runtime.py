@@ -31,9 +31,15 @@ def batch_bytes(batch: Dict) -> int:
 
 
 class PairPipeline:
-    def __init__(self, head, matching_head, device, hyp_pairs: Optional[torch.Tensor] = None, post=None, result_exchange=None):
+    """`compute` (optional): callable(device_batch) -> result rows [B,16]; default = the camera head on backbone feature maps
+    (batch keys planes1, planes2, app1, app2, feats1, feats2).  The full model from RGB passes e.g.
+    `lambda d: model.inference_from_images(d["images"], None, d["planes1"], ...)[5]["pose"]` with a uint8 `images` entry."""
+
+    def __init__(self, head, matching_head, device, hyp_pairs: Optional[torch.Tensor] = None, post=None, result_exchange=None,
+                 compute=None):
         self.head, self.match, self.device, self.hyp_pairs, self.post = head, matching_head, device, hyp_pairs, post
         self.result_exchange = result_exchange
+        self.compute = compute
         self.copy_stream = torch.cuda.Stream(device)
         self.slots = [None, None]
         self.copied = [torch.cuda.Event(), torch.cuda.Event()]
@@ -63,9 +69,12 @@ class PairPipeline:
         cur = torch.cuda.current_stream(self.device)
         cur.wait_event(self.copied[slot])
         d = self.slots[slot]
-        out = self.head(d["feats1"], d["feats2"], d["planes1"], d["planes2"], d["app1"], d["app2"],
-                        matching_net=self.match, hyp_pairs=self.hyp_pairs, result_exchange=self.result_exchange)
-        rows = out[5]["pose"]
+        if self.compute is not None:
+            rows = self.compute(d)
+        else:
+            out = self.head(d["feats1"], d["feats2"], d["planes1"], d["planes2"], d["app1"], d["app2"],
+                            matching_net=self.match, hyp_pairs=self.hyp_pairs, result_exchange=self.result_exchange)
+            rows = out[5]["pose"]
         if self.post is not None:
             rows = self.post(rows)                                     # e.g. the multi-GPU result all-gather
         self.consumed[slot].record(cur)

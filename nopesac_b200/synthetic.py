@@ -197,6 +197,36 @@ def make_weights(shapes, seed: int = 40):
     return out
 
 
+def make_backbone_weights(shapes, seed: int = 8, conv3_scale: float = 0.3):
+    """Seeded random-init state of the R-50 backbone (BASELINE.json configs[1]: "random-init ResNet50") for a {name: shape} spec
+    (`ResNet50Backbone().state_dict()` shapes): He-normal (fan_out) convolutions like c2_msra_fill, FrozenBN statistics drawn
+    non-trivially, and the last norm scale of every block damped by `conv3_scale` so that 16 residual blocks of a RANDOM network
+    keep res5 O(1) like a trained one (otherwise activations grow ~2x per block and the pixel network's correlation softmax
+    saturates).  Both arms of the bench load this same state."""
+    g = torch.Generator().manual_seed(seed)
+    out = {}
+    for name in sorted(shapes):
+        shape = tuple(shapes[name])
+        if name.endswith("running_var"):
+            t = torch.rand(shape, generator=g) + 0.5
+        elif name.endswith("norm.weight"):
+            t = torch.rand(shape, generator=g) * 0.5 + 0.5
+            if name.endswith("conv3.norm.weight"):
+                t = t * conv3_scale
+        elif name.endswith("norm.bias") or name.endswith("running_mean"):
+            t = torch.randn(shape, generator=g) * 0.1
+        else:
+            t = torch.randn(shape, generator=g) * (2.0 / (shape[0] * shape[2] * shape[3])) ** 0.5
+        out[name] = t
+    return out
+
+
+def make_images(seed: int, num_images: int, height: int = 480, width: int = 640) -> torch.Tensor:
+    """Synthetic RGB, uint8 U{0..255} [N,3,H,W] (SURVEY.md 8d "RGB (full-model benches)"), seeded on the host."""
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(0, 256, (num_images, 3, height, width), generator=g, dtype=torch.uint8)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # Row f1: synthetic PlaneTRHead outputs (the inputs of `_postprocess_planeHeadMask`, siamese_planeTR.py:625-803)
 # ---------------------------------------------------------------------------------------------------------------------

@@ -60,11 +60,13 @@ extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scal
   return NSAC_OK;
 }
 
-extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
-                               const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
-                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
-  if (!a_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 2 && !a_lo) || (passes >= 3 && !w_lo) || K % 64 != 0 || lda < K ||
-      ldw < K || (!out_f32 && !out_hi) || (out_hi && !out_lo)) {
+static int gemm_split_standin(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                              const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
+                              float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                              const void* res_hi, const void* res_lo, int ld_res) {
+  // a_lo == NULL: A has no lo plane (exact in 16 bits) - include/nopesac_b200.h
+  if (!a_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 3 && !w_lo) || K % 64 != 0 || lda < K ||
+      ldw < K || (!out_f32 && !out_hi) || (out_hi && !out_lo) || (res_hi && (!res_lo || ld_res < N))) {
     nsac_set_error("nsac_gemm_split (stand-in): bad arguments");
     return NSAC_ERR_ARG;
   }
@@ -82,7 +84,7 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
   for (int m = 0; m < M; ++m) {
     for (int k = 0; k < K; ++k) {
       AH[k] = plane_to_float(ah[(size_t)m * lda + k], fmt);
-      AL[k] = passes >= 2 ? plane_to_float(al[(size_t)m * lda + k], fmt) : 0.0;
+      AL[k] = (passes >= 2 && al) ? plane_to_float(al[(size_t)m * lda + k], fmt) : 0.0;
     }
     const float* brow = bias ? (bias_group_rows > 0 ? bias + (size_t)(m / bias_group_rows) * N : bias) : nullptr;
     for (int n = 0; n < N; ++n) {
@@ -92,12 +94,34 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
       if (passes >= 4)
         for (int k = 0; k < K; ++k) acc += AL[k] * w1[k];
       float v = out_scale * (float)acc + (brow ? brow[n] : 0.f);
+      if (res_hi)
+        v += plane_to_float(static_cast<const uint16_t*>(res_hi)[(size_t)m * ld_res + n], fmt) +
+             plane_to_float(static_cast<const uint16_t*>(res_lo)[(size_t)m * ld_res + n], fmt);
       v = fmaxf(v, slope * v + 0.f);
       if (out_f32) out_f32[(size_t)m * ldo + n] = v;
       if (out_hi) split16(v, fmt, static_cast<uint16_t*>(out_hi)[(size_t)m * ld_split + n], static_cast<uint16_t*>(out_lo)[(size_t)m * ld_split + n]);
     }
   }
   return NSAC_OK;
+}
+
+extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                               const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
+                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
+  return gemm_split_standin(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, bias_group_rows, M, N, K, act, passes, fmt, out_scale, out_f32, ldo,
+                            out_hi, out_lo, ld_split, nullptr, nullptr, 0);
+}
+
+extern "C" int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                                        const float* bias, int M, int N, int K, int act, int passes, int fmt, float out_scale,
+                                        const void* res_hi, const void* res_lo, int ld_res, float* out_f32, int ldo, void* out_hi,
+                                        void* out_lo, int ld_split, void*) {
+  if (!res_hi || !res_lo) {
+    nsac_set_error("nsac_gemm_split_residual (stand-in): null residual planes");
+    return NSAC_ERR_ARG;
+  }
+  return gemm_split_standin(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, 0, M, N, K, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                            ld_split, res_hi, res_lo, ld_res);
 }
 
 // 3x3 / stride 1 / pad 1 convolution over NHWC planes as the same hi/lo-plane product (weights [Cout, 9*Cin], (ky,kx,cin) order)

@@ -129,7 +129,8 @@ def test_plane_lists_to_camera_head_glue_on_host(host_ops):
         _check_against(util.oracle_to_flat(o), cams_i, [lsp[0][i:i + 1, :n1 + 1, :n2 + 1]], ass_i, pro_i, 0, f"plane-list pair {i} ({n1}x{n2})")
 
 
-def test_resnet50_backbone_glue_on_host_matches_oracle(host_ops):
+@pytest.mark.parametrize("u8", [False, True])
+def test_resnet50_backbone_glue_on_host_matches_oracle(host_ops, u8):
     """Row f2: `ResNet50Backbone.forward` (stem normalisation + im2col, 53 convolutions as GEMMs on hi/lo planes with FrozenBN
     folded, max-pool, stride-2 paths, residual adds) on CPU tensors against the backbone oracle (= torchvision's resnet50,
     tests/test_oracle_backbone.py) at a reduced input size; parameter names / shapes are detectron2's."""
@@ -152,9 +153,11 @@ def test_resnet50_backbone_glue_on_host_matches_oracle(host_ops):
             sd[k] = torch.randn(shape, generator=g) * (2.0 / fan_out) ** 0.5
     net.load_state_dict(sd)
     images = torch.rand(2, 3, 64, 96, generator=g) * 255
+    if u8:      # the reference loader's format: the fast stem (one exact fp16 plane, normalisation in the weights, exact borders)
+        images = images.to(torch.uint8)
     got = net(images)
     with torch.no_grad():
-        want = br.resnet50(sd, br.normalize(images, cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
+        want = br.resnet50(sd, br.normalize(images.float(), cfg.MODEL.PIXEL_MEAN, cfg.MODEL.PIXEL_STD))
     assert list(got) == ["res2", "res3", "res4", "res5"]
     for k in want:
         assert got[k].shape == want[k].shape, k
