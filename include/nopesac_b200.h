@@ -267,6 +267,13 @@ int nsac_camera_errors(const float* pose, int ldpose, const float* gt_tran, cons
  *   feats [B,NQ,C] = pred_plane_feats; scores [B,NQ]; centers [B,NQ,2] = pred_plane_ins_center; bboxes [B,NQ,4] = (x,y,w,h)
  *   of pycocotools toBbox; areas [B,NQ]; seg [B,H,W] uint8 label map, 255 = no plane, pred_plane_masks[j] == (seg == j).
  * workspace: nsac_plane_post_workspace_bytes(B,NQ,H,W) bytes; workspace and seg 16-byte aligned. */
+/* nsac_conv3x3_split with a convolution stride of 1 or 2 (H, W = INPUT map; output (H-1)/stride+1 x (W-1)/stride+1, rows in that
+ * order): the A tiles are gathered by TMA with a traversal stride, no im2col matrix.  The strided 3x3 of res3.0 / res4.0 /
+ * res5.0 of the backbone (detectron2 BottleneckBlock with STRIDE_IN_1X1 = False, Base.yaml:2-12). */
+int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               int N, int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt,
+                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                               void* stream);
 size_t nsac_plane_post_workspace_bytes(int B, int NQ, int H, int W);
 int nsac_plane_postprocess(const float* pred_logits, const float* pred_params, const float* mask_logits,
                            const float* query_feat, int B, int NQ, int C, int h, int w, int H, int W,

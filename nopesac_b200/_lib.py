@@ -31,6 +31,9 @@ _SIGNATURES = {
     "nsac_conv3x3_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                      C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int, C.c_void_p,
                                      C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_conv3x3_split_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nsac_nchw_to_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsac_groupnorm_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "nsac_groupnorm_nhwc": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_float,

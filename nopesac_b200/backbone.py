@@ -7,8 +7,8 @@ same registry name, same parameter / buffer names (`stem.conv1.weight`, `stem.co
 `(x - PIXEL_MEAN) / PIXEL_STD` of `preprocess_image` (siamese_planeTR.py `preprocess_image`, Base.yaml:6-7).
 
 Every convolution is a GEMM on NHWC 16-bit hi/lo planes (3 passes ~ fp32): 1x1 -> `nsac_gemm_split`, 3x3 stride 1 ->
-`nsac_conv3x3_split` (implicit GEMM, 4-D TMA gather), 3x3 stride 2 -> `nsac_im2col3x3_from_planes` + GEMM, stem 7x7/2 -> im2col +
-GEMM; FrozenBN is folded into weights and bias, ReLU runs in the GEMM epilogue, and `relu(out + shortcut)` of every bottleneck
+`nsac_conv3x3_split` (implicit GEMM, 4-D TMA gather), 3x3 stride 2 -> `nsac_conv3x3_split_strided` (same kernel, the tensor
+map's traversal stride picks every second pixel), stem 7x7/2 -> im2col + GEMM; FrozenBN is folded into weights and bias, ReLU runs in the GEMM epilogue, and `relu(out + shortcut)` of every bottleneck
 block runs in the epilogue of its last GEMM (`nsac_gemm_split_residual`): activations exist only as hi/lo planes between layers
 (r1 went through fp32 NHWC + a separate add kernel: 11 of 62 ms).  uint8 images (what the reference's loader delivers) take the
 fast stem: one exact fp16 plane of raw pixels, normalisation folded into the weights, borders recomputed exactly
@@ -143,11 +143,9 @@ class ResNet50Backbone(nn.Module):
         w3, b3 = pk[key + ".conv3"]
         Ho, Wo = H, W
         _, y1p = ops.gemm_tc(xp, w1, b1, ops.ACT_RELU, P, want_f32=False, want_split=True)
-        if blk.stride == 1:
-            _, y2p = ops.conv3x3_tc(y1p, N, H, W, w2, b2, ops.ACT_RELU, P, want_f32=False, want_split=True)
-        else:
-            cols, Ho, Wo = ops.im2col3x3_from_planes(y1p, N, H, W, blk.stride)
-            _, y2p = ops.gemm_tc(cols, w2, b2, ops.ACT_RELU, P, want_f32=False, want_split=True)
+        # 3x3, stride 1 or 2 (STRIDE_IN_1X1 = False): implicit GEMM, the stride is the TMA tensor map's traversal stride
+        _, y2p = ops.conv3x3_tc(y1p, N, H, W, w2, b2, ops.ACT_RELU, P, want_f32=False, want_split=True, stride=blk.stride)
+        Ho, Wo = (H - 1) // blk.stride + 1, (W - 1) // blk.stride + 1
         if hasattr(blk, "shortcut"):
             ws, bs = pk[key + ".shortcut"]
             src = xp if blk.stride == 1 else ops.subsample2_planes(xp, N, H, W)[0]

@@ -124,74 +124,107 @@ add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t
 // window leaves the image are recomputed exactly by stem_border_fix_kernel afterwards.
 // One CTA = one output row (n, yo): its 7 x 3 input rows are staged in shared memory with coalesced loads, then every thread
 // emits 16-byte chunks (8 consecutive k of one output pixel).
-constexpr int STEM_U8_MAXW = 2048;     // widest image row that fits the staging buffer (7 rows x 3 channels x (W + 6) bytes <= 43 KB)
-__global__ void __launch_bounds__(256)
+constexpr int STEM_U8_MAXW = 1024;     // widest image row whose staging buffer (7 rows x 3 channels x (W + 6) fp16) fits 48 KB
+constexpr int STEM_U8_THREADS = 256, STEM_U8_LANES = 10;   // 24 k-chunks (8 k each) x 10 pixel lanes (16 threads only help staging)
+__global__ void __launch_bounds__(STEM_U8_THREADS)
 stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int Wo, uint16_t* __restrict__ out) {
-  extern __shared__ uint8_t rows[];                    // [7][3][W + 6], x index shifted by +3, zero outside the image
+  extern __shared__ uint16_t rows[];                   // [7][3][Wp] fp16 bit patterns of the pixel values, x shifted by +3, 0 outside the image
   const int n = blockIdx.x / Ho, yo = blockIdx.x % Ho, Wp = W + 6;
-  for (int i = threadIdx.x; i < 21 * Wp; i += blockDim.x) {
-    const int xs = i % Wp, rc = i / Wp, ky = rc / 3, c = rc % 3;
-    const int y = 2 * yo + ky - 3, x = xs - 3;
-    rows[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(img + (((size_t)n * 3 + c) * H + y) * W + x) : (uint8_t)0;
+  auto h16 = [](uint32_t v) { return __half_as_ushort(__float2half_rn((float)v)); };     // exact for 0..255
+  // coalesced row loads, converted once per input pixel: 4 bytes per thread where rows are 4-byte aligned (W % 4 == 0)
+  if ((W & 3) == 0) {
+    const int W4 = W >> 2;
+    for (int i = threadIdx.x; i < 21 * W4; i += blockDim.x) {
+      const int x4 = i % W4, rc = i / W4, ky = rc / 3, c = rc % 3, y = 2 * yo + ky - 3;
+      uint32_t v = 0u;
+      if (y >= 0 && y < H) v = __ldg(reinterpret_cast<const uint32_t*>(img + (((size_t)n * 3 + c) * H + y) * W) + x4);
+      uint16_t* d = rows + rc * Wp + 3 + 4 * x4;
+      d[0] = h16(v & 255u); d[1] = h16((v >> 8) & 255u); d[2] = h16((v >> 16) & 255u); d[3] = h16(v >> 24);
+    }
+    for (int i = threadIdx.x; i < 21 * 6; i += blockDim.x) {          // the 3 + 3 padding columns
+      const int rc = i / 6, e = i % 6;
+      rows[rc * Wp + (e < 3 ? e : W + e)] = 0;
+    }
+  } else {
+    for (int i = threadIdx.x; i < 21 * Wp; i += blockDim.x) {
+      const int xs = i % Wp, rc = i / Wp, ky = rc / 3, c = rc % 3;
+      const int y = 2 * yo + ky - 3, x = xs - 3;
+      rows[i] = (y >= 0 && y < H && x >= 0 && x < W) ? h16(__ldg(img + (((size_t)n * 3 + c) * H + y) * W + x)) : (uint16_t)0;
+    }
   }
   __syncthreads();
+  // thread = (k-chunk kc, pixel lane xl): its 8 source offsets are fixed, it walks over the output pixels xl, xl + 10, ...
+  const int kc = threadIdx.x % (STEM_KP / 8), xl = threadIdx.x / (STEM_KP / 8);
+  int koff[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kc * 8 + e;
+    if (k < STEM_K) {
+      const int c = k % 3, tap = k / 3, ky = tap / 7, kx = tap - ky * 7;
+      koff[e] = (ky * 3 + c) * Wp + kx;
+    } else {
+      koff[e] = -1;
+    }
+  }
   const size_t row0 = ((size_t)n * Ho + yo) * Wo;
-  for (int i = threadIdx.x; i < Wo * (STEM_KP / 8); i += blockDim.x) {
-    const int xo = i / (STEM_KP / 8), k0 = (i % (STEM_KP / 8)) * 8;
+  for (int xo = xl < STEM_U8_LANES ? xl : Wo; xo < Wo; xo += STEM_U8_LANES) {
     uint32_t w[4];
 #pragma unroll
-    for (int j = 0; j < 8; j += 2) {
-      uint32_t pair = 0;
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        const int k = k0 + j + e;
-        float v = 0.f;
-        if (k < STEM_K) {
-          const int c = k % 3, tap = k / 3, ky = tap / 7, kx = tap - ky * 7;
-          v = (float)rows[(ky * 3 + c) * Wp + 2 * xo + kx];
-        }
-        pair |= (uint32_t)__half_as_ushort(__float2half_rn(v)) << (16 * e);
-      }
-      w[j >> 1] = pair;
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t v0 = koff[2 * j] >= 0 ? rows[koff[2 * j] + 2 * xo] : 0u, v1 = koff[2 * j + 1] >= 0 ? rows[koff[2 * j + 1] + 2 * xo] : 0u;
+      w[j] = v0 | (v1 << 16);
     }
-    *reinterpret_cast<uint4*>(out + (row0 + xo) * STEM_KP + k0) = make_uint4(w[0], w[1], w[2], w[3]);
+    *reinterpret_cast<uint4*>(out + (row0 + xo) * STEM_KP + kc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   }
 }
 
 // Exact fp32 recomputation of the stem outputs whose 7x7 window leaves the image (zero padding applies to the NORMALISED
 // image): out[row, co] = relu(bias[co] + sum_k w[co, k] * (p - mean_c) / std_c over the in-image taps).  w: folded weights
-// [64, 147] in (ky, kx, c) order for normalised input.  One warp per border pixel, lane = 2 output channels.
+// [64, 147] in (ky, kx, c) order for normalised input, transposed into shared memory ([k][64], 37 KB) once per CTA.  One warp
+// per border pixel (grid-stride), lane = 2 output channels.
 __global__ void __launch_bounds__(256)
 stem_border_fix_kernel(const uint8_t* __restrict__ img, const float* __restrict__ w, const float* __restrict__ bias, int N, int H,
                        int W, int Ho, int Wo, float m0, float m1, float m2, float s0, float s1, float s2, float* __restrict__ out) {
+  extern __shared__ float wT[];                        // [147][64]
+  for (int i = threadIdx.x; i < 64 * STEM_K; i += blockDim.x) wT[(i % STEM_K) * 64 + i / STEM_K] = __ldg(w + i);
+  __syncthreads();
   // border pixels of one image: rows yo < 2 or yo >= Ho - 2 (all xo), plus columns xo < 2 or xo >= Wo - 2 of the other rows
   const int top = Ho < 4 ? Ho : 4, side_rows = Ho - top, per_img = top * Wo + side_rows * 4;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N * per_img) return;
-  const int n = warp / per_img, r = warp % per_img;
-  int yo, xo;
-  if (r < top * Wo) {
-    const int t = r / Wo;
-    yo = t < 2 ? t : Ho - 4 + t;          // t = 0,1 -> rows 0,1; t = 2,3 -> rows Ho-2, Ho-1
-    xo = r % Wo;
-  } else {
-    const int q = r - top * Wo, t = q & 3;
-    yo = 2 + (q >> 2);
-    xo = t < 2 ? t : Wo - 4 + t;
-  }
-  if (yo < 0 || yo >= Ho || xo < 0 || xo >= Wo) return;
+  const int lane = threadIdx.x & 31, warps_per_block = blockDim.x >> 5;
   const float mean[3] = {m0, m1, m2}, istd[3] = {1.f / s0, 1.f / s1, 1.f / s2};
-  float a0 = 0.f, a1 = 0.f;
-  for (int k = 0; k < STEM_K; ++k) {
-    const int c = k % 3, tap = k / 3, ky = tap / 7, kx = tap - ky * 7;
-    const int y = 2 * yo + ky - 3, x = 2 * xo + kx - 3;
-    if (y < 0 || y >= H || x < 0 || x >= W) continue;
-    const float v = ((float)__ldg(img + (((size_t)n * 3 + c) * H + y) * W + x) - mean[c]) * istd[c];
-    a0 = fmaf(__ldg(w + (size_t)(2 * lane) * STEM_K + k), v, a0);
-    a1 = fmaf(__ldg(w + (size_t)(2 * lane + 1) * STEM_K + k), v, a1);
+  const float2 b2 = make_float2(__ldg(bias + 2 * lane), __ldg(bias + 2 * lane + 1));
+  for (int wi = blockIdx.x * warps_per_block + (threadIdx.x >> 5); wi < N * per_img; wi += gridDim.x * warps_per_block) {
+    const int n = wi / per_img, r = wi % per_img;
+    int yo, xo;
+    if (r < top * Wo) {
+      const int t = r / Wo;
+      yo = t < 2 ? t : Ho - 4 + t;          // t = 0,1 -> rows 0,1; t = 2,3 -> rows Ho-2, Ho-1
+      xo = r % Wo;
+    } else {
+      const int q = r - top * Wo, t = q & 3;
+      yo = 2 + (q >> 2);
+      xo = t < 2 ? t : Wo - 4 + t;
+    }
+    if (yo < 0 || yo >= Ho || xo < 0 || xo >= Wo) continue;
+    float a0 = 0.f, a1 = 0.f;
+    for (int ky = 0; ky < 7; ++ky) {
+      const int y = 2 * yo + ky - 3;
+      if (y < 0 || y >= H) continue;
+      for (int kx = 0; kx < 7; ++kx) {
+        const int x = 2 * xo + kx - 3;
+        if (x < 0 || x >= W) continue;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float v = ((float)__ldg(img + (((size_t)n * 3 + c) * H + y) * W + x) - mean[c]) * istd[c];
+          const float2 ww = *reinterpret_cast<const float2*>(wT + ((ky * 7 + kx) * 3 + c) * 64 + 2 * lane);
+          a0 = fmaf(ww.x, v, a0);
+          a1 = fmaf(ww.y, v, a1);
+        }
+      }
+    }
+    float* o = out + (((size_t)n * Ho + yo) * Wo + xo) * 64 + 2 * lane;
+    *reinterpret_cast<float2*>(o) = make_float2(fmaxf(a0 + b2.x, 0.f), fmaxf(a1 + b2.y, 0.f));
   }
-  float* o = out + (((size_t)n * Ho + yo) * Wo + xo) * 64 + 2 * lane;
-  *reinterpret_cast<float2*>(o) = make_float2(fmaxf(a0 + __ldg(bias + 2 * lane), 0.f), fmaxf(a1 + __ldg(bias + 2 * lane + 1), 0.f));
 }
 
 // 3x3 / pad 1 / stride s im2col from NHWC planes to planes [N*Ho*Wo, 9*C] in (ky, kx, c) order: 16-byte copies of both planes
@@ -286,8 +319,10 @@ extern "C" int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void
   NSAC_REQUIRE(N >= 0 && H >= 7 && W >= 7 && W <= STEM_U8_MAXW, "nsac_stem_im2col_u8: bad shape N=%d H=%d W=%d", N, H, W);
   if (N == 0) return NSAC_OK;
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
-  const size_t smem = (size_t)21 * (W + 6);
-  stem_im2col_u8_kernel<<<N * Ho, 256, smem, static_cast<cudaStream_t>(stream)>>>(img, H, W, Ho, Wo, static_cast<uint16_t*>(out_hi));
+  NSAC_REQUIRE((reinterpret_cast<uintptr_t>(img) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0,
+               "nsac_stem_im2col_u8: image must be 4-byte aligned, output plane 16-byte aligned");
+  const size_t smem = (size_t)21 * (W + 6) * sizeof(uint16_t);
+  stem_im2col_u8_kernel<<<N * Ho, STEM_U8_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(img, H, W, Ho, Wo, static_cast<uint16_t*>(out_hi));
   NSAC_CHECK_LAUNCH("nsac_stem_im2col_u8");
   return NSAC_OK;
 }
@@ -301,7 +336,10 @@ extern "C" int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, c
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const int top = Ho < 4 ? Ho : 4, per_img = top * Wo + (Ho - top) * 4;
   const size_t warps = (size_t)N * per_img;
-  stem_border_fix_kernel<<<(unsigned)((warps * 32 + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  const size_t smem_w = (size_t)64 * STEM_K * sizeof(float);
+  size_t blocks = (warps + 7) / 8;
+  if (blocks > 148 * 4) blocks = 148 * 4;          // grid-stride: the 37 KB weight transpose is paid once per CTA
+  stem_border_fix_kernel<<<(unsigned)blocks, 256, smem_w, static_cast<cudaStream_t>(stream)>>>(
       img, w_folded, bias, N, H, W, Ho, Wo, mean3_host[0], mean3_host[1], mean3_host[2], std3_host[0], std3_host[1], std3_host[2], out);
   NSAC_CHECK_LAUNCH("nsac_stem_border_fix");
   return NSAC_OK;

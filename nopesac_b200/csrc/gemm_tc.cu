@@ -54,16 +54,20 @@ constexpr uint32_t SPIN_LIMIT = 1u << 24;  // suspended waits of up to ~1 us eac
 
 constexpr int CHUNK_KB = 4;                 // K-blocks (x64 elements) accumulated inside the tensor core per chunk
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool RES = false>
 struct Cfg {
-  static constexpr int STAGES = 3;
+  // RES: the residual tile [128 x BLOCK_N] x (hi, lo) is TMA-prefetched into its own 64 KB (32 KB) of shared memory while the
+  // tile's MMAs run, so the operand ring shrinks to 2 stages (these layers are epilogue / HBM bound, K <= 512)
+  static constexpr int STAGES = RES ? 2 : (BLOCK_N == 64 ? 4 : 3);       // 48 KB / 64 KB per stage
+  static constexpr int RES_PLANE_BYTES = RES ? BLOCK_M * BLOCK_N * 2 : 0;
+  static constexpr int RES_BYTES = 2 * RES_PLANE_BYTES;
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int ACC_COLS = 2 * BLOCK_N;              // one buffer = hi.hi accumulator + lo-terms accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
   static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
 };
@@ -171,7 +175,8 @@ struct GemmParams {
   int bias_group_rows;
   int M, N, K, act, passes, fmt;
   // implicit-GEMM 3x3 / stride 1 / pad 1 convolution over NHWC planes (conv_taps == 9), else plain GEMM
-  int conv_taps, H, W, BW, BH, cblocks, tiles_x, tiles_y;
+  int conv_taps, H, W, BW, BH, cblocks, tiles_x, tiles_y;      // H, W: OUTPUT map
+  int cstride;              // convolution stride (1 or 2): tap (dy, dx) of output pixel (y, x) reads input (cstride*y + dy, cstride*x + dx)
   float out_scale;          // multiplies the accumulator before bias (undoes the power-of-two weight pre-scale)
   float* out_f32;
   int ldo;
@@ -239,9 +244,22 @@ struct EpiOut {
   uint16_t* out_lo;
   int n_valid;            // valid columns from col0 on (>= 32: full chunk)
   bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
-  const uint16_t* res_hi; // residual row pointers (nullptr: none)
-  const uint16_t* res_lo;
+  const uint8_t* res_row; // this lane's row of the TMA-staged residual tile (hi plane; nullptr: none) - 128-byte swizzled rows
+  int res_lo_off;         // byte offset of the lo plane's copy of the same row
+  int res_swz;            // row & 7 (XOR key of the 16-byte chunks)
 };
+
+// 32 residual columns (first column = 16-byte chunk index `chunk0` of the lane's 128-byte row) -> 16 hi words + 16 lo words
+__device__ __forceinline__ void load_res32(const EpiOut& o, int chunk0, uint32_t (&rh)[16], uint32_t (&rl)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const int off = ((chunk0 + c) ^ o.res_swz) << 4;
+    const uint4 h = *reinterpret_cast<const uint4*>(o.res_row + off);
+    const uint4 l = *reinterpret_cast<const uint4*>(o.res_row + o.res_lo_off + off);
+    rh[4 * c] = h.x; rh[4 * c + 1] = h.y; rh[4 * c + 2] = h.z; rh[4 * c + 3] = h.w;
+    rl[4 * c] = l.x; rl[4 * c + 1] = l.y; rl[4 * c + 2] = l.z; rl[4 * c + 3] = l.w;
+  }
+}
 
 // packed 16-bit plane word -> two floats
 template <int FMT>
@@ -252,7 +270,7 @@ __device__ __forceinline__ float2 unsplit16x2(uint32_t w) {
 
 // 32 accumulator columns -> scale, bias, activation, fp32 store, split-plane store
 template <int FMT>
-__device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const EpiOut& o) {
+__device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, int res_chunk0, const EpiOut& o) {
   float f[32];
   const u64 sc = pk2(o.out_scale, o.out_scale);
   const bool full = o.n_valid >= 32 && o.vec_ok;
@@ -273,14 +291,15 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
     upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
     upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
   }
-  if (o.res_hi) {
+  if (o.res_row) {       // (columns beyond N are zero in the staged tile: TMA out-of-bounds fill)
+    uint32_t rh[16], rl[16];
+    load_res32(o, res_chunk0, rh, rl);
 #pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < o.n_valid) {
-        uint16_t h = __ldg(o.res_hi + col0 + i), l = __ldg(o.res_lo + col0 + i);
-        f[i] += FMT == NSAC_SPLIT_F16 ? __half2float(__ushort_as_half(h)) + __half2float(__ushort_as_half(l))
-                                      : __bfloat162float(__ushort_as_bfloat16(h)) + __bfloat162float(__ushort_as_bfloat16(l));
-      }
+    for (int i = 0; i < 32; i += 2) {
+      const float2 h = unsplit16x2<FMT>(rh[i >> 1]), l = unsplit16x2<FMT>(rl[i >> 1]);
+      f[i] += h.x + l.x;
+      f[i + 1] += h.y + l.y;
+    }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
@@ -347,44 +366,16 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t (&w)
   __syncwarp();
 }
 
-// The mirror image for the residual input: coalesced 16-byte global loads (4 or 8 full row segments per instruction) into the
-// warp's staging buffer, then every lane reads its own row.  row_ptr = this lane's own source row segment.
-template <int WORDS>
-__device__ __forceinline__ void staged_load(uint8_t* stage, uint32_t (&w)[WORDS], const uint8_t* row_ptr, int lane) {
-  constexpr int BYTES = WORDS * 4, CPR = BYTES / 16, RPI = 32 / CPR;
-  const int sub = lane / CPR, ch = lane % CPR;
-  const unsigned long long my = reinterpret_cast<unsigned long long>(row_ptr);
-#pragma unroll
-  for (int j = 0; j < 32 / RPI; ++j) {
-    const int row = RPI * j + sub;
-    const int swz_r = CPR == 8 ? (row & 7) : ((row >> 1) & 3);
-    const uint8_t* src = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, my, row));
-    const uint4 x = __ldg(reinterpret_cast<const uint4*>(src + ch * 16));
-    *reinterpret_cast<uint4*>(stage + row * BYTES + ((ch ^ swz_r) << 4)) = x;
-  }
-  __syncwarp();
-  const int swz_w = CPR == 8 ? (lane & 7) : ((lane >> 1) & 3);
-#pragma unroll
-  for (int c = 0; c < CPR; ++c) {
-    const uint4 x = *reinterpret_cast<const uint4*>(stage + lane * BYTES + ((c ^ swz_w) << 4));
-    w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
-  }
-  __syncwarp();
-}
-
 // 64 accumulator columns of a full tile part (every lane of the warp has a valid row, all 64 columns valid, aligned):
 // scale, bias, activation, then fp32 rows and / or split planes through the staged stores, 32 columns at a time
-template <int FMT>
-__device__ __forceinline__ void finish64_staged(const u64 (&sum)[32], int col0, const EpiOut& o, uint8_t* stage, int lane) {
+template <int FMT, int GROUPS>
+__device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], int col0, int res_chunk0, const EpiOut& o, uint8_t* stage, int lane) {
   const u64 sc = pk2(o.out_scale, o.out_scale), sl = pk2(o.slope, o.slope);
 #pragma unroll
-  for (int g = 0; g < 2; ++g) {            // two groups of 32 columns
+  for (int g = 0; g < GROUPS; ++g) {       // groups of 32 columns (two for 128-wide tiles, one for 64-wide tiles)
     uint32_t f[32];                        // fp32 bit patterns
     uint32_t rh[16], rl[16];               // residual planes of these 32 columns (hi + lo = the fp32 value)
-    if (o.res_hi) {
-      staged_load<16>(stage, rh, reinterpret_cast<const uint8_t*>(o.res_hi + col0 + 32 * g), lane);
-      staged_load<16>(stage, rl, reinterpret_cast<const uint8_t*>(o.res_lo + col0 + 32 * g), lane);
-    }
+    if (o.res_row) load_res32(o, res_chunk0 + 4 * g, rh, rl);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       u64 b01 = 0ull, b23 = 0ull;
@@ -392,7 +383,7 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[32], int col0, 
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + 32 * g + i));
         b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
       }
-      if (o.res_hi) {                      // bias + residual first (exact: hi + lo reproduces the fp32 activation)
+      if (o.res_row) {                     // bias + residual first (exact: hi + lo reproduces the fp32 activation)
         const float2 h0 = unsplit16x2<FMT>(rh[i >> 1]), l0 = unsplit16x2<FMT>(rl[i >> 1]);
         const float2 h1 = unsplit16x2<FMT>(rh[(i >> 1) + 1]), l1 = unsplit16x2<FMT>(rl[(i >> 1) + 1]);
         b01 = fadd2(b01, fadd2(pk2(h0.x, h0.y), pk2(l0.x, l0.y)));
@@ -421,21 +412,25 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[32], int col0, 
   }
 }
 
-template <int BLOCK_N, int FMT>
+template <int BLOCK_N, int FMT, bool RES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+                   const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
                    const GemmParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-window pointer
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+  uint8_t* res_stage = smem + C::STAGES * C::STAGE_BYTES;            // RES: [hi | lo][BLOCK_N / 64 column halves][128 rows x 128 B], swizzled
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + C::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + 256;      // [EPI_WARPS][4 KB]
+  uint64_t* res_full = tmem_empty + 2;         // [1]
+  uint64_t* res_empty = res_full + 1;          // [1]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+  uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool conv = p.conv_taps == 9;
@@ -451,6 +446,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
+    mbar_init(res_full, 1); mbar_init(res_empty, EPI_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -466,7 +462,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
+      int stage = 0; uint32_t phase = 0, res_phase = 0;
       const uint32_t a_bytes = conv ? (uint32_t)(p.BW * p.BH * BLOCK_K * 2) : (uint32_t)C::A_BYTES;   // box bytes
       const bool load_alo = p.passes >= 2 && !p.a_lo_zero;
       const uint32_t tx = (load_alo ? 2 * a_bytes : a_bytes) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
@@ -480,6 +476,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           y0 = (t2 / p.tiles_x) * p.BH;
           x0 = (t2 % p.tiles_x) * p.BW;
         }
+        if (RES) {     // this tile's residual [128 x BLOCK_N] x (hi, lo): lands while the MMAs run, read by the epilogue warps
+          mbar_wait(res_empty, res_phase ^ 1);
+          mbar_expect_tx(res_full, (uint32_t)C::RES_BYTES);
+#pragma unroll
+          for (int h = 0; h < BLOCK_N / 64; ++h) {
+            tma_load_2d(res_stage + h * (BLOCK_M * 128), &map_r_hi, res_full, n0 + 64 * h, m0);
+            tma_load_2d(res_stage + C::RES_PLANE_BYTES + h * (BLOCK_M * 128), &map_r_lo, res_full, n0 + 64 * h, m0);
+          }
+          res_phase ^= 1;
+        }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * C::STAGE_BYTES;
@@ -489,8 +495,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // zero-fills the out-of-image halo (padding = 1), so no im2col matrix ever exists
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
             const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            tma_load_4d(st, &map_a_hi, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
-            if (load_alo) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, x0 + dx, y0 + dy, img);
+            const int xi = x0 * p.cstride + dx, yi = y0 * p.cstride + dy;     // (strided maps: the tensor map's traversal stride picks every cstride-th pixel)
+            tma_load_4d(st, &map_a_hi, &full[stage], cb * BLOCK_K, xi, yi, img);
+            if (load_alo) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, xi, yi, img);
           } else {
             tma_load_2d(st, &map_a_hi, &full[stage], kb * BLOCK_K, m0);
             if (load_alo) tma_load_2d(st + C::A_BYTES, &map_a_lo, &full[stage], kb * BLOCK_K, m0);
@@ -546,7 +553,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int quad = warp & 3, half = (warp - 2) >> 2;
     constexpr int HALF_N = BLOCK_N / 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint32_t chunk_ctr = 0;
+    uint32_t chunk_ctr = 0, res_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N + half * HALF_N;
       u64 sum[HALF_N / 2];
@@ -594,11 +601,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       o.out_scale = p.out_scale;
       o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
       o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
-      o.res_hi = nullptr; o.res_lo = nullptr;
-      if (row_ok && p.res_hi) {
-        o.res_hi = p.res_hi + (size_t)row * p.ld_res;
-        o.res_lo = p.res_lo + (size_t)row * p.ld_res;
+      o.res_row = nullptr; o.res_lo_off = C::RES_PLANE_BYTES; o.res_swz = lane & 7;
+      if (RES) {     // the residual tile of this output tile has landed (TMA): lane's row = tile row quad * 32 + lane
+        mbar_wait(res_full, res_phase);
+        res_phase ^= 1;
+        o.res_row = res_stage + (HALF_N == 64 ? half * (BLOCK_M * 128) : 0) + (quad * 32 + lane) * 128;
       }
+      const int res_chunk_base = HALF_N == 64 ? 0 : half * 4;      // 16-byte chunk of the first column of this warp's half
       if (row_ok) {
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
@@ -606,14 +615,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         o.out_lo = p.out_lo ? p.out_lo + (size_t)row * p.ld_split : nullptr;
         o.vec_ok = (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
                    (!o.out_f32 || (reinterpret_cast<uintptr_t>(o.out_f32) & 15) == 0) &&
-                   (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0) &&
-                   (!o.res_hi || ((reinterpret_cast<uintptr_t>(o.res_hi) | reinterpret_cast<uintptr_t>(o.res_lo)) & 15) == 0);
+                   (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0);
       }
       // fast path (warp-uniform): every lane has a valid, aligned row and all 64 columns of this half exist
-      const bool staged = HALF_N == 64 && __all_sync(0xffffffffu, row_ok && o.vec_ok) && n0 + HALF_N <= p.N;
+      const bool staged = __all_sync(0xffffffffu, row_ok && o.vec_ok) && n0 + HALF_N <= p.N;
       if (staged) {
         uint8_t* stage = out_stage + (warp - 2) * 4096;
-        finish64_staged<FMT>(sum, n0, o, stage, lane);
+        finish64_staged<FMT, HALF_N / 32>(sum, n0, res_chunk_base, o, stage, lane);
       } else if (row_ok) {
 #pragma unroll
         for (int c = 0; c < HALF_N; c += 32) {
@@ -623,9 +631,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             u64 acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = sum[(c >> 1) + i];
-            finish32<FMT>(acc, col0, o);
+            finish32<FMT>(acc, col0, res_chunk_base + (c >> 3), o);
           }
         }
+      }
+      if (RES) {     // every lane has read its residual row: the staging tile may be refilled for the next tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(res_empty);
       }
     }
   }
@@ -695,34 +707,35 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N>
-int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl,
-                const GemmParams& p, int tiles_m, cudaStream_t s) {
-  using C = Cfg<BLOCK_N>;
+template <int BLOCK_N, bool RES>
+int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& rh,
+                const CUtensorMap& rl, const GemmParams& p, int tiles_m, cudaStream_t s) {
+  using C = Cfg<BLOCK_N, RES>;
   static bool attr_set = false;
   if (!attr_set) {
-    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_set = true;
   }
   const int tiles = tiles_m * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (p.fmt == NSAC_SPLIT_BF16)
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, p);
   else
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, p);
   NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }
 
 // NHWC 16-bit planes [N,H,W,C] as a 4-D tensor (C, W, H, N); box = [64 ch, BW, BH, 1], 128-byte swizzle
-bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, bool is_bf16) {
+bool make_map_nhwc(CUtensorMap* map, const void* base, int N, int H, int W, int C, int BW, int BH, bool is_bf16, int stride = 1) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) return false;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BW, (cuuint32_t)BH, 1};
-  cuuint32_t estr[4] = {1, 1, 1, 1};
+  // traversal stride s: the box spans BW * s (BH * s) input pixels and TMA loads every s-th of them = BW (BH) elements
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)(BW * stride), (cuuint32_t)(BH * stride), 1};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   return enc(map, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), dims,
              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -739,9 +752,11 @@ extern "C" int nsac_debug_gemm_trace(void* buf) {
   return NSAC_OK;
 }
 
-extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
-                                  int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
-                                  float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                        int N, int Hin, int Win, int Cin, int Cout, int stride, int act, int passes, int fmt, float out_scale,
+                        float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+  NSAC_REQUIRE(stride == 1 || stride == 2, "nsac_conv3x3_split: stride must be 1 or 2");
+  const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;      // output map (3x3, pad 1)
   NSAC_REQUIRE(x_hi && w_hi, "nsac_conv3x3_split: null operand");
   NSAC_REQUIRE(passes >= 1 && passes <= 4 && (passes < 2 || x_lo) && (passes < 3 || w_lo), "nsac_conv3x3_split: bad passes / planes");
   NSAC_REQUIRE(N >= 0 && H >= 1 && W >= 1 && Cin >= 64 && Cin % 64 == 0 && Cout >= 8, "nsac_conv3x3_split: bad shape (Cin %% 64 == 0)");
@@ -755,12 +770,13 @@ extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void
   if (W <= 128) { BW = W; BH = 128 / W; if (BH > H) BH = H; }
   else { BW = 128; BH = 1; }
   if (W % 16 == 0 && W > 64) { BW = 16; BH = 8; }          // e.g. 80-wide maps: 16 x 8 patches fill all 128 rows
-  NSAC_REQUIRE(BW <= 256 && BH <= 256 && BW * BH <= 128, "nsac_conv3x3_split: cannot tile a %d x %d map", H, W);
+  NSAC_REQUIRE(BW * stride <= 256 && BH * stride <= 256 && BW * BH <= 128, "nsac_conv3x3_split: cannot tile a %d x %d map", H, W);
   const bool bf = fmt == NSAC_SPLIT_BF16;
   const int K = 9 * Cin;
   CUtensorMap mah, mal, mwh, mwl;
-  const bool ok = make_map_nhwc(&mah, x_hi, N, H, W, Cin, BW, BH, bf) && make_map_nhwc(&mal, x_lo ? x_lo : x_hi, N, H, W, Cin, BW, BH, bf) &&
-                  make_map(&mwh, w_hi, Cout, K, K, 128, bf) && make_map(&mwl, w_lo ? w_lo : w_hi, Cout, K, K, 128, bf);
+  const bool ok = make_map_nhwc(&mah, x_hi, N, Hin, Win, Cin, BW, BH, bf, stride) &&
+                  make_map_nhwc(&mal, x_lo ? x_lo : x_hi, N, Hin, Win, Cin, BW, BH, bf, stride) &&
+                  make_map(&mwh, w_hi, Cout, K, K, Cout <= 64 ? 64 : 128, bf) && make_map(&mwl, w_lo ? w_lo : w_hi, Cout, K, K, Cout <= 64 ? 64 : 128, bf);
   if (!ok) {
     nsac_set_error("nsac_conv3x3_split: cuTensorMapEncodeTiled failed (N=%d H=%d W=%d Cin=%d Cout=%d)", N, H, W, Cin, Cout);
     return NSAC_ERR_LAUNCH;
@@ -771,9 +787,28 @@ extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void
   p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
   p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0;
-  p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64;
+  p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
-  return launch_gemm<128>(mah, mal, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                  int N, int H, int W, int Cin, int Cout, int act, int passes, int fmt, float out_scale,
+                                  float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+  return conv3x3_impl(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, 1, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                      ld_split, stream);
+}
+
+// Same with a convolution stride of 1 or 2 (H, W = INPUT map; output (H-1)/stride+1 x (W-1)/stride+1): the strided 3x3 of
+// res3.0 / res4.0 / res5.0 (STRIDE_IN_1X1 = False) as an implicit GEMM - the A tiles are gathered by TMA with a traversal
+// stride, no im2col matrix.
+extern "C" int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                          int N, int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt,
+                                          float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                                          void* stream) {
+  return conv3x3_impl(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, stride, act, passes, fmt, out_scale, out_f32, ldo, out_hi,
+                      out_lo, ld_split, stream);
 }
 
 static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
@@ -799,7 +834,7 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   for (const void* ptr : {a_hi, a_lo, w_hi, w_lo})
     NSAC_REQUIRE(!ptr || (reinterpret_cast<uintptr_t>(ptr) & 15) == 0, "nsac_gemm_split: operands must be 16-byte aligned");
   if (M == 0) return NSAC_OK;
-  const int block_n = 128;
+  const int block_n = N <= 64 ? 64 : 128;      // 64-wide tiles for the narrow layers (res2 / stem of the backbone): no half-empty MMAs
   CUtensorMap mah, mal, mwh, mwl;
   const bool bf = fmt == NSAC_SPLIT_BF16;
   bool ok = make_map(&mah, a_hi, M, K, lda, BLOCK_M, bf) && make_map(&mal, a_lo ? a_lo : a_hi, M, K, lda, BLOCK_M, bf) &&
@@ -816,9 +851,19 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
   p.res_hi = static_cast<const uint16_t*>(res_hi); p.res_lo = static_cast<const uint16_t*>(res_lo); p.ld_res = ld_res;
   p.a_lo_zero = a_lo == nullptr ? 1 : 0;
-  p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1;
+  p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1; p.cstride = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  return launch_gemm<128>(mah, mal, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  if (res_hi) {     // residual tiles are TMA-prefetched: [M, N] planes with row stride ld_res, boxes of 64 columns x 128 rows
+    CUtensorMap mrh, mrl;
+    if (!(make_map(&mrh, res_hi, M, N, ld_res, BLOCK_M, bf) && make_map(&mrl, res_lo, M, N, ld_res, BLOCK_M, bf))) {
+      nsac_set_error("nsac_gemm_split_residual: cuTensorMapEncodeTiled failed for the residual planes (M=%d N=%d ld_res=%d)", M, N, ld_res);
+      return NSAC_ERR_LAUNCH;
+    }
+    if (block_n == 64) return launch_gemm<64, true>(mah, mal, mwh, mwl, mrh, mrl, p, nsac_cdiv(M, BLOCK_M), s);
+    return launch_gemm<128, true>(mah, mal, mwh, mwl, mrh, mrl, p, nsac_cdiv(M, BLOCK_M), s);
+  }
+  if (block_n == 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
 }
 
 extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,

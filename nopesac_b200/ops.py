@@ -215,22 +215,26 @@ def nchw_to_planes(x: torch.Tensor, fmt: int = SPLIT_F16, out: Optional[Split] =
 
 
 def conv3x3_tc(x: Split, N: int, H: int, W: int, w: Split, bias=None, act: int = ACT_NONE, passes: int = 3,
-               want_f32: bool = True, want_split: bool = False):
-    """3x3 / stride 1 / pad 1 convolution (implicit GEMM, 4-D TMA gather).  x: NHWC planes [N*H*W, Cin] (contiguous),
-    w: planes [Cout, 9*Cin] in (ky, kx, cin) order.  -> (fp32 [N*H*W, Cout] or None, Split or None)."""
+               want_f32: bool = True, want_split: bool = False, stride: int = 1):
+    """3x3 / pad 1 convolution, stride 1 or 2 (implicit GEMM, 4-D TMA gather; the stride is the tensor map's traversal stride).
+    x: NHWC planes [N*H*W, Cin] (contiguous), w: planes [Cout, 9*Cin] in (ky, kx, cin) order.
+    -> (fp32 [N*Ho*Wo, Cout] or None, Split or None), Ho = (H-1)//stride + 1."""
     Cin, Cout = x.hi.shape[1], w.rows
     assert x.hi.is_contiguous() and x.lo.is_contiguous() and x.rows == N * H * W and Cin % 64 == 0
-    assert w.hi.is_contiguous() and w.hi.shape[1] == 9 * Cin and x.fmt == w.fmt
+    assert w.hi.is_contiguous() and w.hi.shape[1] == 9 * Cin and x.fmt == w.fmt and stride in (1, 2)
     dev = x.hi.device
-    out_f32 = torch.empty(N * H * W, Cout, device=dev, dtype=torch.float32) if want_f32 else None
-    out_split = Split.empty(N * H * W, Cout, dev, x.fmt) if want_split else None
+    rows = N * ((H - 1) // stride + 1) * ((W - 1) // stride + 1)
+    out_f32 = torch.empty(rows, Cout, device=dev, dtype=torch.float32) if want_f32 else None
+    out_split = Split.empty(rows, Cout, dev, x.fmt) if want_split else None
     if bias is not None:
         _chk(bias, "bias")
-    st = _lib.lib().nsac_conv3x3_split(_p(x.hi), _p(x.lo), _p(w.hi), _p(w.lo), _p(bias), N, H, W, Cin, Cout, act, passes,
-                                       x.fmt, 1.0 / (x.scale * w.scale), _p(out_f32), Cout if want_f32 else 0,
-                                       None if out_split is None else _p(out_split.hi),
-                                       None if out_split is None else _p(out_split.lo),
-                                       0 if out_split is None else out_split.hi.stride(0), _stream())
+    tail = (act, passes, x.fmt, 1.0 / (x.scale * w.scale), _p(out_f32), Cout if want_f32 else 0,
+            None if out_split is None else _p(out_split.hi), None if out_split is None else _p(out_split.lo),
+            0 if out_split is None else out_split.hi.stride(0), _stream())
+    if stride == 1:
+        st = _lib.lib().nsac_conv3x3_split(_p(x.hi), _p(x.lo), _p(w.hi), _p(w.lo), _p(bias), N, H, W, Cin, Cout, *tail)
+    else:
+        st = _lib.lib().nsac_conv3x3_split_strided(_p(x.hi), _p(x.lo), _p(w.hi), _p(w.lo), _p(bias), N, H, W, Cin, Cout, stride, *tail)
     _lib.check(st, "nsac_conv3x3_split")
     _count()
     return out_f32, out_split

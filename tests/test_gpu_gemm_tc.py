@@ -102,3 +102,48 @@ def test_fp16_plane_overflow_is_loud():
     out, _ = ops.gemm_tc(ops.split(x), ops.split_weight(w))
     assert not bool(torch.isfinite(out[5, 3]))
     assert bool(torch.isfinite(out[6]).all())
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 512, 128), (130, 64, 576), (4096, 1024, 256), (300, 200, 192), (77, 48, 64)])
+def test_gemm_residual_epilogue_matches_fp64(M, N, K):
+    """nsac_gemm_split_residual: relu(x.W^T + b + residual) with the residual given as hi/lo planes (TMA-prefetched tile) — the
+    fused `out += shortcut; relu` of the backbone's bottleneck blocks; full tiles, ragged M / N, and the 64-wide tile variant."""
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(3 * M + N + K)
+    x, w, b, r = _rand(g, M, K), _rand(g, N, K) / K ** 0.5, _rand(g, N), _rand(g, M, N)
+    xs, ws, rs = ops.split(x.to(dev)), ops.split_weight(w.to(dev)), ops.split(r.to(dev))
+    ref = torch.relu(x.double() @ w.double().T + b.double() + rs.float().double().cpu())      # the planes ARE the residual (22 bits)
+    out, sp = ops.gemm_tc(xs, ws, b.to(dev), ops.ACT_RELU, want_f32=True, want_split=True, residual=rs)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert util.maxdiff(out, ref) <= 2e-6 * scale, util.maxdiff(out, ref) / scale
+    assert util.maxdiff(sp.float(), out) <= 2 ** -20 * scale
+    # residual planes that are a column slice of a wider buffer (row stride > N)
+    wide = ops.split(_rand(g, M, N + 64).to(dev))
+    rv = wide.cols(64, 64 + N)
+    out2, _ = ops.gemm_tc(xs, ws, b.to(dev), ops.ACT_NONE, residual=rv)
+    ref2 = x.double() @ w.double().T + b.double() + rv.float().double().cpu()
+    assert util.maxdiff(out2, ref2) <= 2e-6 * float(ref2.abs().max())
+
+
+@pytest.mark.parametrize("M,N,K", [(1000, 64, 192), (4096, 64, 256), (130, 40, 576)])
+def test_gemm_narrow_tiles_and_single_plane_a(M, N, K):
+    """N <= 64 runs the 64-wide tile variant; `a.lo is None` (A exact in one fp16 plane, e.g. raw 8-bit pixels) skips the lo.hi pass."""
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(M + N)
+    xi = torch.randint(0, 256, (M, K), generator=g).float()             # exact in fp16
+    w, b = _rand(g, N, K) / K ** 0.5, _rand(g, N)
+    ref = torch.relu(xi.double() @ w.double().T + b.double())
+    a = ops.Split(xi.to(dev).half().contiguous(), None, K)
+    ws = ops.split_weight(w.to(dev))
+    out, sp = ops.gemm_tc(a, ws, b.to(dev), ops.ACT_RELU, want_f32=True, want_split=True)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert util.maxdiff(out, ref) <= 2e-6 * scale, util.maxdiff(out, ref) / scale
+    assert util.maxdiff(sp.float(), out) <= 2 ** -20 * scale
+    x = _rand(g, M, K)
+    out3, _ = ops.gemm_tc(ops.split(x.to(dev)), ws, b.to(dev))
+    ref3 = x.double() @ w.double().T + b.double()
+    assert util.maxdiff(out3, ref3) <= 2e-6 * float(ref3.abs().max())

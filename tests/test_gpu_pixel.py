@@ -40,6 +40,31 @@ def test_conv3x3_implicit_gemm(N, C, H, W, Cout):
     assert util.maxdiff(sp.float(), out) <= 2 ** -19 * scale
 
 
+@pytest.mark.parametrize("N,C,H,W,Cout", [(2, 128, 60, 80, 128), (3, 64, 31, 45, 64), (1, 256, 30, 40, 256), (2, 512, 15, 20, 512), (2, 64, 8, 8, 96)])
+def test_conv3x3_stride2_implicit_gemm(N, C, H, W, Cout):
+    """nsac_conv3x3_split_strided (stride 2: the TMA tensor map's traversal stride picks every second pixel) == F.conv2d(stride=2,
+    padding=1), even and odd map sizes; and == the explicit planes im2col + GEMM route it replaces."""
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(7 * N + C + H)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(Cout, C, 3, 3, generator=g) / (9 * C) ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.relu(F.conv2d(x.double(), w.double(), b.double(), padding=1, stride=2))
+    xp = ops.nchw_to_planes(x.to(dev))
+    wp = ops.split_weight(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(dev))
+    out, sp = ops.conv3x3_tc(xp, N, H, W, wp, b.to(dev), ops.ACT_RELU, want_f32=True, want_split=True, stride=2)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert out.shape[0] == N * ref.shape[2] * ref.shape[3]
+    assert util.maxdiff(out, _nhwc(ref)) <= 3e-6 * scale, util.maxdiff(out, _nhwc(ref)) / scale
+    assert util.maxdiff(sp.float(), out) <= 2 ** -19 * scale
+    cols, Ho, Wo = ops.im2col3x3_from_planes(xp, N, H, W, 2)
+    assert (Ho, Wo) == tuple(ref.shape[2:])
+    out2, _ = ops.gemm_tc(cols, wp, b.to(dev), ops.ACT_RELU)
+    assert util.maxdiff(out2, out) <= 3e-6 * scale
+
+
 def test_groupnorm_upsample_add():
     dev = _dev()
     from nopesac_b200 import ops
