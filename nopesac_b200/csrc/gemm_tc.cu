@@ -56,17 +56,20 @@ constexpr int CHUNK_KB = 4;                 // K-blocks (x64 elements) accumulat
 
 template <int BLOCK_N, bool RES = false>
 struct Cfg {
-  // RES: the residual tile [128 x BLOCK_N] x (hi, lo) is TMA-prefetched into its own 64 KB (32 KB) of shared memory while the
-  // tile's MMAs run, so the operand ring shrinks to 2 stages (these layers are epilogue / HBM bound, K <= 512)
-  static constexpr int STAGES = RES ? 2 : (BLOCK_N == 64 ? 4 : 3);       // 48 KB / 64 KB per stage
-  static constexpr int RES_PLANE_BYTES = RES ? BLOCK_M * BLOCK_N * 2 : 0;
-  static constexpr int RES_BYTES = 2 * RES_PLANE_BYTES;
+  // RES (residual epilogue, 64-wide tiles only): two tile buffers [128 x 64] x (hi, lo) = 2 x 32 KB.  The residual tile is
+  // TMA-prefetched into one of them while the tile's MMAs run, the epilogue turns it IN PLACE into the output tile, and a TMA
+  // store writes it out asynchronously - no per-warp staging buffers, no latency-exposed global loads in the epilogue.
+  static_assert(!RES || BLOCK_N == 64, "the residual epilogue uses 64-wide tiles");
+  static constexpr int STAGES = RES ? 3 : (BLOCK_N == 64 ? 4 : 3);       // 48 KB / 64 KB per stage
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int ACC_COLS = 2 * BLOCK_N;              // one buffer = hi.hi accumulator + lo-terms accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
-  static constexpr int OUT_STAGE_BYTES = EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
+  static constexpr int RES_PLANE_BYTES = RES ? BLOCK_M * 128 : 0;          // [128 rows x 64 columns] of one plane, 128-byte swizzled rows
+  static constexpr int TILE_BUF_BYTES = 2 * RES_PLANE_BYTES;               // hi + lo
+  static constexpr int RES_BYTES = 2 * TILE_BUF_BYTES;                     // double-buffered
+  static constexpr int OUT_STAGE_BYTES = RES ? 0 : EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
@@ -112,6 +115,15 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const void* smem_src, const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_commit(uint64_t* bar) {
@@ -244,22 +256,7 @@ struct EpiOut {
   uint16_t* out_lo;
   int n_valid;            // valid columns from col0 on (>= 32: full chunk)
   bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
-  const uint8_t* res_row; // this lane's row of the TMA-staged residual tile (hi plane; nullptr: none) - 128-byte swizzled rows
-  int res_lo_off;         // byte offset of the lo plane's copy of the same row
-  int res_swz;            // row & 7 (XOR key of the 16-byte chunks)
 };
-
-// 32 residual columns (first column = 16-byte chunk index `chunk0` of the lane's 128-byte row) -> 16 hi words + 16 lo words
-__device__ __forceinline__ void load_res32(const EpiOut& o, int chunk0, uint32_t (&rh)[16], uint32_t (&rl)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; ++c) {
-    const int off = ((chunk0 + c) ^ o.res_swz) << 4;
-    const uint4 h = *reinterpret_cast<const uint4*>(o.res_row + off);
-    const uint4 l = *reinterpret_cast<const uint4*>(o.res_row + o.res_lo_off + off);
-    rh[4 * c] = h.x; rh[4 * c + 1] = h.y; rh[4 * c + 2] = h.z; rh[4 * c + 3] = h.w;
-    rl[4 * c] = l.x; rl[4 * c + 1] = l.y; rl[4 * c + 2] = l.z; rl[4 * c + 3] = l.w;
-  }
-}
 
 // packed 16-bit plane word -> two floats
 template <int FMT>
@@ -270,7 +267,7 @@ __device__ __forceinline__ float2 unsplit16x2(uint32_t w) {
 
 // 32 accumulator columns -> scale, bias, activation, fp32 store, split-plane store
 template <int FMT>
-__device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, int res_chunk0, const EpiOut& o) {
+__device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const EpiOut& o) {
   float f[32];
   const u64 sc = pk2(o.out_scale, o.out_scale);
   const bool full = o.n_valid >= 32 && o.vec_ok;
@@ -290,16 +287,6 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, int res
     }
     upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
     upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
-  }
-  if (o.res_row) {       // (columns beyond N are zero in the staged tile: TMA out-of-bounds fill)
-    uint32_t rh[16], rl[16];
-    load_res32(o, res_chunk0, rh, rl);
-#pragma unroll
-    for (int i = 0; i < 32; i += 2) {
-      const float2 h = unsplit16x2<FMT>(rh[i >> 1]), l = unsplit16x2<FMT>(rl[i >> 1]);
-      f[i] += h.x + l.x;
-      f[i + 1] += h.y + l.y;
-    }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
@@ -369,25 +356,17 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t (&w)
 // 64 accumulator columns of a full tile part (every lane of the warp has a valid row, all 64 columns valid, aligned):
 // scale, bias, activation, then fp32 rows and / or split planes through the staged stores, 32 columns at a time
 template <int FMT, int GROUPS>
-__device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], int col0, int res_chunk0, const EpiOut& o, uint8_t* stage, int lane) {
+__device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], int col0, const EpiOut& o, uint8_t* stage, int lane) {
   const u64 sc = pk2(o.out_scale, o.out_scale), sl = pk2(o.slope, o.slope);
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {       // groups of 32 columns (two for 128-wide tiles, one for 64-wide tiles)
     uint32_t f[32];                        // fp32 bit patterns
-    uint32_t rh[16], rl[16];               // residual planes of these 32 columns (hi + lo = the fp32 value)
-    if (o.res_row) load_res32(o, res_chunk0 + 4 * g, rh, rl);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       u64 b01 = 0ull, b23 = 0ull;
       if (o.brow) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + 32 * g + i));
         b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
-      }
-      if (o.res_row) {                     // bias + residual first (exact: hi + lo reproduces the fp32 activation)
-        const float2 h0 = unsplit16x2<FMT>(rh[i >> 1]), l0 = unsplit16x2<FMT>(rl[i >> 1]);
-        const float2 h1 = unsplit16x2<FMT>(rh[(i >> 1) + 1]), l1 = unsplit16x2<FMT>(rl[(i >> 1) + 1]);
-        b01 = fadd2(b01, fadd2(pk2(h0.x, h0.y), pk2(l0.x, l0.y)));
-        b23 = fadd2(b23, fadd2(pk2(h1.x, h1.y), pk2(l1.x, l1.y)));
       }
       float x0, x1, x2, x3;
       upk2(ffma2(sum[16 * g + (i >> 1)], sc, b01), x0, x1);
@@ -417,19 +396,20 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
+                   const __grid_constant__ CUtensorMap map_o_hi, const __grid_constant__ CUtensorMap map_o_lo,
                    const GemmParams p) {
   using C = Cfg<BLOCK_N, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);   // stays a shared-window pointer
-  uint8_t* res_stage = smem + C::STAGES * C::STAGE_BYTES;            // RES: [hi | lo][BLOCK_N / 64 column halves][128 rows x 128 B], swizzled
+  uint8_t* res_stage = smem + C::STAGES * C::STAGE_BYTES;            // RES: two tile buffers [hi | lo][128 rows x 128 B], swizzled
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES);
   uint64_t* full = bars;                       // [STAGES]
   uint64_t* empty = bars + C::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_full = tmem_empty + 2;         // [1]
-  uint64_t* res_empty = res_full + 1;          // [1]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + 1);
+  uint64_t* res_full = tmem_empty + 2;         // [2]
+  uint64_t* res_empty = res_full + 2;          // [2]
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
   uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -446,7 +426,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
-    mbar_init(res_full, 1); mbar_init(res_empty, EPI_WARPS);
+    for (int a = 0; a < 2; ++a) { mbar_init(&res_full[a], 1); mbar_init(&res_empty[a], 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -462,13 +442,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
-      int stage = 0; uint32_t phase = 0, res_phase = 0;
+      int stage = 0; uint32_t phase = 0, tile_ctr = 0;
       const uint32_t a_bytes = conv ? (uint32_t)(p.BW * p.BH * BLOCK_K * 2) : (uint32_t)C::A_BYTES;   // box bytes
       const bool load_alo = p.passes >= 2 && !p.a_lo_zero;
       const uint32_t tx = (load_alo ? 2 * a_bytes : a_bytes) + (p.passes >= 3 ? 2 * C::W_BYTES : C::W_BYTES);
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile % tiles_m;
-        const int m0 = tm * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N;
+        // n fastest: the CTAs running at the same time share a few M blocks, so every A tile comes from HBM once and its other
+        // N tiles hit L2 (m-fastest order swept the whole A matrix once per N tile: 630 MB x 4 for the 64 -> 256 layers of res2)
+        const int tm = tile / tiles_n;
+        const int m0 = tm * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N;
         int img = 0, y0 = 0, x0 = 0;
         if (conv) {
           img = tm / tiles_per_img;
@@ -476,15 +458,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           y0 = (t2 / p.tiles_x) * p.BH;
           x0 = (t2 % p.tiles_x) * p.BW;
         }
-        if (RES) {     // this tile's residual [128 x BLOCK_N] x (hi, lo): lands while the MMAs run, read by the epilogue warps
-          mbar_wait(res_empty, res_phase ^ 1);
-          mbar_expect_tx(res_full, (uint32_t)C::RES_BYTES);
-#pragma unroll
-          for (int h = 0; h < BLOCK_N / 64; ++h) {
-            tma_load_2d(res_stage + h * (BLOCK_M * 128), &map_r_hi, res_full, n0 + 64 * h, m0);
-            tma_load_2d(res_stage + C::RES_PLANE_BYTES + h * (BLOCK_M * 128), &map_r_lo, res_full, n0 + 64 * h, m0);
-          }
-          res_phase ^= 1;
+        if (RES) {     // this tile's residual [128 x 64] x (hi, lo) into tile buffer tile_ctr & 1: lands while the MMAs run
+          const uint32_t b = tile_ctr & 1, use = tile_ctr >> 1;
+          mbar_wait(&res_empty[b], (use & 1) ^ 1);            // the TMA store of the buffer's previous tile has read it out
+          mbar_expect_tx(&res_full[b], (uint32_t)C::TILE_BUF_BYTES);
+          uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
+          tma_load_2d(tb, &map_r_hi, &res_full[b], n0, m0);
+          tma_load_2d(tb + C::RES_PLANE_BYTES, &map_r_lo, &res_full[b], n0, m0);
+          ++tile_ctr;
         }
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
@@ -553,9 +534,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     const int quad = warp & 3, half = (warp - 2) >> 2;
     constexpr int HALF_N = BLOCK_N / 2;
     const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
-    uint32_t chunk_ctr = 0, res_phase = 0;
+    uint32_t chunk_ctr = 0, res_ctr = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m0 = (tile % tiles_m) * BLOCK_M, n0 = (tile / tiles_m) * BLOCK_N + half * HALF_N;
+      const int m0 = (tile / tiles_n) * BLOCK_M, n0 = (tile % tiles_n) * BLOCK_N + half * HALF_N;
       u64 sum[HALF_N / 2];
 #pragma unroll
       for (int i = 0; i < HALF_N / 2; ++i) sum[i] = 0ull;
@@ -587,11 +568,58 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
       if (tile == (int)blockIdx.x && threadIdx.x == 64) GEMM_TRACE(9);
+      if constexpr (RES) {
+        // ---- residual epilogue: out = act(acc * scale + bias + residual), IN PLACE in the tile buffer, then one TMA store.
+        // lane = tile row quad * 32 + lane, this warp's 32 columns = 16-byte chunks half * 4 .. half * 4 + 3 of the 128-byte row
+        const uint32_t b = res_ctr & 1;
+        mbar_wait(&res_full[b], (res_ctr >> 1) & 1);
+        uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
+        uint8_t* rowp = tb + (quad * 32 + lane) * 128;
+        const u64 sc = pk2(p.out_scale, p.out_scale);
+        const float slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
+        const u64 sl = pk2(slope, slope);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int off = ((half * 4 + c) ^ (lane & 7)) << 4;
+          const uint4 rh = *reinterpret_cast<const uint4*>(rowp + off);
+          const uint4 rl = *reinterpret_cast<const uint4*>(rowp + C::RES_PLANE_BYTES + off);
+          const uint32_t rhw[4] = {rh.x, rh.y, rh.z, rh.w}, rlw[4] = {rl.x, rl.y, rl.z, rl.w};
+          uint32_t oh[4], ol[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {                  // two columns per word
+            const int col = n0 + 8 * c + 2 * j;
+            u64 bb = 0ull;
+            if (p.bias) bb = pk2(col < p.N ? __ldg(p.bias + col) : 0.f, col + 1 < p.N ? __ldg(p.bias + col + 1) : 0.f);
+            const float2 h = unsplit16x2<FMT>(rhw[j]), l = unsplit16x2<FMT>(rlw[j]);
+            bb = fadd2(bb, fadd2(pk2(h.x, h.y), pk2(l.x, l.y)));      // bias + residual (hi + lo reproduces the fp32 activation)
+            float x0, x1, t0, t1;
+            upk2(ffma2(sum[4 * c + j], sc, bb), x0, x1);
+            upk2(ffma2(pk2(x0, x1), sl, 0ull), t0, t1);               // activation as max(x, slope * x + 0)
+            split16x2<FMT>(fmaxf(x0, t0), fmaxf(x1, t1), oh[j], ol[j]);
+          }
+          *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+          *reinterpret_cast<uint4*>(rowp + C::RES_PLANE_BYTES + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
+        }
+        fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA (async proxy) store
+        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");       // the whole tile is written
+        if (warp == 2 && lane == 0) {
+          const int nt = (tile % tiles_n) * BLOCK_N;
+          tma_store_2d(tb, &map_o_hi, nt, m0);           // rows >= M / columns >= N are clipped by the tensor map
+          tma_store_2d(tb + C::RES_PLANE_BYTES, &map_o_lo, nt, m0);
+          tma_store_commit();
+          // wait until the store has READ the buffer (a fraction of a microsecond; only this thread stalls) and hand it straight
+          // back: the producer then loads the residual of tile t + 2 into it while tile t + 1's epilogue runs on the other buffer
+          tma_store_wait_read<0>();
+          mbar_arrive(&res_empty[b]);
+        }
+        ++res_ctr;
+        continue;
+      }
       // ---- bias, activation, stores
       int row = m0 + quad * 32 + lane;
       bool row_ok = row < p.M;
       if (conv) {      // tile row r = pixel (y0 + r / BW, x0 + r % BW) of image tm / tiles_per_img
-        const int tm = tile % tiles_m, img = tm / tiles_per_img, t2 = tm % tiles_per_img;
+        const int tm = tile / tiles_n, img = tm / tiles_per_img, t2 = tm % tiles_per_img;
         const int r = quad * 32 + lane;
         const int y = (t2 / p.tiles_x) * p.BH + r / p.BW, x = (t2 % p.tiles_x) * p.BW + r % p.BW;
         row_ok = r < p.BW * p.BH && y < p.H && x < p.W;
@@ -601,13 +629,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       o.out_scale = p.out_scale;
       o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
       o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
-      o.res_row = nullptr; o.res_lo_off = C::RES_PLANE_BYTES; o.res_swz = lane & 7;
-      if (RES) {     // the residual tile of this output tile has landed (TMA): lane's row = tile row quad * 32 + lane
-        mbar_wait(res_full, res_phase);
-        res_phase ^= 1;
-        o.res_row = res_stage + (HALF_N == 64 ? half * (BLOCK_M * 128) : 0) + (quad * 32 + lane) * 128;
-      }
-      const int res_chunk_base = HALF_N == 64 ? 0 : half * 4;      // 16-byte chunk of the first column of this warp's half
       if (row_ok) {
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
@@ -621,7 +642,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       const bool staged = __all_sync(0xffffffffu, row_ok && o.vec_ok) && n0 + HALF_N <= p.N;
       if (staged) {
         uint8_t* stage = out_stage + (warp - 2) * 4096;
-        finish64_staged<FMT, HALF_N / 32>(sum, n0, res_chunk_base, o, stage, lane);
+        finish64_staged<FMT, HALF_N / 32>(sum, n0, o, stage, lane);
       } else if (row_ok) {
 #pragma unroll
         for (int c = 0; c < HALF_N; c += 32) {
@@ -631,14 +652,13 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             u64 acc[16];
 #pragma unroll
             for (int i = 0; i < 16; ++i) acc[i] = sum[(c >> 1) + i];
-            finish32<FMT>(acc, col0, res_chunk_base + (c >> 3), o);
+            finish32<FMT>(acc, col0, o);
           }
         }
       }
-      if (RES) {     // every lane has read its residual row: the staging tile may be refilled for the next tile
-        __syncwarp();
-        if (lane == 0) mbar_arrive(res_empty);
-      }
+    }
+    if (RES) {      // the TMA stores of the last tiles must have left shared memory before the CTA exits
+      if (warp == 2 && lane == 0) tma_store_wait_all();
     }
   }
   if (threadIdx.x == 64) GEMM_TRACE(6);
@@ -709,7 +729,7 @@ int sm_count() {
 
 template <int BLOCK_N, bool RES>
 int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& rh,
-                const CUtensorMap& rl, const GemmParams& p, int tiles_m, cudaStream_t s) {
+                const CUtensorMap& rl, const CUtensorMap& oh, const CUtensorMap& ol, const GemmParams& p, int tiles_m, cudaStream_t s) {
   using C = Cfg<BLOCK_N, RES>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -720,9 +740,9 @@ int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   const int tiles = tiles_m * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (p.fmt == NSAC_SPLIT_BF16)
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
   else
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
   NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }
@@ -789,8 +809,8 @@ static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, co
   p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0;
   p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
-  if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
-  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -818,6 +838,8 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   NSAC_REQUIRE(!res_hi || (res_lo && ld_res >= N && ld_res % 8 == 0 && (reinterpret_cast<uintptr_t>(res_hi) & 15) == 0 &&
                            (reinterpret_cast<uintptr_t>(res_lo) & 15) == 0),
                "nsac_gemm_split_residual: residual needs both planes, 16-byte alignment and ld_res %% 8 == 0");
+  NSAC_REQUIRE(!res_hi || (out_hi && !out_f32 && bias_group_rows == 0),
+               "nsac_gemm_split_residual: the residual epilogue writes hi/lo planes only (out_hi/out_lo, no out_f32, no grouped bias)");
   NSAC_REQUIRE(a_hi && w_hi, "nsac_gemm_split: null operand");
   NSAC_REQUIRE(passes >= 1 && passes <= 4, "nsac_gemm_split: passes must be 1..4");
   NSAC_REQUIRE(passes < 3 || w_lo, "nsac_gemm_split: missing W lo plane for %d passes", passes);     // a_lo == nullptr: A has no lo plane
@@ -853,17 +875,19 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   p.a_lo_zero = a_lo == nullptr ? 1 : 0;
   p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1; p.cstride = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  if (res_hi) {     // residual tiles are TMA-prefetched: [M, N] planes with row stride ld_res, boxes of 64 columns x 128 rows
-    CUtensorMap mrh, mrl;
-    if (!(make_map(&mrh, res_hi, M, N, ld_res, BLOCK_M, bf) && make_map(&mrl, res_lo, M, N, ld_res, BLOCK_M, bf))) {
-      nsac_set_error("nsac_gemm_split_residual: cuTensorMapEncodeTiled failed for the residual planes (M=%d N=%d ld_res=%d)", M, N, ld_res);
+  if (res_hi) {
+    // residual epilogue: 64-wide tiles, residual tiles TMA-prefetched and turned in place into the output tile, TMA store
+    CUtensorMap mrh, mrl, moh, mol, mw64h, mw64l;
+    if (!(make_map(&mrh, res_hi, M, N, ld_res, BLOCK_M, bf) && make_map(&mrl, res_lo, M, N, ld_res, BLOCK_M, bf) &&
+          make_map(&moh, out_hi, M, N, ld_split, BLOCK_M, bf) && make_map(&mol, out_lo, M, N, ld_split, BLOCK_M, bf) &&
+          make_map(&mw64h, w_hi, N, K, ldw, 64, bf) && make_map(&mw64l, w_lo ? w_lo : w_hi, N, K, ldw, 64, bf))) {
+      nsac_set_error("nsac_gemm_split_residual: cuTensorMapEncodeTiled failed (M=%d N=%d ld_res=%d ld_split=%d)", M, N, ld_res, ld_split);
       return NSAC_ERR_LAUNCH;
     }
-    if (block_n == 64) return launch_gemm<64, true>(mah, mal, mwh, mwl, mrh, mrl, p, nsac_cdiv(M, BLOCK_M), s);
-    return launch_gemm<128, true>(mah, mal, mwh, mwl, mrh, mrl, p, nsac_cdiv(M, BLOCK_M), s);
+    return launch_gemm<64, true>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
   }
-  if (block_n == 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
-  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  if (block_n == 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
 }
 
 extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
