@@ -267,6 +267,11 @@ int nsac_camera_errors(const float* pose, int ldpose, const float* gt_tran, cons
  *   feats [B,NQ,C] = pred_plane_feats; scores [B,NQ]; centers [B,NQ,2] = pred_plane_ins_center; bboxes [B,NQ,4] = (x,y,w,h)
  *   of pycocotools toBbox; areas [B,NQ]; seg [B,H,W] uint8 label map, 255 = no plane, pred_plane_masks[j] == (seg == j).
  * workspace: nsac_plane_post_workspace_bytes(B,NQ,H,W) bytes; workspace and seg 16-byte aligned. */
+/* nsac_gemm_split + a per-ROW scalar: out[m, n] = act(out_scale * acc + bias[n] + row_bias[m]) (row_bias [M] fp32, may be NULL). */
+int nsac_gemm_split_rowbias(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                            const float* bias, const float* row_bias, int M, int N, int K, int act, int passes, int fmt,
+                            float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                            void* stream);
 /* nsac_conv3x3_split with a convolution stride of 1 or 2 (H, W = INPUT map; output (H-1)/stride+1 x (W-1)/stride+1, rows in that
  * order): the A tiles are gathered by TMA with a traversal stride, no im2col matrix.  The strided 3x3 of res3.0 / res4.0 /
  * res5.0 of the backbone (detectron2 BottleneckBlock with STRIDE_IN_1X1 = False, Base.yaml:2-12). */
@@ -312,6 +317,28 @@ int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, const float*
                          const float* mean3_host, const float* std3_host, float* out, void* stream);
 int nsac_im2col3x3_from_planes(const void* hi, const void* lo, int N, int H, int W, int C, int stride, void* out_hi,
                                void* out_lo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * PlaneTRHead glue (first half: planeTR_net/planeTR_head.py:116-192, transformer/transformer.py) — what is
+ * not a GEMM; the linear layers / 1x1 convolutions run on nsac_gemm_split*.
+ *   nsac_row_op              per row of [rows, C] fp32 (C % 32 == 0, <= 1024): s = x (+ y);  t = do_ln ? LayerNorm(s; gamma, beta,
+ *                            eps) : s;  optional outputs s (sum_out), t (t_out fp32, t_hi/t_lo planes) and t + pos[row % T]
+ *                            (p_hi/p_lo planes): the residual adds, LayerNorms and `with_pos_embed` adds of
+ *                            transformer.py:170-185 (post-norm encoder) / :284-311 (pre-norm decoder)
+ *   nsac_attention_tiled     multi-head attention softmax(q k^T / sqrt(32)) v, head dim 32, S <= 320 keys, any L: q [B*L, H*32]
+ *                            (row stride ldq), k / v [B*S, H*32] (row stride ldkv) -> out [B*L, H*32] fp32 and / or planes;
+ *                            replaces nn.MultiheadAttention's attention core (transformer.py:153, 238-239)
+ *   nsac_upsample2x_relu_add out = relu(bilinear_2x(a)) + b on NHWC fp32 maps (a [N,h,w,C], b / out [N,2h,2w,C],
+ *                            align_corners = False): the top-down path of planeTR_head.py:240-252 with the 1x1 convolution +
+ *                            BatchNorm applied before the upsampling
+ * ---------------------------------------------------------------------------------------------- */
+int nsac_row_op(const float* x, int ldx, const float* y, int ldy, const float* gamma, const float* beta, float eps, int do_ln,
+                const float* pos, int T, float* sum_out, int ld_sum, float* t_out, int ld_t, void* t_hi, void* t_lo, int ld_tp,
+                void* p_hi, void* p_lo, int ld_pp, int rows, int C, void* stream);
+int nsac_attention_tiled(const float* q, int ldq, const float* k, const float* v, int ldkv, float* out, int ldo, void* out_hi,
+                         void* out_lo, int ld_split, int B, int L, int S, int H, int D, void* stream);
+int nsac_upsample2x_relu_add(const float* a, const float* b, int N, int h, int w, int C, float* out, void* out_hi, void* out_lo,
+                             void* stream);
 
 #ifdef __cplusplus
 }

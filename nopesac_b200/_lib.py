@@ -26,6 +26,16 @@ _SIGNATURES = {
     "nsac_gemm_split_residual": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p,
                                            C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                            C.c_int, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_gemm_split_rowbias": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, c_float_p, c_float_p,
+                                          C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
+                                          C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_row_op": (C.c_int, [c_float_p, C.c_int, c_float_p, C.c_int, c_float_p, c_float_p, C.c_float, C.c_int, c_float_p, C.c_int,
+                              c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                              C.c_int, C.c_int, C.c_void_p]),
+    "nsac_attention_tiled": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, C.c_int, C.c_void_p, C.c_void_p,
+                                       C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_upsample2x_relu_add": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p]),
     "nsac_split16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p]),
     "nsac_conv3x3_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,

@@ -199,6 +199,8 @@ struct GemmParams {
   const uint16_t* res_hi;
   const uint16_t* res_lo;
   int ld_res;
+  const float* row_bias;    // optional per-ROW scalar added with the bias (out[m, n] += row_bias[m]): the mask-logit GEMM of
+                            // PlaneTRHead, whose M rows are plane queries (planeTR_head.py:148-150)
   int a_lo_zero;            // the A operand has no lo plane (exactly representable in 16 bits, e.g. raw 8-bit pixels): the
                             // lo.hi pass and its TMA loads are skipped, passes = 3 then means hi.hi + hi.lo
 };
@@ -256,6 +258,7 @@ struct EpiOut {
   uint16_t* out_lo;
   int n_valid;            // valid columns from col0 on (>= 32: full chunk)
   bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
+  float row_bias;         // per-row scalar added with the bias (0 if none)
 };
 
 // packed 16-bit plane word -> two floats
@@ -285,8 +288,9 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
         b01 = pk2(b[0], b[1]); b23 = pk2(b[2], b[3]);
       }
     }
-    upk2(ffma2(acc[i >> 1], sc, b01), f[i], f[i + 1]);
-    upk2(ffma2(acc[(i >> 1) + 1], sc, b23), f[i + 2], f[i + 3]);
+    const u64 rb = pk2(o.row_bias, o.row_bias);
+    upk2(ffma2(acc[i >> 1], sc, fadd2(b01, rb)), f[i], f[i + 1]);
+    upk2(ffma2(acc[(i >> 1) + 1], sc, fadd2(b23, rb)), f[i + 2], f[i + 3]);
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
@@ -369,8 +373,9 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], i
         b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
       }
       float x0, x1, x2, x3;
-      upk2(ffma2(sum[16 * g + (i >> 1)], sc, b01), x0, x1);
-      upk2(ffma2(sum[16 * g + (i >> 1) + 1], sc, b23), x2, x3);
+      const u64 rb = pk2(o.row_bias, o.row_bias);
+      upk2(ffma2(sum[16 * g + (i >> 1)], sc, fadd2(b01, rb)), x0, x1);
+      upk2(ffma2(sum[16 * g + (i >> 1) + 1], sc, fadd2(b23, rb)), x2, x3);
       {   // activation as max(x, slope * x + 0): the +0 addend makes ReLU of a negative +0, not -0
         float t0, t1, t2, t3;
         upk2(ffma2(pk2(x0, x1), sl, 0ull), t0, t1);
@@ -629,6 +634,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       o.out_scale = p.out_scale;
       o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
       o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
+      o.row_bias = (p.row_bias && row_ok) ? __ldg(p.row_bias + row) : 0.f;
       if (row_ok) {
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
@@ -806,7 +812,7 @@ static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, co
   p.bias = bias; p.bias_group_rows = 0; p.M = N * H * W; p.N = Cout; p.K = K; p.act = act; p.passes = passes;
   p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
-  p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0;
+  p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0; p.row_bias = nullptr;
   p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
   if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
@@ -834,7 +840,8 @@ extern "C" int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, co
 static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
                            int ldw, const float* bias, int bias_group_rows, int M, int N, int K, int act,
                            int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
-                           void* out_lo, int ld_split, const void* res_hi, const void* res_lo, int ld_res, void* stream) {
+                           void* out_lo, int ld_split, const void* res_hi, const void* res_lo, int ld_res, const float* row_bias,
+                           void* stream) {
   NSAC_REQUIRE(!res_hi || (res_lo && ld_res >= N && ld_res % 8 == 0 && (reinterpret_cast<uintptr_t>(res_hi) & 15) == 0 &&
                            (reinterpret_cast<uintptr_t>(res_lo) & 15) == 0),
                "nsac_gemm_split_residual: residual needs both planes, 16-byte alignment and ld_res %% 8 == 0");
@@ -873,6 +880,7 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
   p.res_hi = static_cast<const uint16_t*>(res_hi); p.res_lo = static_cast<const uint16_t*>(res_lo); p.ld_res = ld_res;
   p.a_lo_zero = a_lo == nullptr ? 1 : 0;
+  p.row_bias = row_bias;
   p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1; p.cstride = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (res_hi) {
@@ -895,7 +903,16 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
                                int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
                                void* out_lo, int ld_split, void* stream) {
   return gemm_split_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, bias_group_rows, M, N, K, act, passes, fmt, out_scale, out_f32, ldo,
-                         out_hi, out_lo, ld_split, nullptr, nullptr, 0, stream);
+                         out_hi, out_lo, ld_split, nullptr, nullptr, 0, nullptr, stream);
+}
+
+// nsac_gemm_split + a per-ROW scalar: out[m, n] = act(out_scale * acc + bias[n] + row_bias[m]).
+extern "C" int nsac_gemm_split_rowbias(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
+                                       int ldw, const float* bias, const float* row_bias, int M, int N, int K, int act,
+                                       int passes, int fmt, float out_scale, float* out_f32, int ldo, void* out_hi,
+                                       void* out_lo, int ld_split, void* stream) {
+  return gemm_split_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, 0, M, N, K, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                         ld_split, nullptr, nullptr, 0, row_bias, stream);
 }
 
 // nsac_gemm_split + a residual input given as hi/lo planes [M, ld_res]: out = act(A.W^T * scale + bias + residual) - the
@@ -906,7 +923,7 @@ extern "C" int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int 
                                         int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
   NSAC_REQUIRE(res_hi && res_lo, "nsac_gemm_split_residual: null residual planes");
   return gemm_split_impl(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, 0, M, N, K, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
-                         ld_split, res_hi, res_lo, ld_res, stream);
+                         ld_split, res_hi, res_lo, ld_res, nullptr, stream);
 }
 
 extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,

@@ -27,6 +27,7 @@ from .backbone import build_backbone
 from .camera_head import build_camera_head
 from .compat import Registry, ShapeSpec
 from .matching_head import build_matching_head
+from .planeTR_head import build_planeTR_head
 from .plane_postprocess import PlaneLists, postprocess_plane_head_mask
 
 __all__ = ["META_ARCH_REGISTRY", "PlaneTR_NopeSAC", "build_model"]
@@ -48,12 +49,18 @@ def build_model(cfg):
 
 @META_ARCH_REGISTRY.register()
 class PlaneTR_NopeSAC(nn.Module):
-    def __init__(self, cfg, with_backbone: bool = False):
+    def __init__(self, cfg, with_backbone: bool = False, with_plane_head: bool = False):
         """`with_backbone=True` also builds `self.backbone` (row f2: the R-50 of `build_backbone(cfg)`, siamese_planeTR.py
-        `__init__`; `backbone.*` checkpoint keys then load too) so that `inference_from_images` starts at RGB."""
+        `__init__`; `backbone.*` checkpoint keys then load too) so that `inference_from_images` starts at RGB.
+        `with_plane_head=True` (needs the backbone) also builds `self.sem_seg_head` (row f1: `build_planeTR_head`,
+        siamese_planeTR.py:64): `forward` then accepts the reference's own batched_inputs with `image` entries and runs the
+        whole model, `inference_from_rgb`."""
         super().__init__()
         self.cfg = cfg
         self.backbone = build_backbone(cfg) if with_backbone else None
+        if with_plane_head and not with_backbone:
+            raise ValueError("with_plane_head=True needs with_backbone=True")
+        self.sem_seg_head = build_planeTR_head(cfg, self.backbone.output_shape()) if with_plane_head else None
         self.mask_on = cfg.MODEL.MASK_ON
         self.embedding_on = cfg.MODEL.EMBEDDING_ON
         self.camera_on = cfg.MODEL.CAMERA_ON
@@ -79,7 +86,8 @@ class PlaneTR_NopeSAC(nn.Module):
         (backbone / sem_seg_head / criterion)."""
         mine = {k: v for k, v in state_dict.items()
                 if k.startswith("matching_head.") or k.startswith("camera_head_list.0.") or
-                (self.backbone is not None and k.startswith("backbone."))}
+                (self.backbone is not None and k.startswith("backbone.")) or
+                (self.sem_seg_head is not None and k.startswith("sem_seg_head."))}
         missing, unexpected = self.load_state_dict(mine, strict=False)
         if missing:
             raise KeyError(f"reference checkpoint lacks hot-path keys: {missing[:5]} ...")
@@ -160,7 +168,49 @@ class PlaneTR_NopeSAC(nn.Module):
         return planes, feats, cam, count
 
     @torch.no_grad()
+    def inference_from_rgb(self, batched_inputs: List[dict], max_planes: int = None, **head_kwargs):
+        """The reference's whole inference (siamese_planeTR.py:338-450 with inference_single :452-473) for ANY number of pairs in
+        one call: `batched_inputs[i]["0" / "1"]["image"]` = uint8 (or float 0..255) [3,H,W] of one size ->
+        preprocess (normalisation fused into the stem) -> backbone on all 2B images -> PlaneTRHead -> plane lists on the device
+        (`plane_lists`, no per-plane host round trip) -> camera head on the padded lists with per-pair plane counts.
+        Returns (results, lists1, lists2): `results[i]` has the reference's camera / assignment keys (:411-431) as device tensors
+        (assignment matrices padded to `max_planes` or NUM_OBJECT_QUERIES rows / columns: see lists*.count), `lists*` are the
+        PlaneLists of the first / second views (`.to_reference_results()` gives the reference's per-view dicts)."""
+        if self.backbone is None or self.sem_seg_head is None:
+            raise RuntimeError("PlaneTR_NopeSAC was built without backbone / plane head (with_backbone=True, with_plane_head=True)")
+        B, dev = len(batched_inputs), self.device
+        imgs = [bi[v]["image"] for v in ("0", "1") for bi in batched_inputs]               # first views, then second views
+        images = torch.stack([im.to(dev, non_blocking=True) for im in imgs])
+        if images.dtype != torch.uint8:
+            images = images.float()
+        H, W = images.shape[2:]
+        feats = self.backbone(images, planes=True)
+        outputs, query_feat = self.sem_seg_head(feats)
+        lists = self.plane_lists(outputs, query_feat, H, W)
+        P = self.num_queries if max_planes is None else min(int(max_planes), self.num_queries)
+        cnt = lists.count.clamp(max=P)
+        pl, ft = lists.planes[:, :P], lists.feats[:, :P]
+        out = self.camera_head_list[0](feats, None, pl[:B].contiguous(), pl[B:].contiguous(), planeApp1=ft[:B].contiguous(),
+                                       planeApp2=ft[B:].contiguous(), matching_net=self.matching_head, plane_count1=cnt[:B].contiguous(),
+                                       plane_count2=cnt[B:].contiguous(), **head_kwargs)
+        cams, planeAss = out[0], out[4]
+        results = []
+        for i in range(B):
+            r = {"pred_aff": None, "depth": {"0": None, "1": None}}
+            for key, value in cams.items():
+                j = i if value["tran"].shape[0] == B else 0      # camera_zero is [1,3] regardless of B
+                r[key] = {"tran": value["tran"][j], "rot": value["rot"][j]}
+            for key, value in planeAss.items():
+                r[key] = value[i]
+            results.append(r)
+        sl = lambda a, b: PlaneLists(*[getattr(lists, f)[a:b] for f in ("count", "flags", "ori_idx", "planes", "feats", "scores", "centers",
+                                                                         "bboxes", "areas", "seg")])
+        return results, sl(0, B), sl(B, 2 * B), out
+
+    @torch.no_grad()
     def forward(self, batched_inputs: List[dict]):
+        if self.sem_seg_head is not None and "image" in batched_inputs[0]["0"]:
+            return self.inference_from_rgb(batched_inputs)[0]
         return self.inference(batched_inputs)
 
     @torch.no_grad()

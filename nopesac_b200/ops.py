@@ -395,6 +395,75 @@ def add_relu_nhwc(a: torch.Tensor, b: torch.Tensor, fmt: int = SPLIT_F16, want_f
     return out, sp
 
 
+# ---------------------------------------------------------------------------------------------------
+# PlaneTRHead glue (row f1; csrc/planetr.cu)
+# ---------------------------------------------------------------------------------------------------
+def row_op(x: torch.Tensor, y: Optional[torch.Tensor] = None, ln=None, pos: Optional[torch.Tensor] = None, T: int = 0,
+           sum_out: Optional[torch.Tensor] = None, want_f32: bool = False, want_split: bool = False, want_pos_split: bool = False):
+    """Per row of fp32 [rows, C]: s = x (+ y); t = LayerNorm(s) if `ln` = (gamma, beta, eps) else s.
+    -> (t fp32 or None, t planes or None, (t + pos[row % T]) planes or None); `sum_out` (may alias x) receives s."""
+    _chk(x, "x")
+    rows, Cc = x.shape
+    assert x.stride(1) == 1 and (y is None or (y.shape == x.shape and y.stride(1) == 1))
+    dev = x.device
+    t32 = torch.empty(rows, Cc, device=dev, dtype=torch.float32) if want_f32 else None
+    tp = Split.empty(rows, Cc, dev) if want_split else None
+    pp = Split.empty(rows, Cc, dev) if want_pos_split else None
+    if want_pos_split:
+        _chk(pos, "pos")
+        assert pos.is_contiguous() and pos.shape == (T, Cc)
+    g, b, eps = (ln[0], ln[1], float(ln[2])) if ln is not None else (None, None, 0.0)
+    st = _lib.lib().nsac_row_op(_p(x), x.stride(0), _p(y), 0 if y is None else y.stride(0), _p(g), _p(b), eps, 0 if ln is None else 1,
+                                _p(pos) if want_pos_split else None, T, _p(sum_out), 0 if sum_out is None else sum_out.stride(0),
+                                _p(t32), Cc, None if tp is None else _p(tp.hi), None if tp is None else _p(tp.lo),
+                                0 if tp is None else tp.hi.stride(0), None if pp is None else _p(pp.hi),
+                                None if pp is None else _p(pp.lo), 0 if pp is None else pp.hi.stride(0), rows, Cc, _stream())
+    _lib.check(st, "nsac_row_op")
+    _count()
+    return t32, tp, pp
+
+
+def attention_tiled(q, k, v, B: int, L: int, S: int, H: int = 8, D: int = 32, want_f32: bool = False, out_split: Optional[Split] = None):
+    """softmax(q k^T / sqrt(D)) v per (batch element, head); q [B*L, H*D], k / v [B*S, H*D] (same row stride), S <= 320.
+    -> fp32 [B*L, H*D] (want_f32) and / or planes written into `out_split`."""
+    _chk(q, "q"); _chk(k, "k"); _chk(v, "v")
+    assert k.stride(0) == v.stride(0) and q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1
+    out = torch.empty(B * L, H * D, device=q.device, dtype=torch.float32) if want_f32 else None
+    st = _lib.lib().nsac_attention_tiled(_p(q), q.stride(0), _p(k), _p(v), k.stride(0), _p(out), 0 if out is None else out.stride(0),
+                                         None if out_split is None else _p(out_split.hi), None if out_split is None else _p(out_split.lo),
+                                         0 if out_split is None else out_split.hi.stride(0), B, L, S, H, D, _stream())
+    _lib.check(st, "nsac_attention_tiled")
+    _count()
+    return out if want_f32 else out_split
+
+
+def upsample2x_relu_add(a: torch.Tensor, b: torch.Tensor, N: int, h: int, w: int, want_f32: bool = False, want_split: bool = True):
+    """relu(bilinear_2x(a)) + b on NHWC fp32 rows: a [N*h*w, C], b [N*2h*2w, C] -> (fp32 or None, planes or None)."""
+    a, b = _c(a, "a"), _c(b, "b")
+    Cc = a.shape[1]
+    assert a.shape[0] == N * h * w and b.shape == (N * 4 * h * w, Cc)
+    out = torch.empty_like(b) if want_f32 else None
+    sp = _empty_split(b.shape[0], Cc, b.device) if want_split else None
+    st = _lib.lib().nsac_upsample2x_relu_add(_p(a), _p(b), N, h, w, Cc, _p(out), None if sp is None else _p(sp.hi),
+                                             None if sp is None else _p(sp.lo), _stream())
+    _lib.check(st, "nsac_upsample2x_relu_add")
+    _count()
+    return out, sp
+
+
+def gemm_tc_rowbias(a: Split, w: Split, row_bias: torch.Tensor, out_f32: torch.Tensor, passes: int = 3):
+    """out_f32[M, N] = a @ w^T + row_bias[m] (per-ROW scalar): the mask-logit GEMM whose rows are plane queries."""
+    M, N = a.rows, w.rows
+    K = (a.K + 63) // 64 * 64
+    assert a.K == w.K and a.fmt == w.fmt and out_f32.shape == (M, N) and out_f32.stride(1) == 1 and row_bias.numel() == M
+    st = _lib.lib().nsac_gemm_split_rowbias(_p(a.hi), _p(a.lo), a.hi.stride(0), _p(w.hi), _p(w.lo), w.hi.stride(0), None, _p(row_bias),
+                                            M, N, K, ACT_NONE, passes, a.fmt, 1.0 / (a.scale * w.scale), _p(out_f32),
+                                            out_f32.stride(0), None, None, 0, _stream())
+    _lib.check(st, "nsac_gemm_split_rowbias")
+    _count()
+    return out_f32
+
+
 def layernorm(x, gamma, beta, res=None, out=None, out_split: Optional[Split] = None):
     """out = (res or 0) + LayerNorm(x); optionally also written as fp16 hi/lo planes (`out_split` view)."""
     _chk(x, "x")

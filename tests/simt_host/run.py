@@ -93,4 +93,4 @@ def build(cu_names, extra_cpp=()) -> ctypes.CDLL:
     return ctypes.CDLL(lib)
 
 
-SIMT_SOURCES = ["dense.cu", "geo.cu", "matcher.cu", "score.cu", "evaluate.cu", "planes.cu", "pixel.cu", "backbone.cu"]   # no TMA / tcgen05 / inline PTX
+SIMT_SOURCES = ["dense.cu", "geo.cu", "matcher.cu", "score.cu", "evaluate.cu", "planes.cu", "pixel.cu", "backbone.cu", "planetr.cu"]   # no TMA / tcgen05 / inline PTX

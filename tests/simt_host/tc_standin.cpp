@@ -63,7 +63,7 @@ extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scal
 static int gemm_split_standin(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
                               const float* bias, int bias_group_rows, int M, int N, int K, int act, int passes, int fmt,
                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
-                              const void* res_hi, const void* res_lo, int ld_res) {
+                              const void* res_hi, const void* res_lo, int ld_res, const float* row_bias = nullptr) {
   // a_lo == NULL: A has no lo plane (exact in 16 bits) - include/nopesac_b200.h
   if (!a_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 3 && !w_lo) || K % 64 != 0 || lda < K ||
       ldw < K || (!out_f32 && !out_hi) || (out_hi && !out_lo) || (res_hi && (!res_lo || ld_res < N))) {
@@ -93,7 +93,7 @@ static int gemm_split_standin(const void* a_hi, const void* a_lo, int lda, const
       for (int k = 0; k < K; ++k) acc += (AH[k] + AL[k]) * w0[k] + AH[k] * w1[k];              // hi.hi + lo.hi + hi.lo
       if (passes >= 4)
         for (int k = 0; k < K; ++k) acc += AL[k] * w1[k];
-      float v = out_scale * (float)acc + (brow ? brow[n] : 0.f);
+      float v = out_scale * (float)acc + (brow ? brow[n] : 0.f) + (row_bias ? row_bias[m] : 0.f);
       if (res_hi)
         v += plane_to_float(static_cast<const uint16_t*>(res_hi)[(size_t)m * ld_res + n], fmt) +
              plane_to_float(static_cast<const uint16_t*>(res_lo)[(size_t)m * ld_res + n], fmt);
@@ -110,6 +110,13 @@ extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, cons
                                float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
   return gemm_split_standin(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, bias_group_rows, M, N, K, act, passes, fmt, out_scale, out_f32, ldo,
                             out_hi, out_lo, ld_split, nullptr, nullptr, 0);
+}
+
+extern "C" int nsac_gemm_split_rowbias(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,
+                                       const float* bias, const float* row_bias, int M, int N, int K, int act, int passes, int fmt,
+                                       float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
+  return gemm_split_standin(a_hi, a_lo, lda, w_hi, w_lo, ldw, bias, 0, M, N, K, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                            ld_split, nullptr, nullptr, 0, row_bias);
 }
 
 extern "C" int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo, int ldw,

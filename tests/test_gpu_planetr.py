@@ -1,0 +1,176 @@
+"""GPU: PlaneTRHead (row f1, first half) on the tensor-core engine against the CPU oracle (oracle/planeTR_restate.py, pinned to the
+live reference) and the committed golden fixture; its kernels one by one against torch; and the whole model from RGB
+(backbone -> PlaneTRHead -> plane lists -> camera head, `PlaneTR_NopeSAC.inference_from_rgb`) stage by stage against the
+oracles on identical stage inputs.  Bars: 1e-4 of the tensor's scale for float outputs, index paths exact."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from tests import util
+from tests.test_oracle_planetr import make_features, planetr_state
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900, method="thread")]
+
+
+def _dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("B,L,S", [(3, 300, 300), (2, 50, 300), (2, 50, 50), (1, 7, 13), (2, 256, 256), (1, 70, 320)])
+def test_attention_tiled_matches_torch(B, L, S):
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + L + S)
+    H, D = 8, 32
+    buf = torch.randn(B * L, 3 * H * D, generator=g)         # q lives in a wider row (stride 768), like the fused qkv buffer
+    kv = torch.randn(B * S, 2 * H * D, generator=g)
+    q, k, v = buf[:, :H * D], kv[:, :H * D], kv[:, H * D:]
+    qh = q.reshape(B, L, H, D).permute(0, 2, 1, 3).double()
+    kh = k.reshape(B, S, H, D).permute(0, 2, 1, 3).double()
+    vh = v.reshape(B, S, H, D).permute(0, 2, 1, 3).double()
+    ref = (torch.softmax(qh @ kh.transpose(-1, -2) / D ** 0.5, -1) @ vh).permute(0, 2, 1, 3).reshape(B * L, H * D)
+    bd, kd = buf.to(dev), kv.to(dev)
+    sp = ops.Split.empty(B * L, H * D, dev)
+    out = ops.attention_tiled(bd[:, :H * D], kd[:, :H * D], kd[:, H * D:], B, L, S, want_f32=True, out_split=sp)
+    torch.cuda.synchronize()
+    assert util.maxdiff(out, ref) <= 2e-6 * float(ref.abs().max()), util.maxdiff(out, ref)
+    assert util.maxdiff(sp.float(), out) <= 2 ** -20 * float(ref.abs().max())
+
+
+def test_row_op_and_upsample_match_torch():
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    rows, C, T = 77, 256, 11
+    x, y, pos = torch.randn(rows, C, generator=g), torch.randn(rows, C, generator=g), torch.randn(T, C, generator=g)
+    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    xd, yd = x.to(dev), y.to(dev)
+    s_out = torch.empty_like(xd)
+    t32, tp, pp = ops.row_op(xd, y=yd, ln=(gam.to(dev), bet.to(dev), 1e-5), pos=pos.to(dev), T=T, sum_out=s_out, want_f32=True,
+                             want_split=True, want_pos_split=True)
+    torch.cuda.synchronize()
+    ref = F.layer_norm((x + y).double(), (C,), gam.double(), bet.double(), 1e-5)
+    assert torch.equal(s_out.cpu(), x + y)
+    assert util.maxdiff(t32, ref) <= 2e-6 * float(ref.abs().max())
+    assert util.maxdiff(tp.float(), t32) <= 2 ** -20 * float(ref.abs().max())
+    assert util.maxdiff(pp.float(), t32.cpu() + pos[torch.arange(rows) % T]) <= 2 ** -19 * float(ref.abs().max())
+    t32b, _, _ = ops.row_op(xd, want_f32=True)               # plain copy mode
+    assert torch.equal(t32b, xd)
+    # in-place residual accumulation (sum_out aliases x) as the decoder uses it
+    acc = xd.clone()
+    ops.row_op(acc, y=yd, sum_out=acc, ln=(gam.to(dev), bet.to(dev), 1e-5), want_split=True)
+    assert torch.equal(acc.cpu(), x + y)
+    for N, h, w, Cc in ((2, 15, 20, 256), (1, 3, 4, 64), (3, 7, 5, 128)):
+        a = torch.randn(N, Cc, h, w, generator=g)
+        b = torch.randn(N, Cc, 2 * h, 2 * w, generator=g)
+        want = F.relu(F.interpolate(a, scale_factor=2, mode="bilinear", align_corners=False)) + b
+        nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1]).contiguous()
+        o32, osp = ops.upsample2x_relu_add(nhwc(a).to(dev), nhwc(b).to(dev), N, h, w, want_f32=True, want_split=True)
+        assert util.maxdiff(o32, nhwc(want)) <= 2e-6 * float(want.abs().max())
+        assert util.maxdiff(osp.float(), o32) <= 2 ** -20 * float(want.abs().max())
+
+
+def _build_head(NQ, dev):
+    from nopesac_b200 import config
+    from nopesac_b200.meta_arch import RESNET50_OUTPUT_SHAPE
+    from nopesac_b200.planeTR_head import build_planeTR_head
+    head = build_planeTR_head(config.inference_cfg(NQ), RESNET50_OUTPUT_SHAPE)
+    sd = planetr_state(NQ)
+    head.load_state_dict(sd)
+    return head.to(dev), sd
+
+
+def _check_outputs(got, hs, want, hs_want, tol=1e-4):
+    assert set(want) <= set(got)
+    for k in want:
+        assert got[k].shape == want[k].shape, k
+        scale = max(1.0, float(want[k].abs().max()))
+        assert util.maxdiff(got[k], want[k]) <= tol * scale, (k, util.maxdiff(got[k], want[k]) / scale)
+    assert util.maxdiff(hs, hs_want) <= tol * float(hs_want.abs().max())
+
+
+@pytest.mark.parametrize("NQ,N,H,W", [(20, 2, 96, 128), (50, 2, 480, 640), (50, 3, 224, 320)])
+def test_planetr_head_matches_oracle(NQ, N, H, W):
+    dev = _dev()
+    from oracle import planeTR_restate as R
+    head, sd = _build_head(NQ, dev)
+    feats = make_features(3, N, H, W)
+    got, hs = head({k: v.to(dev) for k, v in feats.items()})
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        want, hs_want = R.plane_tr_head(sd, feats)
+    _check_outputs(got, hs, want, hs_want)
+
+
+def test_planetr_head_matches_golden_from_live_reference():
+    dev = _dev()
+    g = torch.load(os.path.join(util.GOLDEN_DIR, "planetr_nq20.golden"), weights_only=False)
+    c = g["case"]
+    head, _ = _build_head(c["NQ"], dev)
+    got, hs = head({k: v.to(dev) for k, v in make_features(c["feat_seed"], c["N"], c["H"], c["W"]).items()})
+    torch.cuda.synchronize()
+    want = dict(g["outputs"])
+    _check_outputs(got, hs, {k: v for k, v in want.items() if k != "query_feat"}, want["query_feat"])
+
+
+def test_full_model_from_rgb_stage_by_stage():
+    """BASELINE.json configs[3] shape (inference_mp3d.yaml: NUM_OBJECT_QUERIES 50, random weights, synthetic RGB): uint8 images ->
+    backbone -> PlaneTRHead -> plane lists -> camera head in ONE call (`forward` with the reference's batched_inputs), each stage
+    checked against its oracle on the stage's own device inputs (so rounding noise of an upstream stage cannot flip a downstream
+    discrete decision of the comparison): PlaneTRHead 1e-4, plane lists exact (index path), camera head: assignments / counts
+    exact, poses 1e-4."""
+    dev = _dev()
+    from nopesac_b200 import config, meta_arch, synthetic
+    from oracle import planeTR_restate as R
+    from oracle import planes_restate, restate
+    NQ, B, H, W = 50, 2, 480, 640
+    cfg = config.inference_cfg(NQ)
+    model = meta_arch.PlaneTR_NopeSAC(cfg, with_backbone=True, with_plane_head=True)
+    sd, msd = util.make_weights(NQ)
+    psd = planetr_state(NQ)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    model.sem_seg_head.load_state_dict(psd)
+    shapes = {k: tuple(v.shape) for k, v in model.backbone.state_dict().items()}
+    model.backbone.load_state_dict(synthetic.make_backbone_weights(shapes, seed=9))
+    model = model.to(dev)
+    images = synthetic.make_images(11, 2 * B, H, W)
+    batched = [{"0": {"image": images[i], "height": H, "width": W}, "1": {"image": images[B + i], "height": H, "width": W}} for i in range(B)]
+    results, l1, l2, head_out = model.inference_from_rgb(batched, max_planes=20)
+    assert len(model(batched)) == B                                        # the reference's entry point takes the same inputs
+    torch.cuda.synchronize()
+    # stage 1: PlaneTRHead on the backbone's own feature maps
+    feats = model.backbone(images.to(dev))
+    outputs, qf = model.sem_seg_head(feats)
+    with torch.no_grad():
+        want, hs_want = R.plane_tr_head(psd, {k: v.cpu() for k, v in feats.items()})
+    _check_outputs(outputs, qf, want, hs_want)
+    # stage 2: plane lists on the head's own outputs (index path exact)
+    lists = model.plane_lists(outputs, qf, H, W)
+    ref_lists = planes_restate.postprocess_plane_head_mask(outputs["pred_logits"].cpu(), outputs["pred_params"].cpu(),
+                                                           outputs["pred_mask_logits"].cpu(), qf.cpu(), H, W)
+    for i, o in enumerate(ref_lists):
+        n = int(lists.count[i])
+        assert lists.ori_idx[i, :n].cpu().tolist() == o["pred_plane_oriIdxs"], i
+        assert torch.equal(lists.planes[i, :n].cpu(), o["pred_plane"]), i
+    assert torch.equal(torch.cat([l1.count, l2.count]), lists.count) and torch.equal(torch.cat([l1.planes, l2.planes]), lists.planes)
+    # stage 3: camera head on those lists + feature maps, per pair, against the oracle head
+    P = 20
+    for i in range(B):
+        n1, n2 = min(int(l1.count[i]), P), min(int(l2.count[i]), P)
+        f1 = {k: v[i:i + 1].cpu() for k, v in feats.items()}
+        f2 = {k: v[B + i:B + i + 1].cpu() for k, v in feats.items()}
+        with torch.no_grad():
+            o = restate.inference_joint(sd, msd, f1, f2, l1.planes[i:i + 1, :n1].cpu(), l2.planes[i:i + 1, :n2].cpu(),
+                                        l1.feats[i:i + 1, :n1].cpu(), l2.feats[i:i + 1, :n2].cpu(), num_queries=NQ)
+        r = results[i]
+        assert torch.equal(r["pred_assignment_beforeRef0"][:n1, :n2].cpu(), o["assignment_before"][0]), i
+        assert float(r["pred_assignment_beforeRef0"].sum()) == float(o["assignment_before"].sum()), i      # nothing outside the block
+        assert int(head_out[5]["matched_num"][i]) == o["matched_num"], i
+        for key in ("camera_init", "camera_initRec", "camera"):
+            assert util.maxdiff(r[key]["tran"], o[key][0][0]) <= util.ABS_TOL, (key, i, util.maxdiff(r[key]["tran"], o[key][0][0]))
+            assert util.maxdiff(r[key]["rot"], o[key][1][0]) <= util.ABS_TOL, (key, i, util.maxdiff(r[key]["rot"], o[key][1][0]))

@@ -108,3 +108,12 @@ def build_cuda_heads(num_queries, out_cam_type="soft", match_threshold=0.2, devi
 
 def maxdiff(a, b):
     return float((a.detach().double().cpu() - b.detach().double().cpu()).abs().max()) if a.numel() else 0.0
+
+
+def planetr_shapes(num_queries: int):
+    """State-dict shapes of the reference's PlaneTRHead (tests/golden/planetr_state_shapes.json, written from the live reference
+    module at NUM_OBJECT_QUERIES = 50; only `query_embed.weight` depends on it)."""
+    with open(os.path.join(GOLDEN_DIR, "planetr_state_shapes.json")) as f:
+        shapes = json.load(f)
+    shapes["query_embed.weight"] = [num_queries, shapes["query_embed.weight"][1]]
+    return shapes
