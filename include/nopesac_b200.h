@@ -78,6 +78,10 @@ int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_h
                     void* stream);
 int nsac_split16(const float* x, int ldx, int rows, int K, float scale, int fmt, void* hi, void* lo,
                  int ld_split, void* stream);
+/* Sticky fp16-plane overflow flag: *flag_out (HOST int) = 1 if, since the last clearing call, a finite value with |x| > 65504
+ * had to be written into an fp16 plane (nsac_split16, nsac_nchw_to_planes, GEMM epilogues) — it became inf there and every
+ * result computed from it is invalid.  Synchronises `stream`; clear != 0 resets the flag.  Validation aid, not on the hot path. */
+int nsac_plane_overflow(int* flag_out, int clear, void* stream);
 /* nsac_gemm_split with a residual input given as hi/lo planes [M, ld_res] (same fmt): out = act(out_scale * acc + bias +
  * (res_hi + res_lo)) — the `out += shortcut; relu(out)` of a bottleneck block (detectron2 BottleneckBlock.forward, the backbone
  * Base.yaml:2-12 builds) inside the producing GEMM's epilogue.  In both entry points a_lo == NULL means "A has no lo plane"

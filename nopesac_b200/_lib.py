@@ -36,6 +36,7 @@ _SIGNATURES = {
                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "nsac_upsample2x_relu_add": (C.c_int, [c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p]),
+    "nsac_plane_overflow": (C.c_int, [C.POINTER(C.c_int), C.c_int, C.c_void_p]),
     "nsac_split16": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, C.c_void_p, C.c_void_p,
                                C.c_int, C.c_void_p]),
     "nsac_conv3x3_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,

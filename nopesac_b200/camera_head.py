@@ -403,6 +403,23 @@ class PlaneCameraHead(nn.Module):
             fused.append(f32)                                                     # F.relu(decoder_*2(.))
         return fused[0], fused[1]
 
+    @staticmethod
+    def check_finite(outputs) -> None:
+        """Debug guard (one host synchronisation; never called on the hot path): raises if an fp16 plane overflowed since the last
+        check (`nsac_plane_overflow`, a sticky device flag set by the plane writers) or if the result rows are not finite.  The
+        tensor-core layers carry activations as fp16 hi/lo planes (|x| <= 65504)."""
+        pose = outputs[5]["pose"] if outputs[5] is not None else outputs[0]["camera"]["rot"]
+        bad = ~torch.isfinite(pose).all(dim=-1)
+        if ops.plane_overflow(clear=True):
+            raise RuntimeError("fp16 plane overflow: a finite activation or input with |x| > 65504 was written into an fp16 hi/lo plane "
+                               "since the last check (it became inf; normalisation layers can turn that back into finite but WRONG "
+                               "poses) - feature maps / weights are far outside a trained network's scale; use bf16 planes "
+                               "(nopesac_b200.ops.SPLIT_BF16) or rescale the inputs")
+        if bool(bad.any()):
+            raise RuntimeError(f"non-finite camera poses for pairs {bad.nonzero().flatten().tolist()}: an activation left the fp16 plane "
+                               "range (|x| > 65504) - feature maps / weights are far outside a trained network's scale; run these "
+                               "pairs with bf16 planes (nopesac_b200.ops.SPLIT_BF16) or rescale the inputs")
+
     # ------------------------------------------------------------------ forward
     def forward(self, features1, features2, planeParam1, planeParam2, planeApp1=None, planeApp2=None,
                 gt_pose=None, gt_corr_matrix=None, batched_inputs=None, ite=0, matching_net=None,

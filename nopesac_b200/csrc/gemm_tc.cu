@@ -205,9 +205,18 @@ struct GemmParams {
                             // lo.hi pass and its TMA loads are skipped, passes = 3 then means hi.hi + hi.lo
 };
 
+// Sticky overflow flag (nsac_plane_overflow): set when a FINITE value that does not fit an fp16 plane (|x| > 65504) is written as
+// a plane by nsac_split16 or a GEMM epilogue.  Overflow used to be "loud" only through the inf -> NaN it usually causes downstream;
+// the r2k robustness test found inputs where normalisation layers turned it back into finite, plausible, WRONG poses.
+__device__ unsigned int g_plane_overflow = 0u;
+__device__ __forceinline__ void note_overflow(float maxabs) {
+  if (maxabs > 65504.f && maxabs < INFINITY) atomicOr(&g_plane_overflow, 1u);
+}
+
 // x -> (hi, lo) 16-bit planes in the requested format
 __device__ __forceinline__ void split16(float x, int fmt, uint16_t& hi, uint16_t& lo) {
   if (fmt == NSAC_SPLIT_F16) {
+    note_overflow(fabsf(x));
     const __half h = __float2half_rn(x);
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
@@ -307,6 +316,12 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
   }
   if (o.out_hi) {
     uint32_t hi[16], lo[16];
+    if (FMT == NSAC_SPLIT_F16) {
+      float mx = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < o.n_valid ? fabsf(f[i]) : 0.f);
+      note_overflow(mx);
+    }
 #pragma unroll
     for (int i = 0; i < 32; i += 2) split16x2<FMT>(f[i], f[i + 1], hi[i >> 1], lo[i >> 1]);
     uint16_t* dh = o.out_hi + col0;
@@ -388,6 +403,12 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], i
       staged_store<32>(stage, f, reinterpret_cast<uint8_t*>(o.out_f32 + col0 + 32 * g), lane);
     if (o.out_hi) {                        // 32 16-bit columns = one 64-byte segment per row and plane
       uint32_t hi[16], lo[16];
+      if (FMT == NSAC_SPLIT_F16) {           // one FMNMX per element on the ALU pipe; the atomic only fires on an overflow
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, fabsf(__uint_as_float(f[i])));
+        note_overflow(mx);
+      }
 #pragma unroll
       for (int i = 0; i < 32; i += 2) split16x2<FMT>(__uint_as_float(f[i]), __uint_as_float(f[i + 1]), hi[i >> 1], lo[i >> 1]);
       staged_store<16>(stage, hi, reinterpret_cast<uint8_t*>(o.out_hi + col0 + 32 * g), lane);
@@ -583,6 +604,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         const u64 sc = pk2(p.out_scale, p.out_scale);
         const float slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
         const u64 sl = pk2(slope, slope);
+        float ovf = 0.f;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int off = ((half * 4 + c) ^ (lane & 7)) << 4;
@@ -600,11 +622,14 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             float x0, x1, t0, t1;
             upk2(ffma2(sum[4 * c + j], sc, bb), x0, x1);
             upk2(ffma2(pk2(x0, x1), sl, 0ull), t0, t1);               // activation as max(x, slope * x + 0)
-            split16x2<FMT>(fmaxf(x0, t0), fmaxf(x1, t1), oh[j], ol[j]);
+            const float y0v = fmaxf(x0, t0), y1v = fmaxf(x1, t1);
+            ovf = fmaxf(ovf, fmaxf(fabsf(y0v), fabsf(y1v)));
+            split16x2<FMT>(y0v, y1v, oh[j], ol[j]);
           }
           *reinterpret_cast<uint4*>(rowp + off) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
           *reinterpret_cast<uint4*>(rowp + C::RES_PLANE_BYTES + off) = make_uint4(ol[0], ol[1], ol[2], ol[3]);
         }
+        if (FMT == NSAC_SPLIT_F16 && m0 + quad * 32 + lane < p.M) note_overflow(ovf);
         fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA (async proxy) store
         asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");       // the whole tile is written
         if (warp == 2 && lane == 0) {
@@ -938,5 +963,26 @@ extern "C" int nsac_split16(const float* x, int ldx, int rows, int K, float scal
   split16_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, ldx, rows, K, scale, fmt, static_cast<uint16_t*>(hi), static_cast<uint16_t*>(lo), ld_split);
   NSAC_CHECK_LAUNCH("nsac_split16");
+  return NSAC_OK;
+}
+
+unsigned int* nsac_pixel_overflow_ptr();      // csrc/pixel.cu
+
+// Sticky fp16-plane overflow flag: *flag_out = 1 if, since the last clearing call, nsac_split16 / nsac_nchw_to_planes / a GEMM
+// epilogue had to write a finite value with |x| > 65504 into an fp16 plane (it became inf there: every result computed from it
+// is invalid).  Synchronises `stream`; `clear` != 0 resets the flag.  Debug / validation aid, not on the hot path.
+extern "C" int nsac_plane_overflow(int* flag_out, int clear, void* stream) {
+  NSAC_REQUIRE(flag_out, "nsac_plane_overflow: null pointer");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  unsigned int* ptrs[2] = {nullptr, nsac_pixel_overflow_ptr()};
+  NSAC_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&ptrs[0]), g_plane_overflow));
+  unsigned int v[2] = {0u, 0u};
+  for (int i = 0; i < 2; ++i) {
+    if (!ptrs[i]) continue;
+    NSAC_CUDA(cudaMemcpyAsync(&v[i], ptrs[i], sizeof(unsigned int), cudaMemcpyDeviceToHost, s));
+    if (clear) NSAC_CUDA(cudaMemsetAsync(ptrs[i], 0, sizeof(unsigned int), s));
+  }
+  NSAC_CUDA(cudaStreamSynchronize(s));
+  *flag_out = (v[0] | v[1]) ? 1 : 0;
   return NSAC_OK;
 }

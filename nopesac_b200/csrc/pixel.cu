@@ -13,8 +13,13 @@
 
 namespace {
 
+// Sticky overflow flag of this translation unit (see nsac_plane_overflow in gemm_tc.cu): a finite value that does not fit an
+// fp16 plane (|x| > 65504) is recorded instead of silently becoming inf.
+__device__ unsigned int g_pixel_plane_overflow = 0u;
+
 __device__ __forceinline__ void split16(float x, int fmt, uint16_t& hi, uint16_t& lo) {
   if (fmt == NSAC_SPLIT_F16) {
+    if (fabsf(x) > 65504.f && fabsf(x) < INFINITY) atomicOr(&g_pixel_plane_overflow, 1u);
     const __half h = __float2half_rn(x);
     hi = __half_as_ushort(h);
     lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
@@ -431,4 +436,11 @@ extern "C" int nsac_im2col3x3_planes(const float* x, int N, int H, int W, int C,
                                                                                   static_cast<uint16_t*>(hi), static_cast<uint16_t*>(lo));
   NSAC_CHECK_LAUNCH("nsac_im2col3x3_planes");
   return NSAC_OK;
+}
+
+// host access to this translation unit's overflow flag (used by nsac_plane_overflow)
+unsigned int* nsac_pixel_overflow_ptr() {
+  unsigned int* p = nullptr;
+  cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_pixel_plane_overflow);
+  return p;
 }

@@ -151,8 +151,14 @@ class MatchingHead(nn.Module):
         app = ops.split(torch.cat([planeApp1.reshape(R0, 256), planeApp2.reshape(R1, 256)], 0))
         ops.gemm_tc(app, pk["app_ws"], pk["app_b"], passes=P, out_f32=X[:, :256], want_split=True, out_split=Xp.cols(0, 256))
         s0, s1 = (0, R0), (R0, R0 + R1)
+        # 'self' layers apply the SAME weights to both views independently (gnn.py:128-130): with equal plane counts the two calls
+        # are one call over 2B batch elements (rows of view 1 follow those of view 0) - half the launches of these layers
+        both = (0, R0 + R1)
+        count12 = None if count1 is None else torch.cat([count1, count2])
         for w, ws, name in zip(pk["layers"], pk["tc"], self.gnn.layer_names):
-            if name == "self":
+            if name == "self" and n1 == n2:
+                self._layer(w, ws, X, Xp, both, both, 2 * B, n1, n1, True, P, count12)
+            elif name == "self":
                 self._layer(w, ws, X, Xp, s0, s0, B, n1, n1, True, P, count1)
                 self._layer(w, ws, X, Xp, s1, s1, B, n2, n2, True, P, count2)
             else:

@@ -122,6 +122,16 @@ class Split:
         return (self.hi[:, :self.K].float() + lo) / self.scale
 
 
+def plane_overflow(clear: bool = True) -> bool:
+    """True if, since the last clearing call, a finite value beyond fp16 range (|x| > 65504) was written into an fp16 plane
+    (inputs or activations far outside a trained network's scale): every result since then is invalid.  Synchronises the
+    current stream - a validation aid, never called on the hot path."""
+    flag = C.c_int(0)
+    st = _lib.lib().nsac_plane_overflow(C.byref(flag), 1 if clear else 0, _stream())
+    _lib.check(st, "nsac_plane_overflow")
+    return bool(flag.value)
+
+
 def split(x: torch.Tensor, fmt: int = SPLIT_F16, scale: float = 1.0) -> Split:
     """fp32 [rows, K] -> Split of x * scale (zero-padded to a multiple of 64 columns)."""
     _chk(x, "x")

@@ -89,6 +89,21 @@ inline unsigned __reduce_add_sync(unsigned, unsigned x) {
   for (int i = 0; i < 32; ++i) r += (unsigned)v[i];
   return r;
 }
+inline int __reduce_min_sync(unsigned, int x) {
+  unsigned long long v[32];
+  simt::exchange((unsigned long long)(unsigned)x, v);
+  int r = (int)(unsigned)v[0];
+  for (int i = 1; i < 32; ++i) r = (int)(unsigned)v[i] < r ? (int)(unsigned)v[i] : r;
+  return r;
+}
+inline int __reduce_max_sync(unsigned, int x) {
+  unsigned long long v[32];
+  simt::exchange((unsigned long long)(unsigned)x, v);
+  int r = (int)(unsigned)v[0];
+  for (int i = 1; i < 32; ++i) r = (int)(unsigned)v[i] > r ? (int)(unsigned)v[i] : r;
+  return r;
+}
+inline int __all_sync(unsigned m, int pred) { return __ballot_sync(m, pred) == 0xffffffffu; }
 inline float __shfl_xor_sync(unsigned, float x, int o) {
   unsigned long long v[32];
   unsigned bits;
@@ -111,6 +126,8 @@ inline void __syncwarp(unsigned = 0xffffffffu) { pthread_barrier_wait(&simt::cur
 inline int __popc(unsigned x) { return __builtin_popcount(x); }
 
 template <typename T> inline T atomicAdd(T* p, T v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+template <typename T> inline T atomicOr(T* p, T v) { return __atomic_fetch_or(p, v, __ATOMIC_RELAXED); }
+template <typename T> inline int cudaGetSymbolAddress(void** out, T& symbol) { *out = &symbol; return 0; }
 template <typename T> inline T atomicMin(T* p, T v) {
   T old = __atomic_load_n(p, __ATOMIC_RELAXED);
   while (v < old && !__atomic_compare_exchange_n(p, &old, v, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
