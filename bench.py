@@ -261,7 +261,8 @@ def score_case(dev, B, nq, head=None):
     def once():
         return ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"],
                                    pk["param_score_proj"], head.rots.weight, head.rots.bias, head.trans.weight,
-                                   head.trans.bias, out_cam_type="soft", want_scores=False, pack=pk["score_pack"])
+                                   head.trans.bias, out_cam_type="soft", want_scores=False, pack=pk["score_pack"],
+                                   vecs_host=pk["score_vecs_host"])
     return once
 
 

@@ -236,6 +236,16 @@ int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const floa
                             const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
                             float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
                             float* const* peer_rows, int num_peers, int row_offset, void* stream);
+/* Same call with a HOST mirror of the pack's vectors (`vecs_host`: the 6 x 128 floats at byte offset
+ * nsac_score_pack_vecs_offset(NQ) of the pack, copied to the host once after nsac_score_pack): they then travel as kernel
+ * parameters (constant bank) instead of shared-memory broadcast loads in the MLP epilogue.  NULL = nsac_score_aggregate_tc. */
+size_t nsac_score_pack_vecs_offset(int NQ);
+int nsac_score_aggregate_tc_cv(const float* geo_local, const float* q_h, const float* t_h, const float* q0, const float* t0,
+                               const float* feat_rot, const float* feat_tran, const float* feat_rot0, const float* feat_tran0,
+                               const int32_t* matched_num, const void* pack, const float* vecs_host, const float* w_rots,
+                               const float* b_rots, const float* w_trans, const float* b_trans, int B, int NQ, int out_cam_type,
+                               float* pose, float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
+                               float* const* peer_rows, int num_peers, int row_offset, void* stream);
 /* Profiling aid: while `buf` (8 x 256 uint64 device words, zeroed by the caller) is set, CTA `cta` of the scoring
  * kernel records %globaltimer at every role hand-off (rows: residual, mma, epilogue, gather; rows 4 / 5: start / end of every CTA,
  * rows 6 / 7: feature producer / consumer per chunk).  NULL = off. */

@@ -85,6 +85,10 @@ _SIGNATURES = {
     "nsac_score_aggregate_tc": (C.c_int, [c_float_p] * 9 + [c_int_p, C.c_void_p] + [c_float_p] * 4 +
                                 [C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_int_p, C.c_void_p,
                                  C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "nsac_score_pack_vecs_offset": (C.c_size_t, [C.c_int]),
+    "nsac_score_aggregate_tc_cv": (C.c_int, [c_float_p] * 9 + [c_int_p, C.c_void_p, C.c_void_p] + [c_float_p] * 4 +
+                                   [C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, c_float_p, c_int_p, C.c_void_p,
+                                    C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "nsac_debug_score_trace": (C.c_int, [C.c_void_p, C.c_int]),
     "nsac_debug_gemm_trace": (C.c_int, [C.c_void_p]),
     "nsac_camera_errors": (C.c_int, [c_float_p, C.c_int, c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, c_float_p, C.c_void_p]),

@@ -244,6 +244,7 @@ class PlaneCameraHead(nn.Module):
                 for name in ("decoder_rot2", "decoder_tran2"):
                     pk[name + ".w_geo_split"] = ops.split_weight(pk[name + ".w_geo"])
                 pk["score_pack"] = ops.score_pack(pk["normal_score_proj"], pk["param_score_proj"], self.num_queries)
+                pk["score_vecs_host"] = ops.score_pack_host_vectors(pk["score_pack"], self.num_queries)
                 self._prepare_pixel_tc(pk)
         return pk
 
@@ -511,7 +512,8 @@ class PlaneCameraHead(nn.Module):
                                   matched_num, pk["normal_score_proj"], pk["param_score_proj"],
                                   self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
                                   out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
-                                  precision=precision, pack=pk["score_pack"], exchange=result_exchange)
+                                  precision=precision, pack=pk["score_pack"], exchange=result_exchange,
+                                  vecs_host=pk["score_vecs_host"])
         pose = res["pose"]
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]

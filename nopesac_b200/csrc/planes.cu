@@ -43,6 +43,8 @@ struct PlaneWorkspace {
   u64* stats;           // [B,NQ,16]
   uint8_t* remap;       // [B,128]
   uint8_t* raw;         // [B,H,W]
+  u64* xfix;            // [W]  float32(x / W) * 2^40  (exact: the fixed-point centre sums of :808-809)
+  u64* yfix;            // [H]
 };
 
 __host__ inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -57,6 +59,8 @@ __host__ inline size_t carve(PlaneWorkspace& ws, void* base, int B, int NQ, int 
   ws.stats = reinterpret_cast<u64*>(take((size_t)B * NQ * PL_SLOTS * 8));
   ws.remap = reinterpret_cast<uint8_t*>(take((size_t)B * 128));
   ws.raw = reinterpret_cast<uint8_t*>(take((size_t)B * H * W));
+  ws.xfix = reinterpret_cast<u64*>(take((size_t)W * 8));
+  ws.yfix = reinterpret_cast<u64*>(take((size_t)H * 8));
   return off;
 }
 
@@ -64,10 +68,17 @@ __host__ inline size_t carve(PlaneWorkspace& ws, void* base, int B, int NQ, int 
 // 1. query selection (one CTA of 128 threads per image)
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-plane_select_kernel(const float* __restrict__ logits, int NQ, float score_thr, PlaneWorkspace ws, int32_t* __restrict__ flags) {
+plane_select_kernel(const float* __restrict__ logits, int NQ, float score_thr, PlaneWorkspace ws, int32_t* __restrict__ flags, int H,
+                    int W) {
   __shared__ float s_p0[128];
   __shared__ int s_warp_cnt[4];
   const int b = blockIdx.x, q = threadIdx.x, lane = q & 31, wid = q >> 5;
+  // fixed-point coordinate tables float32(x / W), float32(y / H) as integer multiples of 2^-40 (:808-809): once per call, so
+  // the arg-max kernel's threads do no fp64 division (8 per thread before: the kernel was instruction bound)
+  for (int i = b * 128 + q; i < W + H; i += gridDim.x * 128) {
+    if (i < W) ws.xfix[i] = (u64)((double)__double2float_rn((double)i / (double)W) * FIX_SCALE);
+    else ws.yfix[i - W] = (u64)((double)__double2float_rn((double)(i - W) / (double)H) * FIX_SCALE);
+  }
   bool pass = false;
   float score = 0.f, p0 = -1.f;
   if (q < NQ) {
@@ -279,8 +290,8 @@ plane_argmax_kernel(const float* __restrict__ mask_logits, int NQ, int h, int w,
     u64 xfix[S], yfix[S];
 #pragma unroll
     for (int a = 0; a < S; ++a) {
-      xfix[a] = (u64)((double)__double2float_rn((double)max(x0 + a, 0) / (double)W) * FIX_SCALE);   // float32(x / W), :808
-      yfix[a] = (u64)((double)__double2float_rn((double)max(y0 + a, 0) / (double)H) * FIX_SCALE);   // float32(y / H), :809
+      xfix[a] = ws.xfix[min(max(x0 + a, 0), W - 1)];   // float32(x / W) * 2^40, :808 (table written by plane_select_kernel)
+      yfix[a] = ws.yfix[min(max(y0 + a, 0), H - 1)];   // float32(y / H) * 2^40, :809
     }
     uint8_t* raw = ws.raw + (size_t)b * H * W;
 #pragma unroll
@@ -494,7 +505,7 @@ extern "C" int nsac_plane_postprocess(const float* pred_logits, const float* pre
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   PlaneWorkspace ws;
   carve(ws, workspace, B, NQ, H, W);
-  plane_select_kernel<<<B, 128, 0, st>>>(pred_logits, NQ, plane_score_thr, ws, flags);
+  plane_select_kernel<<<B, 128, 0, st>>>(pred_logits, NQ, plane_score_thr, ws, flags, H, W);
   NSAC_CHECK_LAUNCH("nsac_plane_postprocess(select)");
   const dim3 grid(nsac_cdiv(w + 1, 32), nsac_cdiv(h + 1, 8), B), block(32, 8);
   if (H == 4 * h)

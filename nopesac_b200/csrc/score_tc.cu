@@ -29,10 +29,20 @@
 // (precision = 0, and always for the diagnostic outputs).
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <string.h>
 #include "common.cuh"
 
 #ifndef NSAC_SCORE_L2PREFETCH
 #define NSAC_SCORE_L2PREFETCH 0
+#endif
+#ifndef NSAC_SCORE_ABLATE       // profiling builds only (scripts/build_variant.sh): 1 = MUFU ops replaced by multiplies, 2 = HMMAs skipped,
+#define NSAC_SCORE_ABLATE 0     // 3 = residual warps do no math at all, 4 = gather warps skip the feature math, 5 = tcgen05 MMAs skipped.
+#endif                          // Results are WRONG in these builds; they only time what is left.
+#ifndef NSAC_SCORE_PDL          // programmatic dependent launch between prep -> tiles -> selection
+#define NSAC_SCORE_PDL 1
+#endif
+#ifndef NSAC_SCORE_SWPIPE       // residual groups software-pipelined by hand (next group's HMMAs before this group's MUFUs)
+#define NSAC_SCORE_SWPIPE 0      // r2m A/B on one box: 104.2 us without vs 106.5 us with - the kernel is shared-memory-bandwidth bound, not latency bound
 #endif
 
 namespace {
@@ -151,8 +161,13 @@ __device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<uint64_t>(src)), "r"(bytes) : "memory");
 }
 // programmatic dependent launch: let the next kernel of the stream start its prologue / wait for the previous one's results
+#if NSAC_SCORE_PDL
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#else
+__device__ __forceinline__ void pdl_launch_dependents() {}
+__device__ __forceinline__ void pdl_wait() {}
+#endif
 __device__ __forceinline__ void fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -239,7 +254,7 @@ __device__ __forceinline__ uint32_t cvt_h2(float lo, float hi) {
 
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float CJ_BIG = 1000.f;      // |.| of a padded column in log2 units: ex2(-1000) == 0 (ftz)
-constexpr int CJ_FIELDS = 12;         // per column: n^ (0-2), -k n1 (3-5), -k pi1 (6-8), A (9), Bc (10), valid (11); k = log2(e)
+constexpr int CJ_FIELDS = 13;         // per column: n^ (0-2), -k n1 (3-5), -k pi1 (6-8), A (9), Bc (10), valid (11), |pi1| (12); k = log2(e)
 
 // Column constants of matched plane pair j from the geo_local row (p0, p1); layout in memory is per column PAIR:
 // [pair][field][2].  Everything the exponent needs is pre-scaled by k = log2(e) so that x = ex2(-|.|) directly:
@@ -254,14 +269,14 @@ __device__ __forceinline__ void column_fields(const float* __restrict__ g6, bool
     const float d = normalize3(ax, ay, az);
     const float px = g6[3], py = -g6[4], pz = -g6[5];
     float nx = px, ny = py, nz = pz;
-    normalize3(nx, ny, nz);
+    const float d1 = normalize3(nx, ny, nz);
     const float dd = d + 1e-5f, A = d * d / (dd * dd);
     f[0] = ax; f[1] = ay; f[2] = az;
     f[3] = -LOG2E * nx; f[4] = -LOG2E * ny; f[5] = -LOG2E * nz;
     f[6] = -LOG2E * px; f[7] = -LOG2E * py; f[8] = -LOG2E * pz;
-    f[9] = A; f[10] = A * d; f[11] = 1.f;
+    f[9] = A; f[10] = A * d; f[11] = 1.f; f[12] = d1;
   } else {
-    f[3] = CJ_BIG; f[6] = CJ_BIG;
+    f[3] = CJ_BIG; f[6] = CJ_BIG; f[12] = 1.f;       // (|pi1| = 1 keeps d1 * (-k n1) = BIG for the padded columns)
   }
 }
 // One hypothesis row against one column pair.  R = k * rotation, t = translation / k (see above).
@@ -321,23 +336,31 @@ __device__ __forceinline__ void a_words(float v0, float v1, float v2, int q, uin
   w2 = h_bits(v2);
   if (q == 3) { w01 = 0u; w2 = 0u; }
 }
-constexpr int CJ8_FIELDS = 8;         // per column: -k n1 (0-2), -k pi1 (3-5), A (6), Bc (7).  Shared-memory layout: [group of 4 column
+constexpr int CJ8_FIELDS = 6;         // per column: -k n1 (0-2), |pi1| (3), A (4), Bc (5); -k pi1 = |pi1| * (-k n1) is rebuilt with 3
+                                      // packed multiplies per group instead of being loaded: every one of these broadcast loads
+                                      // costs 4 shared-memory wavefronts and the kernel is bound by that pipe (16 -> 12 per group).
+                                      // Shared-memory layout: [group of 4 column
                                       // pairs][16-byte unit i = fields 2i, 2i+1][pair q][field parity][column parity] - the four pairs a
                                       // warp reads with one LDS.128 are 64 contiguous bytes (one wavefront; the [pair][field] layout
                                       // cost 8 wavefronts per load and the shared-memory pipe became the bottleneck, s7 timeline)
 
 // everything after u, first half (FMA pipe): squared distances of one row x one column pair
-__device__ __forceinline__ void residual_dist2(u64 ux, u64 uy, u64 uz, u64 tu, const u64 (&c)[CJ8_FIELDS], u64& dr2, u64& dt2) {
+__device__ __forceinline__ void residual_dist2(u64 ux, u64 uy, u64 uz, u64 tu, const u64 (&c)[CJ8_FIELDS + 3], u64& dr2, u64& dt2) {
   const u64 ax = fadd2(ux, c[0]), ay = fadd2(uy, c[1]), az = fadd2(uz, c[2]);
   dr2 = ffma2(ax, ax, ffma2(ay, ay, fmul2(az, az)));
-  const u64 g = ffma2(tu, c[6], c[7]);
-  const u64 wx = ffma2(g, ux, c[3]), wy = ffma2(g, uy, c[4]), wz = ffma2(g, uz, c[5]);
+  const u64 g = ffma2(tu, c[4], c[5]);
+  const u64 wx = ffma2(g, ux, c[6]), wy = ffma2(g, uy, c[7]), wz = ffma2(g, uz, c[8]);      // c[6..8] = -k pi1 (rebuilt by the caller)
   dt2 = ffma2(wx, wx, ffma2(wy, wy, fmul2(wz, wz)));
 }
 // second half (MUFU pipe): 4 SQRT + 4 EX2 + 2 cvt.  The MUFU instructions are `asm volatile` like the HMMAs, so their order
 // relative to the NEXT group's HMMAs is the source order (see residual_kblock_mma).
+#if NSAC_SCORE_ABLATE == 1
+__device__ __forceinline__ float vsqrt(float x) { return x * 0.5f; }
+__device__ __forceinline__ float vexp2n(float x) { return x * 0.25f; }
+#else
 __device__ __forceinline__ float vsqrt(float x) { float r; asm volatile("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 __device__ __forceinline__ float vexp2n(float x) { float r; asm volatile("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-x)); return r; }
+#endif
 template <bool SUMS>
 __device__ __forceinline__ void residual_finish(u64 dr2, u64 dt2, u64 valid, uint32_t& hr, uint32_t& ht, u64& sum_r, u64& sum_t) {
   float r0, r1, t0, t1;
@@ -367,21 +390,29 @@ __device__ __forceinline__ void residual_kblock_mma(const uint4 (&afrag)[4], con
                                                     int chalf, int lane, int col0, int m, u64 (&sum_r)[2], u64 (&sum_t)[2]) {
   const int q = lane & 3;
   const uint2* bfr = reinterpret_cast<const uint2*>(cjk + 2048) + (chalf * 4) * 32 + lane;
-  const ulonglong2* c8 = reinterpret_cast<const ulonglong2*>(cjk) + (chalf * 4) * 16 + q;
+  const ulonglong2* c8 = reinterpret_cast<const ulonglong2*>(cjk) + (chalf * 4) * (CJ8_FIELDS / 2 * 4) + q;
   u64 dr2[2][2], dt2[2][2];          // [pipeline slot][row half]
   auto front = [&](int grp, u64 (&r2)[2], u64 (&t2)[2]) {
     const uint2 b = bfr[grp * 32];
     float dx[4], dy[4], dz[4], dt[4];
+#if NSAC_SCORE_ABLATE == 2
+    for (int e = 0; e < 4; ++e) {
+      dx[e] = __uint_as_float(afrag[0].x ^ b.x) * 1e-30f; dy[e] = __uint_as_float(afrag[1].y ^ b.y) * 1e-30f;
+      dz[e] = __uint_as_float(afrag[2].z ^ b.x) * 1e-30f; dt[e] = __uint_as_float(afrag[3].w ^ b.y) * 1e-30f;
+    }
+#else
     hmma16816(dx, afrag[0], b.x, b.y);
     hmma16816(dy, afrag[1], b.x, b.y);
     hmma16816(dz, afrag[2], b.x, b.y);
     hmma16816(dt, afrag[3], b.x, b.y);
-    u64 c[CJ8_FIELDS];
+#endif
+    u64 c[CJ8_FIELDS + 3];
 #pragma unroll
     for (int i = 0; i < CJ8_FIELDS / 2; ++i) {
-      const ulonglong2 v = c8[(grp * 4 + i) * 4];
+      const ulonglong2 v = c8[(grp * (CJ8_FIELDS / 2) + i) * 4];
       c[2 * i] = v.x; c[2 * i + 1] = v.y;
     }
+    c[6] = fmul2(c[3], c[0]); c[7] = fmul2(c[3], c[1]); c[8] = fmul2(c[3], c[2]);          // -k pi1 = |pi1| * (-k n1)
 #pragma unroll
     for (int h2 = 0; h2 < 2; ++h2)
       residual_dist2(pk2(dx[2 * h2], dx[2 * h2 + 1]), pk2(dy[2 * h2], dy[2 * h2 + 1]), pk2(dz[2 * h2], dz[2 * h2 + 1]),
@@ -402,12 +433,20 @@ __device__ __forceinline__ void residual_kblock_mma(const uint4 (&afrag)[4], con
       sts32(a + h2 * 1024 + BLK_BYTES, ht);
     }
   };
+#if NSAC_SCORE_SWPIPE
   front(0, dr2[0], dt2[0]);
 #pragma unroll
   for (int grp = 0; grp < 4; ++grp) {
     if (grp + 1 < 4) front(grp + 1, dr2[(grp + 1) & 1], dt2[(grp + 1) & 1]);
     back(grp, dr2[grp & 1], dt2[grp & 1]);
   }
+#else
+#pragma unroll
+  for (int grp = 0; grp < 4; ++grp) {
+    front(grp, dr2[0], dt2[0]);
+    back(grp, dr2[0], dt2[0]);
+  }
+#endif
 }
 
 // Optional in-kernel timeline (debug / profiling aid): one CTA records %globaltimer at role hand-offs into a host-provided
@@ -444,6 +483,10 @@ struct TcParams {
   float* logits;            // [2][B][NQ+1]
   float* sums;              // [2][B][NQ+1]
   float* partials;          // [B][tiles][2][PART_STRIDE]
+  // CVEC kernels: b1[2][128], b2[2][128], w34[2][128] as KERNEL PARAMETERS (constant bank): the epilogue warps read every one of
+  // them once per hypothesis row and tile - as shared-memory broadcast loads that was 3072 of the ~17 K shared-memory
+  // wavefronts per tile the kernel is bound by (r2a ncu: l1tex__data_pipe_lsu_wavefronts_mem_shared 49 % + TMA + UMMA reads)
+  float cvec[6 * HID];
 };
 
 // Work items.  A hypothesis tile = (pair b, hypotheses 1 + 128*tile ... ) scored against the pair's m matched columns.
@@ -469,7 +512,7 @@ __device__ __forceinline__ bool decode_item(const TcParams& p, int item, Item& i
   return it.tile * TILE_H < it.m;
 }
 
-template <bool SUMS>
+template <bool SUMS, bool CVEC>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_constant__ CUtensorMap map_w1t,
                 const __grid_constant__ CUtensorMap map_w2r, const __grid_constant__ CUtensorMap map_w2t,
@@ -503,7 +546,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
     for (int s = 0; s < 2; ++s) { mbar_init(&bars[BAR_LOGIT_READY + s], 4); mbar_init(&bars[BAR_LOGIT_FREE + s], G_THREADS / 32); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  for (int i = threadIdx.x; i < 6 * HID; i += NUM_THREADS) vec[i] = p.vecs[i];
+  if (!CVEC)
+    for (int i = threadIdx.x; i < 6 * HID; i += NUM_THREADS) vec[i] = p.vecs[i];
   if (warp == M_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -642,7 +686,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
             const uint64_t da = sw128_desc(a0 + br * BLK_BYTES), dw = sw128_desc(w0 + br * BLK_BYTES);
 #pragma unroll 1
             for (int k = 0; k < KB / 16; ++k)
-              umma_ss(tmem_base + TM_D + br * HID, da + 2 * k, dw + 2 * k, IDESC, (kb | k) != 0);
+              if (NSAC_SCORE_ABLATE != 5) umma_ss(tmem_base + TM_D + br * HID, da + 2 * k, dw + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&bars[BAR_W_EMPTY + ws]);
           umma_commit(&bars[BAR_A_EMPTY + as]);
@@ -666,7 +710,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
             const uint64_t dw = sw128_desc(w0 + br * BLK_BYTES);
 #pragma unroll 1
             for (int k4 = 0; k4 < 4; ++k4)
-              umma_ts(tmem_base + TM_D2 + br * HID, tmem_base + TM_D + br * HID + (kb2 * 4 + k4) * 8, dw + 2 * k4, IDESC, (kb2 | k4) != 0);
+              if (NSAC_SCORE_ABLATE != 5) umma_ts(tmem_base + TM_D2 + br * HID, tmem_base + TM_D + br * HID + (kb2 * 4 + k4) * 8, dw + 2 * k4, IDESC, (kb2 | k4) != 0);
           }
           umma_commit(&bars[BAR_W_EMPTY + ws]);
           if (++ws == W_STAGES) { ws = 0; wph ^= 1; }
@@ -692,7 +736,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       fence_after();
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        const float* b1 = vec + br * HID;
+        const float* b1 = (CVEC ? p.cvec : vec) + br * HID;
 #pragma unroll
         for (int c = 0; c < HID; c += 32) {
           uint32_t v[32], h[16];
@@ -718,8 +762,8 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
       float lg[2];
 #pragma unroll
       for (int br = 0; br < 2; ++br) {
-        const float* b2 = vec + 2 * HID + br * HID;
-        const float* w34 = vec + 4 * HID + br * HID;
+        const float* b2 = (CVEC ? p.cvec : vec) + 2 * HID + br * HID;
+        const float* w34 = (CVEC ? p.cvec : vec) + 4 * HID + br * HID;
         u64 acc2[2] = {0ull, 0ull};
 #pragma unroll
         for (int c = 0; c < HID; c += 32) {
@@ -809,8 +853,10 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         NSAC_TRACE(0, threadIdx.x == R_WARP0 * 32);
         mbar_wait(&bars[BAR_CJ_FULL + cs], cph);          // column block of this k-block has landed (TMA)
         NSAC_TRACE(0, threadIdx.x == R_WARP0 * 32);
+#if NSAC_SCORE_ABLATE != 3
         residual_kblock_mma<SUMS>(afrag, smem + OFF_CJ + cs * CJK_BYTES, sts_base + (uint32_t)(as * 2 * BLK_BYTES), chalf, lane, kb * KB,
                                   it.m, sum_r, sum_t);
+#endif
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) { mbar_arrive(&bars[BAR_A_FULL + as]); mbar_arrive(&bars[BAR_CJ_EMPTY + cs]); }
@@ -900,7 +946,7 @@ score_tc_kernel(const __grid_constant__ CUtensorMap map_w1r, const __grid_consta
         }
 #pragma unroll
         for (int i = 0; i < HR; ++i) {
-          if (r0 + rs * HR + i < rows) {            // (a partial last chunk leaves stale rows in the stage)
+          if (NSAC_SCORE_ABLATE != 4 && r0 + rs * HR + i < rows) {            // (a partial last chunk leaves stale rows in the stage)
             const ulonglong2 v = fr[i * (C_FEAT / 4)];
             const u64 e2 = bc2(e[i]);
             wxy = ffma2(e2, v.x, wxy); wzw = ffma2(e2, v.y, wzw);
@@ -1009,9 +1055,10 @@ score_prep_kernel(const float* __restrict__ geo_local, const float* __restrict__
     uint8_t* blk = cjk + ((size_t)b * (NQp / KB) + j / KB) * CJK_BYTES;
     const int jj = j % KB;
     // pair jj/2 = group (jj/8) of 4 pairs, q = (jj/2) % 4; field k -> unit k/2, field parity k%2
-    float* c8 = reinterpret_cast<float*>(blk) + (jj >> 3) * 64 + ((jj >> 1) & 3) * 4 + (jj & 1);
+    float* c8 = reinterpret_cast<float*>(blk) + (jj >> 3) * (CJ8_FIELDS / 2 * 16) + ((jj >> 1) & 3) * 4 + (jj & 1);
+    const float f6[CJ8_FIELDS] = {f[3], f[4], f[5], f[12], f[9], f[10]};
 #pragma unroll
-    for (int k = 0; k < CJ8_FIELDS; ++k) c8[(k >> 1) * 16 + (k & 1) * 2] = f[3 + k];
+    for (int k = 0; k < CJ8_FIELDS; ++k) c8[(k >> 1) * 16 + (k & 1) * 2] = f6[k];
     // B fragments: column jj -> group jj / 8, g = jj % 8; lanes 4g + q hold (k = 2q, 2q+1 | 2q+8, 2q+9)
     uint32_t hi01, hi2, lo01, lo2;
     a_words(f[0], f[1], f[2], 0, hi01, hi2);
@@ -1326,6 +1373,8 @@ extern "C" size_t nsac_score_tc_workspace_bytes(int B, int NQ) {
          align256((size_t)B * tiles * TILE_H * 64) + 256;
 }
 
+extern "C" size_t nsac_score_pack_vecs_offset(int NQ) { return NQ < 1 ? 0 : pack_off_vecs(nq_padded(NQ)); }
+
 extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
                                        const float* t0, const float* feat_rot, const float* feat_tran,
                                        const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
@@ -1333,6 +1382,18 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
                                        const float* b_trans, int B, int NQ, int out_cam_type, float* pose, float* score_rot,
                                        float* score_tran, int32_t* sel_idx, void* workspace,
                                        float* const* peer_rows, int num_peers, int row_offset, void* stream) {
+  return nsac_score_aggregate_tc_cv(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num, pack, nullptr,
+                                    w_rots, b_rots, w_trans, b_trans, B, NQ, out_cam_type, pose, score_rot, score_tran, sel_idx,
+                                    workspace, peer_rows, num_peers, row_offset, stream);
+}
+
+extern "C" int nsac_score_aggregate_tc_cv(const float* geo_local, const float* q_h, const float* t_h, const float* q0,
+                                          const float* t0, const float* feat_rot, const float* feat_tran,
+                                          const float* feat_rot0, const float* feat_tran0, const int32_t* matched_num,
+                                          const void* pack, const float* vecs_host, const float* w_rots, const float* b_rots,
+                                          const float* w_trans, const float* b_trans, int B, int NQ, int out_cam_type, float* pose,
+                                          float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
+                                          float* const* peer_rows, int num_peers, int row_offset, void* stream) {
   NSAC_REQUIRE(!peer_rows || (num_peers >= 1 && row_offset >= 0), "nsac_score_aggregate_tc: bad peer arguments");
   NSAC_REQUIRE(geo_local && q_h && t_h && q0 && t0 && feat_rot && feat_tran && feat_rot0 && feat_tran0 && matched_num &&
                    pack && w_rots && b_rots && w_trans && b_trans && pose && workspace,
@@ -1380,10 +1441,13 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   tp.need_sums = out_cam_type == NSAC_CAM_MIN_COST; tp.logits = logits; tp.sums = sums; tp.partials = partials;
   static bool attr = false;
   if (!attr) {
-    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    NSAC_CUDA(cudaFuncSetAttribute(score_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr = true;
   }
+  if (vecs_host) memcpy(tp.cvec, vecs_host, sizeof(tp.cvec));      // host mirror of the pack's vectors -> kernel parameters
   // Item list: B*tiles hypothesis tiles + the row-0 tiles.  Items go round-robin to the persistent CTAs, so the
   // (slightly more expensive) row-0 tiles are inserted where the CTAs that get one item fewer pick them up.
   const int items = B * tiles + row0_tiles;
@@ -1396,14 +1460,18 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
   // in a CUDA graph)
   cudaLaunchAttribute pdl_attr[1];
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = NSAC_SCORE_PDL;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
   cfg.attrs = pdl_attr; cfg.numAttrs = 1;
-  if (tp.need_sums)
-    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<true>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
+  if (tp.need_sums && vecs_host)
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<true, true>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
+  else if (tp.need_sums)
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<true, false>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
+  else if (vecs_host)
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<false, true>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
   else
-    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<false>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
+    NSAC_CUDA(cudaLaunchKernelEx(&cfg, score_tc_kernel<false, false>, m1r, m1t, m2r, m2t, mx0r, mx0t, tp));
   NSAC_CHECK_LAUNCH("score_tc_kernel");
 
   SelParams sp;

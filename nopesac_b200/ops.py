@@ -4,6 +4,7 @@ this library that were enqueued (bench.py's `gpu_launches`)."""
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import torch
@@ -599,9 +600,20 @@ def score_pack(rot_mlp, tran_mlp, num_queries: int) -> torch.Tensor:
     return pack
 
 
+def score_pack_host_vectors(pack: torch.Tensor, num_queries: int) -> Optional[torch.Tensor]:
+    """Host (pinned) mirror of the pack's bias / folded-output vectors (6 x 128 floats): passed to score_aggregate as
+    `vecs_host`, they travel as kernel parameters (constant bank) instead of shared-memory broadcast loads.  One-off device ->
+    host copy per weight version (synchronises), next to split_weight's own one-off range probe."""
+    off = _lib.lib().nsac_score_pack_vecs_offset(num_queries)
+    if off == 0:
+        return None
+    v = pack[off:off + 6 * 128 * 4].view(torch.float32).cpu().contiguous()
+    return v.pin_memory() if pack.is_cuda else v
+
+
 def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num,
                     rot_mlp, tran_mlp, w_rots, b_rots, w_trans, b_trans, out_cam_type="soft",
-                    want_scores=True, want_diag=False, precision="fp16", pack=None, exchange=None):
+                    want_scores=True, want_diag=False, precision="fp16", pack=None, exchange=None, vecs_host=None):
     """rot_mlp / tran_mlp: 8-tuples (w1,b1,w2,b2,w3,b3,w4,b4). Returns dict(pose, score_rot, score_tran,
     sel_idx, diag).  `exchange` (nopesac_b200.dist.FusedResultExchange) makes the selection kernel also store
     every result row into all ranks' result buffers over NVLink.  precision "fp16" = tcgen05 path (score MLPs single-pass fp16, fp32 accumulate);
@@ -623,7 +635,10 @@ def score_aggregate(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0,
         if pack is None:
             pack = score_pack(rot_mlp, tran_mlp, NQ)
         ws = torch.empty(L.nsac_score_tc_workspace_bytes(B, NQ), device=dev, dtype=torch.uint8)
-        st = L.nsac_score_aggregate_tc(*[_p(a) for a in args], _p(matched_num), _p(pack),
+        if os.environ.get("NSAC_SCORE_NO_CVEC"):                                   # A/B knob (scripts/score_quick.py)
+            vecs_host = None
+        vh = None if vecs_host is None else C.c_void_p(vecs_host.data_ptr())       # HOST pointer (see score_pack_host_vectors)
+        st = L.nsac_score_aggregate_tc_cv(*[_p(a) for a in args], _p(matched_num), _p(pack), vh,
                                        _p(w_rots), _p(b_rots), _p(w_trans), _p(b_trans), B, NQ, CAM_TYPES[out_cam_type],
                                        _p(pose), _p(sr), _p(stt), _p(sel), _p(ws),
                                        None if exchange is None else C.c_void_p(exchange.peer_ptrs_dev),

@@ -25,7 +25,7 @@ pk = head.prepare_tc()
 
 def once():
     ops.score_aggregate(geo_local, q_h, t_h, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"], pk["param_score_proj"],
-                        head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias, want_scores=False, pack=pk["score_pack"])
+                        head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias, want_scores=False, pack=pk["score_pack"], vecs_host=pk["score_vecs_host"])
 
 
 for _ in range(3):

@@ -212,3 +212,16 @@ extern "C" int nsac_score_aggregate_tc(const float* geo_local, const float* q_h,
                               w_rots, b_rots, w_trans, b_trans, B, NQ, out_cam_type, pose, score_rot, score_tran, sel_idx, nullptr,
                               workspace, stream);
 }
+
+// host-mirror variant: the stand-in has no vectors to mirror (offset 0 = "nothing to copy", the wrapper then passes NULL)
+extern "C" size_t nsac_score_pack_vecs_offset(int) { return 0; }
+extern "C" int nsac_score_aggregate_tc_cv(const float* geo_local, const float* q_h, const float* t_h, const float* q0, const float* t0,
+                                          const float* feat_rot, const float* feat_tran, const float* feat_rot0,
+                                          const float* feat_tran0, const int32_t* matched_num, const void* pack, const float*,
+                                          const float* w_rots, const float* b_rots, const float* w_trans, const float* b_trans, int B,
+                                          int NQ, int out_cam_type, float* pose, float* score_rot, float* score_tran,
+                                          int32_t* sel_idx, void* workspace, float* const* peers, int np, int ro, void* stream) {
+  return nsac_score_aggregate_tc(geo_local, q_h, t_h, q0, t0, feat_rot, feat_tran, feat_rot0, feat_tran0, matched_num, pack, w_rots,
+                                 b_rots, w_trans, b_trans, B, NQ, out_cam_type, pose, score_rot, score_tran, sel_idx, workspace, peers,
+                                 np, ro, stream);
+}
