@@ -210,6 +210,45 @@ def measure_plane_lists(dev, images: int, iters: int = 10):
             "note": "row f1, both views of this rank's pairs; outside the timed region of `value`"}
 
 
+def measure_full_model(dev, pairs: int, iters: int = 3):
+    """BASELINE.json configs[3] shape on one GPU: the COMPLETE META_ARCH from uint8 RGB (configs/inference_mp3d.yaml:
+    NUM_OBJECT_QUERIES 50, data-dependent plane counts) — backbone -> PlaneTRHead -> plane lists -> matcher + camera head in one
+    `inference_from_rgb` call, random-init weights; plus PlaneTRHead alone on the same 2 * pairs images (from the backbone's planes)."""
+    from nopesac_b200 import config, meta_arch, synthetic
+    from tests import util
+    nq = 50
+    model = meta_arch.PlaneTR_NopeSAC(config.inference_cfg(nq), with_backbone=True, with_plane_head=True)
+    sd, msd = util.make_weights(nq)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    model.sem_seg_head.load_state_dict(synthetic.make_weights(util.planetr_shapes(nq), 77))
+    model.backbone.load_state_dict(backbone_state())
+    model = model.to(dev)
+    images = synthetic.make_images(9100, 2 * pairs, IMG_H, IMG_W).to(dev)
+    batched = [{"0": {"image": images[i], "height": IMG_H, "width": IMG_W},
+                "1": {"image": images[pairs + i], "height": IMG_H, "width": IMG_W}} for i in range(pairs)]
+
+    def timed(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n, r
+    ms_full, res = timed(lambda: model.inference_from_rgb(batched, max_planes=20), iters)
+    feats = model.backbone(images, planes=True)
+    ms_head, _ = timed(lambda: model.sem_seg_head(feats), iters)
+    counts = torch.cat([res[1].count, res[2].count]).float()
+    return {"config": "BASELINE configs[3] shape (inference_mp3d.yaml, NUM_OBJECT_QUERIES=50) on 1 GPU", "pairs": pairs,
+            "ms_per_call": ms_full, "pairs_per_s": pairs / ms_full * 1e3, "planes_per_image": float(counts.mean()),
+            "plane_head": {"images": 2 * pairs, "ms_per_call": ms_head, "images_per_s": 2 * pairs / ms_head * 1e3},
+            "note": "uint8 RGB -> backbone -> PlaneTRHead -> plane lists -> matcher + camera head, one call, inputs resident; "
+                    "outside the timed region of `value`"}
+
+
 def graph_timed(fn, reps: int, flush=None):
     """ms per call of `fn` (a short chain of kernel launches): captured once in a CUDA graph, replays timed with CUDA events on the
     replay stream (launched eagerly from Python the host side is slower than such kernels).  `flush`: tensor zeroed before
@@ -575,6 +614,11 @@ def main():
     except Exception as e:   # never let the side measurement take the bench line down
         plane_lists = {"error": f"{type(e).__name__}: {e}"[:200]}
 
+    try:
+        full_model = measure_full_model(dev, B)
+    except Exception as e:   # noqa: BLE001
+        full_model = {"error": f"{type(e).__name__}: {e}"[:200]}
+
     line = {
         "metric": METRIC, "value": value, "unit": "pairs/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -596,6 +640,7 @@ def main():
         "pose_err": pose_err,
         "from_feature_maps": s4,
         "plane_lists": plane_lists,
+        "full_model": full_model,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
