@@ -354,6 +354,94 @@ int nsac_attention_tiled(const float* q, int ldq, const float* k, const float* v
 int nsac_upsample2x_relu_add(const float* a, const float* b, int N, int h, int w, int C, float* out, void* out_hi, void* out_lo,
                              void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Whole-stage entry points (csrc/forward.cu).  The host-side orchestration nopesac_b200/camera_head.py does in Python, behind
+ * ONE call per stage, so that a host in another language (or the reference, through a single ctypes stub) does not have to
+ * replicate it.  They only enqueue this library's kernels on `stream`: no allocation, no synchronisation, no host round trip;
+ * scratch comes from one caller-provided workspace.
+ *
+ * nsac_refine_forward — the one-plane RANSAC refinement itself, camera_head.py:513-629 + 925-1115:
+ *   geo sequences + sig (K6) -> 8-vector geo encoding -> ~28-layer hypothesis MLP chain on the tensor-core engine (K7) -> one
+ *   pose hypothesis per matched plane pair -> residual scoring, softmax, soft / avg / min-cost / max-score selection (K8, K9) ->
+ *   assignment pruning with the refined pose (K10).
+ *   Inputs : planes1 [B,n1,3], planes2 [B,n2,3]; the matcher's assignment [B,n1,n2] (or an explicit hypothesis list hyp_pairs
+ *            int32 [H,2], shared by all pairs, H <= NQ — the BASELINE "P planes x H hypotheses" workloads; assign is then only
+ *            pruned and may be NULL together with assign_pruned); the initial pose t0 [B,3], q0 [B,4] (w >= 0) and its
+ *            256-d features rot_feat0 / trans_feat0 [B,256] (AIM, camera_head.py:685-735).
+ *   Outputs: pose [B,16] = t(3) q(4) t_avg(3) q_avg(4) m 0 (the row that is all-gathered; see nsac_score_aggregate_tc for the
+ *            fused multi-GPU exchange arguments), assign_pruned [B,n1,n2], geo_local / geo_global [B,NQ,6], sig [B,NQ],
+ *            matched_num [B], pair_idx [B,NQ,2], the per-hypothesis poses q_h [B*NQ,4] / t_h [B*NQ,3], softmax scores
+ *            score_rot / score_tran [B,NQ+1] (NULL = skip), sel_idx [B,2].
+ *   weights: borrowed pointers, built once per weight version by the caller (planes via nsac_split16 of w * w_scale).
+ *   *launches_out (may be NULL) = kernels enqueued.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* w_hi; const void* w_lo;   /* weight planes [N, ldw]: nsac_split16 of (w * w_scale), zero padded to K columns */
+  const float* bias;                    /* [N] or NULL */
+  int N, K, ldw;                        /* K = in-features padded to a multiple of 64 */
+  float w_scale;                        /* power of two (1 for bf16 planes) */
+} nsac_tc_layer;
+
+typedef struct {
+  const float* geo0_w; const float* geo0_b;   /* geo_encoder.layers.0 [1024,8], [1024]: K = 8 runs on the CUDA cores (nsac_linear) */
+  nsac_tc_layer geo_encoder[5];               /* geo_encoder.layers.1-5            (camera_head.py:123) */
+  nsac_tc_layer geo_proj_s1[3];               /* (:124) */
+  nsac_tc_layer decoder_rot[6];               /* (:126) */
+  nsac_tc_layer geo_proj_s2[3];               /* (:128)  K = 1280 = cat[s1, rot] */
+  nsac_tc_layer decoder_tran[6];              /* (:129) */
+  nsac_tc_layer decoder_rot2[3];              /* (:131)  layer 0 = the geo half W[:, 256:512], bias NULL (see rot2_*) */
+  nsac_tc_layer decoder_tran2[3];             /* (:132)  same */
+  const float* rot2_w_init; const float* rot2_b0;     /* decoder_rot2.layers.0: init-feature half W[:, 0:256] [512,256] + bias [512] */
+  const float* tran2_w_init; const float* tran2_b0;   /* decoder_tran2.layers.0, same */
+  const float* rots_w; const float* rots_b;           /* shared pose heads (:64-65): [4,256],[4] / [3,256],[3] */
+  const float* trans_w; const float* trans_b;
+  const void* score_pack;                     /* nsac_score_pack output for this NQ */
+  const float* score_vecs_host;               /* HOST copy of the pack's vectors (nsac_score_pack_vecs_offset) or NULL */
+  const nsac_score_mlp* rot_mlp;              /* raw fp32 score MLPs: only NSAC_CAM_MAX_SCORE needs them (exact-fp32 scoring) */
+  const nsac_score_mlp* tran_mlp;
+  int fmt, passes;                            /* NSAC_SPLIT_F16 / _BF16; 3 = fp32-grade */
+} nsac_refine_weights;
+
+size_t nsac_refine_workspace_bytes(int B, int NQ);
+int nsac_refine_forward(const nsac_refine_weights* w, const float* planes1, const float* planes2, const float* assign,
+                        const int32_t* hyp_pairs, int H, const float* t0, const float* q0, const float* rot_feat0,
+                        const float* trans_feat0, int B, int n1, int n2, int NQ, int out_cam_type, float* pose,
+                        float* assign_pruned, float* geo_local, float* geo_global, float* sig, int32_t* matched_num,
+                        int32_t* pair_idx, float* q_h, float* t_h, float* score_rot, float* score_tran, int32_t* sel_idx,
+                        void* workspace, size_t workspace_bytes, float* const* peer_rows, int num_peers, int row_offset,
+                        int* launches_out, void* stream);
+
+/* nsac_match_forward — the whole MatchingHead forward (matching_head.py:43-133 with transformer/gnn.py:73-138 and the
+ * assignment of camera_modules.py:15-34): appearance projection -> 18 attentional GNN layers (self /
+ * cross alternating, six linears each on the tensor-core engine, attention + LayerNorm kernels emitting operand planes) ->
+ * descriptor projection -> geometry penalties + similarity + Sinkhorn + mutual-NN assignment (nsac_match_sinkhorn_assign).
+ *   app1 [B,n1,256], app2 [B,n2,256] plane appearance embeddings; planes1 [B,n1,3], planes2 [B,n2,3]; cam [B,7] = (t, q) of the
+ *   matcher pose; count1 / count2 (int32 [B], device) = planes per pair in a ragged padded batch, or both NULL.
+ *   -> log_scores_padded [B,n1+1,n2+1], assign [B,n1,n2].
+ * 'self' layers apply the same weights to both views: with n1 == n2 they run as ONE batch of 2B elements. */
+typedef struct {
+  nsac_tc_layer qkv;      /* cat[q_proj, k_proj, v_proj] [768,256], no bias  (self layers) */
+  nsac_tc_layer q, kv;    /* q_proj [256,256]; cat[k_proj, v_proj] [512,256]  (cross layers) */
+  nsac_tc_layer merge, mlp0, mlp2;      /* [256,256], [512,512], [256,512], no bias */
+  const float* n1w; const float* n1b; const float* n2w; const float* n2b;   /* LayerNorm(256) x 2 */
+  int self_attn;          /* 1 = 'self', 0 = 'cross' (gnn.py:128-134) */
+} nsac_gnn_layer;
+
+typedef struct {
+  nsac_tc_layer app_proj, desc_proj;    /* planeApp_proj / planeDesc_proj (Conv1d 256->256, k = 1) with bias */
+  const nsac_gnn_layer* layers; int num_layers;
+  const float* bin_score;               /* device scalar */
+  float offset_multiplier, normal_multiplier;
+  int sinkhorn_iterations;              /* 200 */
+  int fmt, passes;
+} nsac_match_weights;
+
+size_t nsac_match_workspace_bytes(int B, int n1, int n2);
+int nsac_match_forward(const nsac_match_weights* w, const float* app1, const float* app2, const float* planes1,
+                       const float* planes2, const float* cam, const int32_t* count1, const int32_t* count2,
+                       float match_threshold, int B, int n1, int n2, float* log_scores_padded, float* assign, void* workspace,
+                       size_t workspace_bytes, int* launches_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,36 @@ class ScoreMLP(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4")]
 
 
+class TcLayer(C.Structure):
+    """nsac_tc_layer (include/nopesac_b200.h)."""
+    _fields_ = [("w_hi", C.c_void_p), ("w_lo", C.c_void_p), ("bias", C.c_void_p), ("N", C.c_int), ("K", C.c_int), ("ldw", C.c_int),
+                ("w_scale", C.c_float)]
+
+
+class RefineWeights(C.Structure):
+    """nsac_refine_weights (include/nopesac_b200.h)."""
+    _fields_ = [("geo0_w", C.c_void_p), ("geo0_b", C.c_void_p),
+                ("geo_encoder", TcLayer * 5), ("geo_proj_s1", TcLayer * 3), ("decoder_rot", TcLayer * 6), ("geo_proj_s2", TcLayer * 3),
+                ("decoder_tran", TcLayer * 6), ("decoder_rot2", TcLayer * 3), ("decoder_tran2", TcLayer * 3),
+                ("rot2_w_init", C.c_void_p), ("rot2_b0", C.c_void_p), ("tran2_w_init", C.c_void_p), ("tran2_b0", C.c_void_p),
+                ("rots_w", C.c_void_p), ("rots_b", C.c_void_p), ("trans_w", C.c_void_p), ("trans_b", C.c_void_p),
+                ("score_pack", C.c_void_p), ("score_vecs_host", C.c_void_p),
+                ("rot_mlp", C.POINTER(ScoreMLP)), ("tran_mlp", C.POINTER(ScoreMLP)), ("fmt", C.c_int), ("passes", C.c_int)]
+
+
+class GnnLayer(C.Structure):
+    """nsac_gnn_layer."""
+    _fields_ = [("qkv", TcLayer), ("q", TcLayer), ("kv", TcLayer), ("merge", TcLayer), ("mlp0", TcLayer), ("mlp2", TcLayer),
+                ("n1w", C.c_void_p), ("n1b", C.c_void_p), ("n2w", C.c_void_p), ("n2b", C.c_void_p), ("self_attn", C.c_int)]
+
+
+class MatchWeights(C.Structure):
+    """nsac_match_weights."""
+    _fields_ = [("app_proj", TcLayer), ("desc_proj", TcLayer), ("layers", C.POINTER(GnnLayer)), ("num_layers", C.c_int),
+                ("bin_score", C.c_void_p), ("offset_multiplier", C.c_float), ("normal_multiplier", C.c_float),
+                ("sinkhorn_iterations", C.c_int), ("fmt", C.c_int), ("passes", C.c_int)]
+
+
 _SIGNATURES = {
     "nsac_version": (C.c_int, []),
     "nsac_last_error": (C.c_char_p, []),
@@ -109,6 +139,13 @@ _SIGNATURES = {
                                [C.c_float, C.c_float, C.c_double] + [C.c_void_p] * 12),
     "nsac_prune_assignment": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, c_float_p, C.c_void_p]),
+    "nsac_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "nsac_match_forward": (C.c_int, [C.POINTER(MatchWeights)] + [c_float_p] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
+                                    C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
+    "nsac_refine_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int]),
+    "nsac_refine_forward": (C.c_int, [C.POINTER(RefineWeights), c_float_p, c_float_p, c_float_p, C.c_void_p, C.c_int, c_float_p, c_float_p,
+                                      c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 12 +
+                            [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
 }
 
 _lib = None

@@ -20,6 +20,8 @@ Inference only.  Extra keyword arguments (not in the reference):
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, Optional
 
 import torch
@@ -202,6 +204,8 @@ class PlaneCameraHead(nn.Module):
             self.param_score_proj = MLP(self.num_queries, 128, 64, 3)
             self.trans_score_reg = nn.Linear(64, 1)
         self._packed = None
+        # K6 .. K10 through the single C entry nsac_refine_forward (False / NSAC_PY_STAGES=1: the same launches from Python)
+        self.use_stage_entry = not os.environ.get("NSAC_PY_STAGES")
         self.tc_passes = 3     # MMA passes of the tensor-core layers (3 = hi.hi + lo.hi + hi.lo on fp16 planes, ~fp32)
 
     # ------------------------------------------------------------------ weight packing
@@ -404,6 +408,50 @@ class PlaneCameraHead(nn.Module):
             fused.append(f32)                                                     # F.relu(decoder_*2(.))
         return fused[0], fused[1]
 
+    def refine_weights(self):
+        """`nsac_refine_weights` for `ops.refine_forward` (borrowed pointers into the packed weights of this weight version; the
+        struct and everything it points to live in the prepare() cache)."""
+        pk = self.prepare_tc()
+        if "refine_struct" not in pk:
+            from . import _lib
+            W = _lib.RefineWeights()
+            keep = []
+
+            def fill(arr, name, first=None):
+                m = getattr(self, name)
+                layers = list(m.layers)
+                splits = list(pk[name + ".split"])
+                if splits[0] is None:                       # geo_encoder: K = 8 layer runs on the CUDA cores
+                    layers, splits = layers[1:], splits[1:]
+                for i, (l, sp) in enumerate(zip(layers, splits)):
+                    if i == 0 and first is not None:
+                        arr[i] = ops.tc_layer(first, None)
+                    else:
+                        arr[i] = ops.tc_layer(sp, l.bias)
+            g0 = self.geo_encoder.layers[0]
+            W.geo0_w, W.geo0_b = g0.weight.data_ptr(), g0.bias.data_ptr()
+            fill(W.geo_encoder, "geo_encoder")
+            fill(W.geo_proj_s1, "geo_proj_s1")
+            fill(W.decoder_rot, "decoder_rot")
+            fill(W.geo_proj_s2, "geo_proj_s2")
+            fill(W.decoder_tran, "decoder_tran")
+            fill(W.decoder_rot2, "decoder_rot2", pk["decoder_rot2.w_geo_split"])
+            fill(W.decoder_tran2, "decoder_tran2", pk["decoder_tran2.w_geo_split"])
+            W.rot2_w_init, W.rot2_b0 = pk["decoder_rot2.w_init"].data_ptr(), self.decoder_rot2.layers[0].bias.data_ptr()
+            W.tran2_w_init, W.tran2_b0 = pk["decoder_tran2.w_init"].data_ptr(), self.decoder_tran2.layers[0].bias.data_ptr()
+            W.rots_w, W.rots_b = self.rots.weight.data_ptr(), self.rots.bias.data_ptr()
+            W.trans_w, W.trans_b = self.trans.weight.data_ptr(), self.trans.bias.data_ptr()
+            W.score_pack = pk["score_pack"].data_ptr()
+            vh = pk["score_vecs_host"]
+            W.score_vecs_host = None if vh is None else vh.data_ptr()
+            rs, ts = ops._score_mlp_struct(pk["normal_score_proj"]), ops._score_mlp_struct(pk["param_score_proj"])
+            keep += [rs, ts]
+            import ctypes
+            W.rot_mlp, W.tran_mlp = ctypes.pointer(rs), ctypes.pointer(ts)
+            W.fmt, W.passes = ops.SPLIT_F16, self.tc_passes
+            pk["refine_struct"], pk["refine_struct.keep"] = W, keep
+        return pk["refine_struct"]
+
     @staticmethod
     def check_finite(outputs) -> None:
         """Debug guard (one host synchronisation; never called on the hot path): raises if an fp16 plane overflowed since the last
@@ -492,29 +540,46 @@ class PlaneCameraHead(nn.Module):
         # ------------------------------------------------------------ geo sequences (:513-569)
         if assignment_override is not None and tuple(assignment_override.shape) != tuple(assignment.shape):
             raise ValueError(f"assignment_override must be [B,n1,n2] = {tuple(assignment.shape)}, got {tuple(assignment_override.shape)}")
-        geo_local, geo_global, sig, geo8, matched_num, pair_idx = ops.geo_sequence(
-            planeParam1, planeParam2, assignment if assignment_override is None else assignment_override,
-            t0, q0, NQ, hyp_pairs=hyp_pairs)
-
-        # ------------------------------------------------------------ refinement head (:925-1115)
-        fused_rot, fused_tran = self._hypothesis_features(geo8, rot_feat0, trans_feat0, B, NQ)
-        q_h, t_h = ops.pose_heads(fused_rot, fused_tran, self.rots.weight, self.rots.bias,
-                                  self.trans.weight, self.trans.bias)
-        pk = self.prepare_tc()
         # 'max-score' picks argmax of the scores themselves: a discrete decision, so it takes the exact-fp32 scoring path
         # (the single-pass fp16 score MLPs of the tensor-core path move scores by up to ~4e-5 and could flip a near-tie)
-        precision = "fp32" if out_cam_type == "max-score" else "fp16"
-        if precision == "fp32" and result_exchange is not None:
+        if out_cam_type == "max-score" and result_exchange is not None:
             raise NotImplementedError("INFERENCE_OUT_CAM_TYPE='max-score' runs the exact-fp32 scoring kernels, which have no fused "
                                       "result exchange: gather the rows with nopesac_b200.dist.gather_results instead")
-        res = ops.score_aggregate(geo_local, q_h.view(B, NQ, 4), t_h.view(B, NQ, 3), q0, t0,
-                                  fused_rot.view(B, NQ, 256), fused_tran.view(B, NQ, 256), rot_feat0, trans_feat0,
-                                  matched_num, pk["normal_score_proj"], pk["param_score_proj"],
-                                  self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
-                                  out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
-                                  precision=precision, pack=pk["score_pack"], exchange=result_exchange,
-                                  vecs_host=pk["score_vecs_host"])
-        pose = res["pose"]
+        if not want_diag and self.use_stage_entry:
+            # ---------------------------------------------------- K6 .. K10 behind ONE C call (nsac_refine_forward, csrc/forward.cu):
+            # geo sequences (:513-569) -> hypothesis MLP chain (:957-986) -> per-hypothesis poses -> scoring + selection
+            # (:964-1115) -> pruning (:605-629); launch for launch the sequence of the Python branch below
+            W = self.refine_weights()
+            W.passes = self.tc_passes
+            r = ops.refine_forward(W, planeParam1, planeParam2, assignment if assignment_override is None else assignment_override,
+                                   t0, q0, rot_feat0, trans_feat0, NQ, out_cam_type, hyp_pairs=hyp_pairs,
+                                   prune=assignment_override is None, exchange=result_exchange)
+            geo_local, geo_global, sig, matched_num, pair_idx = r["geo_local"], r["geo_global"], r["sig"], r["matched_num"], r["pair_idx"]
+            q_h, t_h, pose = r["q_h"], r["t_h"], r["pose"]
+            res = {"score_rot": r["score_rot"], "score_tran": r["score_tran"], "sel_idx": r["sel_idx"], "diag": None}
+            pruned = r["assign_pruned"] if assignment_override is None else ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
+        else:
+            geo_local, geo_global, sig, geo8, matched_num, pair_idx = ops.geo_sequence(
+                planeParam1, planeParam2, assignment if assignment_override is None else assignment_override,
+                t0, q0, NQ, hyp_pairs=hyp_pairs)
+
+            # ------------------------------------------------------------ refinement head (:925-1115)
+            fused_rot, fused_tran = self._hypothesis_features(geo8, rot_feat0, trans_feat0, B, NQ)
+            q_h, t_h = ops.pose_heads(fused_rot, fused_tran, self.rots.weight, self.rots.bias,
+                                      self.trans.weight, self.trans.bias)
+            pk = self.prepare_tc()
+            precision = "fp32" if out_cam_type == "max-score" else "fp16"
+            res = ops.score_aggregate(geo_local, q_h.view(B, NQ, 4), t_h.view(B, NQ, 3), q0, t0,
+                                      fused_rot.view(B, NQ, 256), fused_tran.view(B, NQ, 256), rot_feat0, trans_feat0,
+                                      matched_num, pk["normal_score_proj"], pk["param_score_proj"],
+                                      self.rots.weight, self.rots.bias, self.trans.weight, self.trans.bias,
+                                      out_cam_type=out_cam_type, want_scores=True, want_diag=want_diag,
+                                      precision=precision, pack=pk["score_pack"], exchange=result_exchange,
+                                      vecs_host=pk["score_vecs_host"])
+            pose = res["pose"]
+            # ------------------------------------------------------------ assignment pruning (:605-629)
+            # (the sign flip of :600-601 does not change R, which is quadratic in q)
+            pruned = ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]
         trans_list += [avg_trans, ref_trans]
@@ -522,9 +587,6 @@ class PlaneCameraHead(nn.Module):
         output_cameras["camera_avgRef0"] = {"tran": avg_trans, "rot": avg_rot}
         output_cameras["camera_softRef0"] = {"tran": ref_trans, "rot": ref_rot}
 
-        # ------------------------------------------------------------ assignment pruning (:605-629)
-        # (the sign flip of :600-601 does not change R, which is quadratic in q)
-        pruned = ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
         output_planeAss["pred_assignment_afterRef0"] = pruned.clone()
         output_planeAss["pred_assignment"] = pruned.clone()
         output_cameras["camera"] = {"tran": ref_trans, "rot": ref_rot}

@@ -1,0 +1,288 @@
+// Whole-stage entry points: host-side orchestration of this library's own kernels behind one C call per stage (no kernels in
+// this file).  Mirrors what nopesac_b200/camera_head.py does in Python, launch for launch, so both give identical bits.
+#include "common.cuh"
+
+namespace {
+
+struct Planes {
+  void* hi; void* lo; int ld;
+  Planes cols(int c0) const { return {static_cast<uint16_t*>(hi) + c0, static_cast<uint16_t*>(lo) + c0, ld}; }
+};
+
+// bump allocator over the caller's workspace (256-byte granules); base == nullptr only counts
+struct Arena {
+  uint8_t* base; size_t off;
+  void* take(size_t bytes) {
+    void* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~size_t(255);
+    return p;
+  }
+  Planes planes(size_t rows, int ld) {
+    Planes p;
+    p.hi = take(rows * ld * 2); p.lo = take(rows * ld * 2); p.ld = ld;
+    return p;
+  }
+};
+
+struct RefineScratch {
+  float *geo8, *x32, *gb_rot, *gb_tran, *fused_rot, *fused_tran;
+  Planes p0, p1, p2, cat;
+  void* score_ws; size_t score_ws_bytes;
+};
+
+size_t carve_refine(Arena& a, int B, int NQ, RefineScratch& s) {
+  const size_t rows = (size_t)B * NQ;
+  s.geo8 = static_cast<float*>(a.take(rows * 8 * 4));
+  s.x32 = static_cast<float*>(a.take(rows * 1024 * 4));            // geo_encoder layer 0 output (fp32, re-split)
+  s.p0 = a.planes(rows, 1024); s.p1 = a.planes(rows, 1024); s.p2 = a.planes(rows, 1024);
+  s.cat = a.planes(rows, 1280);                                     // cat[s1 (1024), rot (256)] of camera_head.py:961
+  s.gb_rot = static_cast<float*>(a.take((size_t)B * 512 * 4));     // per-pair bias rows of decoder_*2.layers.0
+  s.gb_tran = static_cast<float*>(a.take((size_t)B * 512 * 4));
+  s.fused_rot = static_cast<float*>(a.take(rows * 256 * 4));
+  s.fused_tran = static_cast<float*>(a.take(rows * 256 * 4));
+  const size_t tc = nsac_score_tc_workspace_bytes(B, NQ), f32 = nsac_score_workspace_bytes(B, NQ);
+  s.score_ws_bytes = tc > f32 ? tc : f32;
+  s.score_ws = a.take(s.score_ws_bytes);
+  return a.off;
+}
+
+#define NSAC_TRY(call)            \
+  do {                            \
+    int st__ = (call);            \
+    if (st__ != NSAC_OK) return st__; \
+  } while (0)
+
+// MLP on planes: ReLU between the layers, `final_act` after the last.  Intermediates ping-pong between t0 / t1 (neither may
+// alias `in`); the last layer writes `out` planes (hi may be NULL) and / or out_f32.  first_bias / first_group: per-group bias
+// rows of layer 0 (cat[init_feat, geo_feat] W^T = geo_feat W_geo^T + (init_feat W_init^T + b)).
+int run_chain(const nsac_tc_layer* L, int n, Planes in, int M, Planes t0, Planes t1, const float* first_bias, int first_group,
+              int final_act, float* out_f32, int ldo, Planes out, int fmt, int passes, void* stream, int& launches) {
+  for (int i = 0; i < n; ++i) {
+    const bool last = i == n - 1;
+    const Planes dst = last ? out : ((i & 1) ? t1 : t0);
+    const float* bias = (i == 0 && first_bias) ? first_bias : L[i].bias;
+    NSAC_TRY(nsac_gemm_split(in.hi, in.lo, in.ld, L[i].w_hi, L[i].w_lo, L[i].ldw, bias, i == 0 ? first_group : 0, M, L[i].N, L[i].K,
+                             last ? final_act : NSAC_ACT_RELU, passes, fmt, 1.0f / L[i].w_scale, last ? out_f32 : nullptr,
+                             last ? ldo : 0, dst.hi, dst.lo, dst.hi ? dst.ld : 0, stream));
+    ++launches;
+    in = dst;
+  }
+  return NSAC_OK;
+}
+
+}  // namespace
+
+extern "C" size_t nsac_refine_workspace_bytes(int B, int NQ) {
+  if (B <= 0 || NQ <= 0) return 0;
+  Arena a{nullptr, 0};
+  RefineScratch s;
+  return carve_refine(a, B, NQ, s);
+}
+
+extern "C" int nsac_refine_forward(const nsac_refine_weights* w, const float* planes1, const float* planes2, const float* assign,
+                                   const int32_t* hyp_pairs, int H, const float* t0, const float* q0, const float* rot_feat0,
+                                   const float* trans_feat0, int B, int n1, int n2, int NQ, int out_cam_type, float* pose,
+                                   float* assign_pruned, float* geo_local, float* geo_global, float* sig, int32_t* matched_num,
+                                   int32_t* pair_idx, float* q_h, float* t_h, float* score_rot, float* score_tran,
+                                   int32_t* sel_idx, void* workspace, size_t workspace_bytes, float* const* peer_rows,
+                                   int num_peers, int row_offset, int* launches_out, void* stream) {
+  NSAC_REQUIRE(w && planes1 && planes2 && t0 && q0 && rot_feat0 && trans_feat0, "nsac_refine_forward: null input");
+  NSAC_REQUIRE(assign || hyp_pairs, "nsac_refine_forward: need the assignment matrix or a hypothesis list");
+  NSAC_REQUIRE(!assign_pruned || assign, "nsac_refine_forward: assign_pruned needs assign");
+  NSAC_REQUIRE(pose && geo_local && geo_global && sig && matched_num && pair_idx && q_h && t_h && sel_idx,
+               "nsac_refine_forward: null output");
+  NSAC_REQUIRE(B > 0 && n1 > 0 && n2 > 0 && NQ > 0, "nsac_refine_forward: bad sizes B=%d n1=%d n2=%d NQ=%d", B, n1, n2, NQ);
+  NSAC_REQUIRE(w->geo_encoder[0].K == 1024 && w->geo_proj_s2[0].K == 1280 && w->decoder_rot2[0].K == 256 &&
+               w->decoder_rot[5].N == 256 && w->decoder_tran[5].N == 256 && w->decoder_rot2[2].N == 256,
+               "nsac_refine_forward: weight struct does not have the PlaneCameraHead layer shapes");
+  Arena a{static_cast<uint8_t*>(workspace), 0};
+  RefineScratch s;
+  const size_t need = carve_refine(a, B, NQ, s);
+  NSAC_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_refine_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", need, workspace_bytes);
+  const int rows = B * NQ, fmt = w->fmt, P = w->passes;
+  int n = 0;
+  // K6: geo sequences in torch.nonzero order, sig, the 8-vector geo encoding (camera_head.py:513-569, 937-957)
+  NSAC_TRY(nsac_geo_sequence(planes1, planes2, hyp_pairs ? nullptr : assign, hyp_pairs, hyp_pairs ? H : 0, t0, q0, B, n1, n2, NQ,
+                             geo_local, geo_global, sig, s.geo8, matched_num, pair_idx, stream));
+  ++n;
+  // K7 (:957-986).  geo_encoder layer 0 has K = 8: exact fp32 on the CUDA cores, then split into planes
+  NSAC_TRY(nsac_linear(s.geo8, 8, w->geo0_w, w->geo0_b, 0, s.x32, 1024, rows, 1024, 8, NSAC_ACT_RELU, stream));
+  NSAC_TRY(nsac_split16(s.x32, 1024, rows, 1024, 1.0f, fmt, s.p0.hi, s.p0.lo, s.p0.ld, stream));
+  n += 2;
+  const Planes none{nullptr, nullptr, 0};
+  NSAC_TRY(run_chain(w->geo_encoder, 5, s.p0, rows, s.p1, s.p2, nullptr, 0, NSAC_ACT_NONE, nullptr, 0, s.p0, fmt, P, stream, n));
+  NSAC_TRY(run_chain(w->geo_proj_s1, 3, s.p0, rows, s.p1, s.p2, nullptr, 0, NSAC_ACT_NONE, nullptr, 0, s.cat, fmt, P, stream, n));
+  NSAC_TRY(run_chain(w->decoder_rot, 6, s.cat, rows, s.p1, s.p2, nullptr, 0, NSAC_ACT_NONE, nullptr, 0, s.cat.cols(1024), fmt, P,
+                     stream, n));
+  NSAC_TRY(run_chain(w->geo_proj_s2, 3, s.cat, rows, s.p1, s.p2, nullptr, 0, NSAC_ACT_NONE, nullptr, 0, s.p0, fmt, P, stream, n));
+  NSAC_TRY(run_chain(w->decoder_tran, 6, s.p0, rows, s.p1, s.p2, nullptr, 0, NSAC_ACT_NONE, nullptr, 0, s.p0, fmt, P, stream, n));
+  // decoder_*2 on cat[init_feat (per pair), geo_feat (per hypothesis)] (:983-986): the init half is a per-pair bias row
+  NSAC_TRY(nsac_linear(rot_feat0, 256, w->rot2_w_init, w->rot2_b0, 0, s.gb_rot, 512, B, 512, 256, NSAC_ACT_NONE, stream));
+  ++n;
+  NSAC_TRY(run_chain(w->decoder_rot2, 3, s.cat.cols(1024), rows, s.p1, s.p2, s.gb_rot, NQ, NSAC_ACT_RELU, s.fused_rot, 256, none, fmt,
+                     P, stream, n));
+  NSAC_TRY(nsac_linear(trans_feat0, 256, w->tran2_w_init, w->tran2_b0, 0, s.gb_tran, 512, B, 512, 256, NSAC_ACT_NONE, stream));
+  ++n;
+  NSAC_TRY(run_chain(w->decoder_tran2, 3, s.p0, rows, s.p1, s.p2, s.gb_tran, NQ, NSAC_ACT_RELU, s.fused_tran, 256, none, fmt, P,
+                     stream, n));
+  // one pose hypothesis per matched plane pair (:990, 1018)
+  NSAC_TRY(nsac_pose_heads(s.fused_rot, s.fused_tran, w->rots_w, w->rots_b, w->trans_w, w->trans_b, rows, 256, q_h, t_h, stream));
+  ++n;
+  // K8 + K9: scoring, softmax over the hypotheses, selection.  'max-score' is a discrete decision on the scores themselves: exact fp32
+  if (out_cam_type == NSAC_CAM_MAX_SCORE) {
+    NSAC_REQUIRE(w->rot_mlp && w->tran_mlp, "nsac_refine_forward: NSAC_CAM_MAX_SCORE needs the raw fp32 score MLPs (rot_mlp / tran_mlp)");
+    NSAC_REQUIRE(peer_rows == nullptr, "nsac_refine_forward: the fused result exchange is not available with NSAC_CAM_MAX_SCORE");
+    NSAC_TRY(nsac_score_aggregate(geo_local, q_h, t_h, q0, t0, s.fused_rot, s.fused_tran, rot_feat0, trans_feat0, matched_num,
+                                  w->rot_mlp, w->tran_mlp, w->rots_w, w->rots_b, w->trans_w, w->trans_b, B, NQ, out_cam_type, pose,
+                                  score_rot, score_tran, sel_idx, nullptr, s.score_ws, stream));
+  } else {
+    NSAC_REQUIRE(w->score_pack, "nsac_refine_forward: score_pack missing");
+    NSAC_TRY(nsac_score_aggregate_tc_cv(geo_local, q_h, t_h, q0, t0, s.fused_rot, s.fused_tran, rot_feat0, trans_feat0, matched_num,
+                                        w->score_pack, w->score_vecs_host, w->rots_w, w->rots_b, w->trans_w, w->trans_b, B, NQ,
+                                        out_cam_type, pose, score_rot, score_tran, sel_idx, s.score_ws, peer_rows, num_peers,
+                                        row_offset, stream));
+  }
+  n += 3;
+  // K10: assignment pruning with the refined pose (:605-629)
+  if (assign && assign_pruned) {
+    NSAC_TRY(nsac_prune_assignment(assign, planes1, planes2, pose, 16, B, n1, n2, assign_pruned, stream));
+    ++n;
+  }
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// MatchingHead forward (nopesac_b200/matching_head.py, launch for launch)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct MatchScratch {
+  float *X, *qkv, *msg, *desc;
+  Planes Xp, app, msgp, hp;
+  int32_t* count12;
+};
+
+size_t carve_match(Arena& a, int B, int n1, int n2, MatchScratch& s) {
+  const size_t R = (size_t)B * (n1 + n2);
+  s.X = static_cast<float*>(a.take(R * 512 * 4));       // cols 0:256 token, 256:512 message slot: cat[x, message] (gnn.py:93) is free
+  s.Xp = a.planes(R, 512);
+  s.app = a.planes(R, 256);
+  s.qkv = static_cast<float*>(a.take(R * 768 * 4));
+  s.msgp = a.planes(R, 256);
+  s.msg = static_cast<float*>(a.take(R * 256 * 4));
+  s.hp = a.planes(R, 512);
+  s.desc = static_cast<float*>(a.take(R * 256 * 4));
+  s.count12 = static_cast<int32_t*>(a.take((size_t)2 * B * 4));
+  return a.off;
+}
+
+inline Planes prow(Planes p, size_t row) {
+  return {static_cast<uint16_t*>(p.hi) + row * p.ld, static_cast<uint16_t*>(p.lo) + row * p.ld, p.ld};
+}
+
+int tc(const nsac_tc_layer& L, Planes a, int M, int act, float* out_f32, int ldo, Planes out, int fmt, int passes, void* stream,
+       int& launches) {
+  ++launches;
+  return nsac_gemm_split(a.hi, a.lo, a.ld, L.w_hi, L.w_lo, L.ldw, L.bias, 0, M, L.N, L.K, act, passes, fmt, 1.0f / L.w_scale, out_f32, ldo,
+                         out.hi, out.lo, out.hi ? out.ld : 0, stream);
+}
+
+// one TransformerEncoderLayer (gnn.py:73-97) for the query rows [x0, x1) against the source rows starting at s0
+int gnn_layer(const nsac_gnn_layer& w, MatchScratch& s, size_t x0, size_t x1, size_t s0, size_t s1, int B, int L, int S,
+              const int32_t* kv_count, int fmt, int P, void* stream, int& n) {
+  const int rows = (int)(x1 - x0);
+  float* x = s.X + x0 * 512;
+  const Planes xp = prow(s.Xp, x0), none{nullptr, nullptr, 0};
+  const float *q, *k, *v;
+  int ldq, ldkv;
+  if (w.self_attn) {
+    NSAC_TRY(tc(w.qkv, xp, rows, NSAC_ACT_NONE, s.qkv, 768, none, fmt, P, stream, n));
+    q = s.qkv; k = s.qkv + 256; v = s.qkv + 512; ldq = ldkv = 768;
+  } else {
+    float* kv = s.qkv + (size_t)rows * 256;
+    NSAC_TRY(tc(w.q, xp, rows, NSAC_ACT_NONE, s.qkv, 256, none, fmt, P, stream, n));
+    NSAC_TRY(tc(w.kv, prow(s.Xp, s0), (int)(s1 - s0), NSAC_ACT_NONE, kv, 512, none, fmt, P, stream, n));
+    q = s.qkv; k = kv; v = kv + 256; ldq = 256; ldkv = 512;
+  }
+  if (kv_count) {
+    NSAC_TRY(nsac_attention_ragged(q, ldq, k, v, ldkv, nullptr, 0, s.msgp.hi, s.msgp.lo, s.msgp.ld, B, L, S, 8, 32, kv_count, stream));
+  } else {
+    NSAC_TRY(nsac_attention(q, ldq, k, v, ldkv, nullptr, 0, s.msgp.hi, s.msgp.lo, s.msgp.ld, B, L, S, 8, 32, stream));
+  }
+  ++n;
+  NSAC_TRY(tc(w.merge, s.msgp, rows, NSAC_ACT_NONE, s.msg, 256, none, fmt, P, stream, n));
+  NSAC_TRY(nsac_layernorm(s.msg, 256, w.n1w, w.n1b, nullptr, 0, x + 256, 512, static_cast<uint16_t*>(xp.hi) + 256,
+                          static_cast<uint16_t*>(xp.lo) + 256, 512, rows, 256, stream));                       // message slot
+  ++n;
+  NSAC_TRY(tc(w.mlp0, xp, rows, NSAC_ACT_RELU, nullptr, 0, s.hp, fmt, P, stream, n));
+  NSAC_TRY(tc(w.mlp2, s.hp, rows, NSAC_ACT_NONE, s.msg, 256, none, fmt, P, stream, n));
+  NSAC_TRY(nsac_layernorm(s.msg, 256, w.n2w, w.n2b, x, 512, x, 512, xp.hi, xp.lo, 512, rows, 256, stream));     // x + norm2(.)
+  ++n;
+  return NSAC_OK;
+}
+
+}  // namespace
+
+extern "C" size_t nsac_match_workspace_bytes(int B, int n1, int n2) {
+  if (B <= 0 || n1 <= 0 || n2 <= 0) return 0;
+  Arena a{nullptr, 0};
+  MatchScratch s;
+  return carve_match(a, B, n1, n2, s);
+}
+
+extern "C" int nsac_match_forward(const nsac_match_weights* w, const float* app1, const float* app2, const float* planes1,
+                                  const float* planes2, const float* cam, const int32_t* count1, const int32_t* count2,
+                                  float match_threshold, int B, int n1, int n2, float* log_scores_padded, float* assign,
+                                  void* workspace, size_t workspace_bytes, int* launches_out, void* stream) {
+  NSAC_REQUIRE(w && w->layers && w->num_layers > 0 && w->bin_score, "nsac_match_forward: null weights");
+  NSAC_REQUIRE(app1 && app2 && planes1 && planes2 && cam && log_scores_padded && assign, "nsac_match_forward: null argument");
+  NSAC_REQUIRE((count1 == nullptr) == (count2 == nullptr), "nsac_match_forward: count1 and count2 go together");
+  NSAC_REQUIRE(B > 0 && n1 > 0 && n2 > 0, "nsac_match_forward: bad sizes B=%d n1=%d n2=%d", B, n1, n2);
+  Arena a{static_cast<uint8_t*>(workspace), 0};
+  MatchScratch s;
+  const size_t need = carve_match(a, B, n1, n2, s);
+  NSAC_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_match_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", need, workspace_bytes);
+  const size_t R0 = (size_t)B * n1, R1 = (size_t)B * n2, R = R0 + R1;
+  const int fmt = w->fmt, P = w->passes;
+  const Planes none{nullptr, nullptr, 0};
+  int n = 0;
+  // planeApp_proj on the rows of both views (view 1 after view 0), straight into the token half of X and its planes
+  NSAC_TRY(nsac_split16(app1, 256, (int)R0, 256, 1.0f, fmt, s.app.hi, s.app.lo, 256, stream));
+  NSAC_TRY(nsac_split16(app2, 256, (int)R1, 256, 1.0f, fmt, prow(s.app, R0).hi, prow(s.app, R0).lo, 256, stream));
+  n += 2;
+  NSAC_TRY(tc(w->app_proj, s.app, (int)R, NSAC_ACT_NONE, s.X, 512, s.Xp, fmt, P, stream, n));
+  const int32_t* count12 = nullptr;
+  if (count1) {
+    NSAC_CUDA(cudaMemcpyAsync(s.count12, count1, (size_t)B * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    NSAC_CUDA(cudaMemcpyAsync(s.count12 + B, count2, (size_t)B * 4, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+    count12 = s.count12;
+  }
+  for (int i = 0; i < w->num_layers; ++i) {
+    const nsac_gnn_layer& l = w->layers[i];
+    if (l.self_attn && n1 == n2) {
+      NSAC_TRY(gnn_layer(l, s, 0, R, 0, R, 2 * B, n1, n1, count12, fmt, P, stream, n));
+    } else if (l.self_attn) {
+      NSAC_TRY(gnn_layer(l, s, 0, R0, 0, R0, B, n1, n1, count1, fmt, P, stream, n));
+      NSAC_TRY(gnn_layer(l, s, R0, R, R0, R, B, n2, n2, count2, fmt, P, stream, n));
+    } else {
+      NSAC_TRY(gnn_layer(l, s, 0, R0, R0, R, B, n1, n2, count2, fmt, P, stream, n));
+      NSAC_TRY(gnn_layer(l, s, R0, R, 0, R0, B, n2, n1, count1, fmt, P, stream, n));      // sees the UPDATED view-0 tokens (gnn.py:133-134)
+    }
+  }
+  NSAC_TRY(tc(w->desc_proj, s.Xp, (int)R, NSAC_ACT_NONE, s.desc, 256, none, fmt, P, stream, n));
+  if (count1) {
+    NSAC_TRY(nsac_match_sinkhorn_assign_ragged(s.desc, s.desc + R0 * 256, planes1, planes2, cam, w->bin_score, w->offset_multiplier,
+                                               w->normal_multiplier, w->sinkhorn_iterations, match_threshold, B, n1, n2, 256, count1,
+                                               count2, log_scores_padded, assign, stream));
+  } else {
+    NSAC_TRY(nsac_match_sinkhorn_assign(s.desc, s.desc + R0 * 256, planes1, planes2, cam, w->bin_score, w->offset_multiplier,
+                                        w->normal_multiplier, w->sinkhorn_iterations, match_threshold, B, n1, n2, 256,
+                                        log_scores_padded, assign, stream));
+  }
+  ++n;
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}

@@ -11,6 +11,8 @@ reference return value the fused matcher kernel also yields the mutual-NN assign
 """
 from __future__ import annotations
 
+import os
+
 import torch
 from torch import nn
 
@@ -69,6 +71,7 @@ class MatchingHead(nn.Module):
         self.planeApp_proj = nn.Conv1d(256, 256, kernel_size=1, bias=True)
         self.match_threshold = cfg.TEST.MATCHING_SCORE_THRESHOLD
         self._packed = None
+        self.use_stage_entry = not os.environ.get("NSAC_PY_STAGES")    # nsac_match_forward; NSAC_PY_STAGES=1: same launches from Python
         self.tc_passes = 3     # MMA passes of the tensor-core layers (fp16 hi/lo planes, ~fp32)
 
     # ------------------------------------------------------------------ weight packing
@@ -117,6 +120,27 @@ class MatchingHead(nn.Module):
                 pk["tc"] = [{k: ops.split_weight(w[k]) for k in ("qkv", "q", "kv", "merge", "mlp0", "mlp2")} for w in pk["layers"]]
                 pk["app_ws"], pk["desc_ws"] = ops.split_weight(pk["app_w"]), ops.split_weight(pk["desc_w"])
         return pk
+
+    def match_weights(self):
+        """`nsac_match_weights` for `ops.match_forward` (borrowed pointers into this weight version's packed planes)."""
+        pk = self.prepare_tc()
+        if "match_struct" not in pk:
+            from . import _lib
+            W = _lib.MatchWeights()
+            layers = (_lib.GnnLayer * len(pk["layers"]))()
+            for g, w, ws, name in zip(layers, pk["layers"], pk["tc"], self.gnn.layer_names):
+                for k in ("qkv", "q", "kv", "merge", "mlp0", "mlp2"):
+                    setattr(g, k, ops.tc_layer(ws[k], None))
+                g.n1w, g.n1b, g.n2w, g.n2b = (w[k].data_ptr() for k in ("n1w", "n1b", "n2w", "n2b"))
+                g.self_attn = 1 if name == "self" else 0
+            W.app_proj, W.desc_proj = ops.tc_layer(pk["app_ws"], pk["app_b"]), ops.tc_layer(pk["desc_ws"], pk["desc_b"])
+            W.layers, W.num_layers = layers, len(pk["layers"])
+            pk["bin_score"] = self.bin_score.detach().reshape(1).float().contiguous()
+            W.bin_score = pk["bin_score"].data_ptr()
+            W.offset_multiplier, W.normal_multiplier = float(self.offset_multiplier), float(self.normal_multiplier)
+            W.sinkhorn_iterations, W.fmt, W.passes = int(self.sinkhorn_iterations), ops.SPLIT_F16, self.tc_passes
+            pk["match_struct"], pk["match_struct.keep"] = W, layers
+        return pk["match_struct"]
 
     @staticmethod
     def _layer(w, ws, X, Xp, xs, ss, B, L, S, self_attn: bool, P: int, kv_count=None):
@@ -182,8 +206,13 @@ class MatchingHead(nn.Module):
             raise NotImplementedError("decay factors other than 1.0 are never used by the reference (camera_head.py:490-497)")
         if (plane_count1 is None) != (plane_count2 is None):
             raise ValueError("plane_count1 and plane_count2 go together")
-        d1, d2 = self._descriptors(planeApp1.float(), planeApp2.float(), plane_count1, plane_count2)
         thr = self.match_threshold if match_threshold is None else match_threshold
+        if self.use_stage_entry:           # the whole forward behind ONE C call (nsac_match_forward, csrc/forward.cu)
+            W = self.match_weights()
+            W.passes, W.sinkhorn_iterations = self.tc_passes, int(self.sinkhorn_iterations)
+            return ops.match_forward(W, planeApp1.float(), planeApp2.float(), parameters1_local, parameters2_local, matcher_inputCam,
+                                     float(thr), plane_count1, plane_count2)
+        d1, d2 = self._descriptors(planeApp1.float(), planeApp2.float(), plane_count1, plane_count2)
         return ops.match_sinkhorn_assign(d1, d2, parameters1_local, parameters2_local, matcher_inputCam,
                                          self.bin_score.detach(), float(self.offset_multiplier),
                                          float(self.normal_multiplier), self.sinkhorn_iterations, float(thr),

@@ -669,3 +669,83 @@ def prune_assignment(assign, planes1, planes2, pose):
     _lib.check(st, "nsac_prune_assignment")
     _count()
     return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole-stage entry: the one-plane RANSAC refinement (K6 .. K10) behind ONE C call (csrc/forward.cu)
+# ---------------------------------------------------------------------------------------------------
+def tc_layer(w: Split, bias: Optional[torch.Tensor]) -> "_lib.TcLayer":
+    """nsac_tc_layer of a split weight (borrowed pointers: the caller keeps `w` / `bias` alive)."""
+    t = _lib.TcLayer()
+    t.w_hi, t.w_lo = w.hi.data_ptr(), w.lo.data_ptr()
+    t.bias = None if bias is None else bias.data_ptr()
+    t.N, t.K, t.ldw, t.w_scale = w.rows, (w.K + 63) // 64 * 64, w.hi.stride(0), float(w.scale)
+    return t
+
+
+def refine_forward(weights, planes1, planes2, assign, t0, q0, rot_feat0, trans_feat0, num_queries: int, out_cam_type: str = "soft",
+                   hyp_pairs=None, want_scores: bool = True, prune: bool = True, exchange=None):
+    """nsac_refine_forward: geo sequences -> hypothesis MLP chain -> per-hypothesis poses -> scoring / selection -> pruning, one
+    call, no host round trip.  `weights`: a _lib.RefineWeights (PlaneCameraHead.refine_weights()).  Returns a dict with the
+    tensors of the stage (pose [B,16], assign_pruned, geo_local, geo_global, sig, matched_num, pair_idx, q_h, t_h, score_rot,
+    score_tran, sel_idx)."""
+    planes1, planes2, t0, q0 = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(t0, "t0"), _c(q0, "q0")
+    rot_feat0, trans_feat0 = _c(rot_feat0, "rot_feat0"), _c(trans_feat0, "trans_feat0")
+    B, n1, _ = planes1.shape
+    n2, NQ, dev = planes2.shape[1], num_queries, planes1.device
+    H = 0
+    if hyp_pairs is not None:
+        hyp_pairs = _c(hyp_pairs, "hyp_pairs", torch.int32)
+        H = hyp_pairs.shape[0]
+    if assign is not None:
+        assign = _c(assign, "assign")
+    f = lambda *shape: torch.empty(*shape, device=dev)
+    i32 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.int32)
+    out = {"pose": f(B, 16), "assign_pruned": torch.empty_like(assign) if (prune and assign is not None) else None,
+           "geo_local": f(B, NQ, 6), "geo_global": f(B, NQ, 6), "sig": f(B, NQ), "matched_num": i32(B), "pair_idx": i32(B, NQ, 2),
+           "q_h": f(B * NQ, 4), "t_h": f(B * NQ, 3), "score_rot": f(B, NQ + 1) if want_scores else None,
+           "score_tran": f(B, NQ + 1) if want_scores else None, "sel_idx": i32(B, 2)}
+    L = _lib.lib()
+    nbytes = L.nsac_refine_workspace_bytes(B, NQ)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_refine_forward(C.byref(weights), _p(planes1), _p(planes2), _p(assign), _p(hyp_pairs), H, _p(t0), _p(q0), _p(rot_feat0),
+                               _p(trans_feat0), B, n1, n2, NQ, CAM_TYPES[out_cam_type],
+                               *[_p(out[k]) for k in ("pose", "assign_pruned", "geo_local", "geo_global", "sig", "matched_num", "pair_idx",
+                                                      "q_h", "t_h", "score_rot", "score_tran", "sel_idx")],
+                               C.c_void_p(ws_ptr), nbytes, None if exchange is None else C.c_void_p(exchange.peer_ptrs_dev),
+                               0 if exchange is None else exchange.world, 0 if exchange is None else exchange.row_offset,
+                               C.byref(n), _stream())
+    _lib.check(st, "nsac_refine_forward")
+    _count(n.value)
+    return out
+
+
+def _aligned_workspace(nbytes: int, device):
+    ws = torch.empty(nbytes + 256, device=device, dtype=torch.uint8)
+    return ws, (ws.data_ptr() + 255) // 256 * 256                    # 256-byte aligned (CUDA allocations already are)
+
+
+def match_forward(weights, app1, app2, planes1, planes2, cam, threshold: float, count1=None, count2=None):
+    """nsac_match_forward: the whole MatchingHead forward (projection -> 18 GNN layers -> descriptors -> Sinkhorn + mutual-NN
+    assignment) in one call.  `weights`: a _lib.MatchWeights (MatchingHead.match_weights()).
+    -> (log_scores_padded [B,n1+1,n2+1], assign [B,n1,n2])."""
+    app1, app2 = _c(app1, "app1"), _c(app2, "app2")
+    planes1, planes2, cam = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(cam, "cam")
+    B, n1, Cd = app1.shape
+    n2, dev = app2.shape[1], app1.device
+    assert Cd == 256 and app2.shape[2] == 256
+    if count1 is not None:
+        count1, count2 = _c(count1, "count1", torch.int32), _c(count2, "count2", torch.int32)
+        assert count1.numel() == B and count2.numel() == B
+    lsp = torch.empty(B, n1 + 1, n2 + 1, device=dev)
+    assign = torch.empty(B, n1, n2, device=dev)
+    L = _lib.lib()
+    nbytes = L.nsac_match_workspace_bytes(B, n1, n2)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_match_forward(C.byref(weights), _p(app1), _p(app2), _p(planes1), _p(planes2), _p(cam), _p(count1), _p(count2),
+                              float(threshold), B, n1, n2, _p(lsp), _p(assign), C.c_void_p(ws_ptr), nbytes, C.byref(n), _stream())
+    _lib.check(st, "nsac_match_forward")
+    _count(n.value)
+    return lsp, assign

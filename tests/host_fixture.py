@@ -16,7 +16,8 @@ from nopesac_b200 import _lib, ops  # noqa: E402
 
 
 def install(monkeypatch, with_tensor_standins: bool):
-    L = simt_run.build(simt_run.SIMT_SOURCES, extra_cpp=("tc_standin.cpp",) if with_tensor_standins else ())
+    L = simt_run.build(simt_run.SIMT_SOURCES + (simt_run.HOST_ONLY_SOURCES if with_tensor_standins else []),
+                       extra_cpp=("tc_standin.cpp",) if with_tensor_standins else ())
     for name, (res, args) in _lib._SIGNATURES.items():
         if hasattr(L, name):
             fn = getattr(L, name)

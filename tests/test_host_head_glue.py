@@ -8,6 +8,7 @@ What it does NOT cover: the tcgen05 kernels themselves (GPU tests)."""
 import pytest
 import torch
 
+from nopesac_b200 import ops
 from tests import host_fixture, util
 from tests.test_gpu_parity import _check_against, _selection_from_reference
 
@@ -55,6 +56,37 @@ def test_head_glue_on_host_matches_golden(host_ops, name):
         _check_against(want, cams, lsp, ass, pro, i, f"{name}[pair {pi}] (host)")
         if case["cam"] in ("min-cost", "max-score") and int(want["matched_num"]) > 1:
             assert pro["sel_idx"][i].tolist() == list(_selection_from_reference(want, case)), name
+
+
+def _flat(out):
+    cams, tl, rl, lsp, ass, pro = out
+    d = {f"cam.{k}.{kk}": v for k, c in cams.items() for kk, v in c.items()}
+    d.update({f"ass.{k}": v for k, v in ass.items()})
+    d.update({f"pro.{k}": v for k, v in pro.items() if torch.is_tensor(v)})
+    d["lsp"] = lsp[0]
+    return d
+
+
+@pytest.mark.parametrize("name", NO_FEATS[:2])
+def test_stage_entry_equals_python_stages_on_host(host_ops, name, monkeypatch):
+    """K6 .. K10 through the single C entry (nsac_refine_forward, csrc/forward.cu compiled for the host) == the same launches
+    issued from Python (head.use_stage_entry = False): every output bit-identical, incl. an assignment override."""
+    g = util.load_golden(name)
+    case, pairs = g["case"], g["case"]["pairs"][:MAX_PAIRS]
+    outs = {}
+    for flag in (True, False):
+        if flag:
+            monkeypatch.delenv("NSAC_PY_STAGES", raising=False)
+        else:
+            monkeypatch.setenv("NSAC_PY_STAGES", "1")          # read by PlaneCameraHead.__init__
+        n0 = ops.launch_count()
+        outs[flag] = _flat(_run_host_case(case, pairs))
+        assert ops.launch_count() - n0 > 300          # the stage entries report the kernels they enqueue
+    assert set(outs[True]) == set(outs[False])
+    for k in outs[True]:
+        assert torch.equal(outs[True][k], outs[False][k]), (name, k)
+    for i, (pi, want) in enumerate(zip(pairs, g["outputs"][:MAX_PAIRS])):
+        assert int(outs[True]["pro.matched_num"][i]) == int(want["matched_num"]), (name, pi)
 
 
 def test_ragged_batch_glue_on_host_matches_per_pair_oracle(host_ops):
