@@ -442,6 +442,69 @@ int nsac_match_forward(const nsac_match_weights* w, const float* app1, const flo
                        float match_threshold, int B, int n1, int n2, float* log_scores_padded, float* assign, void* workspace,
                        size_t workspace_bytes, int* launches_out, void* stream);
 
+/* Initial-pose hand-off between K1 / K2 and the matcher: q_out = q_in with w >= 0 per pair (camera_head.py:436-437; the reference
+ * flips the whole batch by sample 0), t_eps_out = t_in + 1e-10 (:718); cam [B,7] = [t, q] rows (:493).  Either half of
+ * nsac_pose_canon may be NULL. */
+int nsac_pose_canon(const float* q_in, const float* t_in, int B, float* q_out, float* t_eps_out, void* stream);
+int nsac_cam_rows(const float* t, const float* q, int B, float* cam, void* stream);
+
+/* nsac_pixel_forward — K1 + K2: the pixel pose network (camera_head.py:642-683 with camera_modules.py:246-348: top-down pixel
+ * decoder res5 -> res3, six conv-BN-LeakyReLU blocks with two max-pools, correlation volume + softmax, two strided regression
+ * branches, fc, shared pose heads) on the stacked views, then the w >= 0 canonicalisation and the AIM embedding MLPs
+ * (:685-735).  Inputs are the backbone's res3 / res4 / res5 maps of N = 2B images (first views, then second views) as NHWC
+ * hi/lo planes [N*H*W, C] (nsac_nchw_to_planes, or the backbone's own output): C = 512 / 1024 / 2048, H4 = H3/2, H5 = H3/4.
+ * If res5_hi == NULL the network is skipped and init_tran / init_rot are INPUTS (an externally supplied initial pose).
+ *   -> init_tran [B,3], init_rot [B,4] (camera_init, w >= 0), pix_tran_feat / pix_rot_feat [B,256] (NULL = drop),
+ *      t0 [B,3], q0 [B,4] (camera_initRec), rot_feat0 / trans_feat0 [B,256]. */
+typedef struct {
+  nsac_tc_layer pd_layer_3, pd_layer_2, pd_layer_1, pd_mask_features;   /* 3x3 convolutions as [Cout, 9*Cin] planes, (ky,kx,cin) */
+  nsac_tc_layer pd_adapter_2, pd_adapter_1;                             /* 1x1 convolutions */
+  const float* gn_w[5]; const float* gn_b[5];                           /* GroupNorm of layer_3, adapter_2, layer_2, adapter_1, layer_1 */
+  int gn_groups; float gn_eps;
+  nsac_tc_layer cb[6];                    /* convs_backbone.{0,1,3,4,6,7}: BatchNorm(eval) folded, bias = folded shift */
+  nsac_tc_layer ct0;                      /* first conv of convs_trans | convs_rots on the shared correlation input [256, 9*320] */
+  nsac_tc_layer convs_trans[5]; nsac_tc_layer convs_rots[5];            /* layers 1-5 as im2col GEMMs [128, 1152] */
+  const float* fc_trans_w; const float* fc_trans_b;                     /* fc weights re-ordered for NHWC flattening [256,768] */
+  const float* fc_rots_w; const float* fc_rots_b;
+  const float* rot_emb0_w; const float* rot_emb0_b;                     /* rot_emb_proj.layers.0 [256,4]  (CUDA cores) */
+  const float* trans_emb0_w; const float* trans_emb0_b;                 /* trans_emb_proj.layers.0 [256,3] */
+  nsac_tc_layer rot_emb[5]; nsac_tc_layer trans_emb[5];                 /* layers 1-5 */
+  const float* rots_w; const float* rots_b; const float* trans_w; const float* trans_b;
+  int fmt, passes;
+} nsac_pixel_weights;
+
+size_t nsac_pixel_workspace_bytes(int B, int H3, int W3);
+int nsac_pixel_forward(const nsac_pixel_weights* w, const void* res3_hi, const void* res3_lo, const void* res4_hi,
+                       const void* res4_lo, const void* res5_hi, const void* res5_lo, int B, int H3, int W3, float* init_tran,
+                       float* init_rot, float* pix_tran_feat, float* pix_rot_feat, float* t0, float* q0, float* rot_feat0,
+                       float* trans_feat0, void* workspace, size_t workspace_bytes, int* launches_out, void* stream);
+
+/* nsac_head_forward — PlaneCameraHead.inference_Joint (camera_head.py:400-640) with its MatchingHead in ONE call: the three
+ * stage entries above chained on `stream` (nsac_pixel_forward -> cam = [t0, q0] -> nsac_match_forward -> nsac_refine_forward).
+ * Everything the reference returns from inference_Joint is an output buffer of this call:
+ *   camera_init = (init_tran, init_rot), camera_initRec = (t0, q0), log_scores_padded, pred_assignment_beforeRef0 = assign,
+ *   pred_assignment(_afterRef0) = assign_pruned, camera_softRef0 / camera = pose[:,0:7], camera_avgRef0 = pose[:,7:14],
+ *   camera_onePP = (t_h, q_h) with matched_num, sig_seq = sig, score_soft_rot / _offset = score_rot / score_tran.
+ * Feature planes / plane lists / counts / hyp_pairs as in the stage entries; rot_feat0 / trans_feat0 [B,256] are scratch the
+ * caller provides (the AIM features, consumed by the refinement). */
+typedef struct {
+  const nsac_pixel_weights* pixel;
+  const nsac_match_weights* match;
+  const nsac_refine_weights* refine;
+} nsac_head_weights;
+
+size_t nsac_head_workspace_bytes(int B, int H3, int W3, int n1, int n2, int NQ);
+int nsac_head_forward(const nsac_head_weights* w, const void* res3_hi, const void* res3_lo, const void* res4_hi,
+                      const void* res4_lo, const void* res5_hi, const void* res5_lo, int B, int H3, int W3,
+                      const float* planes1, const float* planes2, const float* app1, const float* app2, const int32_t* count1,
+                      const int32_t* count2, int n1, int n2, const int32_t* hyp_pairs, int H, int NQ, float match_threshold,
+                      int out_cam_type, float* init_tran, float* init_rot, float* t0, float* q0, float* rot_feat0,
+                      float* trans_feat0, float* log_scores_padded, float* assign, float* pose, float* assign_pruned,
+                      float* geo_local, float* geo_global, float* sig, int32_t* matched_num, int32_t* pair_idx, float* q_h,
+                      float* t_h, float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace,
+                      size_t workspace_bytes, float* const* peer_rows, int num_peers, int row_offset, int* launches_out,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -45,6 +45,24 @@ class MatchWeights(C.Structure):
                 ("sinkhorn_iterations", C.c_int), ("fmt", C.c_int), ("passes", C.c_int)]
 
 
+class PixelWeights(C.Structure):
+    """nsac_pixel_weights."""
+    _fields_ = [("pd_layer_3", TcLayer), ("pd_layer_2", TcLayer), ("pd_layer_1", TcLayer), ("pd_mask_features", TcLayer),
+                ("pd_adapter_2", TcLayer), ("pd_adapter_1", TcLayer), ("gn_w", C.c_void_p * 5), ("gn_b", C.c_void_p * 5),
+                ("gn_groups", C.c_int), ("gn_eps", C.c_float), ("cb", TcLayer * 6), ("ct0", TcLayer),
+                ("convs_trans", TcLayer * 5), ("convs_rots", TcLayer * 5),
+                ("fc_trans_w", C.c_void_p), ("fc_trans_b", C.c_void_p), ("fc_rots_w", C.c_void_p), ("fc_rots_b", C.c_void_p),
+                ("rot_emb0_w", C.c_void_p), ("rot_emb0_b", C.c_void_p), ("trans_emb0_w", C.c_void_p), ("trans_emb0_b", C.c_void_p),
+                ("rot_emb", TcLayer * 5), ("trans_emb", TcLayer * 5),
+                ("rots_w", C.c_void_p), ("rots_b", C.c_void_p), ("trans_w", C.c_void_p), ("trans_b", C.c_void_p),
+                ("fmt", C.c_int), ("passes", C.c_int)]
+
+
+class HeadWeights(C.Structure):
+    """nsac_head_weights."""
+    _fields_ = [("pixel", C.POINTER(PixelWeights)), ("match", C.POINTER(MatchWeights)), ("refine", C.POINTER(RefineWeights))]
+
+
 _SIGNATURES = {
     "nsac_version": (C.c_int, []),
     "nsac_last_error": (C.c_char_p, []),
@@ -139,6 +157,15 @@ _SIGNATURES = {
                                [C.c_float, C.c_float, C.c_double] + [C.c_void_p] * 12),
     "nsac_prune_assignment": (C.c_int, [c_float_p, c_float_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                         C.c_int, c_float_p, C.c_void_p]),
+    "nsac_pose_canon": (C.c_int, [c_float_p, c_float_p, C.c_int, c_float_p, c_float_p, C.c_void_p]),
+    "nsac_cam_rows": (C.c_int, [c_float_p, c_float_p, C.c_int, c_float_p, C.c_void_p]),
+    "nsac_pixel_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "nsac_pixel_forward": (C.c_int, [C.POINTER(PixelWeights)] + [C.c_void_p] * 6 + [C.c_int] * 3 + [c_float_p] * 8 +
+                           [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
+    "nsac_head_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "nsac_head_forward": (C.c_int, [C.POINTER(HeadWeights)] + [C.c_void_p] * 6 + [C.c_int] * 3 + [c_float_p] * 4 + [C.c_void_p] * 2 +
+                          [C.c_int] * 2 + [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 20 +
+                          [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
     "nsac_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "nsac_match_forward": (C.c_int, [C.POINTER(MatchWeights)] + [c_float_p] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
                                     C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),

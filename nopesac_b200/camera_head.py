@@ -408,6 +408,61 @@ class PlaneCameraHead(nn.Module):
             fused.append(f32)                                                     # F.relu(decoder_*2(.))
         return fused[0], fused[1]
 
+    def pixel_weights(self):
+        """`nsac_pixel_weights` for `ops.pixel_forward` (K1 + K2; borrowed pointers into this weight version's packed planes)."""
+        pk = self.prepare_tc()
+        if "pixel_struct" not in pk:
+            from . import _lib
+            W = _lib.PixelWeights()
+            pd = self.pixel_decoder
+            if not hasattr(pd.layer_3, "norm"):
+                raise NotImplementedError("SEM_SEG_HEAD.NORM must be 'GN' (as in every reference config)")
+            tl = ops.tc_layer
+            W.pd_layer_3, W.pd_layer_2, W.pd_layer_1 = (tl(pk[f"pd.{k}.w"], None) for k in ("layer_3", "layer_2", "layer_1"))
+            W.pd_mask_features = tl(pk["pd.mask_features.w"], pd.mask_features.bias)
+            W.pd_adapter_2, W.pd_adapter_1 = tl(pk["pd.adapter_2.w"], None), tl(pk["pd.adapter_1.w"], None)
+            norms = [getattr(pd, k).norm for k in ("layer_3", "adapter_2", "layer_2", "adapter_1", "layer_1")]
+            assert len({(m.num_groups, m.eps) for m in norms}) == 1
+            for i, m in enumerate(norms):
+                W.gn_w[i], W.gn_b[i] = m.weight.data_ptr(), m.bias.data_ptr()
+            W.gn_groups, W.gn_eps = norms[0].num_groups, float(norms[0].eps)
+            for j, i in enumerate((0, 1, 3, 4, 6, 7)):
+                W.cb[j] = tl(pk[f"cb.{i}.w"], pk[f"cb.{i}.b"])
+            W.ct0 = tl(pk["ct0.w"], pk["ct0.b"])
+            for i in range(1, 6):
+                W.convs_trans[i - 1] = tl(pk[f"convs_trans.{i}.w"], pk[f"convs_trans.{i}.b"])
+                W.convs_rots[i - 1] = tl(pk[f"convs_rots.{i}.w"], pk[f"convs_rots.{i}.b"])
+            W.fc_trans_w, W.fc_trans_b = pk["fc_trans.w_nhwc"].data_ptr(), self.fc_trans.bias.data_ptr()
+            W.fc_rots_w, W.fc_rots_b = pk["fc_rots.w_nhwc"].data_ptr(), self.fc_rots.bias.data_ptr()
+            r0, t0 = self.rot_emb_proj.layers[0], self.trans_emb_proj.layers[0]
+            W.rot_emb0_w, W.rot_emb0_b, W.trans_emb0_w, W.trans_emb0_b = (x.data_ptr() for x in (r0.weight, r0.bias, t0.weight, t0.bias))
+            for i in range(1, 6):
+                W.rot_emb[i - 1] = tl(pk["rot_emb_proj.split"][i], self.rot_emb_proj.layers[i].bias)
+                W.trans_emb[i - 1] = tl(pk["trans_emb_proj.split"][i], self.trans_emb_proj.layers[i].bias)
+            W.rots_w, W.rots_b = self.rots.weight.data_ptr(), self.rots.bias.data_ptr()
+            W.trans_w, W.trans_b = self.trans.weight.data_ptr(), self.trans.bias.data_ptr()
+            W.fmt, W.passes = ops.SPLIT_F16, self.tc_passes
+            pk["pixel_struct"] = W
+        return pk["pixel_struct"]
+
+    def _feature_planes(self, features1, features2):
+        """res3 / res4 / res5 of both views as stacked NHWC planes: a backbone.PlaneFeatures as is, NCHW fp32 dicts converted."""
+        from .backbone import PlaneFeatures
+        if isinstance(features1, PlaneFeatures):
+            B = features1.num_images // 2
+            return B, {k: features1[k] for k in ("res3", "res4", "res5")}
+        B = features1["res5"].shape[0]
+        out = {}
+        for name in ("res3", "res4", "res5"):
+            f1, f2 = features1[name], features2[name]
+            _, C, H, W = f1.shape
+            sp = ops.Split(torch.empty(2 * B * H * W, C, device=f1.device, dtype=torch.float16),
+                           torch.empty(2 * B * H * W, C, device=f1.device, dtype=torch.float16), C)
+            ops.nchw_to_planes(f1.float(), out=sp, row_offset=0)
+            ops.nchw_to_planes(f2.float(), out=sp, row_offset=B * H * W)
+            out[name] = (sp, H, W)
+        return B, out
+
     def refine_weights(self):
         """`nsac_refine_weights` for `ops.refine_forward` (borrowed pointers into the packed weights of this weight version; the
         struct and everything it points to live in the prepare() cache)."""
@@ -500,29 +555,80 @@ class PlaneCameraHead(nn.Module):
         output_cameras = {"camera_zero": {"tran": torch.zeros(1, 3, device=device), "rot": zero_rot}}
         out_cam_type = self.inference_out_cam_type if self.cam_ref_on else "initial"
 
-        if initial_pose is None:
-            initial_trans, initial_rot, pix_tfeat, pix_rfeat = self._forward_pixel_camera_head(cam_feats1, cam_feats2)
-        else:
-            initial_trans, initial_rot = initial_pose
-            pix_tfeat = pix_rfeat = None
-        # w >= 0, per pair (the reference flips the whole batch by sample 0, :436-437)
-        initial_rot = torch.where(initial_rot[:, 0:1] < 0, -initial_rot, initial_rot)
-        trans_list.append(initial_trans)
-        rot_list.append(initial_rot)
-        output_cameras["camera_init"] = {"tran": initial_trans, "rot": initial_rot}
-        if not self.plane_matcher_on:
-            output_cameras["camera"] = {"tran": trans_list[-1], "rot": rot_list[-1]}
-            return output_cameras, trans_list, rot_list, [], {}, None
+        single_call = (self.use_stage_entry and self.cam_rec_on and self.plane_matcher_on and out_cam_type != "initial" and not want_diag
+                       and assignment_override is None and getattr(matching_net, "use_stage_entry", False)
+                       and not (out_cam_type == "max-score" and result_exchange is not None))
+        if single_call:
+            # ------------------------------------------------ the WHOLE head + matcher behind ONE C call (nsac_head_forward,
+            # csrc/forward.cu: nsac_pixel_forward -> nsac_match_forward -> nsac_refine_forward on the current stream)
+            PW, MW, RW = self.pixel_weights(), matching_net.match_weights(), self.refine_weights()
+            PW.passes = RW.passes = self.tc_passes
+            MW.passes, MW.sinkhorn_iterations = matching_net.tc_passes, int(matching_net.sinkhorn_iterations)
+            if (plane_count1 is None) != (plane_count2 is None):
+                raise ValueError("plane_count1 and plane_count2 go together")
+            if initial_pose is None:
+                _, lv = self._feature_planes(cam_feats1, cam_feats2)
+                (p3, H3, W3), (p4, H4, W4), (p5, H5, W5) = lv["res3"], lv["res4"], lv["res5"]
+                if (H4, W4, H5, W5) != (H3 // 2, W3 // 2, H3 // 4, W3 // 4) or H3 % 4 or W3 % 4:
+                    raise ValueError(f"feature map sizes must halve level to level: res3 {H3}x{W3}, res4 {H4}x{W4}, res5 {H5}x{W5}")
+            else:
+                p3 = p4 = p5 = None
+                H3 = W3 = 0
+            r = ops.head_forward(PW, MW, RW, p3, p4, p5, B, H3, W3, planeParam1, planeParam2, planeApp1.float(), planeApp2.float(), NQ,
+                                 self.matching_score_threshold, out_cam_type, plane_count1, plane_count2, hyp_pairs, initial_pose,
+                                 exchange=result_exchange)
+            trans_list += [r["init_tran"], r["t0"]]
+            rot_list += [r["init_rot"], r["q0"]]
+            output_cameras["camera_init"] = {"tran": r["init_tran"], "rot": r["init_rot"]}
+            output_cameras["camera_initRec"] = {"tran": r["t0"], "rot": r["q0"]}
+            output_planeAss = {"pred_assignment_beforeRef0": r["assign"]}
+            res = {"score_rot": r["score_rot"], "score_tran": r["score_tran"], "sel_idx": r["sel_idx"], "diag": None}
+            return self._pack_refined(output_cameras, trans_list, rot_list, r["log_scores_padded"], output_planeAss, r["pose"],
+                                      r["assign_pruned"], r["q0"], r["t0"], r["q_h"], r["t_h"], res, r["sig"], r["matched_num"],
+                                      r["pair_idx"], r["geo_local"], r["geo_global"], False)
 
-        if self.cam_rec_on:
-            q0, rot_feat0, t0, trans_feat0 = self._forward_rec_heads(initial_rot, initial_trans)
-            trans_list.append(t0)
-            rot_list.append(q0)
+        if self.use_stage_entry and self.cam_rec_on and self.plane_matcher_on:
+            # K1 + w >= 0 + K2 behind ONE C call (nsac_pixel_forward, csrc/forward.cu); the Python branch below issues the same launches
+            W = self.pixel_weights()
+            W.passes = self.tc_passes
+            if initial_pose is None:
+                _, lv = self._feature_planes(cam_feats1, cam_feats2)
+                (p3, H3, W3), (p4, H4, W4), (p5, H5, W5) = lv["res3"], lv["res4"], lv["res5"]
+                if (H4, W4, H5, W5) != (H3 // 2, W3 // 2, H3 // 4, W3 // 4) or H3 % 4 or W3 % 4:
+                    raise ValueError(f"feature map sizes must halve level to level: res3 {H3}x{W3}, res4 {H4}x{W4}, res5 {H5}x{W5}")
+                r = ops.pixel_forward(W, p3, p4, p5, B, H3, W3)
+            else:
+                r = ops.pixel_forward(W, None, None, None, B, 0, 0, initial_pose=initial_pose)
+            initial_trans, initial_rot = r["init_tran"], r["init_rot"]
+            q0, rot_feat0, t0, trans_feat0 = r["q0"], r["rot_feat0"], r["t0"], r["trans_feat0"]
+            trans_list += [initial_trans, t0]
+            rot_list += [initial_rot, q0]
+            output_cameras["camera_init"] = {"tran": initial_trans, "rot": initial_rot}
             output_cameras["camera_initRec"] = {"tran": t0, "rot": q0}
         else:
-            if pix_rfeat is None:
-                raise ValueError("initial_pose override needs CAM_REC_ON (the pixel features are skipped)")
-            q0, rot_feat0, t0, trans_feat0 = initial_rot, pix_rfeat, initial_trans, pix_tfeat
+            if initial_pose is None:
+                initial_trans, initial_rot, pix_tfeat, pix_rfeat = self._forward_pixel_camera_head(cam_feats1, cam_feats2)
+            else:
+                initial_trans, initial_rot = initial_pose
+                pix_tfeat = pix_rfeat = None
+            # w >= 0, per pair (the reference flips the whole batch by sample 0, :436-437)
+            initial_rot = torch.where(initial_rot[:, 0:1] < 0, -initial_rot, initial_rot)
+            trans_list.append(initial_trans)
+            rot_list.append(initial_rot)
+            output_cameras["camera_init"] = {"tran": initial_trans, "rot": initial_rot}
+            if not self.plane_matcher_on:
+                output_cameras["camera"] = {"tran": trans_list[-1], "rot": rot_list[-1]}
+                return output_cameras, trans_list, rot_list, [], {}, None
+
+            if self.cam_rec_on:
+                q0, rot_feat0, t0, trans_feat0 = self._forward_rec_heads(initial_rot, initial_trans)
+                trans_list.append(t0)
+                rot_list.append(q0)
+                output_cameras["camera_initRec"] = {"tran": t0, "rot": q0}
+            else:
+                if pix_rfeat is None:
+                    raise ValueError("initial_pose override needs CAM_REC_ON (the pixel features are skipped)")
+                q0, rot_feat0, t0, trans_feat0 = initial_rot, pix_rfeat, initial_trans, pix_tfeat
 
         # ------------------------------------------------------------ matching (:493-503)
         if matching_net is None or not hasattr(matching_net, "match"):
@@ -580,6 +686,13 @@ class PlaneCameraHead(nn.Module):
             # ------------------------------------------------------------ assignment pruning (:605-629)
             # (the sign flip of :600-601 does not change R, which is quadratic in q)
             pruned = ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
+        return self._pack_refined(output_cameras, trans_list, rot_list, log_scores_padded, output_planeAss, pose, pruned, q0, t0, q_h, t_h,
+                                  res, sig, matched_num, pair_idx, geo_local, geo_global, want_diag)
+
+    def _pack_refined(self, output_cameras, trans_list, rot_list, log_scores_padded, output_planeAss, pose, pruned, q0, t0, q_h, t_h,
+                      res, sig, matched_num, pair_idx, geo_local, geo_global, want_diag):
+        """The reference's return value of inference_Joint (:589-640) from the tensors of the refinement stage."""
+        B, NQ = pose.shape[0], self.num_queries
         ref_trans, ref_rot = pose[:, 0:3], pose[:, 3:7]
         avg_trans, avg_rot = pose[:, 7:10], pose[:, 10:14]
         trans_list += [avg_trans, ref_trans]

@@ -371,3 +371,44 @@ extern "C" int nsac_pose_heads(const float* feat_rot, const float* feat_tran, co
   NSAC_CHECK_LAUNCH("nsac_pose_heads");
   return NSAC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Initial-pose hand-off (camera_head.py:436-437, 718): quaternion with w >= 0 (per pair), t + 1e-10 for the AIM translation
+// embedding, and the matcher pose cam = [t, q] rows (:493) — the three elementwise torch ops between K1 / K2 and the matcher.
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void pose_canon_kernel(const float* q_in, const float* t_in, int B, float* q_out, float* t_eps) {   // q_out may alias q_in
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  if (q_in && q_out) {
+    const float w = q_in[b * 4];
+    const float s = w < 0.f ? -1.f : 1.f;
+    for (int j = 0; j < 4; ++j) q_out[b * 4 + j] = s < 0.f ? -q_in[b * 4 + j] : q_in[b * 4 + j];
+  }
+  if (t_in && t_eps)
+    for (int j = 0; j < 3; ++j) t_eps[b * 3 + j] = t_in[b * 3 + j] + 1e-10f;
+}
+__global__ void cam_rows_kernel(const float* __restrict__ t, const float* __restrict__ q, int B, float* __restrict__ cam) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int j = 0; j < 3; ++j) cam[b * 7 + j] = t[b * 3 + j];
+  for (int j = 0; j < 4; ++j) cam[b * 7 + 3 + j] = q[b * 4 + j];
+}
+}  // namespace
+
+extern "C" int nsac_pose_canon(const float* q_in, const float* t_in, int B, float* q_out, float* t_eps_out, void* stream) {
+  NSAC_REQUIRE((q_in && q_out) || (t_in && t_eps_out), "nsac_pose_canon: nothing to do");
+  NSAC_REQUIRE(B >= 0, "nsac_pose_canon: bad batch size");
+  if (B == 0) return NSAC_OK;
+  pose_canon_kernel<<<nsac_cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(q_in, t_in, B, q_out, t_eps_out);
+  NSAC_CHECK_LAUNCH("nsac_pose_canon");
+  return NSAC_OK;
+}
+
+extern "C" int nsac_cam_rows(const float* t, const float* q, int B, float* cam, void* stream) {
+  NSAC_REQUIRE(t && q && cam && B >= 0, "nsac_cam_rows: bad arguments");
+  if (B == 0) return NSAC_OK;
+  cam_rows_kernel<<<nsac_cdiv(B, 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(t, q, B, cam);
+  NSAC_CHECK_LAUNCH("nsac_cam_rows");
+  return NSAC_OK;
+}

@@ -286,3 +286,210 @@ extern "C" int nsac_match_forward(const nsac_match_weights* w, const float* app1
   if (launches_out) *launches_out = n;
   return NSAC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// K1 + K2: pixel pose network + AIM (nopesac_b200/camera_head.py _forward_pixel_camera_head / _forward_rec_heads)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct PixelScratch {
+  float *t5, *y5, *t4, *y4, *t3, *f, *tc0, *ysl, *ya, *yb, *feat_t, *feat_r, *x32, *teps;
+  Planes u4, u3, y3, xa, xb, aff, cols, e0, e1, e2;
+  void* gn_ws; size_t gn_ws_bytes;
+};
+
+size_t carve_pixel(Arena& a, int B, int H3, int W3, PixelScratch& s) {
+  const size_t N = 2 * (size_t)B, r3 = N * H3 * W3, r4 = N * (H3 / 2) * (W3 / 2), r5 = N * (H3 / 4) * (W3 / 4);
+  const size_t hw = (size_t)(H3 / 4) * (W3 / 4), rb = (size_t)B * hw;
+  auto f32 = [&](size_t n) { return static_cast<float*>(a.take(n * 4)); };
+  s.t5 = f32(r5 * 128); s.y5 = f32(r5 * 128);
+  s.t4 = f32(r4 * 128); s.y4 = f32(r4 * 128); s.u4 = a.planes(r4, 128);
+  s.t3 = f32(r3 * 128); s.u3 = a.planes(r3, 128); s.y3 = a.planes(r3, 128);
+  s.xa = a.planes(r3, 256); s.xb = a.planes(r3, 256); s.f = f32(r3 * 256);
+  const int Cp = (int)((hw + 63) / 64 * 64);
+  s.aff = a.planes(rb, Cp);
+  s.tc0 = f32(rb * 256); s.ysl = f32(rb * 128); s.ya = f32(rb * 128); s.yb = f32(rb * 128);
+  s.cols = a.planes(rb, 1152);
+  s.feat_t = f32((size_t)B * 256); s.feat_r = f32((size_t)B * 256);
+  s.x32 = f32((size_t)B * 256); s.teps = f32((size_t)B * 3);
+  s.e0 = a.planes(B, 256); s.e1 = a.planes(B, 256); s.e2 = a.planes(B, 256);
+  s.gn_ws_bytes = nsac_groupnorm_ws_bytes((int)N, H3, W3, 32);
+  if (s.gn_ws_bytes < 16) s.gn_ws_bytes = 16;
+  s.gn_ws = a.take(s.gn_ws_bytes);
+  return a.off;
+}
+
+int conv3(const nsac_tc_layer& L, Planes x, int N, int H, int W, int Cin, int act, float* out_f32, Planes out, int fmt, int P,
+          void* stream, int& n) {
+  ++n;
+  return nsac_conv3x3_split(x.hi, x.lo, L.w_hi, L.w_lo, L.bias, N, H, W, Cin, L.N, act, P, fmt, 1.0f / L.w_scale, out_f32,
+                            out_f32 ? L.N : 0, out.hi, out.lo, out.hi ? out.ld : 0, stream);
+}
+
+}  // namespace
+
+extern "C" size_t nsac_pixel_workspace_bytes(int B, int H3, int W3) {
+  if (B <= 0 || H3 < 4 || W3 < 4) return 0;
+  Arena a{nullptr, 0};
+  PixelScratch s;
+  return carve_pixel(a, B, H3, W3, s);
+}
+
+extern "C" int nsac_pixel_forward(const nsac_pixel_weights* w, const void* res3_hi, const void* res3_lo, const void* res4_hi,
+                                  const void* res4_lo, const void* res5_hi, const void* res5_lo, int B, int H3, int W3,
+                                  float* init_tran, float* init_rot, float* pix_tran_feat, float* pix_rot_feat, float* t0,
+                                  float* q0, float* rot_feat0, float* trans_feat0, void* workspace, size_t workspace_bytes,
+                                  int* launches_out, void* stream) {
+  NSAC_REQUIRE(w && init_tran && init_rot && t0 && q0 && rot_feat0 && trans_feat0, "nsac_pixel_forward: null argument");
+  NSAC_REQUIRE(B > 0, "nsac_pixel_forward: bad batch size %d", B);
+  const bool run_k1 = res5_hi != nullptr;
+  if (run_k1) {
+    NSAC_REQUIRE(res3_hi && res3_lo && res4_hi && res4_lo && res5_lo, "nsac_pixel_forward: null feature planes");
+    NSAC_REQUIRE(H3 % 4 == 0 && W3 % 4 == 0 && H3 >= 4 && W3 >= 4, "nsac_pixel_forward: res3 size %dx%d must be a multiple of 4", H3, W3);
+  } else {
+    H3 = W3 = 4;     // scratch of the skipped network is still carved (tiny)
+  }
+  Arena a{static_cast<uint8_t*>(workspace), 0};
+  PixelScratch s;
+  const size_t need = carve_pixel(a, B, H3, W3, s);
+  NSAC_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_pixel_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", need, workspace_bytes);
+  const int fmt = w->fmt, P = w->passes, N = 2 * B, G = w->gn_groups;
+  const Planes none{nullptr, nullptr, 0};
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  int n = 0;
+  if (run_k1) {
+    const int H4 = H3 / 2, W4 = W3 / 2, H5 = H3 / 4, W5 = W3 / 4;
+    auto gn = [&](const float* x, int H, int W, int idx, int relu, const float* skip, float* o32, Planes op) {
+      ++n;
+      return nsac_groupnorm_nhwc(x, N, H, W, 128, G, w->gn_w[idx], w->gn_b[idx], w->gn_eps, relu, skip, fmt, o32, op.hi, op.lo, s.gn_ws,
+                                 s.gn_ws_bytes, stream);
+    };
+    // BasePixelDecoder.forward_features (camera_modules.py:335-348): res5 -> res4 -> res3, top-down
+    const Planes p5{const_cast<void*>(res5_hi), const_cast<void*>(res5_lo), 2048}, p4{const_cast<void*>(res4_hi), const_cast<void*>(res4_lo), 1024},
+        p3{const_cast<void*>(res3_hi), const_cast<void*>(res3_lo), 512};
+    NSAC_TRY(conv3(w->pd_layer_3, p5, N, H5, W5, 2048, NSAC_ACT_NONE, s.t5, none, fmt, P, stream, n));
+    NSAC_TRY(gn(s.t5, H5, W5, 0, 1, nullptr, s.y5, none));
+    NSAC_TRY(tc(w->pd_adapter_2, p4, N * H4 * W4, NSAC_ACT_NONE, s.t4, 128, none, fmt, P, stream, n));
+    NSAC_TRY(gn(s.t4, H4, W4, 1, 0, s.y5, nullptr, s.u4));
+    NSAC_TRY(conv3(w->pd_layer_2, s.u4, N, H4, W4, 128, NSAC_ACT_NONE, s.t4, none, fmt, P, stream, n));
+    NSAC_TRY(gn(s.t4, H4, W4, 2, 1, nullptr, s.y4, none));
+    NSAC_TRY(tc(w->pd_adapter_1, p3, N * H3 * W3, NSAC_ACT_NONE, s.t3, 128, none, fmt, P, stream, n));
+    NSAC_TRY(gn(s.t3, H3, W3, 3, 0, s.y4, nullptr, s.u3));
+    NSAC_TRY(conv3(w->pd_layer_1, s.u3, N, H3, W3, 128, NSAC_ACT_NONE, s.t3, none, fmt, P, stream, n));
+    NSAC_TRY(gn(s.t3, H3, W3, 4, 1, nullptr, nullptr, s.y3));
+    NSAC_TRY(conv3(w->pd_mask_features, s.y3, N, H3, W3, 128, NSAC_ACT_NONE, nullptr, s.xa, fmt, P, stream, n));
+    // convs_backbone (camera_head.py:78-91): conv-BN-LeakyReLU x2, pool, x2, pool, x2
+    int H = H3, W = W3;
+    Planes x = s.xa, y = s.xb;
+    for (int i = 0; i < 3; ++i) {
+      NSAC_TRY(conv3(w->cb[2 * i], x, N, H, W, 256, NSAC_ACT_LEAKY, nullptr, y, fmt, P, stream, n));
+      NSAC_TRY(conv3(w->cb[2 * i + 1], y, N, H, W, 256, NSAC_ACT_LEAKY, s.f, none, fmt, P, stream, n));
+      if (i < 2) {
+        NSAC_TRY(nsac_maxpool2_planes(s.f, N, H, W, 256, fmt, x.hi, x.lo, stream));
+        ++n;
+        H /= 2; W /= 2;
+      }
+    }
+    // correlation volume + softmax (:652, :1117-1133), then the two regression branches (:655-662)
+    const int HW = H * W, Cp = (HW + 63) / 64 * 64;
+    NSAC_TRY(nsac_corr_softmax(s.f, s.f + (size_t)B * HW * 256, B, H, W, 256, Cp, fmt, s.aff.hi, s.aff.lo, stream));
+    ++n;
+    NSAC_REQUIRE(w->ct0.K == 9 * Cp, "nsac_pixel_forward: correlation width %d does not match the packed ct0 weights (K = %d)", Cp, w->ct0.K);
+    NSAC_TRY(conv3(w->ct0, s.aff, B, H, W, Cp, NSAC_ACT_LEAKY, s.tc0, none, fmt, P, stream, n));          // [B*HW, 256] = trans | rots
+    for (int br = 0; br < 2; ++br) {
+      const nsac_tc_layer* L = br == 0 ? w->convs_trans : w->convs_rots;
+      NSAC_CUDA(cudaMemcpy2DAsync(s.ysl, 128 * 4, s.tc0 + br * 128, 256 * 4, 128 * 4, (size_t)B * HW, cudaMemcpyDeviceToDevice, cs));
+      const float* yin = s.ysl;
+      int h = H, ww = W;
+      for (int i = 0; i < 5; ++i) {
+        const int stride = (i % 2 == 0) ? 2 : 1;          // layers 1..5 of the branch: strides 2,1,2,1,2
+        const int ho = (h - 1) / stride + 1, wo = (ww - 1) / stride + 1;
+        NSAC_TRY(nsac_im2col3x3_planes(yin, B, h, ww, 128, stride, 1152, fmt, s.cols.hi, s.cols.lo, stream));
+        ++n;
+        float* yout = (i & 1) ? s.yb : s.ya;
+        NSAC_TRY(tc(L[i], s.cols, B * ho * wo, NSAC_ACT_LEAKY, yout, 128, none, fmt, P, stream, n));
+        yin = yout; h = ho; ww = wo;
+      }
+      NSAC_REQUIRE(h * ww * 128 == 768, "nsac_pixel_forward: regression branch ends at %dx%d, fc expects 2x3", h, ww);
+      float* feat = br == 0 ? (pix_tran_feat ? pix_tran_feat : s.feat_t) : (pix_rot_feat ? pix_rot_feat : s.feat_r);
+      NSAC_TRY(nsac_linear(yin, 768, br == 0 ? w->fc_trans_w : w->fc_rots_w, br == 0 ? w->fc_trans_b : w->fc_rots_b, 0, feat, 256, B, 256,
+                           768, NSAC_ACT_RELU, stream));
+      ++n;
+    }
+    float* ft = pix_tran_feat ? pix_tran_feat : s.feat_t;
+    float* fr = pix_rot_feat ? pix_rot_feat : s.feat_r;
+    NSAC_TRY(nsac_pose_heads(fr, ft, w->rots_w, w->rots_b, w->trans_w, w->trans_b, B, 256, init_rot, init_tran, stream));
+    ++n;
+  }
+  // w >= 0 per pair (the reference flips the whole batch by sample 0, :436-437); t + 1e-10 for the AIM embedding (:718)
+  NSAC_TRY(nsac_pose_canon(init_rot, init_tran, B, init_rot, s.teps, stream));
+  ++n;
+  // K2: AIM (:685-735) - layer 0 (K = 4 / 3) on the CUDA cores, the five 256-wide layers on the tensor-core engine
+  for (int br = 0; br < 2; ++br) {
+    const int K0 = br == 0 ? 4 : 3;
+    NSAC_TRY(nsac_linear(br == 0 ? init_rot : s.teps, K0, br == 0 ? w->rot_emb0_w : w->trans_emb0_w, br == 0 ? w->rot_emb0_b : w->trans_emb0_b,
+                         0, s.x32, 256, B, 256, K0, NSAC_ACT_RELU, stream));
+    NSAC_TRY(nsac_split16(s.x32, 256, B, 256, 1.0f, fmt, s.e0.hi, s.e0.lo, 256, stream));
+    n += 2;
+    NSAC_TRY(run_chain(br == 0 ? w->rot_emb : w->trans_emb, 5, s.e0, B, s.e1, s.e2, nullptr, 0, NSAC_ACT_RELU,
+                       br == 0 ? rot_feat0 : trans_feat0, 256, none, fmt, P, stream, n));
+  }
+  NSAC_TRY(nsac_pose_heads(rot_feat0, trans_feat0, w->rots_w, w->rots_b, w->trans_w, w->trans_b, B, 256, q0, t0, stream));
+  ++n;
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The whole head: K1 + K2 -> matcher -> refinement (PlaneCameraHead.inference_Joint)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+size_t head_stage_bytes(int B, int H3, int W3, int n1, int n2, int NQ) {
+  size_t m = nsac_pixel_workspace_bytes(B, H3 >= 4 ? H3 : 4, W3 >= 4 ? W3 : 4);
+  const size_t a = nsac_match_workspace_bytes(B, n1, n2), r = nsac_refine_workspace_bytes(B, NQ);
+  if (a > m) m = a;
+  if (r > m) m = r;
+  return m;
+}
+}  // namespace
+
+extern "C" size_t nsac_head_workspace_bytes(int B, int H3, int W3, int n1, int n2, int NQ) {
+  if (B <= 0 || n1 <= 0 || n2 <= 0 || NQ <= 0) return 0;
+  return 256 + head_stage_bytes(B, H3, W3, n1, n2, NQ);          // cam rows [B,7] in the first granules
+}
+
+extern "C" int nsac_head_forward(const nsac_head_weights* w, const void* res3_hi, const void* res3_lo, const void* res4_hi,
+                                 const void* res4_lo, const void* res5_hi, const void* res5_lo, int B, int H3, int W3,
+                                 const float* planes1, const float* planes2, const float* app1, const float* app2,
+                                 const int32_t* count1, const int32_t* count2, int n1, int n2, const int32_t* hyp_pairs, int H,
+                                 int NQ, float match_threshold, int out_cam_type, float* init_tran, float* init_rot, float* t0,
+                                 float* q0, float* rot_feat0, float* trans_feat0, float* log_scores_padded, float* assign,
+                                 float* pose, float* assign_pruned, float* geo_local, float* geo_global, float* sig,
+                                 int32_t* matched_num, int32_t* pair_idx, float* q_h, float* t_h, float* score_rot,
+                                 float* score_tran, int32_t* sel_idx, void* workspace, size_t workspace_bytes,
+                                 float* const* peer_rows, int num_peers, int row_offset, int* launches_out, void* stream) {
+  NSAC_REQUIRE(w && w->pixel && w->match && w->refine, "nsac_head_forward: null weights");
+  NSAC_REQUIRE(B > 0 && n1 > 0 && n2 > 0 && NQ > 0, "nsac_head_forward: bad sizes B=%d n1=%d n2=%d NQ=%d", B, n1, n2, NQ);
+  const size_t cam_bytes = ((size_t)B * 7 * 4 + 255) & ~size_t(255);
+  const size_t stage = head_stage_bytes(B, H3, W3, n1, n2, NQ);
+  NSAC_REQUIRE(workspace && workspace_bytes >= cam_bytes + stage && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_head_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", cam_bytes + stage, workspace_bytes);
+  float* cam = static_cast<float*>(workspace);
+  void* ws = static_cast<uint8_t*>(workspace) + cam_bytes;
+  int n = 0, k = 0;
+  NSAC_TRY(nsac_pixel_forward(w->pixel, res3_hi, res3_lo, res4_hi, res4_lo, res5_hi, res5_lo, B, H3, W3, init_tran, init_rot, nullptr,
+                              nullptr, t0, q0, rot_feat0, trans_feat0, ws, stage, &k, stream));
+  n += k;
+  NSAC_TRY(nsac_cam_rows(t0, q0, B, cam, stream));                 // matcher pose = the AIM-refined initial pose (:493)
+  ++n;
+  NSAC_TRY(nsac_match_forward(w->match, app1, app2, planes1, planes2, cam, count1, count2, match_threshold, B, n1, n2, log_scores_padded,
+                              assign, ws, stage, &k, stream));
+  n += k;
+  NSAC_TRY(nsac_refine_forward(w->refine, planes1, planes2, assign, hyp_pairs, H, t0, q0, rot_feat0, trans_feat0, B, n1, n2, NQ,
+                               out_cam_type, pose, assign_pruned, geo_local, geo_global, sig, matched_num, pair_idx, q_h, t_h, score_rot,
+                               score_tran, sel_idx, ws, stage, peer_rows, num_peers, row_offset, &k, stream));
+  n += k;
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}

@@ -749,3 +749,86 @@ def match_forward(weights, app1, app2, planes1, planes2, cam, threshold: float, 
     _lib.check(st, "nsac_match_forward")
     _count(n.value)
     return lsp, assign
+
+
+def pixel_forward(weights, res3, res4, res5, B: int, H3: int, W3: int, initial_pose=None):
+    """nsac_pixel_forward: K1 (pixel pose network on the stacked views' res3 / res4 / res5 planes) + w >= 0 canonicalisation +
+    K2 (AIM), one call.  `res*`: ops.Split NHWC planes of the 2B images, or all None with `initial_pose = (tran [B,3], rot [B,4])`
+    (the network is skipped).  -> dict(init_tran, init_rot, pix_tran_feat, pix_rot_feat, t0, q0, rot_feat0, trans_feat0)."""
+    L = _lib.lib()
+    if res5 is None:
+        t_in, q_in = initial_pose
+        dev = t_in.device
+        out = {"init_tran": _c(t_in, "initial tran").clone(), "init_rot": _c(q_in, "initial rot").clone(),
+               "pix_tran_feat": None, "pix_rot_feat": None}
+        assert out["init_tran"].shape == (B, 3) and out["init_rot"].shape == (B, 4)
+        planes = [None] * 6
+        H3 = W3 = 4
+    else:
+        dev = res5.hi.device
+        for r, c, hw in ((res3, 512, H3 * W3), (res4, 1024, H3 * W3 // 4), (res5, 2048, H3 * W3 // 16)):
+            assert r.hi.is_contiguous() and r.lo.is_contiguous() and tuple(r.hi.shape) == (2 * B * hw, c) and r.scale == 1.0, \
+                f"pixel_forward: expected contiguous planes [{2 * B * hw}, {c}], got {tuple(r.hi.shape)}"
+        out = {"init_tran": torch.empty(B, 3, device=dev), "init_rot": torch.empty(B, 4, device=dev),
+               "pix_tran_feat": torch.empty(B, 256, device=dev), "pix_rot_feat": torch.empty(B, 256, device=dev)}
+        planes = [_p(res3.hi), _p(res3.lo), _p(res4.hi), _p(res4.lo), _p(res5.hi), _p(res5.lo)]
+    out.update(t0=torch.empty(B, 3, device=dev), q0=torch.empty(B, 4, device=dev), rot_feat0=torch.empty(B, 256, device=dev),
+               trans_feat0=torch.empty(B, 256, device=dev))
+    nbytes = L.nsac_pixel_workspace_bytes(B, H3, W3)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_pixel_forward(C.byref(weights), *planes, B, H3, W3,
+                              *[_p(out[k]) for k in ("init_tran", "init_rot", "pix_tran_feat", "pix_rot_feat", "t0", "q0", "rot_feat0",
+                                                     "trans_feat0")], C.c_void_p(ws_ptr), nbytes, C.byref(n), _stream())
+    _lib.check(st, "nsac_pixel_forward")
+    _count(n.value)
+    return out
+
+
+def head_forward(pixel_w, match_w, refine_w, res3, res4, res5, B: int, H3: int, W3: int, planes1, planes2, app1, app2,
+                 num_queries: int, match_threshold: float, out_cam_type: str = "soft", count1=None, count2=None, hyp_pairs=None,
+                 initial_pose=None, want_scores: bool = True, exchange=None):
+    """nsac_head_forward: PlaneCameraHead.inference_Joint + MatchingHead in ONE C call (pixel pose network + AIM -> matcher ->
+    one-plane RANSAC refinement).  Arguments as in pixel_forward / match_forward / refine_forward; returns one dict with every
+    output tensor of the three stages."""
+    planes1, planes2, app1, app2 = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(app1, "app1"), _c(app2, "app2")
+    n1, n2, NQ, dev = planes1.shape[1], planes2.shape[1], num_queries, planes1.device
+    assert planes1.shape[0] == B and tuple(app1.shape) == (B, n1, 256) and tuple(app2.shape) == (B, n2, 256)
+    f = lambda *shape: torch.empty(*shape, device=dev)
+    i32 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.int32)
+    if res5 is None:
+        t_in, q_in = initial_pose
+        init_tran, init_rot = _c(t_in, "initial tran").clone(), _c(q_in, "initial rot").clone()
+        assert init_tran.shape == (B, 3) and init_rot.shape == (B, 4)
+        planes = [None] * 6
+        H3 = W3 = 0
+    else:
+        for r, c, hw in ((res3, 512, H3 * W3), (res4, 1024, H3 * W3 // 4), (res5, 2048, H3 * W3 // 16)):
+            assert r.hi.is_contiguous() and r.lo.is_contiguous() and tuple(r.hi.shape) == (2 * B * hw, c) and r.scale == 1.0, \
+                f"head_forward: expected contiguous planes [{2 * B * hw}, {c}], got {tuple(r.hi.shape)}"
+        init_tran, init_rot = f(B, 3), f(B, 4)
+        planes = [_p(res3.hi), _p(res3.lo), _p(res4.hi), _p(res4.lo), _p(res5.hi), _p(res5.lo)]
+    Hn = 0
+    if hyp_pairs is not None:
+        hyp_pairs = _c(hyp_pairs, "hyp_pairs", torch.int32)
+        Hn = hyp_pairs.shape[0]
+    if count1 is not None:
+        count1, count2 = _c(count1, "count1", torch.int32), _c(count2, "count2", torch.int32)
+    out = {"init_tran": init_tran, "init_rot": init_rot, "t0": f(B, 3), "q0": f(B, 4), "rot_feat0": f(B, 256), "trans_feat0": f(B, 256),
+           "log_scores_padded": f(B, n1 + 1, n2 + 1), "assign": f(B, n1, n2), "pose": f(B, 16), "assign_pruned": f(B, n1, n2),
+           "geo_local": f(B, NQ, 6), "geo_global": f(B, NQ, 6), "sig": f(B, NQ), "matched_num": i32(B), "pair_idx": i32(B, NQ, 2),
+           "q_h": f(B * NQ, 4), "t_h": f(B * NQ, 3), "score_rot": f(B, NQ + 1) if want_scores else None,
+           "score_tran": f(B, NQ + 1) if want_scores else None, "sel_idx": i32(B, 2)}
+    L = _lib.lib()
+    W = _lib.HeadWeights(C.pointer(pixel_w), C.pointer(match_w), C.pointer(refine_w))
+    nbytes = L.nsac_head_workspace_bytes(B, H3, W3, n1, n2, NQ)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_head_forward(C.byref(W), *planes, B, H3, W3, _p(planes1), _p(planes2), _p(app1), _p(app2), _p(count1), _p(count2), n1, n2,
+                             _p(hyp_pairs), Hn, NQ, float(match_threshold), CAM_TYPES[out_cam_type], *[_p(v) for v in out.values()],
+                             C.c_void_p(ws_ptr), nbytes, None if exchange is None else C.c_void_p(exchange.peer_ptrs_dev),
+                             0 if exchange is None else exchange.world, 0 if exchange is None else exchange.row_offset,
+                             C.byref(n), _stream())
+    _lib.check(st, "nsac_head_forward")
+    _count(n.value)
+    return out

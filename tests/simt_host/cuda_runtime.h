@@ -52,6 +52,11 @@ inline cudaError_t cudaMemcpyAsync(void* dst, const void* src, size_t n, cudaMem
   memcpy(dst, src, n);
   return cudaSuccess;
 }
+inline cudaError_t cudaMemcpy2DAsync(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height,
+                                     cudaMemcpyKind, cudaStream_t) {
+  for (size_t r = 0; r < height; ++r) memcpy(static_cast<char*>(dst) + r * dpitch, static_cast<const char*>(src) + r * spitch, width);
+  return cudaSuccess;
+}
 
 namespace simt {
 struct Block {

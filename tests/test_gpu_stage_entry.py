@@ -1,6 +1,7 @@
 """GPU: whole stages behind ONE C-ABI call each (csrc/forward.cu; the entries SURVEY.md §8b lists for a host that does not want to
 replicate the Python orchestration) — `nsac_match_forward` (MatchingHead: projection, 18 GNN layers, Sinkhorn, assignment) and
-`nsac_refine_forward` (the one-plane RANSAC refinement K6 .. K10).  The heads use them by default; NSAC_PY_STAGES=1 issues the
+`nsac_refine_forward` (the one-plane RANSAC refinement K6 .. K10), `nsac_pixel_forward` (pixel pose network + AIM) and their
+composition `nsac_head_forward` (= PlaneCameraHead.inference_Joint in one call).  The heads use them by default; NSAC_PY_STAGES=1 issues the
 same launches from Python.  Both must give identical bits on every output, for every
 selection rule, with an explicit hypothesis list, with an assignment override, and the entry must validate its arguments."""
 import ctypes
@@ -69,6 +70,30 @@ def test_stage_entry_with_hypothesis_list_and_override(monkeypatch):
     out = _both(monkeypatch, NQ, "soft", lambda head, match: head(None, None, b.planes1, b.planes2, b.app1, b.app2, matching_net=match,
                                                                  initial_pose=ip, assignment_override=ov))
     assert out["pro.matched_num"].cpu().tolist() == [P] * B
+
+
+def test_single_call_head_with_pixel_network(monkeypatch):
+    """From backbone feature maps (stage set S4): nsac_head_forward (K1 + K2 + matcher + refinement in one call) == the
+    per-kernel Python path, bit for bit, and the result is within 1e-4 of the oracle for every pair."""
+    dev = _gpu()
+    from nopesac_b200 import synthetic
+    from oracle import restate
+    from tests.test_gpu_parity import _check_against
+    NQ, P, B = 64, 8, 3
+    b = synthetic.make_batch(7400, B, P, with_features=True)
+    bd = b.to(dev)
+    out = _both(monkeypatch, NQ, "soft", lambda head, match: head(bd.feats1, bd.feats2, bd.planes1, bd.planes2, bd.app1, bd.app2,
+                                                                 matching_net=match))
+    head, match, sd, msd = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    assert head.use_stage_entry and match.use_stage_entry
+    cams, _, _, lsp, ass, pro = head(bd.feats1, bd.feats2, bd.planes1, bd.planes2, bd.app1, bd.app2, matching_net=match)
+    torch.cuda.synchronize()
+    assert torch.equal(pro["pose"], out["pro.pose"])
+    with torch.no_grad():
+        for i in range(B):
+            o = restate.inference_joint(sd, msd, {k: v[i:i + 1] for k, v in b.feats1.items()}, {k: v[i:i + 1] for k, v in b.feats2.items()},
+                                        b.planes1[i:i + 1], b.planes2[i:i + 1], b.app1[i:i + 1], b.app2[i:i + 1], num_queries=NQ)
+            _check_against(util.oracle_to_flat(o), cams, lsp, ass, pro, i, f"single-call pair {i}")
 
 
 def test_stage_entry_ragged_batch(monkeypatch):
