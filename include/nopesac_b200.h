@@ -293,6 +293,12 @@ int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, const void* w
                                int N, int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt,
                                float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
                                void* stream);
+/* 1x1 convolution with a stride of 1 or 2, no padding (weights [Cout, Cin]): the projection shortcut of res3.0 / res4.0 / res5.0
+ * reads every second pixel of every second row through the tensor map's traversal stride - no subsampled copy of the input. */
+int nsac_conv1x1_split_strided(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                               int N, int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt,
+                               float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                               void* stream);
 size_t nsac_plane_post_workspace_bytes(int B, int NQ, int H, int W);
 int nsac_plane_postprocess(const float* pred_logits, const float* pred_params, const float* mask_logits,
                            const float* query_feat, int B, int NQ, int C, int h, int w, int H, int W,
@@ -327,6 +333,11 @@ int nsac_add_relu_nhwc(const float* a, const float* b, size_t count, int fmt, fl
  *                              [N*Ho*Wo, 64] whose 7x7 window leaves the image; w_folded [64,147] (ky,kx,c) for normalised input
  *   nsac_im2col3x3_from_planes 3x3 / pad 1 / stride 1|2 im2col NHWC planes -> planes [N*Ho*Wo, 9*C] (16-byte copies) */
 int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream);
+/* Same plus 24 one-hot border-class columns (k = 147 .. 170; class = (row class, column class) of the output pixel, each of
+ * {first, second, interior, second-to-last, last}, index = 5 * row class + column class, skipping interior x interior): with the
+ * per-class padding correction sum_{taps outside the image} w * mean / std in rows 147 + idx of the weight matrix, the stem GEMM
+ * gives the zero-padded convolution of the NORMALISED image for every pixel and nsac_stem_border_fix is not needed. H, W >= 9. */
+int nsac_stem_im2col_u8_cls(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream);
 int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, const float* bias, int N, int H, int W,
                          const float* mean3_host, const float* std3_host, float* out, void* stream);
 int nsac_im2col3x3_from_planes(const void* hi, const void* lo, int N, int H, int W, int C, int stride, void* out_hi,

@@ -93,6 +93,9 @@ _SIGNATURES = {
     "nsac_conv3x3_split_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
                                              C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "nsac_conv1x1_split_strided": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_float_p, C.c_int, C.c_int, C.c_int,
+                                             C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, c_float_p, C.c_int,
+                                             C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "nsac_nchw_to_planes": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsac_groupnorm_ws_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "nsac_groupnorm_nhwc": (C.c_int, [c_float_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, c_float_p, C.c_float,
@@ -148,6 +151,7 @@ _SIGNATURES = {
                                          C.c_void_p]),
     "nsac_add_relu_nhwc": (C.c_int, [c_float_p, c_float_p, C.c_size_t, C.c_int, c_float_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nsac_stem_im2col_u8": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "nsac_stem_im2col_u8_cls": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "nsac_stem_border_fix": (C.c_int, [C.c_void_p, c_float_p, c_float_p, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                        C.POINTER(C.c_float), c_float_p, C.c_void_p]),
     "nsac_im2col3x3_from_planes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p,

@@ -148,17 +148,45 @@ class ResNet50Backbone(nn.Module):
         Ho, Wo = (H - 1) // blk.stride + 1, (W - 1) // blk.stride + 1
         if hasattr(blk, "shortcut"):
             ws, bs = pk[key + ".shortcut"]
-            src = xp if blk.stride == 1 else ops.subsample2_planes(xp, N, H, W)[0]
-            _, sc = ops.gemm_tc(src, ws, bs, ops.ACT_NONE, P, want_f32=False, want_split=True)
+            if blk.stride == 1:
+                _, sc = ops.gemm_tc(xp, ws, bs, ops.ACT_NONE, P, want_f32=False, want_split=True)
+            else:       # strided projection: the TMA gather skips the pixels a stride-2 1x1 convolution never reads
+                sc = ops.conv1x1_tc_strided(xp, N, H, W, ws, bs, ops.ACT_NONE, P, stride=blk.stride)
         else:
             sc = xp
         _, out = ops.gemm_tc(y2p, w3, b3, ops.ACT_RELU, P, want_f32=False, want_split=True, residual=sc)
         return out, Ho, Wo
 
+    def _stem_u8_weights(self, pk, H, W):
+        """Stem weights for raw uint8 pixels of an H x W image: [64, 171] = w / std (147 taps) followed by the 24 border-class
+        corrections sum_{taps outside the image} w * mean / std (fp64 on the host, then hi/lo planes), + the folded bias."""
+        key = f"stem.u8.{H}x{W}"
+        if key not in pk:
+            with torch.no_grad():
+                wf, bf = self.stem.conv1.folded()                                   # [64, 147] in (ky, kx, c) order
+                dev = wf.device
+                istd = (1.0 / torch.tensor(self.pixel_std, dtype=torch.float64, device=dev)).repeat(49)
+                mean = torch.tensor(self.pixel_mean, dtype=torch.float64, device=dev).repeat(49)
+                w8 = wf.double() * istd
+                wm = (w8 * mean).view(64, 7, 7, 3)
+                ext = torch.zeros(64, 171, dtype=torch.float64, device=dev)
+                ext[:, :147] = w8
+                for idx, oob in ops.stem_border_classes(H, W):
+                    ext[:, 147 + idx] = (wm * oob.to(dev)[None, :, :, None]).sum(dim=(1, 2, 3))
+                pk[key] = (ops.split_weight(ext.float().contiguous()), (bf.double() - (w8 * mean).sum(1)).float().contiguous())
+        return pk[key]
+
     def _stem(self, pk, images):
         N = images.shape[0]
-        if images.dtype == torch.uint8:
-            # raw pixels are exact in fp16: one plane, normalisation folded into the weights; borders recomputed exactly
+        if images.dtype == torch.uint8 and min(images.shape[2:]) >= 9:
+            # raw pixels are exact in fp16: one plane, normalisation folded into the weights.  The reference zero-pads the
+            # NORMALISED image, i.e. an out-of-image tap contributes 0 instead of w * (0 - mean) / std: 24 one-hot border-class
+            # columns of the im2col matrix select the matching correction row of the weight matrix (_stem_u8_weights)
+            cols, H, W = ops.stem_im2col_u8(images, border_classes=True)
+            ws, bs = self._stem_u8_weights(pk, images.shape[2], images.shape[3])
+            x, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU, self.tc_passes)
+        elif images.dtype == torch.uint8:
+            # tiny images (border classes overlap): plain im2col + exact fp32 recomputation of the border pixels
             cols, H, W = ops.stem_im2col_u8(images)
             ws, bs = pk["stem.u8"]
             x, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU, self.tc_passes)

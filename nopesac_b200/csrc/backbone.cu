@@ -127,7 +127,7 @@ add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, size_t
 constexpr int STEM_U8_MAXW = 1024;     // widest image row whose staging buffer (7 rows x 3 channels x (W + 6) fp16) fits 48 KB
 constexpr int STEM_U8_THREADS = 256, STEM_U8_LANES = 10;   // 24 k-chunks (8 k each) x 10 pixel lanes (16 threads only help staging)
 __global__ void __launch_bounds__(STEM_U8_THREADS)
-stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int Wo, uint16_t* __restrict__ out) {
+stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int Wo, int border_cols, uint16_t* __restrict__ out) {
   extern __shared__ uint16_t rows[];                   // [7][3][Wp] fp16 bit patterns of the pixel values, x shifted by +3, 0 outside the image
   const int n = blockIdx.x / Ho, yo = blockIdx.x % Ho, Wp = W + 6;
   auto h16 = [](uint32_t v) { return __half_as_ushort(__float2half_rn((float)v)); };     // exact for 0..255
@@ -167,11 +167,20 @@ stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int
     }
   }
   const size_t row0 = ((size_t)n * Ho + yo) * Wo;
+  // border-class indicator columns (border_cols): column STEM_K + idx holds 1.0 for the pixels of border class idx, so that the
+  // GEMM adds that class's padding correction (a row of the weight matrix) — see nsac_stem_im2col_u8_cls
+  const int rowc = yo == 0 ? 0 : yo == 1 ? 1 : yo == Ho - 2 ? 3 : yo == Ho - 1 ? 4 : 2;
   for (int xo = xl < STEM_U8_LANES ? xl : Wo; xo < Wo; xo += STEM_U8_LANES) {
+    int ind = -1;
+    if (border_cols) {
+      const int colc = xo == 0 ? 0 : xo == 1 ? 1 : xo == Wo - 2 ? 3 : xo == Wo - 1 ? 4 : 2, cls = rowc * 5 + colc;
+      if (cls != 12) ind = STEM_K + (cls < 12 ? cls : cls - 1) - kc * 8;      // position inside this thread's chunk, if 0..7
+    }
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t v0 = koff[2 * j] >= 0 ? rows[koff[2 * j] + 2 * xo] : 0u, v1 = koff[2 * j + 1] >= 0 ? rows[koff[2 * j + 1] + 2 * xo] : 0u;
+      const uint32_t v0 = koff[2 * j] >= 0 ? rows[koff[2 * j] + 2 * xo] : (ind == 2 * j ? 0x3C00u : 0u);
+      const uint32_t v1 = koff[2 * j + 1] >= 0 ? rows[koff[2 * j + 1] + 2 * xo] : (ind == 2 * j + 1 ? 0x3C00u : 0u);
       w[j] = v0 | (v1 << 16);
     }
     *reinterpret_cast<uint4*>(out + (row0 + xo) * STEM_KP + kc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
@@ -314,7 +323,7 @@ extern "C" int nsac_add_relu_nhwc(const float* a, const float* b, size_t count, 
   return NSAC_OK;
 }
 
-extern "C" int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream) {
+static int stem_im2col_u8_impl(const uint8_t* img, int N, int H, int W, int border_cols, void* out_hi, void* stream) {
   NSAC_REQUIRE(img && out_hi, "nsac_stem_im2col_u8: null pointer");
   NSAC_REQUIRE(N >= 0 && H >= 7 && W >= 7 && W <= STEM_U8_MAXW, "nsac_stem_im2col_u8: bad shape N=%d H=%d W=%d", N, H, W);
   if (N == 0) return NSAC_OK;
@@ -322,9 +331,23 @@ extern "C" int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void
   NSAC_REQUIRE((reinterpret_cast<uintptr_t>(img) & 3) == 0 && (reinterpret_cast<uintptr_t>(out_hi) & 15) == 0,
                "nsac_stem_im2col_u8: image must be 4-byte aligned, output plane 16-byte aligned");
   const size_t smem = (size_t)21 * (W + 6) * sizeof(uint16_t);
-  stem_im2col_u8_kernel<<<N * Ho, STEM_U8_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(img, H, W, Ho, Wo, static_cast<uint16_t*>(out_hi));
+  stem_im2col_u8_kernel<<<N * Ho, STEM_U8_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(img, H, W, Ho, Wo, border_cols,
+                                                                                              static_cast<uint16_t*>(out_hi));
   NSAC_CHECK_LAUNCH("nsac_stem_im2col_u8");
   return NSAC_OK;
+}
+
+extern "C" int nsac_stem_im2col_u8(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream) {
+  return stem_im2col_u8_impl(img, N, H, W, 0, out_hi, stream);
+}
+
+// Same, plus 24 one-hot BORDER-CLASS columns (k = 147 .. 170): class = (row class, column class) of the output pixel, each of
+// {first, second, interior, second-to-last, last}; interior x interior has no column.  The caller puts, into row 147 + idx of
+// the weight matrix, the sum of w * mean / std over the taps that fall outside the image for that class: the GEMM then yields
+// the zero-padded convolution of the NORMALISED image for every pixel, and no border pass is needed.
+extern "C" int nsac_stem_im2col_u8_cls(const uint8_t* img, int N, int H, int W, void* out_hi, void* stream) {
+  NSAC_REQUIRE(H >= 9 && W >= 9, "nsac_stem_im2col_u8_cls: image %dx%d too small for distinct border classes (use nsac_stem_border_fix)", H, W);
+  return stem_im2col_u8_impl(img, N, H, W, 1, out_hi, stream);
 }
 
 extern "C" int nsac_stem_border_fix(const uint8_t* img, const float* w_folded, const float* bias, int N, int H, int W,

@@ -456,7 +456,7 @@ size_t head_stage_bytes(int B, int H3, int W3, int n1, int n2, int NQ) {
 
 extern "C" size_t nsac_head_workspace_bytes(int B, int H3, int W3, int n1, int n2, int NQ) {
   if (B <= 0 || n1 <= 0 || n2 <= 0 || NQ <= 0) return 0;
-  return 256 + head_stage_bytes(B, H3, W3, n1, n2, NQ);          // cam rows [B,7] in the first granules
+  return (((size_t)B * 7 * 4 + 255) & ~size_t(255)) + head_stage_bytes(B, H3, W3, n1, n2, NQ);      // cam rows [B,7] first
 }
 
 extern "C" int nsac_head_forward(const nsac_head_weights* w, const void* res3_hi, const void* res3_lo, const void* res4_hi,

@@ -187,7 +187,8 @@ struct GemmParams {
   int bias_group_rows;
   int M, N, K, act, passes, fmt;
   // implicit-GEMM 3x3 / stride 1 / pad 1 convolution over NHWC planes (conv_taps == 9), else plain GEMM
-  int conv_taps, H, W, BW, BH, cblocks, tiles_x, tiles_y;      // H, W: OUTPUT map
+  int conv_taps, H, W, BW, BH, cblocks, tiles_x, tiles_y;      // H, W: OUTPUT map; conv_taps: 9 = 3x3 (pad 1), 1 = 1x1 (conv mode only)
+  int conv;                 // 1 = implicit-GEMM convolution (A gathered from NHWC planes by 4-D TMA), 0 = plain GEMM
   int cstride;              // convolution stride (1 or 2): tap (dy, dx) of output pixel (y, x) reads input (cstride*y + dy, cstride*x + dx)
   float out_scale;          // multiplies the accumulator before bias (undoes the power-of-two weight pre-scale)
   float* out_f32;
@@ -439,7 +440,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool conv = p.conv_taps == 9;
+  const bool conv = p.conv != 0;
   const int tiles_per_img = p.tiles_x * p.tiles_y;     // conv: an M tile is a BW x BH pixel patch of one image
   const int tiles_m = conv ? (p.M / (p.H * p.W)) * tiles_per_img : (p.M + BLOCK_M - 1) / BLOCK_M;
   const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -501,7 +502,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
             // k-block = (filter tap, 64-channel block): the A tile is the input patch shifted by the tap; TMA
             // zero-fills the out-of-image halo (padding = 1), so no im2col matrix ever exists
             const int tap = kb / p.cblocks, cb = kb - tap * p.cblocks;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            const int dy = p.conv_taps == 9 ? tap / 3 - 1 : 0, dx = p.conv_taps == 9 ? tap % 3 - 1 : 0;
             const int xi = x0 * p.cstride + dx, yi = y0 * p.cstride + dy;     // (strided maps: the tensor map's traversal stride picks every cstride-th pixel)
             tma_load_4d(st, &map_a_hi, &full[stage], cb * BLOCK_K, xi, yi, img);
             if (load_alo) tma_load_4d(st + C::A_BYTES, &map_a_lo, &full[stage], cb * BLOCK_K, xi, yi, img);
@@ -805,7 +806,7 @@ extern "C" int nsac_debug_gemm_trace(void* buf) {
 
 static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
                         int N, int Hin, int Win, int Cin, int Cout, int stride, int act, int passes, int fmt, float out_scale,
-                        float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream) {
+                        float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void* stream, int taps = 9) {
   NSAC_REQUIRE(stride == 1 || stride == 2, "nsac_conv3x3_split: stride must be 1 or 2");
   const int H = (Hin - 1) / stride + 1, W = (Win - 1) / stride + 1;      // output map (3x3, pad 1)
   NSAC_REQUIRE(x_hi && w_hi, "nsac_conv3x3_split: null operand");
@@ -823,7 +824,7 @@ static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, co
   if (W % 16 == 0 && W > 64) { BW = 16; BH = 8; }          // e.g. 80-wide maps: 16 x 8 patches fill all 128 rows
   NSAC_REQUIRE(BW * stride <= 256 && BH * stride <= 256 && BW * BH <= 128, "nsac_conv3x3_split: cannot tile a %d x %d map", H, W);
   const bool bf = fmt == NSAC_SPLIT_BF16;
-  const int K = 9 * Cin;
+  const int K = taps * Cin;
   CUtensorMap mah, mal, mwh, mwl;
   const bool ok = make_map_nhwc(&mah, x_hi, N, Hin, Win, Cin, BW, BH, bf, stride) &&
                   make_map_nhwc(&mal, x_lo ? x_lo : x_hi, N, Hin, Win, Cin, BW, BH, bf, stride) &&
@@ -838,7 +839,7 @@ static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, co
   p.fmt = fmt; p.out_scale = out_scale; p.out_f32 = out_f32; p.ldo = ldo;
   p.out_hi = static_cast<uint16_t*>(out_hi); p.out_lo = static_cast<uint16_t*>(out_lo); p.ld_split = ld_split;
   p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0; p.row_bias = nullptr;
-  p.conv_taps = 9; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
+  p.conv = 1; p.conv_taps = taps; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
   if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
   return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
@@ -860,6 +861,16 @@ extern "C" int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, co
                                           void* stream) {
   return conv3x3_impl(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, stride, act, passes, fmt, out_scale, out_f32, ldo, out_hi,
                       out_lo, ld_split, stream);
+}
+
+// 1x1 convolution with a stride (no padding): the projection shortcut of res3.0 / res4.0 / res5.0 reads every second pixel of
+// every second row straight through the tensor map's traversal stride - no subsampled copy of the input.
+extern "C" int nsac_conv1x1_split_strided(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
+                                          int N, int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt,
+                                          float out_scale, float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split,
+                                          void* stream) {
+  return conv3x3_impl(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, stride, act, passes, fmt, out_scale, out_f32, ldo, out_hi,
+                      out_lo, ld_split, stream, 1);
 }
 
 static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
@@ -906,7 +917,7 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
   p.res_hi = static_cast<const uint16_t*>(res_hi); p.res_lo = static_cast<const uint16_t*>(res_lo); p.ld_res = ld_res;
   p.a_lo_zero = a_lo == nullptr ? 1 : 0;
   p.row_bias = row_bias;
-  p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1; p.cstride = 1;
+  p.conv = 0; p.conv_taps = 1; p.H = p.W = p.BW = p.BH = p.cblocks = p.tiles_x = p.tiles_y = 1; p.cstride = 1;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   if (res_hi) {
     // residual epilogue: 64-wide tiles, residual tiles TMA-prefetched and turned in place into the output tile, TMA store

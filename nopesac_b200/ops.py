@@ -251,6 +251,22 @@ def conv3x3_tc(x: Split, N: int, H: int, W: int, w: Split, bias=None, act: int =
     return out_f32, out_split
 
 
+def conv1x1_tc_strided(x: Split, N: int, H: int, W: int, w: Split, bias=None, act: int = ACT_NONE, passes: int = 3, stride: int = 2):
+    """1x1 convolution with a stride (no padding) on NHWC planes [N*H*W, Cin] -> planes [N*Ho*Wo, Cout]: the strided projection
+    shortcut of a bottleneck block, gathered by TMA (no subsampled copy)."""
+    Cin, Cout = x.hi.shape[1], w.rows
+    assert x.hi.is_contiguous() and x.lo.is_contiguous() and x.rows == N * H * W and Cin % 64 == 0
+    assert w.hi.is_contiguous() and w.hi.shape[1] == Cin and x.fmt == w.fmt and stride in (1, 2)
+    rows = N * ((H - 1) // stride + 1) * ((W - 1) // stride + 1)
+    out = Split.empty(rows, Cout, x.hi.device, x.fmt)
+    st = _lib.lib().nsac_conv1x1_split_strided(_p(x.hi), _p(x.lo), _p(w.hi), _p(w.lo), _p(bias), N, H, W, Cin, Cout, stride, act, passes,
+                                               x.fmt, 1.0 / (x.scale * w.scale), None, 0, _p(out.hi), _p(out.lo), out.hi.stride(0),
+                                               _stream())
+    _lib.check(st, "nsac_conv1x1_split_strided")
+    _count()
+    return out
+
+
 def groupnorm_nhwc(x: torch.Tensor, N: int, H: int, W: int, gamma, beta, groups: int = 32, eps: float = 1e-5,
                    relu: bool = False, skip: Optional[torch.Tensor] = None, want_f32: bool = True, want_split: bool = False,
                    fmt: int = SPLIT_F16):
@@ -324,18 +340,41 @@ def stem_im2col_planes(img: torch.Tensor, mean, std, fmt: int = SPLIT_F16):
     return out, Ho, Wo
 
 
-def stem_im2col_u8(img: torch.Tensor):
+def stem_im2col_u8(img: torch.Tensor, border_classes: bool = False):
     """[N,3,H,W] uint8 -> (Split with ONE fp16 plane [N*Ho*Wo, 192] of raw pixel values (K = 147 in (ky,kx,c) order, `lo` is
-    None: exact), Ho, Wo).  Out-of-image taps are 0 — see stem_border_fix."""
+    None: exact), Ho, Wo).  Out-of-image taps are 0 — see stem_border_fix, or `border_classes=True`: 24 one-hot border-class
+    columns follow (K = 171), see stem_border_classes / nsac_stem_im2col_u8_cls."""
     img = _c(img, "img", torch.uint8)
     N, Cc, H, W = img.shape
     assert Cc == 3
     Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
     hi = torch.empty(N * Ho * Wo, 192, device=img.device, dtype=torch.float16)
-    st = _lib.lib().nsac_stem_im2col_u8(_p(img), N, H, W, _p(hi), _stream())
+    fn = _lib.lib().nsac_stem_im2col_u8_cls if border_classes else _lib.lib().nsac_stem_im2col_u8
+    st = fn(_p(img), N, H, W, _p(hi), _stream())
     _lib.check(st, "nsac_stem_im2col_u8")
     _count()
-    return Split(hi, None, 147), Ho, Wo
+    return Split(hi, None, 171 if border_classes else 147), Ho, Wo
+
+
+def stem_border_classes(H: int, W: int):
+    """The 24 border classes of nsac_stem_im2col_u8_cls for an H x W image: list of (idx, oob [7,7] bool) — which taps of the 7x7 /
+    stride 2 / pad 3 window fall outside the image for output pixels of class idx."""
+    Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+    rep = lambda n: (0, 1, 2, n - 2, n - 1)                       # a representative output coordinate per class
+    out = []
+    for rc, yo in enumerate(rep(Ho)):
+        for cc, xo in enumerate(rep(Wo)):
+            cls = rc * 5 + cc
+            if cls == 12:
+                continue
+            oob = torch.zeros(7, 7, dtype=torch.bool)
+            for k in range(7):
+                if not 0 <= 2 * yo + k - 3 < H:
+                    oob[k, :] = True
+                if not 0 <= 2 * xo + k - 3 < W:
+                    oob[:, k] = True
+            out.append((cls if cls < 12 else cls - 1, oob))
+    return out
 
 
 def stem_border_fix(img: torch.Tensor, w_folded: torch.Tensor, bias: torch.Tensor, mean, std, out: torch.Tensor):

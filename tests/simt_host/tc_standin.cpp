@@ -134,14 +134,14 @@ extern "C" int nsac_gemm_split_residual(const void* a_hi, const void* a_lo, int 
 // 3x3 / stride 1 / pad 1 convolution over NHWC planes as the same hi/lo-plane product (weights [Cout, 9*Cin], (ky,kx,cin) order)
 static int conv3x3_standin(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int N,
                            int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt, float out_scale, float* out_f32,
-                           int ldo, void* out_hi, void* out_lo, int ld_split) {
+                           int ldo, void* out_hi, void* out_lo, int ld_split, int taps = 9) {
   const int Ho = (H - 1) / stride + 1, Wo = (W - 1) / stride + 1;
   if (!x_hi || !w_hi || passes < 1 || passes > 4 || (passes >= 2 && !x_lo) || (passes >= 3 && !w_lo) || Cin % 64 != 0 ||
       (!out_f32 && !out_hi) || (out_hi && !out_lo)) {
     nsac_set_error("nsac_conv3x3_split (stand-in): bad arguments");
     return NSAC_ERR_ARG;
   }
-  const int K = 9 * Cin;
+  const int K = taps * Cin;
   const uint16_t *xh = static_cast<const uint16_t*>(x_hi), *xl = static_cast<const uint16_t*>(x_lo);
   const uint16_t *wh = static_cast<const uint16_t*>(w_hi), *wl = static_cast<const uint16_t*>(w_lo);
   std::vector<double> WH((size_t)Cout * K), WL((size_t)Cout * K, 0.0);
@@ -154,8 +154,8 @@ static int conv3x3_standin(const void* x_hi, const void* x_lo, const void* w_hi,
 #pragma omp parallel for firstprivate(AH, AL)
   for (int m = 0; m < N * Ho * Wo; ++m) {
     const int n = m / (Ho * Wo), y = (m / Wo) % Ho, x = m % Wo;
-    for (int t = 0; t < 9; ++t) {
-      const int yy = y * stride + t / 3 - 1, xx = x * stride + t % 3 - 1;
+    for (int t = 0; t < taps; ++t) {
+      const int yy = y * stride + (taps == 9 ? t / 3 - 1 : 0), xx = x * stride + (taps == 9 ? t % 3 - 1 : 0);
       const bool in = yy >= 0 && yy < H && xx >= 0 && xx < W;
       const size_t src = (((size_t)n * H + yy) * W + xx) * Cin;
       for (int c = 0; c < Cin; ++c) {
@@ -191,6 +191,17 @@ extern "C" int nsac_conv3x3_split_strided(const void* x_hi, const void* x_lo, co
     return NSAC_ERR_ARG;
   }
   return conv3x3_standin(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, stride, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo, ld_split);
+}
+
+extern "C" int nsac_conv1x1_split_strided(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias, int N,
+                                          int H, int W, int Cin, int Cout, int stride, int act, int passes, int fmt, float out_scale,
+                                          float* out_f32, int ldo, void* out_hi, void* out_lo, int ld_split, void*) {
+  if (stride != 1 && stride != 2) {
+    nsac_set_error("nsac_conv1x1_split_strided (stand-in): stride must be 1 or 2");
+    return NSAC_ERR_ARG;
+  }
+  return conv3x3_standin(x_hi, x_lo, w_hi, w_lo, bias, N, H, W, Cin, Cout, stride, act, passes, fmt, out_scale, out_f32, ldo, out_hi, out_lo,
+                         ld_split, 1);
 }
 
 // ---- scoring on the "tensor pipe": the exact CUDA-core twin does the work

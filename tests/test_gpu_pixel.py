@@ -65,6 +65,29 @@ def test_conv3x3_stride2_implicit_gemm(N, C, H, W, Cout):
     assert util.maxdiff(out2, out) <= 3e-6 * scale
 
 
+@pytest.mark.parametrize("N,C,H,W,Cout", [(2, 256, 120, 160, 512), (3, 64, 31, 45, 64), (2, 1024, 30, 40, 2048), (1, 128, 9, 7, 96)])
+def test_conv1x1_stride2_implicit_gemm(N, C, H, W, Cout):
+    """nsac_conv1x1_split_strided (the strided projection shortcut of res3.0 / res4.0 / res5.0, gathered through the tensor map's
+    traversal stride) == F.conv2d(kernel 1, stride 2, no padding), even and odd map sizes; == subsample + plain GEMM bit for bit."""
+    dev = _dev()
+    from nopesac_b200 import ops
+    g = torch.Generator().manual_seed(11 * N + C + H)
+    x = torch.randn(N, C, H, W, generator=g)
+    w = torch.randn(Cout, C, generator=g) / C ** 0.5
+    b = torch.randn(Cout, generator=g)
+    ref = F.conv2d(x.double(), w.double()[:, :, None, None], b.double(), stride=2)
+    xp = ops.nchw_to_planes(x.to(dev))
+    wp = ops.split_weight(w.contiguous().to(dev))
+    sp = ops.conv1x1_tc_strided(xp, N, H, W, wp, b.to(dev), ops.ACT_NONE, stride=2)
+    torch.cuda.synchronize()
+    scale = float(ref.abs().max())
+    assert sp.rows == N * ref.shape[2] * ref.shape[3]
+    assert util.maxdiff(sp.float(), _nhwc(ref)) <= 2 ** -18 * scale, util.maxdiff(sp.float(), _nhwc(ref)) / scale
+    sub = ops.subsample2_planes(xp, N, H, W)[0]
+    _, sp2 = ops.gemm_tc(sub, wp, b.to(dev), ops.ACT_NONE, want_f32=False, want_split=True)
+    assert torch.equal(sp.hi, sp2.hi) and torch.equal(sp.lo, sp2.lo)
+
+
 def test_groupnorm_upsample_add():
     dev = _dev()
     from nopesac_b200 import ops
