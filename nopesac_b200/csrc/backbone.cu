@@ -167,23 +167,26 @@ stem_im2col_u8_kernel(const uint8_t* __restrict__ img, int H, int W, int Ho, int
     }
   }
   const size_t row0 = ((size_t)n * Ho + yo) * Wo;
-  // border-class indicator columns (border_cols): column STEM_K + idx holds 1.0 for the pixels of border class idx, so that the
-  // GEMM adds that class's padding correction (a row of the weight matrix) — see nsac_stem_im2col_u8_cls
-  const int rowc = yo == 0 ? 0 : yo == 1 ? 1 : yo == Ho - 2 ? 3 : yo == Ho - 1 ? 4 : 2;
   for (int xo = xl < STEM_U8_LANES ? xl : Wo; xo < Wo; xo += STEM_U8_LANES) {
-    int ind = -1;
-    if (border_cols) {
-      const int colc = xo == 0 ? 0 : xo == 1 ? 1 : xo == Wo - 2 ? 3 : xo == Wo - 1 ? 4 : 2, cls = rowc * 5 + colc;
-      if (cls != 12) ind = STEM_K + (cls < 12 ? cls : cls - 1) - kc * 8;      // position inside this thread's chunk, if 0..7
-    }
     uint32_t w[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const uint32_t v0 = koff[2 * j] >= 0 ? rows[koff[2 * j] + 2 * xo] : (ind == 2 * j ? 0x3C00u : 0u);
-      const uint32_t v1 = koff[2 * j + 1] >= 0 ? rows[koff[2 * j + 1] + 2 * xo] : (ind == 2 * j + 1 ? 0x3C00u : 0u);
+      const uint32_t v0 = koff[2 * j] >= 0 ? rows[koff[2 * j] + 2 * xo] : 0u, v1 = koff[2 * j + 1] >= 0 ? rows[koff[2 * j + 1] + 2 * xo] : 0u;
       w[j] = v0 | (v1 << 16);
     }
     *reinterpret_cast<uint4*>(out + (row0 + xo) * STEM_KP + kc * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  if (border_cols) {
+    // the one-hot class column of the row's border pixels (all pixels of the two first / last rows, four pixels of the others),
+    // patched in after the zero padding above has been written by this CTA
+    __syncthreads();
+    const int rowc = yo == 0 ? 0 : yo == 1 ? 1 : yo == Ho - 2 ? 3 : yo == Ho - 1 ? 4 : 2;
+    const int count = rowc != 2 ? Wo : 4;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+      const int xo = rowc != 2 ? i : (i < 2 ? i : Wo - 4 + i);
+      const int colc = xo == 0 ? 0 : xo == 1 ? 1 : xo == Wo - 2 ? 3 : xo == Wo - 1 ? 4 : 2, cls = rowc * 5 + colc;
+      if (cls != 12) out[(row0 + xo) * STEM_KP + STEM_K + (cls < 12 ? cls : cls - 1)] = 0x3C00;      // 1.0 in fp16
+    }
   }
 }
 

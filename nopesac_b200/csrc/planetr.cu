@@ -78,8 +78,9 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
                        float* __restrict__ out, int ldo, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int ld_split,
                        int L, int S, int SP, int H) {
   extern __shared__ float sm[];
-  float* Kt = sm;                       // [32][SP]   K transposed (zero beyond S)
-  float* Vs = Kt + AT_D * SP;           // [S][32]
+  const int SK = SP + 1;                // odd row stride: the transposing stores below hit 32 different banks
+  float* Kt = sm;                       // [32][SK]   K transposed (zero beyond S)
+  float* Vs = Kt + AT_D * SP + AT_D;    // [S][32]    (16-byte aligned: 32 * (SP + 1) floats before it)
   float* Qt = Vs + (size_t)SP * AT_D;   // [32][64]   this block's queries, scaled, transposed
   float* Pw = Qt + AT_D * AT_QB;        // [8 warps][SP][8]  softmax numerators of the warp's 8 queries
   const int b = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -91,7 +92,7 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
       kv = k[((size_t)b * S + s) * ldkv + h * AT_D + d];
       vv = v[((size_t)b * S + s) * ldkv + h * AT_D + d];
     }
-    Kt[d * SP + s] = kv;
+    Kt[d * SK + s] = kv;
     Vs[idx] = vv;
   }
   float* Pmine = Pw + (size_t)warp * SP * 8;
@@ -118,7 +119,7 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
 #pragma unroll
       for (int j = 0; j < AT_KPL; ++j) {
         if (j < nj) {
-          const float kk = Kt[d * SP + lane + 32 * j];
+          const float kk = Kt[d * SK + lane + 32 * j];
 #pragma unroll
           for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(qv[i], kk, acc[i][j]);
         }
@@ -153,38 +154,30 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
       }
     }
     __syncwarp();
-    // ---- O = P V: lane = (query qi of the 8, group dg of 8 channels)
-    const int qi = lane & 7, dg = lane >> 3;
-    float o8[8];
+    // ---- O = P V: lane = channel d, all 8 queries of the warp per lane.  Per key: one conflict-free row read of V (32 lanes x 4 B)
+    // + two broadcast float4 of P = 3 shared-memory wavefronts for 8 FMAs (the (query, 8-channel group) mapping needed 9)
+    float o[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o8[e] = 0.f;
+    for (int i = 0; i < 8; ++i) o[i] = 0.f;
+#pragma unroll 4
     for (int s = 0; s < S; ++s) {
-      const float pv = Pmine[s * 8 + qi];
-      const float4 va = *reinterpret_cast<const float4*>(Vs + s * AT_D + dg * 8);
-      const float4 vb = *reinterpret_cast<const float4*>(Vs + s * AT_D + dg * 8 + 4);
-      o8[0] = fmaf(pv, va.x, o8[0]); o8[1] = fmaf(pv, va.y, o8[1]); o8[2] = fmaf(pv, va.z, o8[2]); o8[3] = fmaf(pv, va.w, o8[3]);
-      o8[4] = fmaf(pv, vb.x, o8[4]); o8[5] = fmaf(pv, vb.y, o8[5]); o8[6] = fmaf(pv, vb.z, o8[6]); o8[7] = fmaf(pv, vb.w, o8[7]);
+      const float vv = Vs[s * AT_D + lane];
+      const float4 pa = *reinterpret_cast<const float4*>(Pmine + s * 8), pb = *reinterpret_cast<const float4*>(Pmine + s * 8 + 4);
+      o[0] = fmaf(pa.x, vv, o[0]); o[1] = fmaf(pa.y, vv, o[1]); o[2] = fmaf(pa.z, vv, o[2]); o[3] = fmaf(pa.w, vv, o[3]);
+      o[4] = fmaf(pb.x, vv, o[4]); o[5] = fmaf(pb.y, vv, o[5]); o[6] = fmaf(pb.z, vv, o[6]); o[7] = fmaf(pb.w, vv, o[7]);
     }
-    float inv = inv_sum[0];
 #pragma unroll
-    for (int i = 1; i < 8; ++i) inv = qi == i ? inv_sum[i] : inv;
-    const int qrow = q0 + warp * 8 + qi;
-    if (qrow < L) {
-      const size_t base = ((size_t)b * L + qrow);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) o8[e] *= inv;
-      if (out) {
-        float* o = out + base * ldo + h * AT_D + dg * 8;
-        *reinterpret_cast<float4*>(o) = make_float4(o8[0], o8[1], o8[2], o8[3]);
-        *reinterpret_cast<float4*>(o + 4) = make_float4(o8[4], o8[5], o8[6], o8[7]);
-      }
-      if (out_hi) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
+    for (int i = 0; i < 8; ++i) {
+      const int qrow = q0 + warp * 8 + i;
+      if (qrow < L) {
+        const size_t base = ((size_t)b * L + qrow);
+        const float val = o[i] * inv_sum[i];
+        if (out) out[base * ldo + h * AT_D + lane] = val;
+        if (out_hi) {
           uint16_t hh, ll;
-          pt_split16(o8[e], hh, ll);
-          out_hi[base * ld_split + h * AT_D + dg * 8 + e] = hh;
-          out_lo[base * ld_split + h * AT_D + dg * 8 + e] = ll;
+          pt_split16(val, hh, ll);
+          out_hi[base * ld_split + h * AT_D + lane] = hh;
+          out_lo[base * ld_split + h * AT_D + lane] = ll;
         }
       }
     }
@@ -254,7 +247,7 @@ extern "C" int nsac_attention_tiled(const float* q, int ldq, const float* k, con
   NSAC_REQUIRE(ldq % 4 == 0 && ldkv >= H * D && (!out || ldo % 4 == 0), "nsac_attention_tiled: row strides must be multiples of 4");
   if (B == 0 || L == 0) return NSAC_OK;
   const int SP = (S + 31) / 32 * 32;
-  const size_t smem = ((size_t)AT_D * SP * 2 + AT_D * AT_QB + (size_t)(AT_THREADS / 32) * SP * 8) * sizeof(float);
+  const size_t smem = ((size_t)AT_D * SP * 2 + AT_D + AT_D * AT_QB + (size_t)(AT_THREADS / 32) * SP * 8) * sizeof(float);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     NSAC_CUDA(cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -84,6 +84,7 @@ def test_single_call_head_with_pixel_network(monkeypatch):
     bd = b.to(dev)
     out = _both(monkeypatch, NQ, "soft", lambda head, match: head(bd.feats1, bd.feats2, bd.planes1, bd.planes2, bd.app1, bd.app2,
                                                                  matching_net=match))
+    monkeypatch.delenv("NSAC_PY_STAGES", raising=False)
     head, match, sd, msd = util.build_cuda_heads(NQ, "soft", 0.2, dev)
     assert head.use_stage_entry and match.use_stage_entry
     cams, _, _, lsp, ass, pro = head(bd.feats1, bd.feats2, bd.planes1, bd.planes2, bd.app1, bd.app2, matching_net=match)
