@@ -70,6 +70,7 @@ struct Cfg {
   static constexpr int TILE_BUF_BYTES = 2 * RES_PLANE_BYTES;               // hi + lo
   static constexpr int RES_BYTES = 2 * TILE_BUF_BYTES;                     // double-buffered
   static constexpr int OUT_STAGE_BYTES = RES ? 0 : EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
+  static constexpr int THREADS = NUM_THREADS + (RES ? 32 : 0);             // RES: + one warp that owns the TMA stores of the output tiles
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
@@ -419,7 +420,7 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], i
 }
 
 template <int BLOCK_N, int FMT, bool RES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__((Cfg<BLOCK_N, RES>::THREADS), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                    const __grid_constant__ CUtensorMap map_r_hi, const __grid_constant__ CUtensorMap map_r_lo,
@@ -436,7 +437,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
   uint64_t* res_full = tmem_empty + 2;         // [2]
   uint64_t* res_empty = res_full + 2;          // [2]
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_empty + 2);
+  uint64_t* tile_ready = res_empty + 2;        // [2]  RES: the epilogue warps have turned tile buffer b into the output tile
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tile_ready + 2);
   uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -453,7 +455,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&res_full[a], 1); mbar_init(&res_empty[a], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&res_full[a], 1); mbar_init(&res_empty[a], 1); mbar_init(&tile_ready[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -555,6 +557,25 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
       }
     }
+  } else if (RES && warp == 2 + EPI_WARPS) {
+    // ===================================================================== TMA store warp (residual epilogue only)
+    // Takes everything after the epilogue math off the epilogue warps' critical path: they arrive on tile_ready[b] and go on to the
+    // next tile; this thread stores the finished tile, waits until the store has READ the buffer and hands it back to the producer.
+    if (lane == 0) {
+      uint32_t ctr = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ctr) {
+        const uint32_t b = ctr & 1;
+        mbar_wait(&tile_ready[b], (ctr >> 1) & 1);         // (the writers issued fence.proxy.async before arriving)
+        uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
+        const int m0 = (tile / tiles_n) * BLOCK_M, nt = (tile % tiles_n) * BLOCK_N;
+        tma_store_2d(tb, &map_o_hi, nt, m0);               // rows >= M / columns >= N are clipped by the tensor map
+        tma_store_2d(tb + C::RES_PLANE_BYTES, &map_o_lo, nt, m0);
+        tma_store_commit();
+        tma_store_wait_read<0>();
+        mbar_arrive(&res_empty[b]);                         // the producer may load the residual of tile t + 2 into it
+      }
+      tma_store_wait_all();                                 // the last stores must have left shared memory before the CTA exits
+    }
   } else {
     // ===================================================================== epilogue warps 2..9
     // TMEM lane quadrant = warp % 4 (hardware rule); the two warps of a quadrant split the tile's columns in halves
@@ -632,17 +653,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
         if (FMT == NSAC_SPLIT_F16 && m0 + quad * 32 + lane < p.M) note_overflow(ovf);
         fence_proxy_async_smem();                        // generic-proxy writes -> visible to the TMA (async proxy) store
-        asm volatile("bar.sync 1, %0;" ::"n"(EPI_WARPS * 32) : "memory");       // the whole tile is written
-        if (warp == 2 && lane == 0) {
-          const int nt = (tile % tiles_n) * BLOCK_N;
-          tma_store_2d(tb, &map_o_hi, nt, m0);           // rows >= M / columns >= N are clipped by the tensor map
-          tma_store_2d(tb + C::RES_PLANE_BYTES, &map_o_lo, nt, m0);
-          tma_store_commit();
-          // wait until the store has READ the buffer (a fraction of a microsecond; only this thread stalls) and hand it straight
-          // back: the producer then loads the residual of tile t + 2 into it while tile t + 1's epilogue runs on the other buffer
-          tma_store_wait_read<0>();
-          mbar_arrive(&res_empty[b]);
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tile_ready[b]);      // 8 arrivals = the whole tile is written: the store warp takes over
         ++res_ctr;
         continue;
       }
@@ -688,9 +700,6 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           }
         }
       }
-    }
-    if (RES) {      // the TMA stores of the last tiles must have left shared memory before the CTA exits
-      if (warp == 2 && lane == 0) tma_store_wait_all();
     }
   }
   if (threadIdx.x == 64) GEMM_TRACE(6);
@@ -772,9 +781,9 @@ int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap&
   const int tiles = tiles_m * nsac_cdiv(p.N, BLOCK_N);
   const int grid = tiles < sm_count() ? tiles : sm_count();
   if (p.fmt == NSAC_SPLIT_BF16)
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_BF16, RES><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
   else
-    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES><<<grid, NUM_THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
+    gemm_bf16x3_kernel<BLOCK_N, NSAC_SPLIT_F16, RES><<<grid, C::THREADS, C::SMEM_BYTES, s>>>(ah, al, wh, wl, rh, rl, oh, ol, p);
   NSAC_CHECK_LAUNCH("nsac_gemm_split");
   return NSAC_OK;
 }
