@@ -127,3 +127,34 @@ def test_max_score_selection_is_exact_through_the_head():
             if o["matched_num"] > 1:
                 assert pro["sel_idx"][i].cpu().tolist() == [o["ref"]["sel_rot"], o["ref"]["sel_tran"]], (NQ, i)
             _check_against(util.oracle_to_flat(o), cams, lsp, ass, pro, i, f"max-score NQ={NQ} pair {i}")
+
+
+def test_scoring_roofline_configuration_b512_nq256():
+    """The exact configuration `roofline` in the bench line is measured on (B = 512 pairs, m = NQ = 256: 276.8 MB of algorithmic
+    traffic): tensor-core path vs the exact-fp32 CUDA-core twin on ALL 512 pairs (1e-4), two calls give identical bytes,
+    scores are a softmax over the 257 hypotheses of every pair (sum = 1), result rows carry m = 256 and unit quaternions."""
+    dev = _gpu()
+    from nopesac_b200 import ops
+    B, NQ = 512, 256
+    head, _, _, _ = util.build_cuda_heads(NQ, "soft", 0.2, dev)
+    pk = head.prepare_tc()
+    g = torch.Generator(device=dev).manual_seed(512)
+    rnd = lambda *s: torch.randn(*s, device=dev, generator=g)
+    geo = rnd(B, NQ, 6)
+    qh = torch.nn.functional.normalize(rnd(B, NQ, 4), dim=-1)
+    th, q0, t0 = rnd(B, NQ, 3) * 0.3, torch.nn.functional.normalize(rnd(B, 4), dim=-1), rnd(B, 3) * 0.3
+    fr, ft, fr0, ft0 = rnd(B, NQ, 256) * 0.3, rnd(B, NQ, 256) * 0.3, rnd(B, 256) * 0.3, rnd(B, 256) * 0.3
+    mnum = torch.full((B,), NQ, device=dev, dtype=torch.int32)
+    call = lambda precision: ops.score_aggregate(geo, qh, th, q0, t0, fr, ft, fr0, ft0, mnum, pk["normal_score_proj"], pk["param_score_proj"],
+                                                 head.rots.weight, head.rots.bias, head.trans.weight, head.trans.bias, out_cam_type="soft",
+                                                 precision=precision, pack=pk["score_pack"], vecs_host=pk["score_vecs_host"])
+    a, b, b2 = call("fp32"), call("fp16"), call("fp16")
+    torch.cuda.synchronize()
+    for k in ("pose", "score_rot", "score_tran"):
+        assert torch.equal(b[k], b2[k]), f"{k}: two calls differ"
+    assert util.maxdiff(a["score_rot"], b["score_rot"]) <= 1e-4 and util.maxdiff(a["score_tran"], b["score_tran"]) <= 1e-4
+    lin = [0, 1, 2, 7, 8, 9, 10, 11, 12, 13]
+    assert util.maxdiff(a["pose"][:, lin], b["pose"][:, lin]) <= 1e-4
+    assert util.maxdiff(b["score_rot"].sum(1), torch.ones(B)) <= 1e-5 and util.maxdiff(b["score_tran"].sum(1), torch.ones(B)) <= 1e-5
+    assert torch.equal(b["pose"][:, 14], mnum.float())
+    assert util.maxdiff(b["pose"][:, 3:7].norm(dim=-1), torch.ones(B)) <= 1e-5

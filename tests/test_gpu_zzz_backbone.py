@@ -104,3 +104,49 @@ def test_rgb_to_camera_head():
         for key, ok in (("camera_init", "camera_init"), ("camera_initRec", "camera_initRec"), ("camera", "camera")):
             assert util.maxdiff(want[0][key]["tran"][i], o[ok][0][0]) <= util.ABS_TOL, (key, i, util.maxdiff(want[0][key]["tran"][i], o[ok][0][0]))
             assert util.maxdiff(want[0][key]["rot"][i], o[ok][1][0]) <= util.ABS_TOL, (key, i, util.maxdiff(want[0][key]["rot"][i], o[ok][1][0]))
+
+
+def test_s5_full_size_properties():
+    """Size-independent properties of the headline configuration (BASELINE configs[1]: 16 planes x 256 hypotheses, NQ = 256, from
+    uint8 RGB) that need no oracle at full size:
+      * determinism — two runs of the same batch give identical bytes (atomics-free reductions, fixed summation orders);
+      * batch invariance — pairs are independent: a pair computed alone, in a batch of 6, or at another position of a permuted
+        batch has the same result rows (1e-6: tiles are per image / per pair, so the arithmetic of a row does not depend on its
+        neighbours), with identical assignment matrices and matched counts;
+      * the result rows are well formed: unit quaternions, matched_num = 256, finite."""
+    dev = _gpu()
+    from nopesac_b200 import config, meta_arch, synthetic
+    NQ, P, B = 256, 16, 6
+    model = meta_arch.PlaneTR_NopeSAC(config.inference_cfg(NQ), with_backbone=True)
+    sd, msd = util.make_weights(NQ)
+    model.camera_head_list[0].load_state_dict(sd)
+    model.matching_head.load_state_dict(msd)
+    shapes = {k: tuple(v.shape) for k, v in model.backbone.state_dict().items()}
+    model.backbone.load_state_dict(synthetic.make_backbone_weights(shapes, seed=8))
+    model = model.to(dev)
+    hp = synthetic.all_pairs_hypotheses(P, NQ).to(dev, torch.int32)
+    b = synthetic.make_batch(9000, B, P).to(dev)
+    images = synthetic.make_images(9000, 2 * B).to(dev)
+
+    def run(idx):
+        idx = torch.as_tensor(idx, device=dev)
+        img = torch.cat([images[idx], images[B + idx]])
+        out = model.inference_from_images(img, None, b.planes1[idx], b.planes2[idx], b.app1[idx], b.app2[idx], hyp_pairs=hp)
+        torch.cuda.synchronize()
+        return out[5]["pose"].clone(), out[4]["pred_assignment"].clone(), out[5]["matched_num"].clone(), out[0]["camera_init"]["rot"].clone()
+
+    pose, ass, m, q_init = run(list(range(B)))
+    pose2, ass2, m2, _ = run(list(range(B)))
+    assert torch.equal(pose, pose2) and torch.equal(ass, ass2) and torch.equal(m, m2), "two runs of the same batch differ"
+    assert torch.isfinite(pose).all() and m.cpu().tolist() == [NQ] * B
+    for cols in (slice(3, 7), slice(10, 14)):
+        assert util.maxdiff(pose[:, cols].norm(dim=-1), torch.ones(B)) <= 1e-5
+    assert bool((q_init[:, 0] >= 0).all())
+    perm = [4, 0, 5, 2, 1, 3]
+    pose_p, ass_p, m_p, _ = run(perm)
+    assert util.maxdiff(pose_p, pose[perm]) <= 1e-6, util.maxdiff(pose_p, pose[perm])
+    assert torch.equal(ass_p, ass[perm]) and torch.equal(m_p, m[perm])
+    for i in (0, 3):
+        pose_1, ass_1, m_1, _ = run([i])
+        assert util.maxdiff(pose_1, pose[i:i + 1]) <= 1e-6, (i, util.maxdiff(pose_1, pose[i:i + 1]))
+        assert torch.equal(ass_1, ass[i:i + 1]) and torch.equal(m_1, m[i:i + 1])
