@@ -6,7 +6,8 @@
 //                            `with_pos_embed` adds of the DETR layers (transformer.py:170-185, 284-311) in one pass per row
 //   attention_tiled_kernel   softmax(Q K^T / sqrt(32)) V for sequences that do not fit one warp's shared-memory slice
 //                            (300 context tokens): one CTA per (image, head), K^T / V of the head staged once in shared
-//                            memory, 64-query blocks, register-tiled fp32 (8 queries x 10 keys per lane), exact expf softmax
+//                            memory, 64-query blocks, register-tiled fp32 (8 queries x 5 keys per lane, two warps per query
+//                            group), exact expf softmax
 //   upsample2x_relu_add_kernel  out = relu(bilinear_2x(a)) + b (align_corners = False) on NHWC maps: the top-down path of
 //                            planeTR_head.py:240-252 with the 1x1 convolution + BatchNorm moved BEFORE the upsampling (both
 //                            are linear / affine per pixel, so conv(up(x)) == up(conv(x)): 4x fewer GEMM rows)
@@ -72,7 +73,12 @@ row_op_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ y,
 }
 
 // ------------------------------------------------------------------------------------------------ attention
-constexpr int AT_D = 32, AT_QB = 64, AT_THREADS = 256, AT_KPL = 10;        // keys per lane: S <= 320
+// One CTA per (image, head): K^T / V of the head staged once in shared memory, then 64-query blocks.  16 warps: warp = (query
+// group g of 8 queries, key half kh) - the two warps of a group split the keys (5 of the 10 key slots per lane each), exchange
+// their row maxima / sums through shared memory, and split the P V sum by key range as well.  (One warp per group - 8 warps
+// per SM at this shared-memory footprint - left the FMA pipe half idle.)
+constexpr int AT_D = 32, AT_QB = 64, AT_THREADS = 512, AT_KPL = 10, AT_KH = AT_KPL / 2;        // keys per lane: S <= 320
+constexpr int AT_GROUPS = AT_QB / 8;
 __global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __restrict__ k, const float* __restrict__ v, int ldkv,
                        float* __restrict__ out, int ldo, uint16_t* __restrict__ out_hi, uint16_t* __restrict__ out_lo, int ld_split,
@@ -82,8 +88,12 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
   float* Kt = sm;                       // [32][SK]   K transposed (zero beyond S)
   float* Vs = Kt + AT_D * SP + AT_D;    // [S][32]    (16-byte aligned: 32 * (SP + 1) floats before it)
   float* Qt = Vs + (size_t)SP * AT_D;   // [32][64]   this block's queries, scaled, transposed
-  float* Pw = Qt + AT_D * AT_QB;        // [8 warps][SP][8]  softmax numerators of the warp's 8 queries
+  float* Pw = Qt + AT_D * AT_QB;        // [8 groups][SP][8]  softmax numerators of the group's 8 queries
+  float* Xm = Pw + (size_t)AT_GROUPS * SP * 8;      // [2 key halves][8 groups][8]  row maxima of each half
+  float* Xs = Xm + 2 * AT_QB;                       // [2][8][8]                   row sums of each half
+  float* Ox = Xs + 2 * AT_QB;                       // [8 groups][8][32]           P V partial of the second key half
   const int b = blockIdx.x / H, h = blockIdx.x % H, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = warp & (AT_GROUPS - 1), kh = warp / AT_GROUPS;
   const float scale = 0.17677669529663687f;  // 1/sqrt(32)
   for (int idx = tid; idx < AT_D * SP; idx += AT_THREADS) {       // idx = s * 32 + d: coalesced 128-byte rows
     const int s = idx >> 5, d = idx & 31;
@@ -95,93 +105,117 @@ attention_tiled_kernel(const float* __restrict__ q, int ldq, const float* __rest
     Kt[d * SK + s] = kv;
     Vs[idx] = vv;
   }
-  float* Pmine = Pw + (size_t)warp * SP * 8;
+  float* Pmine = Pw + (size_t)g * SP * 8;
+  const int nj = SP >> 5, j0 = kh * AT_KH;                      // this warp's key slots: j0 .. j0 + 4 (keys lane + 32 j)
+  const int s_mid = S < 32 * AT_KH ? S : 32 * AT_KH;            // P V: keys [0, s_mid) on kh = 0, [s_mid, S) on kh = 1
   for (int q0 = 0; q0 < L; q0 += AT_QB) {
-    __syncthreads();                    // K / V staged (first block); every warp is done with the previous Qt
+    __syncthreads();                    // K / V staged (first block); every warp is done with the previous Qt / Xm / Xs / Ox
     for (int idx = tid; idx < AT_QB * AT_D; idx += AT_THREADS) {
       const int qq = idx >> 5, d = idx & 31;
       Qt[d * AT_QB + qq] = q0 + qq < L ? q[((size_t)b * L + q0 + qq) * ldq + h * AT_D + d] * scale : 0.f;
     }
     __syncthreads();
-    if (q0 + warp * 8 >= L) continue;   // (warp-uniform; the barriers above are reached by every warp of the next iteration)
-    // ---- scores of the warp's 8 queries against keys lane, lane + 32, ...
-    float acc[8][AT_KPL];
+    const bool active = q0 + g * 8 < L;   // warp-uniform; inactive warps only keep the barriers below company
+    // ---- scores of the group's 8 queries against this warp's keys
+    float acc[8][AT_KH];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < AT_KPL; ++j) acc[i][j] = 0.f;
-    const int nj = SP >> 5;
+      for (int j = 0; j < AT_KH; ++j) acc[i][j] = 0.f;
+    if (active) {
 #pragma unroll 4
-    for (int d = 0; d < AT_D; ++d) {
-      const float4 qa = *reinterpret_cast<const float4*>(Qt + d * AT_QB + warp * 8);
-      const float4 qb = *reinterpret_cast<const float4*>(Qt + d * AT_QB + warp * 8 + 4);
-      const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+      for (int d = 0; d < AT_D; ++d) {
+        const float4 qa = *reinterpret_cast<const float4*>(Qt + d * AT_QB + g * 8);
+        const float4 qb = *reinterpret_cast<const float4*>(Qt + d * AT_QB + g * 8 + 4);
+        const float qv[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
 #pragma unroll
-      for (int j = 0; j < AT_KPL; ++j) {
-        if (j < nj) {
-          const float kk = Kt[d * SK + lane + 32 * j];
+        for (int j = 0; j < AT_KH; ++j) {
+          if (j0 + j < nj) {
+            const float kk = Kt[d * SK + lane + 32 * (j0 + j)];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(qv[i], kk, acc[i][j]);
+            for (int i = 0; i < 8; ++i) acc[i][j] = fmaf(qv[i], kk, acc[i][j]);
+          }
         }
       }
+      // row maxima over this warp's keys
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < AT_KH; ++j)
+          if (j0 + j < nj && lane + 32 * (j0 + j) < S) mx = fmaxf(mx, acc[i][j]);
+        mx = warp_max(mx);
+        if (lane == 0) Xm[(kh * AT_GROUPS + g) * 8 + i] = mx;
+      }
     }
-    // ---- softmax numerators (exact expf, max-subtracted) into the warp's P buffer, row sums in registers
+    __syncthreads();
     float inv_sum[8];
+    if (active) {
+      // ---- softmax numerators (exact expf, subtracted maximum = maximum over ALL keys) into the group's P buffer
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float mx = -INFINITY;
+      for (int i = 0; i < 8; ++i) {
+        const float mx = fmaxf(Xm[g * 8 + i], Xm[(AT_GROUPS + g) * 8 + i]);
+        float sum = 0.f;
 #pragma unroll
-      for (int j = 0; j < AT_KPL; ++j)
-        if (j < nj && lane + 32 * j < S) mx = fmaxf(mx, acc[i][j]);
-      mx = warp_max(mx);
-      float sum = 0.f;
+        for (int j = 0; j < AT_KH; ++j) {
+          if (j0 + j < nj) {
+            const float e = lane + 32 * (j0 + j) < S ? expf(acc[i][j] - mx) : 0.f;
+            acc[i][j] = e;
+            sum += e;
+          }
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) Xs[(kh * AT_GROUPS + g) * 8 + i] = sum;
+      }
 #pragma unroll
-      for (int j = 0; j < AT_KPL; ++j) {
-        if (j < nj) {
-          const float e = lane + 32 * j < S ? expf(acc[i][j] - mx) : 0.f;
-          acc[i][j] = e;
-          sum += e;
+      for (int j = 0; j < AT_KH; ++j) {
+        if (j0 + j < nj) {
+          float* dst = Pmine + (size_t)(lane + 32 * (j0 + j)) * 8;
+          *reinterpret_cast<float4*>(dst) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
+          *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
         }
       }
-      inv_sum[i] = 1.f / warp_sum(sum);
     }
-#pragma unroll
-    for (int j = 0; j < AT_KPL; ++j) {
-      if (j < nj) {
-        float* dst = Pmine + (size_t)(lane + 32 * j) * 8;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[0][j], acc[1][j], acc[2][j], acc[3][j]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[4][j], acc[5][j], acc[6][j], acc[7][j]);
-      }
-    }
-    __syncwarp();
-    // ---- O = P V: lane = channel d, all 8 queries of the warp per lane.  Per key: one conflict-free row read of V (32 lanes x 4 B)
-    // + two broadcast float4 of P = 3 shared-memory wavefronts for 8 FMAs (the (query, 8-channel group) mapping needed 9)
+    __syncthreads();
+    // ---- O = P V: lane = channel d, all 8 queries of the group per lane; this warp sums over its half of the keys.  Per key:
+    // one conflict-free row read of V (32 lanes x 4 B) + two broadcast float4 of P = 3 shared-memory wavefronts for 8 FMAs
     float o[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i] = 0.f;
-#pragma unroll 4
-    for (int s = 0; s < S; ++s) {
-      const float vv = Vs[s * AT_D + lane];
-      const float4 pa = *reinterpret_cast<const float4*>(Pmine + s * 8), pb = *reinterpret_cast<const float4*>(Pmine + s * 8 + 4);
-      o[0] = fmaf(pa.x, vv, o[0]); o[1] = fmaf(pa.y, vv, o[1]); o[2] = fmaf(pa.z, vv, o[2]); o[3] = fmaf(pa.w, vv, o[3]);
-      o[4] = fmaf(pb.x, vv, o[4]); o[5] = fmaf(pb.y, vv, o[5]); o[6] = fmaf(pb.z, vv, o[6]); o[7] = fmaf(pb.w, vv, o[7]);
-    }
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int qrow = q0 + warp * 8 + i;
-      if (qrow < L) {
-        const size_t base = ((size_t)b * L + qrow);
-        const float val = o[i] * inv_sum[i];
-        if (out) out[base * ldo + h * AT_D + lane] = val;
-        if (out_hi) {
-          uint16_t hh, ll;
-          pt_split16(val, hh, ll);
-          out_hi[base * ld_split + h * AT_D + lane] = hh;
-          out_lo[base * ld_split + h * AT_D + lane] = ll;
+      for (int i = 0; i < 8; ++i) inv_sum[i] = 1.f / (Xs[g * 8 + i] + Xs[(AT_GROUPS + g) * 8 + i]);
+      const int s_begin = kh == 0 ? 0 : s_mid, s_end = kh == 0 ? s_mid : S;
+#pragma unroll 4
+      for (int s = s_begin; s < s_end; ++s) {
+        const float vv = Vs[s * AT_D + lane];
+        const float4 pa = *reinterpret_cast<const float4*>(Pmine + s * 8), pb = *reinterpret_cast<const float4*>(Pmine + s * 8 + 4);
+        o[0] = fmaf(pa.x, vv, o[0]); o[1] = fmaf(pa.y, vv, o[1]); o[2] = fmaf(pa.z, vv, o[2]); o[3] = fmaf(pa.w, vv, o[3]);
+        o[4] = fmaf(pb.x, vv, o[4]); o[5] = fmaf(pb.y, vv, o[5]); o[6] = fmaf(pb.z, vv, o[6]); o[7] = fmaf(pb.w, vv, o[7]);
+      }
+      if (kh == 1) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) Ox[(g * 8 + i) * AT_D + lane] = o[i];
+      }
+    }
+    __syncthreads();
+    if (active && kh == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int qrow = q0 + g * 8 + i;
+        if (qrow < L) {
+          const size_t base = ((size_t)b * L + qrow);
+          const float val = (o[i] + Ox[(g * 8 + i) * AT_D + lane]) * inv_sum[i];
+          if (out) out[base * ldo + h * AT_D + lane] = val;
+          if (out_hi) {
+            uint16_t hh, ll;
+            pt_split16(val, hh, ll);
+            out_hi[base * ld_split + h * AT_D + lane] = hh;
+            out_lo[base * ld_split + h * AT_D + lane] = ll;
+          }
         }
       }
     }
-    __syncwarp();
   }
 }
 
@@ -247,7 +281,7 @@ extern "C" int nsac_attention_tiled(const float* q, int ldq, const float* k, con
   NSAC_REQUIRE(ldq % 4 == 0 && ldkv >= H * D && (!out || ldo % 4 == 0), "nsac_attention_tiled: row strides must be multiples of 4");
   if (B == 0 || L == 0) return NSAC_OK;
   const int SP = (S + 31) / 32 * 32;
-  const size_t smem = ((size_t)AT_D * SP * 2 + AT_D + AT_D * AT_QB + (size_t)(AT_THREADS / 32) * SP * 8) * sizeof(float);
+  const size_t smem = ((size_t)AT_D * SP * 2 + AT_D + AT_D * AT_QB + (size_t)AT_GROUPS * SP * 8 + 4 * AT_QB + AT_QB * AT_D) * sizeof(float);
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     NSAC_CUDA(cudaFuncSetAttribute(attention_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
