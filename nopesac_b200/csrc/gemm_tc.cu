@@ -54,13 +54,14 @@ constexpr uint32_t SPIN_LIMIT = 1u << 24;  // suspended waits of up to ~1 us eac
 
 constexpr int CHUNK_KB = 4;                 // K-blocks (x64 elements) accumulated inside the tensor core per chunk
 
-template <int BLOCK_N, bool RES = false>
+template <int BLOCK_N, int RES = 0>      // RES: 0 = plain epilogue; residual epilogue with 1 = 3 operand stages + 2 tile buffers, 2 = 2 + 4
 struct Cfg {
   // RES (residual epilogue, 64-wide tiles only): two tile buffers [128 x 64] x (hi, lo) = 2 x 32 KB.  The residual tile is
   // TMA-prefetched into one of them while the tile's MMAs run, the epilogue turns it IN PLACE into the output tile, and a TMA
   // store writes it out asynchronously - no per-warp staging buffers, no latency-exposed global loads in the epilogue.
   static_assert(!RES || BLOCK_N == 64, "the residual epilogue uses 64-wide tiles");
-  static constexpr int STAGES = RES ? 3 : (BLOCK_N == 64 ? 4 : 3);       // 48 KB / 64 KB per stage
+  static constexpr int STAGES = RES == 2 ? 2 : (RES == 1 ? 3 : (BLOCK_N == 64 ? 4 : 3));       // 48 KB / 64 KB per stage
+  static constexpr int RES_BUFS = RES == 2 ? 4 : (RES == 1 ? 2 : 0);    // tile buffers: residual prefetch that many tiles ahead, stores drain behind
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
   static constexpr int W_BYTES = BLOCK_N * BLOCK_K * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
@@ -68,7 +69,7 @@ struct Cfg {
   static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
   static constexpr int RES_PLANE_BYTES = RES ? BLOCK_M * 128 : 0;          // [128 rows x 64 columns] of one plane, 128-byte swizzled rows
   static constexpr int TILE_BUF_BYTES = 2 * RES_PLANE_BYTES;               // hi + lo
-  static constexpr int RES_BYTES = 2 * TILE_BUF_BYTES;                     // double-buffered
+  static constexpr int RES_BYTES = RES_BUFS * TILE_BUF_BYTES;
   static constexpr int OUT_STAGE_BYTES = RES ? 0 : EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
   static constexpr int THREADS = NUM_THREADS + (RES ? 32 : 0);             // RES: + one warp that owns the TMA stores of the output tiles
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
@@ -419,7 +420,7 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], i
   }
 }
 
-template <int BLOCK_N, int FMT, bool RES>
+template <int BLOCK_N, int FMT, int RES>
 __global__ void __launch_bounds__((Cfg<BLOCK_N, RES>::THREADS), 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -435,10 +436,11 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
   uint64_t* empty = bars + C::STAGES;          // [STAGES]
   uint64_t* tmem_full = bars + 2 * C::STAGES;  // [2]
   uint64_t* tmem_empty = tmem_full + 2;        // [2]
-  uint64_t* res_full = tmem_empty + 2;         // [2]
-  uint64_t* res_empty = res_full + 2;          // [2]
-  uint64_t* tile_ready = res_empty + 2;        // [2]  RES: the epilogue warps have turned tile buffer b into the output tile
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tile_ready + 2);
+  constexpr int RB = C::RES_BUFS > 0 ? C::RES_BUFS : 1;
+  uint64_t* res_full = tmem_empty + 2;         // [RB]
+  uint64_t* res_empty = res_full + RB;         // [RB]
+  uint64_t* tile_ready = res_empty + RB;       // [RB]  RES: the epilogue warps have turned tile buffer b into the output tile
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tile_ready + RB);
   uint8_t* out_stage = smem + C::STAGES * C::STAGE_BYTES + C::RES_BYTES + 256;      // [EPI_WARPS][4 KB]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -455,7 +457,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&map_w_hi)) : "memory");
     for (int s = 0; s < C::STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], EPI_WARPS); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&res_full[a], 1); mbar_init(&res_empty[a], 1); mbar_init(&tile_ready[a], EPI_WARPS); }
+    for (int a = 0; a < RB; ++a) { mbar_init(&res_full[a], 1); mbar_init(&res_empty[a], 1); mbar_init(&tile_ready[a], EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation (whole warp), address lands in shared memory
@@ -488,7 +490,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           x0 = (t2 % p.tiles_x) * p.BW;
         }
         if (RES) {     // this tile's residual [128 x 64] x (hi, lo) into tile buffer tile_ctr & 1: lands while the MMAs run
-          const uint32_t b = tile_ctr & 1, use = tile_ctr >> 1;
+          const uint32_t b = tile_ctr % RB, use = tile_ctr / RB;
           mbar_wait(&res_empty[b], (use & 1) ^ 1);            // the TMA store of the buffer's previous tile has read it out
           mbar_expect_tx(&res_full[b], (uint32_t)C::TILE_BUF_BYTES);
           uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
@@ -564,15 +566,15 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
     if (lane == 0) {
       uint32_t ctr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ctr) {
-        const uint32_t b = ctr & 1;
-        mbar_wait(&tile_ready[b], (ctr >> 1) & 1);         // (the writers issued fence.proxy.async before arriving)
+        const uint32_t b = ctr % RB;
+        mbar_wait(&tile_ready[b], (ctr / RB) & 1);         // (the writers issued fence.proxy.async before arriving)
         uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
         const int m0 = (tile / tiles_n) * BLOCK_M, nt = (tile % tiles_n) * BLOCK_N;
         tma_store_2d(tb, &map_o_hi, nt, m0);               // rows >= M / columns >= N are clipped by the tensor map
         tma_store_2d(tb + C::RES_PLANE_BYTES, &map_o_lo, nt, m0);
         tma_store_commit();
         tma_store_wait_read<0>();
-        mbar_arrive(&res_empty[b]);                         // the producer may load the residual of tile t + 2 into it
+        mbar_arrive(&res_empty[b]);                         // the producer may load the residual of tile t + RES_BUFS into it
       }
       tma_store_wait_all();                                 // the last stores must have left shared memory before the CTA exits
     }
@@ -619,8 +621,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       if constexpr (RES) {
         // ---- residual epilogue: out = act(acc * scale + bias + residual), IN PLACE in the tile buffer, then one TMA store.
         // lane = tile row quad * 32 + lane, this warp's 32 columns = 16-byte chunks half * 4 .. half * 4 + 3 of the 128-byte row
-        const uint32_t b = res_ctr & 1;
-        mbar_wait(&res_full[b], (res_ctr >> 1) & 1);
+        const uint32_t b = res_ctr % RB;
+        mbar_wait(&res_full[b], (res_ctr / RB) & 1);
         uint8_t* tb = res_stage + b * C::TILE_BUF_BYTES;
         uint8_t* rowp = tb + (quad * 32 + lane) * 128;
         const u64 sc = pk2(p.out_scale, p.out_scale);
@@ -768,7 +770,7 @@ int sm_count() {
   return n;
 }
 
-template <int BLOCK_N, bool RES>
+template <int BLOCK_N, int RES>
 int launch_gemm(const CUtensorMap& ah, const CUtensorMap& al, const CUtensorMap& wh, const CUtensorMap& wl, const CUtensorMap& rh,
                 const CUtensorMap& rl, const CUtensorMap& oh, const CUtensorMap& ol, const GemmParams& p, int tiles_m, cudaStream_t s) {
   using C = Cfg<BLOCK_N, RES>;
@@ -850,8 +852,8 @@ static int conv3x3_impl(const void* x_hi, const void* x_lo, const void* w_hi, co
   p.res_hi = nullptr; p.res_lo = nullptr; p.ld_res = 0; p.a_lo_zero = 0; p.row_bias = nullptr;
   p.conv = 1; p.conv_taps = taps; p.H = H; p.W = W; p.BW = BW; p.BH = BH; p.cblocks = Cin / 64; p.cstride = stride;
   p.tiles_x = nsac_cdiv(W, BW); p.tiles_y = nsac_cdiv(H, BH);
-  if (Cout <= 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
-  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  if (Cout <= 64) return launch_gemm<64, 0>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
+  return launch_gemm<128, 0>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, N * p.tiles_x * p.tiles_y, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int nsac_conv3x3_split(const void* x_hi, const void* x_lo, const void* w_hi, const void* w_lo, const float* bias,
@@ -937,10 +939,14 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
       nsac_set_error("nsac_gemm_split_residual: cuTensorMapEncodeTiled failed (M=%d N=%d ld_res=%d ld_split=%d)", M, N, ld_res, ld_split);
       return NSAC_ERR_LAUNCH;
     }
-    return launch_gemm<64, true>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
+    // K <= 128 (res2 / res3 of the backbone: one or two k-blocks per tile, HBM-bound): the smem budget goes to FOUR tile buffers
+    // (residual prefetch + store drain depth: 0.69 -> 0.88 of the HBM bound) and two operand stages; deeper K keeps three
+    // operand stages and two tile buffers (operand delivery is what bounds those; measured both ways, profiles/README.md r2y)
+    if (K <= 128) return launch_gemm<64, 2>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
+    return launch_gemm<64, 1>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
   }
-  if (block_n == 64) return launch_gemm<64, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
-  return launch_gemm<128, false>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  if (block_n == 64) return launch_gemm<64, 0>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
+  return launch_gemm<128, 0>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
 }
 
 extern "C" int nsac_gemm_split(const void* a_hi, const void* a_lo, int lda, const void* w_hi, const void* w_lo,
