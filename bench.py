@@ -69,7 +69,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
-        self.gpu, self.rows, self.proc = gpu_index, [], None
+        self.gpu, self.rows, self.proc, self.first = gpu_index, [], None, 0
 
     def start(self):
         try:
@@ -84,9 +84,14 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up) are dropped."""
+        self.first = len(self.rows)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        end = len(self.rows)              # rows that arrived while the timed region ran (+ one if none did: its last 100 ms)
         time.sleep(0.15)
         self.proc.terminate()
         try:
@@ -94,7 +99,7 @@ class ClockSampler:
         except Exception:  # noqa: BLE001
             self.proc.kill()
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in self.rows[self.first:max(end, self.first + 1)]:
             if len(r) < 9:
                 continue
             try:
@@ -428,15 +433,18 @@ def main():
 
     # ------------------------------------------------------------------ value: inputs resident in HBM
     flush = torch.empty(256 << 20, device=dev, dtype=torch.uint8)        # > 126 MB L2
-    for _ in range(args.warmup):
-        step(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2)
-    barrier()
+    # nvidia-smi needs a few hundred ms before its first sample: start it before the warm-up, keep only the rows that arrive
+    # between the two barriers of the timed region
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+    for _ in range(args.warmup):
+        step(images, dbatch.planes1, dbatch.planes2, dbatch.app1, dbatch.app2)
+    barrier()
     ops.reset_launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark()
     e0.record()
     for _ in range(args.steps):
         flush.zero_()
