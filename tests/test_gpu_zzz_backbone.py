@@ -150,3 +150,43 @@ def test_s5_full_size_properties():
         pose_1, ass_1, m_1, _ = run([i])
         assert util.maxdiff(pose_1, pose[i:i + 1]) <= 1e-6, (i, util.maxdiff(pose_1, pose[i:i + 1]))
         assert torch.equal(ass_1, ass[i:i + 1]) and torch.equal(m_1, m[i:i + 1])
+
+
+@pytest.mark.parametrize("H,W", [(70, 90), (33, 47), (480, 640)])
+def test_stem_uint8_paths_match_reference_convolution(H, W):
+    """The two uint8 stem routes against relu(conv2d(normalise(img), w, b, stride 2, padding 3)) in fp64, border pixels included:
+    (A) border-class indicator columns in the im2col matrix + correction rows in the weight matrix (the path the backbone takes),
+    (B) plain im2col + exact fp32 recomputation of the border pixels (nsac_stem_border_fix, kept for tiny images)."""
+    dev = _gpu()
+    import torch.nn.functional as F
+    from nopesac_b200 import backbone, config, ops
+    cfg = config.inference_cfg()
+    net = backbone.build_backbone(cfg)
+    net.load_state_dict(_seeded_state())
+    net = net.to(dev)
+    pk = net.prepare()
+    N = 2
+    images = torch.randint(0, 256, (N, 3, H, W), generator=torch.Generator().manual_seed(H + W), dtype=torch.uint8)
+    wf, bf = net.stem.conv1.folded()                                  # [64, 147] in (ky, kx, c) order, FrozenBN folded
+    w4 = wf.view(64, 7, 7, 3).permute(0, 3, 1, 2).double().cpu()
+    mean = torch.tensor(cfg.MODEL.PIXEL_MEAN, dtype=torch.float64).view(1, 3, 1, 1)
+    std = torch.tensor(cfg.MODEL.PIXEL_STD, dtype=torch.float64).view(1, 3, 1, 1)
+    ref = F.relu(F.conv2d((images.double() - mean) / std, w4, bf.double().cpu(), stride=2, padding=3))
+    ref = ref.permute(0, 2, 3, 1).reshape(-1, 64)
+    scale = float(ref.abs().max())
+    img = images.to(dev)
+    cols, Ho, Wo = ops.stem_im2col_u8(img, border_classes=True)
+    ws, bs = net._stem_u8_weights(pk, H, W)
+    xa, _ = ops.gemm_tc(cols, ws, bs, ops.ACT_RELU)
+    cols_b, _, _ = ops.stem_im2col_u8(img)
+    wsb, bsb = pk["stem.u8"]
+    xb, _ = ops.gemm_tc(cols_b, wsb, bsb, ops.ACT_RELU)
+    wf32, bf32 = pk["stem.f32"]
+    ops.stem_border_fix(img, wf32, bf32, net.pixel_mean, net.pixel_std, xb)
+    torch.cuda.synchronize()
+    assert (Ho, Wo) == ((H - 1) // 2 + 1, (W - 1) // 2 + 1) and xa.shape == ref.shape
+    for name, x in (("border classes", xa), ("border recomputation", xb)):
+        d = (x.double().cpu() - ref).abs().view(N, Ho, Wo, 64)
+        assert float(d.max()) <= 3e-6 * scale, (name, float(d.max()) / scale)
+        ring = torch.cat([d[:, :2].reshape(-1), d[:, -2:].reshape(-1), d[:, :, :2].reshape(-1), d[:, :, -2:].reshape(-1)])
+        assert float(ring.max()) <= 3e-6 * scale, (name, "border ring", float(ring.max()) / scale)
