@@ -516,6 +516,44 @@ int nsac_head_forward(const nsac_head_weights* w, const void* res3_hi, const voi
                       size_t workspace_bytes, float* const* peer_rows, int num_peers, int row_offset, int* launches_out,
                       void* stream);
 
+/* nsac_backbone_forward — the ResNet-50 backbone (detectron2 build_resnet_backbone as configured by
+ * Base.yaml:2-12) from UINT8 images in one call: stem (7x7/2 patches of the raw pixels + border-class columns -> GEMM ->
+ * max-pool 3x3/2) and the 16 bottleneck blocks (conv1 1x1 -> conv2 3x3, stride 1 or 2 through the TMA gather -> [projection
+ * shortcut] -> conv3 1x1 with the shortcut + ReLU in its epilogue), activations as NHWC hi/lo planes end to end.
+ *   images [N,3,H,W] uint8 (cfg.INPUT.FORMAT order, NOT normalised: PIXEL_MEAN / PIXEL_STD are folded into `stem`), H, W >= 9.
+ *   -> res2 / res3 / res4 / res5 planes [N*h*w, C] (C = 256 / 512 / 1024 / 2048; h = H/4 .. H/32 rounded up), any pair NULL = that
+ *      level is not kept (scratch is used).  Weights: FrozenBN folded into planes + bias; `stem` is the [64, 171] matrix of
+ *      nsac_stem_im2col_u8_cls for THIS image size (w / std, then the 24 border-class corrections). */
+typedef struct {
+  nsac_tc_layer conv1, conv2, conv3, shortcut;    /* conv2: [mid, 9*mid] in (ky,kx,cin) order; shortcut unused if !has_shortcut */
+  int has_shortcut, stride;                       /* stride of conv2 / shortcut (STRIDE_IN_1X1 = False) */
+} nsac_bottleneck;
+
+typedef struct {
+  nsac_tc_layer stem;
+  const nsac_bottleneck* blocks; int num_blocks;  /* 3 + 4 + 6 + 3 */
+  int stage_blocks[4];                            /* blocks per stage res2 .. res5 */
+  int fmt, passes;
+} nsac_backbone_weights;
+
+size_t nsac_backbone_workspace_bytes(int N, int H, int W);
+int nsac_backbone_forward(const nsac_backbone_weights* w, const uint8_t* images, int N, int H, int W, void* res2_hi, void* res2_lo,
+                          void* res3_hi, void* res3_lo, void* res4_hi, void* res4_lo, void* res5_hi, void* res5_lo,
+                          void* workspace, size_t workspace_bytes, int* launches_out, void* stream);
+
+/* nsac_model_forward — stage set S5 in ONE call: nsac_backbone_forward on the 2B uint8 images of B pairs (first views, then
+ * second views; H, W multiples of 32) -> res3 / res4 / res5 planes in the workspace -> nsac_head_forward.  Arguments and outputs as
+ * in those two entries; plane lists (planes / appearance embeddings / counts) come from the caller. */
+size_t nsac_model_workspace_bytes(int B, int H, int W, int n1, int n2, int NQ);
+int nsac_model_forward(const nsac_backbone_weights* bw, const nsac_head_weights* hw, const uint8_t* images, int B, int H, int W,
+                       const float* planes1, const float* planes2, const float* app1, const float* app2, const int32_t* count1,
+                       const int32_t* count2, int n1, int n2, const int32_t* hyp_pairs, int Hn, int NQ, float match_threshold,
+                       int out_cam_type, float* init_tran, float* init_rot, float* t0, float* q0, float* rot_feat0,
+                       float* trans_feat0, float* log_scores_padded, float* assign, float* pose, float* assign_pruned,
+                       float* geo_local, float* geo_global, float* sig, int32_t* matched_num, int32_t* pair_idx, float* q_h,
+                       float* t_h, float* score_rot, float* score_tran, int32_t* sel_idx, void* workspace, size_t workspace_bytes,
+                       float* const* peer_rows, int num_peers, int row_offset, int* launches_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

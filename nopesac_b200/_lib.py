@@ -63,6 +63,17 @@ class HeadWeights(C.Structure):
     _fields_ = [("pixel", C.POINTER(PixelWeights)), ("match", C.POINTER(MatchWeights)), ("refine", C.POINTER(RefineWeights))]
 
 
+class Bottleneck(C.Structure):
+    """nsac_bottleneck."""
+    _fields_ = [("conv1", TcLayer), ("conv2", TcLayer), ("conv3", TcLayer), ("shortcut", TcLayer), ("has_shortcut", C.c_int), ("stride", C.c_int)]
+
+
+class BackboneWeights(C.Structure):
+    """nsac_backbone_weights."""
+    _fields_ = [("stem", TcLayer), ("blocks", C.POINTER(Bottleneck)), ("num_blocks", C.c_int), ("stage_blocks", C.c_int * 4),
+                ("fmt", C.c_int), ("passes", C.c_int)]
+
+
 _SIGNATURES = {
     "nsac_version": (C.c_int, []),
     "nsac_last_error": (C.c_char_p, []),
@@ -170,6 +181,13 @@ _SIGNATURES = {
     "nsac_head_forward": (C.c_int, [C.POINTER(HeadWeights)] + [C.c_void_p] * 6 + [C.c_int] * 3 + [c_float_p] * 4 + [C.c_void_p] * 2 +
                           [C.c_int] * 2 + [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 20 +
                           [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
+    "nsac_model_workspace_bytes": (C.c_size_t, [C.c_int] * 6),
+    "nsac_model_forward": (C.c_int, [C.POINTER(BackboneWeights), C.POINTER(HeadWeights), C.c_void_p] + [C.c_int] * 3 + [c_float_p] * 4 +
+                           [C.c_void_p] * 2 + [C.c_int] * 2 + [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int] + [C.c_void_p] * 20 +
+                           [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_void_p]),
+    "nsac_backbone_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "nsac_backbone_forward": (C.c_int, [C.POINTER(BackboneWeights), C.c_void_p, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 8 +
+                              [C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),
     "nsac_match_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "nsac_match_forward": (C.c_int, [C.POINTER(MatchWeights)] + [c_float_p] * 5 + [C.c_void_p, C.c_void_p, C.c_float, C.c_int, C.c_int,
                                     C.c_int, c_float_p, c_float_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.c_void_p]),

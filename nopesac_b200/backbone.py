@@ -17,6 +17,8 @@ head's pixel network (`PlaneFeatures`), skipping the NCHW fp32 round trip.  No c
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict
 
 import torch
@@ -94,6 +96,7 @@ class ResNet50Backbone(nn.Module):
             cin = cout
         self._packed = None
         self.tc_passes = 3
+        self.use_stage_entry = not os.environ.get("NSAC_PY_STAGES")      # nsac_backbone_forward; NSAC_PY_STAGES=1: same launches from Python
         self.eval()
 
     def output_shape(self) -> Dict[str, ShapeSpec]:
@@ -176,6 +179,34 @@ class ResNet50Backbone(nn.Module):
                 pk[key] = (ops.split_weight(ext.float().contiguous()), (bf.double() - (w8 * mean).sum(1)).float().contiguous())
         return pk[key]
 
+    def backbone_weights(self, H: int, W: int):
+        """`nsac_backbone_weights` for `ops.backbone_forward` on H x W uint8 images (the stem's border corrections depend on the
+        image size; borrowed pointers into this weight version's packed planes)."""
+        pk = self.prepare()
+        key = f"struct.{H}x{W}"
+        if key not in pk:
+            from . import _lib
+            blocks = []
+            for name, *_ in STAGES:
+                for i, blk in enumerate(getattr(self, name)):
+                    b = _lib.Bottleneck()
+                    for c in ("conv1", "conv2", "conv3"):
+                        setattr(b, c, ops.tc_layer(*pk[f"{name}.{i}.{c}"]))
+                    b.has_shortcut = 1 if hasattr(blk, "shortcut") else 0
+                    if b.has_shortcut:
+                        b.shortcut = ops.tc_layer(*pk[f"{name}.{i}.shortcut"])
+                    b.stride = int(blk.stride)
+                    blocks.append(b)
+            arr = (_lib.Bottleneck * len(blocks))(*blocks)
+            Wt = _lib.BackboneWeights()
+            Wt.stem = ops.tc_layer(*self._stem_u8_weights(pk, H, W))
+            Wt.blocks, Wt.num_blocks = arr, len(blocks)
+            for j, (name, *_r) in enumerate(STAGES):
+                Wt.stage_blocks[j] = len(getattr(self, name))
+            Wt.fmt, Wt.passes = ops.SPLIT_F16, self.tc_passes
+            pk[key], pk[key + ".keep"] = Wt, arr
+        return pk[key]
+
     def _stem(self, pk, images):
         N = images.shape[0]
         if images.dtype == torch.uint8 and min(images.shape[2:]) >= 9:
@@ -206,6 +237,19 @@ class ResNet50Backbone(nn.Module):
         `planes=True`: a `PlaneFeatures` (NHWC hi/lo planes, the engine's own format) for `PlaneCameraHead`."""
         pk = self.prepare()
         N = images.shape[0]
+        if self.use_stage_entry and images.dtype == torch.uint8 and min(images.shape[2:]) >= 9:
+            # the whole backbone behind ONE C call (nsac_backbone_forward, csrc/forward.cu); the loop below issues the same launches
+            Wt = self.backbone_weights(images.shape[2], images.shape[3])
+            Wt.passes = self.tc_passes
+            lv = ops.backbone_forward(Wt, images, keep=self._out_features)
+            out = PlaneFeatures(N) if planes else {}
+            for name, (sp, h, w) in lv.items():
+                if planes:
+                    out[name] = (sp, h, w)
+                else:
+                    x_f32 = sp.float()
+                    out[name] = x_f32 if nhwc else x_f32.view(N, h, w, -1).permute(0, 3, 1, 2).contiguous()
+            return out
         xp, H, W = self._stem(pk, images)
         out = PlaneFeatures(N) if planes else {}
         for name, *_ in STAGES:
@@ -228,6 +272,24 @@ class PlaneFeatures(dict):
     def __init__(self, num_images: int):
         super().__init__()
         self.num_images = num_images
+
+
+class RawImages:
+    """The uint8 images of both views of B pairs (stacked [2B,3,H,W]: first views, then second views) together with the backbone
+    that turns them into features.  `PlaneCameraHead` takes it as `features1` (with `features2=None`): when everything else allows,
+    backbone AND head then run behind ONE C call (`nsac_model_forward`); otherwise `.features()` runs the backbone first."""
+
+    def __init__(self, backbone: "ResNet50Backbone", images: torch.Tensor):
+        self.backbone, self.images, self.num_images = backbone, images, images.shape[0]
+
+    @property
+    def single_call_ok(self) -> bool:
+        im = self.images
+        return bool(self.backbone.use_stage_entry and im.dtype == torch.uint8 and im.shape[2] % 32 == 0 and im.shape[3] % 32 == 0
+                    and im.shape[2] >= 32 and im.shape[3] >= 32)
+
+    def features(self) -> "PlaneFeatures":
+        return self.backbone(self.images, planes=True)
 
 
 @BACKBONE_REGISTRY.register()

@@ -558,6 +558,26 @@ class PlaneCameraHead(nn.Module):
         single_call = (self.use_stage_entry and self.cam_rec_on and self.plane_matcher_on and out_cam_type != "initial" and not want_diag
                        and assignment_override is None and getattr(matching_net, "use_stage_entry", False)
                        and not (out_cam_type == "max-score" and result_exchange is not None))
+        from .backbone import RawImages
+        raw = cam_feats1 if isinstance(cam_feats1, RawImages) else None
+        if raw is not None and not (single_call and initial_pose is None and raw.single_call_ok):
+            cam_feats1, raw = raw.features(), None           # backbone first, then the head on its feature planes
+        if single_call and raw is not None:
+            # ------------------------------------------------ stage set S5 behind ONE C call (nsac_model_forward): ResNet-50 on both
+            # views' uint8 images -> the whole head + matcher
+            PW, MW, RW = self.pixel_weights(), matching_net.match_weights(), self.refine_weights()
+            BW = raw.backbone.backbone_weights(raw.images.shape[2], raw.images.shape[3])
+            PW.passes = RW.passes = self.tc_passes
+            BW.passes = raw.backbone.tc_passes
+            MW.passes, MW.sinkhorn_iterations = matching_net.tc_passes, int(matching_net.sinkhorn_iterations)
+            if (plane_count1 is None) != (plane_count2 is None):
+                raise ValueError("plane_count1 and plane_count2 go together")
+            if raw.num_images != 2 * B:
+                raise ValueError(f"{raw.num_images} images for {B} pairs (expected both views stacked: 2B)")
+            r = ops.model_forward(BW, PW, MW, RW, raw.images, planeParam1, planeParam2, planeApp1.float(), planeApp2.float(), NQ,
+                                  self.matching_score_threshold, out_cam_type, plane_count1, plane_count2, hyp_pairs,
+                                  exchange=result_exchange)
+            return self._pack_single_call(r, output_cameras, trans_list, rot_list)
         if single_call:
             # ------------------------------------------------ the WHOLE head + matcher behind ONE C call (nsac_head_forward,
             # csrc/forward.cu: nsac_pixel_forward -> nsac_match_forward -> nsac_refine_forward on the current stream)
@@ -577,15 +597,7 @@ class PlaneCameraHead(nn.Module):
             r = ops.head_forward(PW, MW, RW, p3, p4, p5, B, H3, W3, planeParam1, planeParam2, planeApp1.float(), planeApp2.float(), NQ,
                                  self.matching_score_threshold, out_cam_type, plane_count1, plane_count2, hyp_pairs, initial_pose,
                                  exchange=result_exchange)
-            trans_list += [r["init_tran"], r["t0"]]
-            rot_list += [r["init_rot"], r["q0"]]
-            output_cameras["camera_init"] = {"tran": r["init_tran"], "rot": r["init_rot"]}
-            output_cameras["camera_initRec"] = {"tran": r["t0"], "rot": r["q0"]}
-            output_planeAss = {"pred_assignment_beforeRef0": r["assign"]}
-            res = {"score_rot": r["score_rot"], "score_tran": r["score_tran"], "sel_idx": r["sel_idx"], "diag": None}
-            return self._pack_refined(output_cameras, trans_list, rot_list, r["log_scores_padded"], output_planeAss, r["pose"],
-                                      r["assign_pruned"], r["q0"], r["t0"], r["q_h"], r["t_h"], res, r["sig"], r["matched_num"],
-                                      r["pair_idx"], r["geo_local"], r["geo_global"], False)
+            return self._pack_single_call(r, output_cameras, trans_list, rot_list)
 
         if self.use_stage_entry and self.cam_rec_on and self.plane_matcher_on:
             # K1 + w >= 0 + K2 behind ONE C call (nsac_pixel_forward, csrc/forward.cu); the Python branch below issues the same launches
@@ -688,6 +700,18 @@ class PlaneCameraHead(nn.Module):
             pruned = ops.prune_assignment(assignment, planeParam1, planeParam2, pose)
         return self._pack_refined(output_cameras, trans_list, rot_list, log_scores_padded, output_planeAss, pose, pruned, q0, t0, q_h, t_h,
                                   res, sig, matched_num, pair_idx, geo_local, geo_global, want_diag)
+
+    def _pack_single_call(self, r, output_cameras, trans_list, rot_list):
+        """The reference's return value from the output dict of ops.head_forward / ops.model_forward."""
+        trans_list += [r["init_tran"], r["t0"]]
+        rot_list += [r["init_rot"], r["q0"]]
+        output_cameras["camera_init"] = {"tran": r["init_tran"], "rot": r["init_rot"]}
+        output_cameras["camera_initRec"] = {"tran": r["t0"], "rot": r["q0"]}
+        output_planeAss = {"pred_assignment_beforeRef0": r["assign"]}
+        res = {"score_rot": r["score_rot"], "score_tran": r["score_tran"], "sel_idx": r["sel_idx"], "diag": None}
+        return self._pack_refined(output_cameras, trans_list, rot_list, r["log_scores_padded"], output_planeAss, r["pose"],
+                                  r["assign_pruned"], r["q0"], r["t0"], r["q_h"], r["t_h"], res, r["sig"], r["matched_num"],
+                                  r["pair_idx"], r["geo_local"], r["geo_global"], False)
 
     def _pack_refined(self, output_cameras, trans_list, rot_list, log_scores_padded, output_planeAss, pose, pruned, q0, t0, q_h, t_h,
                       res, sig, matched_num, pair_idx, geo_local, geo_global, want_diag):

@@ -493,3 +493,168 @@ extern "C" int nsac_head_forward(const nsac_head_weights* w, const void* res3_hi
   if (launches_out) *launches_out = n;
   return NSAC_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ResNet-50 backbone from uint8 images (nopesac_b200/backbone.py, launch for launch)
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+
+struct BackboneScratch {
+  void* cols; float* stem_out;
+  Planes x[2], y1, y2, sc;       // block input / output ping-pong (256..2048 wide at the level's size), conv1 / conv2 / shortcut outputs
+};
+
+inline int half_up(int v) { return (v - 1) / 2 + 1; }
+
+size_t carve_backbone(Arena& a, int N, int H, int W, BackboneScratch& s) {
+  const size_t Ho = half_up(H), Wo = half_up(W), r1 = (size_t)N * Ho * Wo;           // stem output
+  const size_t H2 = half_up((int)Ho), W2 = half_up((int)Wo), r2 = (size_t)N * H2 * W2;    // res2 level
+  s.cols = a.take(r1 * 192 * 2);
+  s.stem_out = static_cast<float*>(a.take(r1 * 64 * 4));
+  // widest tensors per role, all at the res2 level (later levels have 2x the channels on 4x fewer pixels)
+  auto pl = [&](size_t rows, int ld) { Planes p = a.planes(rows, ld); return p; };
+  s.x[0] = pl(r2, 256); s.x[1] = pl(r2, 256);
+  s.y1 = pl(r2, 128);           // conv1 output: 64 @ res2 .. 512 @ res5; res3.0.conv1 runs at the res2 level with 128 channels
+  s.y2 = pl(r2, 64);            // conv2 output (after the stride)
+  s.sc = pl(r2, 256);           // projection shortcut
+  return a.off;
+}
+
+}  // namespace
+
+extern "C" size_t nsac_backbone_workspace_bytes(int N, int H, int W) {
+  if (N <= 0 || H < 9 || W < 9) return 0;
+  Arena a{nullptr, 0};
+  BackboneScratch s;
+  return carve_backbone(a, N, H, W, s);
+}
+
+extern "C" int nsac_backbone_forward(const nsac_backbone_weights* w, const uint8_t* images, int N, int H, int W, void* res2_hi,
+                                     void* res2_lo, void* res3_hi, void* res3_lo, void* res4_hi, void* res4_lo, void* res5_hi,
+                                     void* res5_lo, void* workspace, size_t workspace_bytes, int* launches_out, void* stream) {
+  NSAC_REQUIRE(w && w->blocks && images, "nsac_backbone_forward: null argument");
+  NSAC_REQUIRE(N > 0 && H >= 9 && W >= 9, "nsac_backbone_forward: bad shape N=%d H=%d W=%d (H, W >= 9)", N, H, W);
+  NSAC_REQUIRE(w->num_blocks == w->stage_blocks[0] + w->stage_blocks[1] + w->stage_blocks[2] + w->stage_blocks[3],
+               "nsac_backbone_forward: stage_blocks do not add up to num_blocks");
+  NSAC_REQUIRE((res2_hi == nullptr) == (res2_lo == nullptr) && (res3_hi == nullptr) == (res3_lo == nullptr) &&
+               (res4_hi == nullptr) == (res4_lo == nullptr) && (res5_hi == nullptr) == (res5_lo == nullptr),
+               "nsac_backbone_forward: hi / lo output planes go together");
+  Arena a{static_cast<uint8_t*>(workspace), 0};
+  BackboneScratch s;
+  const size_t need = carve_backbone(a, N, H, W, s);
+  NSAC_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_backbone_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", need, workspace_bytes);
+  const int fmt = w->fmt, P = w->passes;
+  const Planes none{nullptr, nullptr, 0};
+  int n = 0;
+  // stem: raw pixels are exact in fp16 (one plane), normalisation folded into the weights, zero padding of the NORMALISED image
+  // through the border-class columns; ReLU in the GEMM epilogue; max-pool 3x3 / 2 writes planes
+  int h = half_up(H), ww = half_up(W);
+  NSAC_TRY(nsac_stem_im2col_u8_cls(images, N, H, W, s.cols, stream));
+  ++n;
+  NSAC_TRY(nsac_gemm_split(s.cols, nullptr, 192, w->stem.w_hi, w->stem.w_lo, w->stem.ldw, w->stem.bias, 0, N * h * ww, 64, 192, NSAC_ACT_RELU,
+                           P, fmt, 1.0f / w->stem.w_scale, s.stem_out, 64, nullptr, nullptr, 0, stream));
+  ++n;
+  Planes x = s.x[0];
+  x.ld = 64;
+  NSAC_TRY(nsac_maxpool3x3s2_nhwc(s.stem_out, N, h, ww, 64, fmt, nullptr, x.hi, x.lo, stream));
+  ++n;
+  h = half_up(h); ww = half_up(ww);
+  void* outs[4][2] = {{res2_hi, res2_lo}, {res3_hi, res3_lo}, {res4_hi, res4_lo}, {res5_hi, res5_lo}};
+  int cur = 0, bi = 0;
+  for (int st = 0; st < 4; ++st) {
+    for (int b = 0; b < w->stage_blocks[st]; ++b, ++bi) {
+      const nsac_bottleneck& blk = w->blocks[bi];
+      const int cin = blk.conv1.K, mid = blk.conv1.N, cout = blk.conv3.N, stride = blk.stride;
+      NSAC_REQUIRE(x.ld == cin && blk.conv2.K == 9 * mid && blk.conv3.K == mid && (stride == 1 || stride == 2),
+                   "nsac_backbone_forward: block %d does not chain (input %d channels, conv1 expects %d)", bi, x.ld, cin);
+      const int rows_in = N * h * ww, ho = stride == 1 ? h : half_up(h), wo = stride == 1 ? ww : half_up(ww), rows_out = N * ho * wo;
+      Planes y1 = s.y1, y2 = s.y2, sc = s.sc;
+      y1.ld = mid; y2.ld = mid; sc.ld = cout;
+      // the last block of a stage writes the caller's output planes directly
+      const bool last = b == w->stage_blocks[st] - 1;
+      Planes out = (last && outs[st][0]) ? Planes{outs[st][0], outs[st][1], cout} : s.x[cur ^ 1];
+      out.ld = cout;
+      NSAC_TRY(tc(blk.conv1, x, rows_in, NSAC_ACT_RELU, nullptr, 0, y1, fmt, P, stream, n));
+      NSAC_TRY(nsac_conv3x3_split_strided(y1.hi, y1.lo, blk.conv2.w_hi, blk.conv2.w_lo, blk.conv2.bias, N, h, ww, mid, mid, stride,
+                                          NSAC_ACT_RELU, P, fmt, 1.0f / blk.conv2.w_scale, nullptr, 0, y2.hi, y2.lo, y2.ld, stream));
+      ++n;
+      Planes res = x;
+      if (blk.has_shortcut) {
+        if (stride == 1) {
+          NSAC_TRY(tc(blk.shortcut, x, rows_in, NSAC_ACT_NONE, nullptr, 0, sc, fmt, P, stream, n));
+        } else {       // strided projection: the TMA gather skips the pixels a stride-2 1x1 convolution never reads
+          NSAC_TRY(nsac_conv1x1_split_strided(x.hi, x.lo, blk.shortcut.w_hi, blk.shortcut.w_lo, blk.shortcut.bias, N, h, ww, cin, cout,
+                                              stride, NSAC_ACT_NONE, P, fmt, 1.0f / blk.shortcut.w_scale, nullptr, 0, sc.hi, sc.lo, sc.ld,
+                                              stream));
+          ++n;
+        }
+        res = sc;
+      } else {
+        NSAC_REQUIRE(cin == cout && stride == 1, "nsac_backbone_forward: block %d has no shortcut but changes shape", bi);
+      }
+      ++n;      // conv3 + shortcut + ReLU in its epilogue
+      NSAC_TRY(nsac_gemm_split_residual(y2.hi, y2.lo, y2.ld, blk.conv3.w_hi, blk.conv3.w_lo, blk.conv3.ldw, blk.conv3.bias, rows_out, cout, mid,
+                                        NSAC_ACT_RELU, P, fmt, 1.0f / blk.conv3.w_scale, res.hi, res.lo, res.ld, nullptr, 0, out.hi, out.lo,
+                                        out.ld, stream));
+      x = out;
+      if (!(last && outs[st][0])) cur ^= 1;
+      h = ho; ww = wo;
+    }
+  }
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Stage set S5 in one call: backbone on both views' uint8 images -> head
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+struct ModelScratch { Planes r3, r4, r5; void* stage; size_t stage_bytes; };
+size_t carve_model(Arena& a, int B, int H, int W, int n1, int n2, int NQ, ModelScratch& s) {
+  const size_t N = 2 * (size_t)B, h3 = H / 8, w3 = W / 8;
+  s.r3 = a.planes(N * h3 * w3, 512);
+  s.r4 = a.planes(N * (h3 / 2) * (w3 / 2), 1024);
+  s.r5 = a.planes(N * (h3 / 4) * (w3 / 4), 2048);
+  const size_t bb = nsac_backbone_workspace_bytes((int)N, H, W), hd = nsac_head_workspace_bytes(B, (int)h3, (int)w3, n1, n2, NQ);
+  s.stage_bytes = bb > hd ? bb : hd;
+  s.stage = a.take(s.stage_bytes);
+  return a.off;
+}
+}  // namespace
+
+extern "C" size_t nsac_model_workspace_bytes(int B, int H, int W, int n1, int n2, int NQ) {
+  if (B <= 0 || H < 32 || W < 32 || H % 32 || W % 32 || n1 <= 0 || n2 <= 0 || NQ <= 0) return 0;
+  Arena a{nullptr, 0};
+  ModelScratch s;
+  return carve_model(a, B, H, W, n1, n2, NQ, s);
+}
+
+extern "C" int nsac_model_forward(const nsac_backbone_weights* bw, const nsac_head_weights* hw, const uint8_t* images, int B, int H,
+                                  int W, const float* planes1, const float* planes2, const float* app1, const float* app2,
+                                  const int32_t* count1, const int32_t* count2, int n1, int n2, const int32_t* hyp_pairs, int Hn,
+                                  int NQ, float match_threshold, int out_cam_type, float* init_tran, float* init_rot, float* t0,
+                                  float* q0, float* rot_feat0, float* trans_feat0, float* log_scores_padded, float* assign,
+                                  float* pose, float* assign_pruned, float* geo_local, float* geo_global, float* sig,
+                                  int32_t* matched_num, int32_t* pair_idx, float* q_h, float* t_h, float* score_rot,
+                                  float* score_tran, int32_t* sel_idx, void* workspace, size_t workspace_bytes,
+                                  float* const* peer_rows, int num_peers, int row_offset, int* launches_out, void* stream) {
+  NSAC_REQUIRE(bw && hw && images, "nsac_model_forward: null argument");
+  NSAC_REQUIRE(B > 0 && H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "nsac_model_forward: image size %dx%d must be a multiple of 32", H, W);
+  Arena a{static_cast<uint8_t*>(workspace), 0};
+  ModelScratch s;
+  const size_t need = carve_model(a, B, H, W, n1, n2, NQ, s);
+  NSAC_REQUIRE(workspace && workspace_bytes >= need && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0,
+               "nsac_model_forward: workspace of %zu bytes (256-byte aligned) needed, got %zu", need, workspace_bytes);
+  int n = 0, k = 0;
+  NSAC_TRY(nsac_backbone_forward(bw, images, 2 * B, H, W, nullptr, nullptr, s.r3.hi, s.r3.lo, s.r4.hi, s.r4.lo, s.r5.hi, s.r5.lo, s.stage,
+                                 s.stage_bytes, &k, stream));
+  n += k;
+  NSAC_TRY(nsac_head_forward(hw, s.r3.hi, s.r3.lo, s.r4.hi, s.r4.lo, s.r5.hi, s.r5.lo, B, H / 8, W / 8, planes1, planes2, app1, app2, count1,
+                             count2, n1, n2, hyp_pairs, Hn, NQ, match_threshold, out_cam_type, init_tran, init_rot, t0, q0, rot_feat0,
+                             trans_feat0, log_scores_padded, assign, pose, assign_pruned, geo_local, geo_global, sig, matched_num, pair_idx,
+                             q_h, t_h, score_rot, score_tran, sel_idx, s.stage, s.stage_bytes, peer_rows, num_peers, row_offset, &k, stream));
+  n += k;
+  if (launches_out) *launches_out = n;
+  return NSAC_OK;
+}

@@ -120,7 +120,10 @@ class PlaneTR_NopeSAC(nn.Module):
             raise RuntimeError("PlaneTR_NopeSAC was built without a backbone (with_backbone=True)")
         # `images2 is None`: `images1` already holds both views stacked, [2B,3,H,W] = first views then second views
         images = images1 if images2 is None else torch.cat([images1, images2], 0)
-        feats = self.backbone(images, planes=True)     # NHWC hi/lo planes, views stacked: no NCHW round trip
+        # both views stacked; the head runs backbone + head behind ONE C call (nsac_model_forward) when it can, otherwise the
+        # backbone's NHWC hi/lo planes are handed over (no NCHW round trip either way)
+        from .backbone import RawImages
+        feats = RawImages(self.backbone, images)
         return self.camera_head_list[0](feats, None, planeParam1, planeParam2, planeApp1=planeApp1, planeApp2=planeApp2,
                                         matching_net=self.matching_head, **head_kwargs)
 

@@ -871,3 +871,70 @@ def head_forward(pixel_w, match_w, refine_w, res3, res4, res5, B: int, H3: int, 
     _lib.check(st, "nsac_head_forward")
     _count(n.value)
     return out
+
+
+def backbone_forward(weights, images: torch.Tensor, keep=("res2", "res3", "res4", "res5")):
+    """nsac_backbone_forward: ResNet-50 from uint8 images [N,3,H,W] (not normalised) in one call -> {name: (Split NHWC planes, h, w)}
+    for the levels in `keep`.  `weights`: a _lib.BackboneWeights for this image size (ResNet50Backbone.backbone_weights(H, W))."""
+    images = _c(images, "images", torch.uint8)
+    N, Cc, H, W = images.shape
+    assert Cc == 3
+    dev = images.device
+    up = lambda v: (v - 1) // 2 + 1
+    h, w = up(up(H)), up(up(W))
+    out, ptrs = {}, []
+    for name, ch in (("res2", 256), ("res3", 512), ("res4", 1024), ("res5", 2048)):
+        if name in keep:
+            sp = Split(torch.empty(N * h * w, ch, device=dev, dtype=torch.float16), torch.empty(N * h * w, ch, device=dev, dtype=torch.float16), ch)
+            out[name] = (sp, h, w)
+            ptrs += [_p(sp.hi), _p(sp.lo)]
+        else:
+            ptrs += [None, None]
+        h, w = up(h), up(w)
+    L = _lib.lib()
+    nbytes = L.nsac_backbone_workspace_bytes(N, H, W)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_backbone_forward(C.byref(weights), _p(images), N, H, W, *ptrs, C.c_void_p(ws_ptr), nbytes, C.byref(n), _stream())
+    _lib.check(st, "nsac_backbone_forward")
+    _count(n.value)
+    return out
+
+
+def model_forward(backbone_w, pixel_w, match_w, refine_w, images: torch.Tensor, planes1, planes2, app1, app2, num_queries: int,
+                  match_threshold: float, out_cam_type: str = "soft", count1=None, count2=None, hyp_pairs=None, want_scores: bool = True,
+                  exchange=None):
+    """nsac_model_forward: stage set S5 in ONE C call — ResNet-50 on the 2B uint8 images (first views, then second views; H, W
+    multiples of 32) -> pixel pose network + AIM -> matcher -> one-plane RANSAC refinement.  Returns the dict of head_forward."""
+    images = _c(images, "images", torch.uint8)
+    planes1, planes2, app1, app2 = _c(planes1, "planes1"), _c(planes2, "planes2"), _c(app1, "app1"), _c(app2, "app2")
+    B, n1, n2, NQ, dev = planes1.shape[0], planes1.shape[1], planes2.shape[1], num_queries, planes1.device
+    N2, Cc, H, W = images.shape
+    assert N2 == 2 * B and Cc == 3 and H % 32 == 0 and W % 32 == 0, f"model_forward: images {tuple(images.shape)} for {B} pairs"
+    assert tuple(app1.shape) == (B, n1, 256) and tuple(app2.shape) == (B, n2, 256)
+    f = lambda *shape: torch.empty(*shape, device=dev)
+    i32 = lambda *shape: torch.empty(*shape, device=dev, dtype=torch.int32)
+    Hn = 0
+    if hyp_pairs is not None:
+        hyp_pairs = _c(hyp_pairs, "hyp_pairs", torch.int32)
+        Hn = hyp_pairs.shape[0]
+    if count1 is not None:
+        count1, count2 = _c(count1, "count1", torch.int32), _c(count2, "count2", torch.int32)
+    out = {"init_tran": f(B, 3), "init_rot": f(B, 4), "t0": f(B, 3), "q0": f(B, 4), "rot_feat0": f(B, 256), "trans_feat0": f(B, 256),
+           "log_scores_padded": f(B, n1 + 1, n2 + 1), "assign": f(B, n1, n2), "pose": f(B, 16), "assign_pruned": f(B, n1, n2),
+           "geo_local": f(B, NQ, 6), "geo_global": f(B, NQ, 6), "sig": f(B, NQ), "matched_num": i32(B), "pair_idx": i32(B, NQ, 2),
+           "q_h": f(B * NQ, 4), "t_h": f(B * NQ, 3), "score_rot": f(B, NQ + 1) if want_scores else None,
+           "score_tran": f(B, NQ + 1) if want_scores else None, "sel_idx": i32(B, 2)}
+    L = _lib.lib()
+    HW_ = _lib.HeadWeights(C.pointer(pixel_w), C.pointer(match_w), C.pointer(refine_w))
+    nbytes = L.nsac_model_workspace_bytes(B, H, W, n1, n2, NQ)
+    ws, ws_ptr = _aligned_workspace(nbytes, dev)
+    n = C.c_int(0)
+    st = L.nsac_model_forward(C.byref(backbone_w), C.byref(HW_), _p(images), B, H, W, _p(planes1), _p(planes2), _p(app1), _p(app2),
+                              _p(count1), _p(count2), n1, n2, _p(hyp_pairs), Hn, NQ, float(match_threshold), CAM_TYPES[out_cam_type],
+                              *[_p(v) for v in out.values()], C.c_void_p(ws_ptr), nbytes,
+                              None if exchange is None else C.c_void_p(exchange.peer_ptrs_dev), 0 if exchange is None else exchange.world,
+                              0 if exchange is None else exchange.row_offset, C.byref(n), _stream())
+    _lib.check(st, "nsac_model_forward")
+    _count(n.value)
+    return out

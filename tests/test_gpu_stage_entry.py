@@ -115,6 +115,62 @@ def test_stage_entry_ragged_batch(monkeypatch):
         assert float(ass[i, int(c1[i]):].abs().sum()) == 0 and float(ass[i, :, int(c2[i]):].abs().sum()) == 0
 
 
+@pytest.mark.parametrize("N,H,W", [(2, 97, 131), (2, 480, 640)])
+def test_backbone_entry_equals_python_stages(monkeypatch, N, H, W):
+    """nsac_backbone_forward (ResNet-50 from uint8 images in one call) == the per-kernel Python loop, every level, every bit."""
+    dev = _gpu()
+    from nopesac_b200 import backbone, config, synthetic
+    images = synthetic.make_images(31, N, H, W).to(dev)
+    outs = {}
+    for stage_entry in (True, False):
+        if stage_entry:
+            monkeypatch.delenv("NSAC_PY_STAGES", raising=False)
+        else:
+            monkeypatch.setenv("NSAC_PY_STAGES", "1")
+        net = backbone.build_backbone(config.inference_cfg())
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        net.load_state_dict(synthetic.make_backbone_weights(shapes, seed=8))
+        net = net.to(dev)
+        assert net.use_stage_entry == stage_entry
+        outs[stage_entry] = net(images, planes=True)
+        torch.cuda.synchronize()
+    for k in ("res2", "res3", "res4", "res5"):
+        (a, ha, wa), (b, hb, wb) = outs[True][k], outs[False][k]
+        assert (ha, wa) == (hb, wb) and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo), k
+
+
+def test_model_entry_equals_python_stages(monkeypatch):
+    """Stage set S5 behind ONE C call (nsac_model_forward: backbone on both views' uint8 images + the whole head) == backbone and
+    head issued kernel by kernel from Python (NSAC_PY_STAGES=1), every output bit for bit; one launch counter for the whole step."""
+    dev = _gpu()
+    from nopesac_b200 import config, meta_arch, ops, synthetic
+    NQ, P, B = 64, 8, 2
+    b = synthetic.make_batch(7500, B, P).to(dev)
+    images = synthetic.make_images(75, 2 * B).to(dev)
+    outs, launches = {}, {}
+    for stage_entry in (True, False):
+        if stage_entry:
+            monkeypatch.delenv("NSAC_PY_STAGES", raising=False)
+        else:
+            monkeypatch.setenv("NSAC_PY_STAGES", "1")
+        model = meta_arch.PlaneTR_NopeSAC(config.inference_cfg(NQ), with_backbone=True)
+        sd, msd = util.make_weights(NQ)
+        model.camera_head_list[0].load_state_dict(sd)
+        model.matching_head.load_state_dict(msd)
+        shapes = {k: tuple(v.shape) for k, v in model.backbone.state_dict().items()}
+        model.backbone.load_state_dict(synthetic.make_backbone_weights(shapes, seed=8))
+        model = model.to(dev)
+        assert model.backbone.use_stage_entry == stage_entry and model.camera_head_list[0].use_stage_entry == stage_entry
+        n0 = ops.launch_count()
+        outs[stage_entry] = _flat(model.inference_from_images(images, None, b.planes1, b.planes2, b.app1, b.app2))
+        torch.cuda.synchronize()
+        launches[stage_entry] = ops.launch_count() - n0
+    assert set(outs[True]) == set(outs[False])
+    for k in outs[True]:
+        assert torch.equal(outs[True][k], outs[False][k]), k
+    assert 300 < launches[True] <= launches[False] + 2
+
+
 def test_stage_entry_argument_checks():
     dev = _gpu()
     from nopesac_b200 import _lib, ops

@@ -196,3 +196,24 @@ def test_resnet50_backbone_glue_on_host_matches_oracle(host_ops, u8):
         rel = util.maxdiff(got[k], want[k]) / float(want[k].abs().max())
         assert rel <= 1e-4, (k, rel)
     assert {k: (v.channels, v.stride) for k, v in net.output_shape().items()} == {"res2": (256, 4), "res3": (512, 8), "res4": (1024, 16), "res5": (2048, 32)}
+
+
+def test_backbone_entry_equals_python_stages_on_host(host_ops, monkeypatch):
+    """nsac_backbone_forward (csrc/forward.cu compiled for the host, tensor engine = stand-ins) == the Python loop of
+    backbone.py, bit for bit, on a small uint8 batch with odd sizes."""
+    from nopesac_b200 import backbone, config, synthetic
+    images = synthetic.make_images(3, 1, 37, 52)
+    outs = {}
+    for flag in (True, False):
+        if flag:
+            monkeypatch.delenv("NSAC_PY_STAGES", raising=False)
+        else:
+            monkeypatch.setenv("NSAC_PY_STAGES", "1")
+        net = backbone.build_backbone(config.inference_cfg())
+        shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+        net.load_state_dict(synthetic.make_backbone_weights(shapes, seed=8))
+        assert net.use_stage_entry == flag
+        outs[flag] = net(images, planes=True)
+    for k in ("res2", "res3", "res4", "res5"):
+        (a, ha, wa), (b, hb, wb) = outs[True][k], outs[False][k]
+        assert (ha, wa) == (hb, wb) and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo), k
