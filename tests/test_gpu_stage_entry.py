@@ -168,7 +168,7 @@ def test_model_entry_equals_python_stages(monkeypatch):
     assert set(outs[True]) == set(outs[False])
     for k in outs[True]:
         assert torch.equal(outs[True][k], outs[False][k]), k
-    assert 300 < launches[True] <= launches[False] + 2
+    assert 300 < launches[True] <= launches[False] + 8        # (the C path splits the two views and builds the matcher pose with its own tiny kernels)
 
 
 def test_stage_entry_argument_checks():
