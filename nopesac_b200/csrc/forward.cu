@@ -509,14 +509,20 @@ inline int half_up(int v) { return (v - 1) / 2 + 1; }
 size_t carve_backbone(Arena& a, int N, int H, int W, BackboneScratch& s) {
   const size_t Ho = half_up(H), Wo = half_up(W), r1 = (size_t)N * Ho * Wo;           // stem output
   const size_t H2 = half_up((int)Ho), W2 = half_up((int)Wo), r2 = (size_t)N * H2 * W2;    // res2 level
-  s.cols = a.take(r1 * 192 * 2);
-  s.stem_out = static_cast<float*>(a.take(r1 * 64 * 4));
-  // widest tensors per role, all at the res2 level (later levels have 2x the channels on 4x fewer pixels)
-  auto pl = [&](size_t rows, int ld) { Planes p = a.planes(rows, ld); return p; };
-  s.x[0] = pl(r2, 256); s.x[1] = pl(r2, 256);
-  s.y1 = pl(r2, 128);           // conv1 output: 64 @ res2 .. 512 @ res5; res3.0.conv1 runs at the res2 level with 128 channels
-  s.y2 = pl(r2, 64);            // conv2 output (after the stride)
-  s.sc = pl(r2, 256);           // projection shortcut
+  // The stem's im2col matrix (r1 x 192 fp16) and its fp32 output (r1 x 64) are dead once the max-pool has run: the block
+  // ping-pong buffers (widest at the res2 level: r2 x 256, two planes) live in the same memory.  x[0] (the max-pool's output)
+  // overlays the im2col matrix, which the stem GEMM has consumed by then; x[1] overlays the stem output, first written by
+  // res2.0's last convolution.
+  const size_t xb = r2 * 256 * 2 * 2, cols_b = r1 * 192 * 2, so_b = r1 * 64 * 4;
+  uint8_t* reg0 = static_cast<uint8_t*>(a.take(cols_b > xb ? cols_b : xb));
+  uint8_t* reg1 = static_cast<uint8_t*>(a.take(so_b > xb ? so_b : xb));
+  s.cols = reg0;
+  s.stem_out = reinterpret_cast<float*>(reg1);
+  s.x[0] = Planes{reg0, reg0 ? reg0 + xb / 2 : nullptr, 256};
+  s.x[1] = Planes{reg1, reg1 ? reg1 + xb / 2 : nullptr, 256};
+  s.y1 = a.planes(r2, 128);     // conv1 output: 64 @ res2 .. 512 @ res5; res3.0.conv1 runs at the res2 level with 128 channels
+  s.y2 = a.planes(r2, 64);      // conv2 output (after the stride)
+  s.sc = a.planes(r2, 256);     // projection shortcut
   return a.off;
 }
 
