@@ -59,7 +59,11 @@ struct Cfg {
   // RES (residual epilogue, 64-wide tiles only): two tile buffers [128 x 64] x (hi, lo) = 2 x 32 KB.  The residual tile is
   // TMA-prefetched into one of them while the tile's MMAs run, the epilogue turns it IN PLACE into the output tile, and a TMA
   // store writes it out asynchronously - no per-warp staging buffers, no latency-exposed global loads in the epilogue.
-  static_assert(!RES || BLOCK_N == 64, "the residual epilogue uses 64-wide tiles");
+  // RES = 3: residual read straight from global memory in the plain row-per-lane epilogue of the 128-wide kernel (no tile
+  // buffers, no TMA store): for the deep-K layers (res4 / res5), where 64-wide tiles are bound by re-fetching A from L2
+  static constexpr bool RES_TMA = RES == 1 || RES == 2;
+  static_assert(!RES_TMA || BLOCK_N == 64, "the in-place residual epilogue uses 64-wide tiles");
+  static_assert(RES != 3 || BLOCK_N == 128, "the global-residual epilogue is the 128-wide kernel's");
   static constexpr int STAGES = RES == 2 ? 2 : (RES == 1 ? 3 : (BLOCK_N == 64 ? 4 : 3));       // 48 KB / 64 KB per stage
   static constexpr int RES_BUFS = RES == 2 ? 4 : (RES == 1 ? 2 : 0);    // tile buffers: residual prefetch that many tiles ahead, stores drain behind
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;     // one plane
@@ -67,11 +71,11 @@ struct Cfg {
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * W_BYTES;
   static constexpr int ACC_COLS = 2 * BLOCK_N;              // one buffer = hi.hi accumulator + lo-terms accumulator
   static constexpr int TMEM_COLS = 2 * ACC_COLS;            // two buffers (ping-pong between chunks / tiles)
-  static constexpr int RES_PLANE_BYTES = RES ? BLOCK_M * 128 : 0;          // [128 rows x 64 columns] of one plane, 128-byte swizzled rows
+  static constexpr int RES_PLANE_BYTES = RES_TMA ? BLOCK_M * 128 : 0;          // [128 rows x 64 columns] of one plane, 128-byte swizzled rows
   static constexpr int TILE_BUF_BYTES = 2 * RES_PLANE_BYTES;               // hi + lo
   static constexpr int RES_BYTES = RES_BUFS * TILE_BUF_BYTES;
-  static constexpr int OUT_STAGE_BYTES = RES ? 0 : EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
-  static constexpr int THREADS = NUM_THREADS + (RES ? 32 : 0);             // RES: + one warp that owns the TMA stores of the output tiles
+  static constexpr int OUT_STAGE_BYTES = RES_TMA ? 0 : EPI_WARPS * 4096;  // per epilogue warp: 32 rows x 128 B, to turn row-per-lane data into coalesced stores
+  static constexpr int THREADS = NUM_THREADS + (RES_TMA ? 32 : 0);             // RES: + one warp that owns the TMA stores of the output tiles
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + RES_BYTES + 1024 /*align*/ + 256 /*barriers*/ + OUT_STAGE_BYTES;
   static_assert(SMEM_BYTES <= 232448, "shared memory budget");
   static_assert(TMEM_COLS <= 512, "TMEM has 512 columns");
@@ -271,6 +275,8 @@ struct EpiOut {
   int n_valid;            // valid columns from col0 on (>= 32: full chunk)
   bool vec_ok;            // 16-byte aligned rows: vector loads / stores allowed
   float row_bias;         // per-row scalar added with the bias (0 if none)
+  const uint16_t* res_hi; // RES = 3: this row's residual planes (nullptr: none); added before the activation
+  const uint16_t* res_lo;
 };
 
 // packed 16-bit plane word -> two floats
@@ -303,6 +309,15 @@ __device__ __forceinline__ void finish32(const u64 (&acc)[16], int col0, const E
     const u64 rb = pk2(o.row_bias, o.row_bias);
     upk2(ffma2(acc[i >> 1], sc, fadd2(b01, rb)), f[i], f[i + 1]);
     upk2(ffma2(acc[(i >> 1) + 1], sc, fadd2(b23, rb)), f[i + 2], f[i + 3]);
+  }
+  if (o.res_hi) {          // slow path of the global-residual epilogue (ragged tiles): element loads
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+      if (i < o.n_valid) {
+        const uint32_t h = o.res_hi[col0 + i], l = o.res_lo[col0 + i];
+        f[i] += unsplit16x2<FMT>(h).x + unsplit16x2<FMT>(l).x;
+      }
+    }
   }
 #pragma unroll
   for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], fmaf(o.slope, f[i], 0.f));      // (+0 addend: ReLU of a negative is +0, not -0)
@@ -375,6 +390,31 @@ __device__ __forceinline__ void staged_store(uint8_t* stage, const uint32_t (&w)
   __syncwarp();
 }
 
+// The reverse: coalesced global loads -> row-per-lane data.  row_ptr = this lane's own source (start of its row segment of
+// WORDS * 4 bytes); every load instruction reads full lines (the rows of `RPI` lanes at a time) into the warp's staging buffer,
+// then each lane picks up its own row.
+template <int WORDS>
+__device__ __forceinline__ void staged_load(uint8_t* stage, uint32_t (&w)[WORDS], const uint8_t* row_ptr, int lane) {
+  constexpr int BYTES = WORDS * 4, CPR = BYTES / 16, RPI = 32 / CPR;
+  const int sub = lane / CPR, ch = lane % CPR;
+  const unsigned long long my = reinterpret_cast<unsigned long long>(row_ptr);
+#pragma unroll
+  for (int j = 0; j < 32 / RPI; ++j) {
+    const int row = RPI * j + sub;
+    const int swz_r = CPR == 8 ? (row & 7) : ((row >> 1) & 3);
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, my, row));
+    *reinterpret_cast<uint4*>(stage + row * BYTES + ((ch ^ swz_r) << 4)) = __ldg(reinterpret_cast<const uint4*>(src + ch * 16));
+  }
+  __syncwarp();
+  const int swz_w = CPR == 8 ? (lane & 7) : ((lane >> 1) & 3);
+#pragma unroll
+  for (int c = 0; c < CPR; ++c) {
+    const uint4 x = *reinterpret_cast<const uint4*>(stage + lane * BYTES + ((c ^ swz_w) << 4));
+    w[4 * c] = x.x; w[4 * c + 1] = x.y; w[4 * c + 2] = x.z; w[4 * c + 3] = x.w;
+  }
+  __syncwarp();
+}
+
 // 64 accumulator columns of a full tile part (every lane of the warp has a valid row, all 64 columns valid, aligned):
 // scale, bias, activation, then fp32 rows and / or split planes through the staged stores, 32 columns at a time
 template <int FMT, int GROUPS>
@@ -383,12 +423,23 @@ __device__ __forceinline__ void finish64_staged(const u64 (&sum)[16 * GROUPS], i
 #pragma unroll
   for (int g = 0; g < GROUPS; ++g) {       // groups of 32 columns (two for 128-wide tiles, one for 64-wide tiles)
     uint32_t f[32];                        // fp32 bit patterns
+    uint32_t rh[16], rl[16];               // RES = 3: this row's 32 residual columns, both planes (2 x 64 contiguous bytes),
+    if (o.res_hi) {                        // fetched with full-line loads through the staging buffer (warp-uniform branch)
+      staged_load<16>(stage, rh, reinterpret_cast<const uint8_t*>(o.res_hi + col0 + 32 * g), lane);
+      staged_load<16>(stage, rl, reinterpret_cast<const uint8_t*>(o.res_lo + col0 + 32 * g), lane);
+    }
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
       u64 b01 = 0ull, b23 = 0ull;
       if (o.brow) {
         const float4 b4 = __ldg(reinterpret_cast<const float4*>(o.brow + col0 + 32 * g + i));
         b01 = pk2(b4.x, b4.y); b23 = pk2(b4.z, b4.w);
+      }
+      if (o.res_hi) {                      // bias + residual (hi + lo reproduces the fp32 activation)
+        const uint32_t hw0 = rh[i >> 1], hw1 = rh[(i >> 1) + 1], lw0 = rl[i >> 1], lw1 = rl[(i >> 1) + 1];
+        const float2 a0 = unsplit16x2<FMT>(hw0), a1 = unsplit16x2<FMT>(hw1), c0 = unsplit16x2<FMT>(lw0), c1 = unsplit16x2<FMT>(lw1);
+        b01 = fadd2(b01, fadd2(pk2(a0.x, a0.y), pk2(c0.x, c0.y)));
+        b23 = fadd2(b23, fadd2(pk2(a1.x, a1.y), pk2(c1.x, c1.y)));
       }
       float x0, x1, x2, x3;
       const u64 rb = pk2(o.row_bias, o.row_bias);
@@ -489,7 +540,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
           y0 = (t2 / p.tiles_x) * p.BH;
           x0 = (t2 % p.tiles_x) * p.BW;
         }
-        if (RES) {     // this tile's residual [128 x 64] x (hi, lo) into tile buffer tile_ctr & 1: lands while the MMAs run
+        if (C::RES_TMA) {     // this tile's residual [128 x 64] x (hi, lo) into a tile buffer: lands while the MMAs run
           const uint32_t b = tile_ctr % RB, use = tile_ctr / RB;
           mbar_wait(&res_empty[b], (use & 1) ^ 1);            // the TMA store of the buffer's previous tile has read it out
           mbar_expect_tx(&res_full[b], (uint32_t)C::TILE_BUF_BYTES);
@@ -559,7 +610,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         }
       }
     }
-  } else if (RES && warp == 2 + EPI_WARPS) {
+  } else if (C::RES_TMA && warp == 2 + EPI_WARPS) {
     // ===================================================================== TMA store warp (residual epilogue only)
     // Takes everything after the epilogue math off the epilogue warps' critical path: they arrive on tile_ready[b] and go on to the
     // next tile; this thread stores the finished tile, waits until the store has READ the buffer and hands it back to the producer.
@@ -618,7 +669,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
         if (lane == 0) mbar_arrive(&tmem_empty[buf]);
       }
       if (tile == (int)blockIdx.x && threadIdx.x == 64) GEMM_TRACE(9);
-      if constexpr (RES) {
+      if constexpr (C::RES_TMA) {
         // ---- residual epilogue: out = act(acc * scale + bias + residual), IN PLACE in the tile buffer, then one TMA store.
         // lane = tile row quad * 32 + lane, this warp's 32 columns = 16-byte chunks half * 4 .. half * 4 + 3 of the 128-byte row
         const uint32_t b = res_ctr % RB;
@@ -674,13 +725,16 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_co
       o.out_scale = p.out_scale;
       o.slope = p.act == NSAC_ACT_RELU ? 0.f : (p.act == NSAC_ACT_LEAKY ? 0.01f : 1.f);
       o.brow = nullptr; o.out_f32 = nullptr; o.out_hi = nullptr; o.out_lo = nullptr; o.vec_ok = false; o.n_valid = 0;
+      o.res_hi = nullptr; o.res_lo = nullptr;
       o.row_bias = (p.row_bias && row_ok) ? __ldg(p.row_bias + row) : 0.f;
       if (row_ok) {
         if (p.bias) o.brow = p.bias_group_rows > 0 ? p.bias + (size_t)(row / p.bias_group_rows) * p.N : p.bias;
         o.out_f32 = p.out_f32 ? p.out_f32 + (size_t)row * p.ldo : nullptr;
         o.out_hi = p.out_hi ? p.out_hi + (size_t)row * p.ld_split : nullptr;
         o.out_lo = p.out_lo ? p.out_lo + (size_t)row * p.ld_split : nullptr;
-        o.vec_ok = (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
+        if (RES == 3) { o.res_hi = p.res_hi + (size_t)row * p.ld_res; o.res_lo = p.res_lo + (size_t)row * p.ld_res; }
+        o.vec_ok = (RES != 3 || ((reinterpret_cast<uintptr_t>(o.res_hi) | reinterpret_cast<uintptr_t>(o.res_lo)) & 15) == 0) &&
+                   (!o.brow || (reinterpret_cast<uintptr_t>(o.brow) & 15) == 0) &&
                    (!o.out_f32 || (reinterpret_cast<uintptr_t>(o.out_f32) & 15) == 0) &&
                    (!o.out_hi || ((reinterpret_cast<uintptr_t>(o.out_hi) | reinterpret_cast<uintptr_t>(o.out_lo)) & 15) == 0);
       }
@@ -943,6 +997,11 @@ static int gemm_split_impl(const void* a_hi, const void* a_lo, int lda, const vo
     // (residual prefetch + store drain depth: 0.69 -> 0.88 of the HBM bound) and two operand stages; deeper K keeps three
     // operand stages and two tile buffers (operand delivery is what bounds those; measured both ways, profiles/README.md r2y)
     if (K <= 128) return launch_gemm<64, 2>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
+    // K >= 512 (res5): 128-wide tiles halve the A traffic from L2 and the MMAs of a tile last long enough to hide the heavier
+    // epilogue (residual fetched from global through the staging buffer): 341 -> 295 us; at K = 256 (res4) that epilogue is
+    // the limiter (482 vs 424 us) and the 64-wide in-place variant stays (profiles/README.md, r2dd / r2ee)
+    if (block_n == 128 && K >= 512)
+      return launch_gemm<128, 3>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);
     return launch_gemm<64, 1>(mah, mal, mw64h, mw64l, mrh, mrl, moh, mol, p, nsac_cdiv(M, BLOCK_M), s);
   }
   if (block_n == 64) return launch_gemm<64, 0>(mah, mal, mwh, mwl, mwh, mwl, mwh, mwl, p, nsac_cdiv(M, BLOCK_M), s);

@@ -105,7 +105,7 @@ def test_fp16_plane_overflow_is_loud():
 
 
 @pytest.mark.parametrize("M,N,K", [(256, 256, 64), (1000, 512, 128), (130, 64, 576), (4096, 1024, 256), (300, 200, 192), (77, 48, 64),
-                                   (40000, 256, 64), (20000, 512, 128), (30000, 1024, 256)])    # many tiles per CTA: every tile buffer is reused
+                                   (40000, 256, 64), (20000, 512, 128), (30000, 1024, 256), (5000, 2048, 512), (333, 200, 640)])    # many tiles per CTA: every tile buffer is reused; K >= 512: 128-wide tiles, residual from global
 def test_gemm_residual_epilogue_matches_fp64(M, N, K):
     """nsac_gemm_split_residual: relu(x.W^T + b + residual) with the residual given as hi/lo planes (TMA-prefetched tile) — the
     fused `out += shortcut; relu` of the backbone's bottleneck blocks; full tiles, ragged M / N, and the 64-wide tile variant."""
