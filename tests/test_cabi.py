@@ -63,3 +63,34 @@ def test_evaluation_fails_loudly_without_cuda_tensors():
         evaluation.camera_metrics(torch.zeros(2, 16), torch.zeros(2, 3), torch.zeros(2, 4))
     assert evaluation.CameraEvaluator().evaluate() == {}
     assert evaluation.METRIC_KEYS[0] == "T median err" and len(evaluation.METRIC_KEYS) == 10
+
+
+def test_stage_entry_workspaces_and_argument_checks_without_gpu():
+    """The whole-stage entries (csrc/forward.cu) size their own workspaces (pure host functions) and validate arguments before any
+    CUDA call: a null weight struct or too small a workspace comes back as NSAC_ERR_ARG with a message, nothing is launched."""
+    from nopesac_b200 import _lib
+    L = _lib.lib()
+    B, H, W, n1, n2, NQ = 64, 480, 640, 16, 16, 256
+    pix, mat, ref = L.nsac_pixel_workspace_bytes(B, H // 8, W // 8), L.nsac_match_workspace_bytes(B, n1, n2), L.nsac_refine_workspace_bytes(B, NQ)
+    head, bb, model = (L.nsac_head_workspace_bytes(B, H // 8, W // 8, n1, n2, NQ), L.nsac_backbone_workspace_bytes(2 * B, H, W),
+                       L.nsac_model_workspace_bytes(B, H, W, n1, n2, NQ))
+    assert min(pix, mat, ref) > 0 and all(v % 256 == 0 for v in (pix, mat, ref, bb))
+    assert max(pix, mat, ref) <= head <= max(pix, mat, ref) + 4096            # stages run one after the other: the max, + the cam rows
+    assert max(bb, head) < model <= max(bb, head) + (3 << 30)                 # + the res3 / res4 / res5 planes of 128 images
+    assert model < 16 << 30, "the S5 workspace of a 64-pair step should stay well inside 180 GB of HBM"
+    assert L.nsac_refine_workspace_bytes(2 * B, NQ) > ref and L.nsac_backbone_workspace_bytes(B, H, W) < bb
+    # degenerate sizes -> 0 (the callers treat it as "cannot run")
+    assert L.nsac_model_workspace_bytes(B, 481, 640, n1, n2, NQ) == 0 and L.nsac_backbone_workspace_bytes(1, 8, 8) == 0
+    assert L.nsac_head_workspace_bytes(0, 60, 80, n1, n2, NQ) == 0
+    # null weights / workspace: refused before anything touches the device
+    nul = [None] * 20
+    assert L.nsac_refine_forward(None, None, None, None, None, 0, None, None, None, None, B, n1, n2, NQ, 0, *[None] * 12, None, 0, None, 0, 0,
+                                 None, None) == -1
+    assert b"nsac_refine_forward" in L.nsac_last_error()
+    assert L.nsac_match_forward(None, None, None, None, None, None, None, None, 0.2, B, n1, n2, None, None, None, 0, None, None) == -1
+    assert b"nsac_match_forward" in L.nsac_last_error()
+    assert L.nsac_backbone_forward(None, None, 2 * B, H, W, *[None] * 8, None, 0, None, None) == -1
+    assert b"nsac_backbone_forward" in L.nsac_last_error()
+    assert L.nsac_model_forward(None, None, None, B, H, W, None, None, None, None, None, None, n1, n2, None, 0, NQ, 0.2, 0, *nul, None, 0, None, 0, 0,
+                                None, None) == -1
+    assert b"nsac_model_forward" in L.nsac_last_error()
