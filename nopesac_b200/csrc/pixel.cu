@@ -237,22 +237,37 @@ gn4_apply_kernel(const float* __restrict__ x, int H, int W, int C, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------ 2x2 max-pool
+// VEC = 4: one thread = 4 channels of one output pixel (16-byte loads, 8-byte plane stores); VEC = 1: any C / alignment
+template <int VEC>
 __global__ void maxpool2_planes_kernel(const float* __restrict__ x, int N, int H, int W, int C, int fmt,
                                        uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
-  const int Ho = H >> 1, Wo = W >> 1;
-  const size_t total = (size_t)N * Ho * Wo * C;
+  const int Ho = H >> 1, Wo = W >> 1, Cv = C / VEC;
+  const size_t total = (size_t)N * Ho * Wo * Cv;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C);
-    size_t t = i / C;
+    const int c = (int)(i % Cv) * VEC;
+    size_t t = i / Cv;
     const int xo = (int)(t % Wo); t /= Wo;
     const int yo = (int)(t % Ho);
     const int n = (int)(t / Ho);
     const float* p = x + (((size_t)n * H + 2 * yo) * W + 2 * xo) * C + c;
-    const float m = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(size_t)W * C], p[(size_t)W * C + C]));
-    uint16_t h, l;
-    split16(m, fmt, h, l);
-    hi[i] = h;
-    lo[i] = l;
+    const size_t o = ((((size_t)n * Ho + yo) * Wo + xo)) * C + c;
+    if (VEC == 4) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p + C));
+      const float4 d = __ldg(reinterpret_cast<const float4*>(p + (size_t)W * C)), e = __ldg(reinterpret_cast<const float4*>(p + (size_t)W * C + C));
+      const float m[4] = {fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                          fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w))};
+      uint16_t h[4], l[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) split16(m[k], fmt, h[k], l[k]);
+      *reinterpret_cast<uint2*>(hi + o) = make_uint2((uint32_t)h[0] | ((uint32_t)h[1] << 16), (uint32_t)h[2] | ((uint32_t)h[3] << 16));
+      *reinterpret_cast<uint2*>(lo + o) = make_uint2((uint32_t)l[0] | ((uint32_t)l[1] << 16), (uint32_t)l[2] | ((uint32_t)l[3] << 16));
+    } else {
+      const float m = fmaxf(fmaxf(p[0], p[C]), fmaxf(p[(size_t)W * C], p[(size_t)W * C + C]));
+      uint16_t h, l;
+      split16(m, fmt, h, l);
+      hi[o] = h;
+      lo[o] = l;
+    }
   }
 }
 
@@ -261,7 +276,7 @@ __global__ void maxpool2_planes_kernel(const float* __restrict__ x, int N, int H
 // positions enumerated w-major (c2 = w2 * H + h2), softmax over c2.  NHWC in, NHWC planes out:
 // out[(b*HW + p1), c2], channels padded to Cp (multiple of 64) with zeros.  One CTA per (pair, 8 view-1 pixels).
 constexpr int CORR_PIX = 8;
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 corr_softmax_kernel(const float* __restrict__ f1, const float* __restrict__ f2, int H, int W, int C, int Cp, int fmt,
                     uint16_t* __restrict__ hi, uint16_t* __restrict__ lo) {
   extern __shared__ float sm[];
@@ -400,11 +415,16 @@ extern "C" int nsac_groupnorm_nhwc(const float* x, int N, int H, int W, int C, i
 extern "C" int nsac_maxpool2_planes(const float* x, int N, int H, int W, int C, int fmt, void* hi, void* lo, void* stream) {
   NSAC_REQUIRE(x && hi && lo && N >= 0 && H >= 2 && W >= 2 && C >= 1, "nsac_maxpool2_planes: bad arguments");
   if (N == 0) return NSAC_OK;
-  const size_t total = (size_t)N * (H / 2) * (W / 2) * C;
+  const bool vec = C % 4 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0 && ((reinterpret_cast<uintptr_t>(hi) | reinterpret_cast<uintptr_t>(lo)) & 7) == 0;
+  const size_t total = (size_t)N * (H / 2) * (W / 2) * (vec ? C / 4 : C);
   int blocks = (int)((total + 255) / 256);
   if (blocks > 148 * 32) blocks = 148 * 32;
-  maxpool2_planes_kernel<<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, N, H, W, C, fmt, static_cast<uint16_t*>(hi),
-                                                                                 static_cast<uint16_t*>(lo));
+  if (vec)
+    maxpool2_planes_kernel<4><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, N, H, W, C, fmt, static_cast<uint16_t*>(hi),
+                                                                                      static_cast<uint16_t*>(lo));
+  else
+    maxpool2_planes_kernel<1><<<blocks, 256, 0, static_cast<cudaStream_t>(stream)>>>(x, N, H, W, C, fmt, static_cast<uint16_t*>(hi),
+                                                                                      static_cast<uint16_t*>(lo));
   NSAC_CHECK_LAUNCH("nsac_maxpool2_planes");
   return NSAC_OK;
 }
@@ -417,8 +437,11 @@ extern "C" int nsac_corr_softmax(const float* f1, const float* f2, int B, int H,
   NSAC_REQUIRE(smem <= 200 * 1024, "nsac_corr_softmax: feature map too large");
   if (smem > 48 * 1024) NSAC_CUDA(cudaFuncSetAttribute(corr_softmax_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   dim3 grid(nsac_cdiv(H * W, CORR_PIX), B);
-  corr_softmax_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(f1, f2, H, W, C, Cp, fmt, static_cast<uint16_t*>(hi),
-                                                                               static_cast<uint16_t*>(lo));
+  // one thread per view-2 position where that fits (15 x 20 maps: 320 threads, a single pass instead of 256 threads + a ragged second one)
+  int threads = (H * W + 31) / 32 * 32;
+  threads = threads < 256 ? 256 : (threads > 512 ? 512 : threads);
+  corr_softmax_kernel<<<grid, threads, smem, static_cast<cudaStream_t>(stream)>>>(f1, f2, H, W, C, Cp, fmt, static_cast<uint16_t*>(hi),
+                                                                                   static_cast<uint16_t*>(lo));
   NSAC_CHECK_LAUNCH("nsac_corr_softmax");
   return NSAC_OK;
 }
