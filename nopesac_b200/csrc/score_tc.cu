@@ -51,7 +51,16 @@ constexpr int TILE_H = 128;        // hypotheses per tile (UMMA M)
 constexpr int HID = 128;           // hidden width of the score MLPs (UMMA N)
 constexpr int KB = 64;             // residual columns per k-block (one 128-byte swizzle row of fp16)
 constexpr int C_FEAT = 256;
-constexpr int W_STAGES = 2, A_STAGES = 2;
+#ifndef NSAC_SCORE_W_STAGES
+#define NSAC_SCORE_W_STAGES 2
+#endif
+#ifndef NSAC_SCORE_F_STAGES
+#define NSAC_SCORE_F_STAGES 4
+#endif
+#ifndef NSAC_SCORE_A_STAGES
+#define NSAC_SCORE_A_STAGES 2
+#endif
+constexpr int W_STAGES = NSAC_SCORE_W_STAGES, A_STAGES = NSAC_SCORE_A_STAGES;
 constexpr int BLK_BYTES = TILE_H * KB * 2;           // 16 KB: one [128 x 64] fp16 operand block
 // warp roles, aligned to warpgroups of 4 warps so that setmaxnreg can move registers between the roles
 // (launch: 1024 threads x 64 registers = the whole register file):
@@ -75,7 +84,7 @@ constexpr int PART_HDR = 4;                          // max, sumexp, pad, pad (k
 constexpr int PART_STRIDE = PART_HDR + 2 * C_FEAT;   // per (pair, tile, branch): header, wsum[256], fsum[256]
 
 // shared memory map (offsets from a 1024-aligned base)
-constexpr int F_STAGES = 4, F_BYTES = 16384;                       // feature ring: 16 hypothesis rows x 256 fp32 per stage (the single
+constexpr int F_STAGES = NSAC_SCORE_F_STAGES, F_BYTES = 16384;                       // feature ring: 16 hypothesis rows x 256 fp32 per stage (the single
                                                                    // producer thread needs ~0.26 us per bulk copy: 8 KB chunks capped the stream at 31 GB/s per SM)
 constexpr int F_ROWS = F_BYTES / (C_FEAT * 4);
 constexpr int OFF_F = 0;                                         // [F_STAGES][F_BYTES] feature ring (TMA bulk copies)
@@ -83,7 +92,7 @@ constexpr int OFF_W1 = OFF_F + F_STAGES * F_BYTES;               // [stage][bran
 constexpr int OFF_A = OFF_W1 + W_STAGES * 2 * BLK_BYTES;         // [stage][branch][16 KB]
 constexpr int CJK_BYTES = 4096;                                   // per k-block: 2 KB column constants + 2 KB B fragments
 constexpr int OFF_CJ = OFF_A + A_STAGES * 2 * BLK_BYTES;         // [A_STAGES][CJK_BYTES] column block of the k-block (TMA)
-constexpr int OFF_VEC = OFF_CJ + W_STAGES * CJK_BYTES;           // b1[2][128], b2[2][128], w34[2][128] floats
+constexpr int OFF_VEC = OFF_CJ + A_STAGES * CJK_BYTES;           // b1[2][128], b2[2][128], w34[2][128] floats
 constexpr int OFF_LOGIT = OFF_VEC + 6 * HID * 4;                 // [2 bufs][2 branches][128] floats
 constexpr int OFF_ROWSUM = OFF_LOGIT + 2 * 2 * TILE_H * 4;       // [2 column halves][2 branches][128] floats (min-cost sums)
 constexpr int OFF_EXP = OFF_ROWSUM + 2 * 2 * TILE_H * 4;         // [2 branches][128] softmax numerators of the tile
@@ -91,6 +100,7 @@ constexpr int OFF_GPART = OFF_EXP + 2 * TILE_H * 4;              // [2 branches]
 constexpr int OFF_BAR = OFF_GPART + 2 * 64 * 12 * 4;
 constexpr int SMEM_BYTES = OFF_BAR + 512 + 1024;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget");
+static_assert(F_STAGES % 2 == 0, "rot / tran chunks alternate through the feature ring");
 
 // tensor-memory columns
 constexpr uint32_t TM_D = 0;          // layer 1: D_rot [0,128), D_tran [128,256); H1 (fp16 pairs) overwrites the first 64
@@ -99,9 +109,11 @@ constexpr uint32_t TM_D2 = 256;       // layer 2: D2_rot [256,384), D2_tran [384
                                       // while the epilogue warps still read D2 (MMAs execute in issue order: no barrier)
 constexpr uint32_t TM_COLS = 512;
 
-enum { BAR_CJ_FULL = 0, BAR_W_FULL = 2, BAR_W_EMPTY = 4, BAR_A_FULL = 6, BAR_A_EMPTY = 8, BAR_ACC_FULL = 10, BAR_H1_READY = 11,
-       BAR_ACC2_FULL = 12, BAR_LOGIT_READY = 13, BAR_LOGIT_FREE = 15, BAR_CJ_EMPTY = 17, BAR_F_FULL = 19,
-       BAR_F_EMPTY = BAR_F_FULL + F_STAGES, BAR_COUNT = BAR_F_EMPTY + F_STAGES };
+enum { BAR_CJ_FULL = 0, BAR_CJ_EMPTY = BAR_CJ_FULL + A_STAGES, BAR_W_FULL = BAR_CJ_EMPTY + A_STAGES, BAR_W_EMPTY = BAR_W_FULL + W_STAGES,
+       BAR_A_FULL = BAR_W_EMPTY + W_STAGES, BAR_A_EMPTY = BAR_A_FULL + A_STAGES, BAR_ACC_FULL = BAR_A_EMPTY + A_STAGES,
+       BAR_H1_READY = BAR_ACC_FULL + 1, BAR_ACC2_FULL = BAR_H1_READY + 1, BAR_LOGIT_READY = BAR_ACC2_FULL + 1,
+       BAR_LOGIT_FREE = BAR_LOGIT_READY + 2, BAR_F_FULL = BAR_LOGIT_FREE + 2, BAR_F_EMPTY = BAR_F_FULL + F_STAGES,
+       BAR_COUNT = BAR_F_EMPTY + F_STAGES };
 static_assert(BAR_COUNT * 8 + 8 <= 512, "barrier area");
 
 // ------------------------------------------------------------------------------------------------ PTX helpers
