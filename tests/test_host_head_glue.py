@@ -217,3 +217,11 @@ def test_backbone_entry_equals_python_stages_on_host(host_ops, monkeypatch):
     for k in ("res2", "res3", "res4", "res5"):
         (a, ha, wa), (b, hb, wb) = outs[True][k], outs[False][k]
         assert (ha, wa) == (hb, wb) and torch.equal(a.hi, b.hi) and torch.equal(a.lo, b.lo), k
+
+
+def test_empty_batch_is_refused_loudly(host_ops):
+    """B = 0 never reaches a kernel: the single-call entry refuses it with a message (the reference only ever runs one pair)."""
+    head, match, _, _ = util.build_cuda_heads(32, "soft", 0.2, "cpu")
+    z = lambda *s: torch.zeros(*s)
+    with pytest.raises(RuntimeError, match="bad sizes B=0"):
+        head(None, None, z(0, 8, 3), z(0, 8, 3), z(0, 8, 256), z(0, 8, 256), matching_net=match, initial_pose=(z(0, 3), z(0, 4)))
