@@ -94,3 +94,23 @@ def test_stage_entry_workspaces_and_argument_checks_without_gpu():
     assert L.nsac_model_forward(None, None, None, B, H, W, None, None, None, None, None, None, n1, n2, None, 0, NQ, 0.2, 0, *nul, None, 0, None, 0, 0,
                                 None, None) == -1
     assert b"nsac_model_forward" in L.nsac_last_error()
+
+
+def test_header_compiles_as_plain_c(tmp_path):
+    """include/nopesac_b200.h is the drop-in boundary: it must be consumable by a C compiler (cgo / JNI / N-API style binders),
+    not only by nvcc — plain pointers and sizes, no C++ in the signatures."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "use_header.c"
+    src.write_text('#include "nopesac_b200.h"\n'
+                   "int probe(void) {\n"
+                   "  nsac_refine_weights rw; nsac_match_weights mw; nsac_pixel_weights pw; nsac_backbone_weights bw;\n"
+                   "  nsac_head_weights hw; hw.pixel = &pw; hw.match = &mw; hw.refine = &rw; (void)bw;\n"
+                   "  return (int)sizeof(nsac_tc_layer) + (hw.pixel != 0) + NSAC_VERSION + NSAC_CAM_SOFT + NSAC_ACT_RELU;\n"
+                   "}\n")
+    res = subprocess.run([gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
+                          str(tmp_path / "use_header.o")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
